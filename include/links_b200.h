@@ -1,0 +1,220 @@
+/*
+ * links_b200.h -- C ABI of the B200-native LInKs lifting hot path.
+ *
+ * The reference (Aswarin/LInKs-3D-Human-Pose-Estimation) is pure Python/PyTorch and has no
+ * FFI of its own: the drop-in boundary is its Python module surface
+ * (utils/models_def.py, utils/helpers.py, utils/rotation_conversions.py, utils/metrics_batch.py,
+ * utils/metrics.py, FrEIA SequenceINN/AllInOneBlock).  This header is what those Python modules
+ * bind (ctypes); each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory owned by the caller (PyTorch);
+ *     the library never allocates, frees or synchronises; all launches are asynchronous on
+ *     `stream` (a cudaStream_t passed as void*) and CUDA-graph capturable.
+ *   - return 0 on success, negative = argument error (LINKS_E_*), positive = cudaError_t.
+ *   - fp32 tensors are row-major and dense unless a leading dimension is given.
+ *   - "bf16" tensors are raw 16-bit bfloat16.
+ *   - 2D poses are [M,34] = (17 x, 17 y); 3D poses are [M,51] = (17 X, 17 Y, 17 Z)
+ *     (reference utils/helpers.py:262-267 layout).
+ */
+#ifndef LINKS_B200_H
+#define LINKS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LINKS_ABI_VERSION 1
+
+#define LINKS_E_ARG (-1)      /* null pointer / bad size */
+#define LINKS_E_ALIGN (-2)    /* pointer or leading dimension not 16-byte aligned */
+#define LINKS_E_RANGE (-3)    /* value outside the supported range */
+#define LINKS_E_DRIVER (-4)   /* cuTensorMapEncodeTiled unavailable / failed */
+
+#define LINKS_MAX_GEMM_PROBLEMS 8
+#define LINKS_HEAD_LD 32      /* leading dimension of fp32 head outputs / part-gradient buffers */
+#define LINKS_KPAD 64         /* bf16 operand rows are padded to a multiple of 64 in K */
+#define LINKS_J 17
+
+int links_abi_version(void);
+/* 1 if the library was built for sm_100a and the current device is CC 10.x, else 0. */
+int links_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Grouped GEMM with fused epilogue (tcgen05 / TMEM / TMA).   D = epi(A[M,K] * B[N,K]^T)
+ * Replaces every nn.Linear (+LeakyReLU, +residual) of reference utils/models_def.py:10-39,
+ * 111-327 in forward, and its autograd backward (dgrad / wgrad).  A and B are bf16, K-major
+ * (row-major, K contiguous), accumulate fp32.
+ *
+ * Epilogue, applied per element in this order (null pointer = step skipped):
+ *   v = acc (+ bias[n])
+ *   sign_out bit (m, n) = !(v > 0)                       [1 bit / element, 32 columns / word]
+ *   LEAKY_PRE : v = v > 0 ? v : 0.01 v      (RELU_PRE : v = max(v, 0))
+ *   v += add0[m,n]  ; v += add1[m,n]                     [bf16]
+ *   LEAKY_POST: v = v > 0 ? v : 0.01 v
+ *   v *= (ymask[m,n] > 0 ? 1 : 0.01)                     [bf16 activation, leaky' of its producer]
+ *   mid[m,n] = bf16(v)
+ *   v *= (bits(m,n) ? 0.01 : 1)
+ *   out[m,n] = bf16(v); outT[n, outT_col0 + m] = bf16(v); out_f32[m,n] (+)= v
+ * ------------------------------------------------------------------------------------------ */
+#define LINKS_EPI_LEAKY_PRE 1u
+#define LINKS_EPI_LEAKY_POST 2u
+#define LINKS_EPI_RELU_PRE 4u
+#define LINKS_EPI_ACCUM_F32 8u
+
+typedef struct LinksGemmProblem {
+  const void* A;      /* bf16 [M, lda]  */
+  const void* B;      /* bf16 [N, ldb]  */
+  int M, N, K;        /* K = contraction length; lda, ldb >= K, multiples of 8 */
+  int lda, ldb;
+  uint32_t flags;
+  const float* bias;  /* [N] */
+  const void* add0; int ld_add0;   /* bf16 [M, ld] */
+  const void* add1; int ld_add1;
+  const void* ymask; int ld_ymask; /* bf16 [M, ld] */
+  const uint32_t* bits; int ld_bits;   /* [M, ld_bits] words, bit (n & 31) of word n >> 5 */
+  uint32_t* sign_out; int ld_sign;
+  void* mid; int ld_mid;           /* bf16 [M, ld] */
+  void* out; int ld_out;           /* bf16 [M, ld] */
+  void* outT; int ld_outT; int outT_col0;  /* bf16 [N, ld], written at columns outT_col0 + m */
+  float* out_f32; int ld_f32;      /* fp32 [M, ld] */
+} LinksGemmProblem;
+
+int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operand packing / reductions around the GEMMs
+ * ------------------------------------------------------------------------------------------ */
+/* Gather a joint subset of fp32 rows into a zero-padded bf16 GEMM operand (+ transposed copy).
+ * Replaces split_data_left_right (utils/helpers.py:55-65), the leg/torso slices
+ * (train_leg_torso_lifter.py:147-148) and the occlusion input gathers
+ * (train_occlusion_models.py:185-191) as integer index maps:
+ *   dst[m, c] = bf16(src[m * ld_src + idx[c]]) for c < n_idx, 0 for n_idx <= c < 64
+ *   dstT[c, colT0 + m] = same, for c < n_idx                   (dstT may be null)
+ * period > 1: idx holds period*n_idx offsets relative to a group of `period` rows
+ * (split_data_left_right_3d, utils/helpers.py:81-91, mixes row pairs; period = 2).          */
+int links_pack_rows(const float* src, int ld_src, int M, const int* idx_dev, int n_idx, int period,
+                    void* dst_bf16, void* dstT_bf16, int ldT, int colT0, void* stream);
+
+/* Column sums of a bf16 matrix: out[n] (+)= sum_m G[m, n]  (bias gradients). */
+int links_colsum_bf16(const void* G, int ldg, int M, int N, float* out, int accumulate, void* stream);
+
+/* fp32 master weights -> bf16 shadow W[N, Kpad] and W^T[K, Npad] (zero padded). */
+int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
+                      void* stream);
+
+/* torch.optim.Adam step with coupled L2 decay (train_leg_torso_lifter.py:111-114), flat buffers. */
+int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Geometry + losses (train_leg_torso_lifter.py:153-272, train_left_right_lifter.py:150-423)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct LinksGeomMaps {
+  int V;                 /* pose variants: 1 (leg/torso) or 2 (left-choice, right-choice) */
+  int n_joints[2];       /* joints per part net (7,10) or (11,11) */
+  int src_net[2][17];    /* [v][j]: which net's depth head feeds joint j of variant v */
+  int col[17];           /* column of that head (same for both variants) */
+  int part_net[2][17];   /* [v][j]: part net whose pass-2 / flow input takes joint j of variant v, or -1 */
+  int part_idx[2][17];   /* index of joint j inside that part */
+  float bone_rel[16];    /* bone-length prior constants */
+  float depth, w_likeli, w_2d, w_3d, w_vel, w_bl;
+} LinksGeomMaps;
+
+/* (mean, unbiased std) of props = (ang0 + ang1)/2 over N rows -> stats[2]
+ * (train_leg_torso_lifter.py:153,168).  ang* are head outputs with leading dim LINKS_HEAD_LD. */
+int links_elev_stats(const float* ang0, const float* ang1, int N, float* stats, void* stream);
+
+/* lift, rotate, project (:159-199).  Writes per-part projected inputs qpart[p] fp32 [N, 2*n_joints[p]]
+ * (x's then y's) and optionally the full rot_2d per variant q[v] [N,34]. */
+int links_geom_forward(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                       const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                       const float* stats, int N, float* qpart0, float* qpart1, float* q_full0,
+                       float* q_full1, void* stream);
+
+/* Re-lift consistency / reprojection / pairwise / bone losses and their gradient w.r.t. the pass-2
+ * depth heads (:228-259).  loss_sums[4] += (sum L3d, sum rep_rot, sum pair, sum bl) (un-normalised);
+ * g2_head[p] bf16 [N,64] = dLoss/d(pass-2 head p) (+ transposed copies at column colT0). */
+int links_geom_loss(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                    const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                    const float* stats, const float* head2_0, const float* head2_1, int N,
+                    float* loss_sums, void* g2_head0, void* g2_head1, void* g2T_head0, void* g2T_head1,
+                    int ldT, int colT0, void* stream);
+
+/* Backward of the whole geometry given external gradients on the projected parts
+ * (dpart_flow[p] [N, 2*n_joints[p]] from the flows, dpart_lift[p] [N, LINKS_HEAD_LD] from the pass-2
+ * upscale dgrad).  Phase A: per-row gradients, writes g1_head[p] (bf16 [N,64] + T), dgamma_direct[N],
+ * da[N] and accumulates red[2] += (sum da, sum eps*da).  Phase B (links_geom_backward_angles) adds the
+ * batch-statistic terms and writes the angle-head gradients. */
+int links_geom_backward(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                        const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                        const float* stats, const float* head2_0, const float* head2_1,
+                        const float* dpart_flow0, const float* dpart_flow1, const float* dpart_lift0,
+                        const float* dpart_lift1, int N, void* g1_head0, void* g1_head1, void* g1T_head0,
+                        void* g1T_head1, int ldT, int colT0, float* dgamma_direct, float* da, float* red,
+                        void* stream);
+int links_geom_backward_angles(const float* ang0, const float* ang1, const float* eps_x, const float* stats,
+                               const float* dgamma_direct, const float* red, int N, void* g_ang0,
+                               void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalising flow (FrEIA SequenceINN of 8 AllInOneBlock, permute_soft=True; call sites
+ * train_leg_torso_lifter.py:134-136,207-214; train_full_pose_norm_flow.py:75-90)
+ * ------------------------------------------------------------------------------------------ */
+/* Packed per-flow parameters are produced by links_flow_pack from FrEIA-layout tensors. */
+size_t links_flow_packed_floats(int C, int n_blocks);
+int links_flow_pack(int C, int n_blocks, const float* const* w0, const float* const* b0,
+                    const float* const* w2, const float* const* b2, const float* const* gscale,
+                    const float* const* goffset, const float* const* wperm, const float* const* wperm_inv,
+                    float* packed, void* stream);
+/* z, log_jac_det = inn(x, rev) for x [M,C] (ld = C). */
+int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, int M, int rev,
+                     float* out, float* log_jac_det, void* stream);
+/* nll[m] = 0.5*|z|^2 - log_jac_det, nll_sum += sum_m nll, dx = scale * d(nll)/dx (frozen flow). */
+int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
+                          float* nll_sum, float* dx, void* stream);
+/* Sampling block (train_leg_torso_lifter.py:133-142): out = [x ; s], s = inn^-1(z + 0.2*noise*z) with
+ * the root joint zeroed; C must be 34.  out is [2M,34]. */
+int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metrics (utils/metrics_batch.py:8-159, utils/metrics.py:35-171)
+ * per_pose / per_pose_max [M] and dist [M, num_joints] (each may be null) receive per-pose mean / max joint
+ * distance and all joint distances; sum (may be null) accumulates sum_m per_pose[m] in double.
+ * ------------------------------------------------------------------------------------------ */
+int links_mpjpe(const float* p_ref, const float* p, int M, int num_joints, int root_joint, int use_scaling,
+                float* per_pose, float* per_pose_max, float* dist, double* sum, void* stream);
+/* counts[k] += #(values[i] < thresholds[k]) (strict != 0) or #(values[i] <= thresholds[k]); thresholds ascending,
+ * n_thresh <= 512.  With dist / per_pose_max from links_mpjpe this gives PCK, AUC and CPS
+ * (utils/metrics_batch.py:26-102) as exact integer counts. */
+int links_threshold_counts(const float* values, size_t n, const float* thresholds, int n_thresh, int strict,
+                           unsigned long long* counts, void* stream);
+/* mode 0: metrics_batch.pmpjpe semantics (RMS scale match, R = diag(1,1,det)UV^T);
+ * mode 1: metrics.pmpjpe(reflection='best') semantics (optimal scale, reflection allowed). */
+int links_pmpjpe(const float* p_ref, const float* p, int M, int num_joints, int mode, float* per_pose,
+                 double* sum, void* stream);
+/* Eval fusion (eval_h36m.py:58-78): lift 2D poses with combined depths, score against GT. */
+int links_eval_lift_score(const float* poses_2d, const float* depth_off, int ld_depth, const float* gt_3d,
+                          int M, float depth, double* sums3, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Occlusion step pieces (train_occlusion_models.py:164-217)
+ * ------------------------------------------------------------------------------------------ */
+/* pose[M,51] = root-centred lift of x[M,34] with depth heads (no clamp), :164-174 */
+int links_occ_lift(const float* x, const float* head_leg, const float* head_torso, int M, float depth,
+                   float* pose, void* stream);
+/* pose_out = Ry((u-0.5)*1.99*pi) @ pose, :213-217 */
+int links_occ_rotate_y(const float* pose, const float* u, int M, float* pose_out, void* stream);
+/* loss_sum += sum_m sum_c (pred[m,c]-pose_flat[m*51+tidx[c]])^2 ; g (bf16 [M,64] + T) = scale*2*(pred-target) */
+int links_occ_mse(const float* pred, int ld_pred, const float* pose, const int* tidx_dev, int n_out, int M,
+                  float scale, float* loss_sum, void* g_bf16, void* gT_bf16, int ldT, int colT0, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LINKS_B200_H */

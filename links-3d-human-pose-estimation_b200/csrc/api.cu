@@ -1,0 +1,347 @@
+// extern "C" launch wrappers (see include/links_b200.h) for the non-tensor-core kernels.
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "metrics.cuh"
+#include "geom.cuh"
+#include "flow.cuh"
+#include "occ.cuh"
+#include <math.h>
+
+using namespace links;
+
+extern "C" __attribute__((visibility("default"))) int links_abi_version(void) { return LINKS_ABI_VERSION; }
+
+extern "C" __attribute__((visibility("default"))) int links_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return prop.major == 10 ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) int links_pack_rows(const float* src, int ld_src, int M, const int* idx_dev, int n_idx, int period,
+                               void* dst_bf16, void* dstT_bf16, int ldT, int colT0, void* stream) {
+  LINKS_CHECK_PTR(src); LINKS_CHECK_PTR(idx_dev); LINKS_CHECK_PTR(dst_bf16);
+  if (M < 1 || n_idx < 1 || n_idx > 64 || period < 1 || (M % period) != 0) return LINKS_E_RANGE;
+  const long long total = static_cast<long long>(M) * 64;
+  const int threads = 256;
+  const int blocks = static_cast<int>((total + threads - 1) / threads);
+  pack_rows_kernel<<<blocks, threads, 0, links_stream(stream)>>>(
+      src, ld_src, M, idx_dev, n_idx, period, static_cast<__nv_bfloat16*>(dst_bf16),
+      static_cast<__nv_bfloat16*>(dstT_bf16), ldT, colT0);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_colsum_bf16(const void* G, int ldg, int M, int N, float* out, int accumulate, void* stream) {
+  LINKS_CHECK_PTR(G); LINKS_CHECK_PTR(out);
+  if (M < 1 || N < 1) return LINKS_E_RANGE;
+  cudaStream_t s = links_stream(stream);
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * N, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  const int rows_per_block = 256;
+  dim3 grid((N + 31) / 32, (M + rows_per_block - 1) / rows_per_block);
+  colsum_bf16_kernel<<<grid, dim3(32, 8), 0, s>>>(static_cast<const __nv_bfloat16*>(G), ldg, M, N, out, rows_per_block);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
+                                 void* stream) {
+  LINKS_CHECK_PTR(W);
+  if (N < 1 || K < 1) return LINKS_E_RANGE;
+  if (W_bf16 && ldw < K) return LINKS_E_RANGE;
+  if (WT_bf16 && ldwt < N) return LINKS_E_RANGE;
+  const int kx = ((W_bf16 ? (ldw > K ? ldw : K) : K) + 31) / 32;
+  const int ny = ((WT_bf16 ? (ldwt > N ? ldwt : N) : N) + 31) / 32;
+  cast_weight_kernel<<<dim3(kx, ny), dim3(32, 8), 0, links_stream(stream)>>>(
+      W, N, K, static_cast<__nv_bfloat16*>(W_bf16), ldw, static_cast<__nv_bfloat16*>(WT_bf16), ldwt);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                               void* stream) {
+  LINKS_CHECK_PTR(param); LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(exp_avg); LINKS_CHECK_PTR(exp_avg_sq);
+  if (n == 0 || step < 1) return LINKS_E_RANGE;
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  const int threads = 256;
+  size_t blocks = (n + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  return links_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------
+static int check_maps(const LinksGeomMaps* m) {
+  if (!m) return LINKS_E_ARG;
+  if (m->V < 1 || m->V > 2) return LINKS_E_RANGE;
+  for (int p = 0; p < 2; ++p) if (m->n_joints[p] < 1 || m->n_joints[p] > 16) return LINKS_E_RANGE;
+  for (int v = 0; v < m->V; ++v)
+    for (int j = 0; j < 17; ++j) {
+      if (m->src_net[v][j] < 0 || m->src_net[v][j] > 1) return LINKS_E_RANGE;
+      if (m->part_net[v][j] < -1 || m->part_net[v][j] > 1) return LINKS_E_RANGE;
+      if (m->col[j] < 0 || m->col[j] >= LINKS_HEAD_LD) return LINKS_E_RANGE;
+    }
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int links_elev_stats(const float* ang0, const float* ang1, int N, float* stats, void* stream) {
+  LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1); LINKS_CHECK_PTR(stats);
+  if (N < 2) return LINKS_E_RANGE;
+  elev_stats_kernel<<<1, 1024, 0, links_stream(stream)>>>(ang0, ang1, N, stats);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_geom_forward(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                                  const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                                  const float* stats, int N, float* qpart0, float* qpart1, float* q_full0,
+                                  float* q_full1, void* stream) {
+  int rc = check_maps(maps);
+  if (rc) return rc;
+  LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(head0); LINKS_CHECK_PTR(head1); LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1);
+  LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(qpart0); LINKS_CHECK_PTR(qpart1);
+  if (N < 1) return LINKS_E_RANGE;
+  GeomArgs A;
+  memset(&A, 0, sizeof(A));
+  A.maps = *maps;
+  A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
+  A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
+  A.qpart[0] = qpart0; A.qpart[1] = qpart1; A.qfull[0] = q_full0; A.qfull[1] = q_full1;
+  geom_forward_kernel<<<(N + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_geom_loss(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                               const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                               const float* stats, const float* head2_0, const float* head2_1, int N,
+                               float* loss_sums, void* g2_head0, void* g2_head1, void* g2T_head0, void* g2T_head1,
+                               int ldT, int colT0, void* stream) {
+  int rc = check_maps(maps);
+  if (rc) return rc;
+  LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(head0); LINKS_CHECK_PTR(head1); LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1);
+  LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(head2_0); LINKS_CHECK_PTR(head2_1);
+  LINKS_CHECK_PTR(loss_sums); LINKS_CHECK_PTR(g2_head0); LINKS_CHECK_PTR(g2_head1);
+  if (N < 1) return LINKS_E_RANGE;
+  GeomArgs A;
+  memset(&A, 0, sizeof(A));
+  A.maps = *maps;
+  A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
+  A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
+  A.head2[0] = head2_0; A.head2[1] = head2_1;
+  A.loss_sums = loss_sums;
+  A.g2[0] = static_cast<__nv_bfloat16*>(g2_head0); A.g2[1] = static_cast<__nv_bfloat16*>(g2_head1);
+  A.g2T[0] = static_cast<__nv_bfloat16*>(g2T_head0); A.g2T[1] = static_cast<__nv_bfloat16*>(g2T_head1);
+  A.ldT = ldT; A.colT0 = colT0;
+  const int pairs = (N + 1) / 2;
+  geom_lossgrad_kernel<false><<<(pairs + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_geom_backward(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
+                                   const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
+                                   const float* stats, const float* head2_0, const float* head2_1,
+                                   const float* dpart_flow0, const float* dpart_flow1, const float* dpart_lift0,
+                                   const float* dpart_lift1, int N, void* g1_head0, void* g1_head1, void* g1T_head0,
+                                   void* g1T_head1, int ldT, int colT0, float* dgamma_direct, float* da, float* red,
+                                   void* stream) {
+  int rc = check_maps(maps);
+  if (rc) return rc;
+  LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(head0); LINKS_CHECK_PTR(head1); LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1);
+  LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(head2_0); LINKS_CHECK_PTR(head2_1);
+  LINKS_CHECK_PTR(dpart_flow0); LINKS_CHECK_PTR(dpart_flow1); LINKS_CHECK_PTR(dpart_lift0); LINKS_CHECK_PTR(dpart_lift1);
+  LINKS_CHECK_PTR(g1_head0); LINKS_CHECK_PTR(g1_head1); LINKS_CHECK_PTR(dgamma_direct); LINKS_CHECK_PTR(da); LINKS_CHECK_PTR(red);
+  if (N < 1) return LINKS_E_RANGE;
+  GeomArgs A;
+  memset(&A, 0, sizeof(A));
+  A.maps = *maps;
+  A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
+  A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
+  A.head2[0] = head2_0; A.head2[1] = head2_1;
+  A.dflow[0] = dpart_flow0; A.dflow[1] = dpart_flow1; A.dlift[0] = dpart_lift0; A.dlift[1] = dpart_lift1;
+  A.g1[0] = static_cast<__nv_bfloat16*>(g1_head0); A.g1[1] = static_cast<__nv_bfloat16*>(g1_head1);
+  A.g1T[0] = static_cast<__nv_bfloat16*>(g1T_head0); A.g1T[1] = static_cast<__nv_bfloat16*>(g1T_head1);
+  A.ldT = ldT; A.colT0 = colT0;
+  A.dgamma = dgamma_direct; A.da = da; A.red = red;
+  const int pairs = (N + 1) / 2;
+  geom_lossgrad_kernel<true><<<(pairs + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_geom_backward_angles(const float* ang0, const float* ang1, const float* eps_x, const float* stats,
+                                          const float* dgamma_direct, const float* red, int N, void* g_ang0,
+                                          void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0,
+                                          void* stream) {
+  (void)eps_x;
+  LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(dgamma_direct);
+  LINKS_CHECK_PTR(red); LINKS_CHECK_PTR(g_ang0); LINKS_CHECK_PTR(g_ang1);
+  if (N < 2) return LINKS_E_RANGE;
+  geom_backward_angles_kernel<<<(N + 255) / 256, 256, 0, links_stream(stream)>>>(
+      ang0, ang1, stats, dgamma_direct, red, N, static_cast<__nv_bfloat16*>(g_ang0),
+      static_cast<__nv_bfloat16*>(g_ang1), static_cast<__nv_bfloat16*>(gT_ang0), static_cast<__nv_bfloat16*>(gT_ang1),
+      ldT, colT0);
+  return links_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) size_t links_flow_packed_floats(int C, int n_blocks) {
+  if (C < 2 || C > 34 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return 0;
+  return static_cast<size_t>(flow_block_floats(C)) * n_blocks;
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_pack(int C, int n_blocks, const float* const* w0, const float* const* b0,
+                               const float* const* w2, const float* const* b2, const float* const* gscale,
+                               const float* const* goffset, const float* const* wperm, const float* const* wperm_inv,
+                               float* packed, void* stream) {
+  if (C < 2 || C > 34 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_ALIGN16(packed);
+  FlowPackArgs A;
+  memset(&A, 0, sizeof(A));
+  for (int k = 0; k < n_blocks; ++k) {
+    if (!w0[k] || !b0[k] || !w2[k] || !b2[k] || !gscale[k] || !goffset[k] || !wperm[k] || !wperm_inv[k]) return LINKS_E_ARG;
+    A.w0[k] = w0[k]; A.b0[k] = b0[k]; A.w2[k] = w2[k]; A.b2[k] = b2[k];
+    A.gs[k] = gscale[k]; A.go[k] = goffset[k]; A.wp[k] = wperm[k]; A.wpi[k] = wperm_inv[k];
+  }
+  A.packed = packed; A.C = C; A.n_blocks = n_blocks;
+  flow_pack_kernel<<<n_blocks, 256, 0, links_stream(stream)>>>(A);
+  return links_launch_status();
+}
+
+template <int C, int MODE>
+static int launch_flow_c(const FlowArgs& A, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(flow_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(FlowSmem<C>::bytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  const int blocks = (A.M + kFlowRows - 1) / kFlowRows;
+  flow_kernel<C, MODE><<<blocks, kFlowWarps * 32, FlowSmem<C>::bytes, s>>>(A);
+  return links_launch_status();
+}
+
+template <int MODE>
+static int launch_flow(int C, const FlowArgs& A, cudaStream_t s) {
+  switch (C) {
+    case 14: return launch_flow_c<14, MODE>(A, s);
+    case 20: return launch_flow_c<20, MODE>(A, s);
+    case 22: return launch_flow_c<22, MODE>(A, s);
+    case 32: return launch_flow_c<32, MODE>(A, s);
+    case 34: return launch_flow_c<34, MODE>(A, s);
+    default: return LINKS_E_RANGE;
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, int M, int rev, float* out,
+                                float* log_jac_det, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(out); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = out; A.ld = log_jac_det; A.M = M; A.n_blocks = n_blocks;
+  return rev ? launch_flow<FLOW_REV>(C, A, links_stream(stream)) : launch_flow<FLOW_FWD>(C, A, links_stream(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
+                                     float* nll_sum, float* dx, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = n_blocks;
+  return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,
+                                 float* out, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(noise); LINKS_CHECK_PTR(out); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.noise = noise; A.out = out; A.M = M; A.n_blocks = n_blocks;
+  return launch_flow_c<34, FLOW_SAMPLE>(A, links_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+static int check_pose_args(const float* a, const float* b, int M, int J) {
+  if (!a || !b) return LINKS_E_ARG;
+  if (M < 1 || J < 2 || J > 17) return LINKS_E_RANGE;
+  if ((reinterpret_cast<uintptr_t>(a) & 15u) || (reinterpret_cast<uintptr_t>(b) & 15u)) return LINKS_E_ALIGN;
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int links_mpjpe(const float* p_ref, const float* p, int M, int num_joints, int root_joint, int use_scaling,
+                           float* per_pose, float* per_pose_max, float* dist, double* sum, void* stream) {
+  int rc = check_pose_args(p_ref, p, M, num_joints);
+  if (rc) return rc;
+  if (root_joint < 0 || root_joint >= num_joints) return LINKS_E_RANGE;
+  mpjpe_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+      p_ref, p, M, num_joints, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_threshold_counts(const float* values, size_t n, const float* thresholds, int n_thresh, int strict,
+                                      unsigned long long* counts, void* stream) {
+  LINKS_CHECK_PTR(values); LINKS_CHECK_PTR(thresholds); LINKS_CHECK_PTR(counts);
+  if (n == 0 || n_thresh < 1 || n_thresh > 512) return LINKS_E_RANGE;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  threshold_counts_kernel<<<static_cast<int>(blocks), 256, 0, links_stream(stream)>>>(values, n, thresholds, n_thresh,
+                                                                                    strict, counts);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_pmpjpe(const float* p_ref, const float* p, int M, int num_joints, int mode, float* per_pose,
+                            double* sum, void* stream) {
+  int rc = check_pose_args(p_ref, p, M, num_joints);
+  if (rc) return rc;
+  if (mode < 0 || mode > 1) return LINKS_E_RANGE;
+  pmpjpe_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+      p_ref, p, M, num_joints, mode, per_pose, sum);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_eval_lift_score(const float* poses_2d, const float* depth_off, int ld_depth, const float* gt_3d,
+                                     int M, float depth, double* sums3, void* stream) {
+  int rc = check_pose_args(poses_2d, gt_3d, M, 17);
+  if (rc) return rc;
+  LINKS_CHECK_PTR(depth_off); LINKS_CHECK_PTR(sums3);
+  if (ld_depth < 17) return LINKS_E_RANGE;
+  eval_lift_score_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+      poses_2d, depth_off, ld_depth, gt_3d, M, depth, sums3);
+  return links_launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) int links_occ_lift(const float* x, const float* head_leg, const float* head_torso, int M, float depth,
+                              float* pose, void* stream) {
+  LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(head_leg); LINKS_CHECK_PTR(head_torso); LINKS_CHECK_PTR(pose);
+  if (M < 1) return LINKS_E_RANGE;
+  const long long total = static_cast<long long>(M) * 17;
+  occ_lift_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, links_stream(stream)>>>(x, head_leg, head_torso, M,
+                                                                                        depth, pose);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_occ_rotate_y(const float* pose, const float* u, int M, float* pose_out, void* stream) {
+  LINKS_CHECK_PTR(pose); LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(pose_out);
+  if (M < 1) return LINKS_E_RANGE;
+  const long long total = static_cast<long long>(M) * 17;
+  occ_rotate_y_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, links_stream(stream)>>>(pose, u, M, pose_out);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_occ_mse(const float* pred, int ld_pred, const float* pose, const int* tidx_dev, int n_out, int M,
+                             float scale, float* loss_sum, void* g_bf16, void* gT_bf16, int ldT, int colT0,
+                             void* stream) {
+  LINKS_CHECK_PTR(pred); LINKS_CHECK_PTR(pose); LINKS_CHECK_PTR(tidx_dev); LINKS_CHECK_PTR(loss_sum); LINKS_CHECK_PTR(g_bf16);
+  if (M < 1 || n_out < 1 || n_out > 64) return LINKS_E_RANGE;
+  occ_mse_kernel<<<(M + 3) / 4, 128, 0, links_stream(stream)>>>(pred, ld_pred, pose, tidx_dev, n_out, M, scale, loss_sum,
+                                                               static_cast<__nv_bfloat16*>(g_bf16),
+                                                               static_cast<__nv_bfloat16*>(gT_bf16), ldT, colT0);
+  return links_launch_status();
+}

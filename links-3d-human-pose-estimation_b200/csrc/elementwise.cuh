@@ -1,0 +1,95 @@
+// Operand packing, bias-gradient column sums, weight shadow casts and the fused Adam step.
+// Device code only (also compiled by tests/hostsim with a CUDA shim).
+#pragma once
+#include "devdefs.cuh"
+
+namespace links {
+
+// dst[m, c] = bf16(src[m*ld_src + idx[c]]) (zero padded to 64 columns), dstT[c, colT0 + m] likewise.
+// One thread per (row, 64-col slot); reference index maps: utils/helpers.py:55-65,
+// train_leg_torso_lifter.py:147-148, train_occlusion_models.py:185-191.
+// `period` > 1 supports gathers that mix `period` consecutive rows (split_data_left_right_3d,
+// utils/helpers.py:81-91, period 2): idx then holds period*n_idx offsets relative to the row group.
+__global__ void pack_rows_kernel(const float* __restrict__ src, int ld_src, int M, const int* __restrict__ idx,
+                                 int n_idx, int period, __nv_bfloat16* __restrict__ dst,
+                                 __nv_bfloat16* __restrict__ dstT, int ldT, int colT0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = t >> 6;
+  const int c = t & 63;
+  if (m >= M) return;
+  float v = 0.f;
+  if (c < n_idx) {
+    const int grp = m / period, sub = m - grp * period;
+    v = src[static_cast<size_t>(grp) * period * ld_src + idx[sub * n_idx + c]];
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  dst[static_cast<size_t>(m) * 64 + c] = h;
+  if (dstT != nullptr && c < n_idx) dstT[static_cast<size_t>(c) * ldT + colT0 + m] = h;
+}
+
+// out[n] (+)= sum_m G[m, n].  Block = 32 x 8 threads: 32 columns, 8 row phases; grid.x over column
+// groups, grid.y over row slabs (atomics combine slabs).
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, int ldg, int M, int N,
+                                   float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.y * rows_per_block;
+  int m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float acc = 0.f;
+  if (n < N) {
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) acc += __bfloat162float(G[static_cast<size_t>(m) * ldg + n]);
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+
+// fp32 W[N,K] -> bf16 Wb[N, ldw] (cols >= K zero) and bf16 WT[K, ldwt] (cols >= N zero), 32x32 smem tiles.
+__global__ void cast_weight_kernel(const float* __restrict__ W, int N, int K, __nv_bfloat16* __restrict__ Wb, int ldw,
+                                   __nv_bfloat16* __restrict__ WT, int ldwt) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N && k < K) v = W[static_cast<size_t>(n) * K + k];
+    tile[r][threadIdx.x] = v;
+    if (Wb != nullptr && n < N && k < ldw) Wb[static_cast<size_t>(n) * ldw + k] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (WT != nullptr) {
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int k = k0 + r, n = n0 + threadIdx.x;
+      if (k < K && n < ldwt) WT[static_cast<size_t>(k) * ldwt + n] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    }
+  }
+}
+
+// torch.optim.Adam (coupled L2 weight decay), same operation order as torch's single-tensor path:
+//   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g;
+//   denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= (lr/(1-b1^t)) * m/denom
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float grad_scale) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float pi = p[i];
+    float gi = g[i] * grad_scale;
+    gi = gi + wd * pi;
+    const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // torch: exp_avg.lerp_(grad, 1-beta1)
+    const float vi = v[i] * b2 + (1.f - b2) * gi * gi;         // torch: mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    const float step = lr / bc1;
+    p[i] = pi - step * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+}  // namespace links

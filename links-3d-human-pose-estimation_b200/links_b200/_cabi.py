@@ -1,0 +1,119 @@
+"""ctypes binding of liblinks_b200.so (include/links_b200.h).
+
+The product path has no CPU fallback: ``lib()`` raises if the CUDA library is missing or the
+device is not a compute-capability-10.x GPU.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblinks_b200.so")
+
+HEAD_LD = 32
+KPAD = 64
+MAX_GEMM_PROBLEMS = 8
+
+EPI_LEAKY_PRE, EPI_LEAKY_POST, EPI_RELU_PRE, EPI_ACCUM_F32 = 1, 2, 4, 8
+
+vp = C.c_void_p
+ci = C.c_int
+cf = C.c_float
+sz = C.c_size_t
+
+
+class GemmProblem(C.Structure):
+    _fields_ = [("A", vp), ("B", vp), ("M", ci), ("N", ci), ("K", ci), ("lda", ci), ("ldb", ci),
+                ("flags", C.c_uint32), ("bias", vp),
+                ("add0", vp), ("ld_add0", ci), ("add1", vp), ("ld_add1", ci),
+                ("ymask", vp), ("ld_ymask", ci), ("bits", vp), ("ld_bits", ci),
+                ("sign_out", vp), ("ld_sign", ci), ("mid", vp), ("ld_mid", ci),
+                ("out", vp), ("ld_out", ci), ("outT", vp), ("ld_outT", ci), ("outT_col0", ci),
+                ("out_f32", vp), ("ld_f32", ci)]
+
+
+class GeomMaps(C.Structure):
+    _fields_ = [("V", ci), ("n_joints", ci * 2), ("src_net", (ci * 17) * 2), ("col", ci * 17),
+                ("part_net", (ci * 17) * 2), ("part_idx", (ci * 17) * 2), ("bone_rel", cf * 16),
+                ("depth", cf), ("w_likeli", cf), ("w_2d", cf), ("w_3d", cf), ("w_vel", cf), ("w_bl", cf)]
+
+
+PP = C.POINTER(vp)
+# name -> (restype, argtypes WITHOUT the trailing stream argument)
+SIGNATURES = {
+    "links_pack_rows": (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, ci]),
+    "links_colsum_bf16": (ci, [vp, ci, ci, ci, vp, ci]),
+    "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
+    "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, cf]),
+    "links_elev_stats": (ci, [vp, vp, ci, vp]),
+    "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
+    "links_geom_loss": (ci, [C.POINTER(GeomMaps)] + [vp] * 10 + [ci] + [vp] * 5 + [ci, ci]),
+    "links_geom_backward": (ci, [C.POINTER(GeomMaps)] + [vp] * 14 + [ci] + [vp] * 4 + [ci, ci] + [vp] * 3),
+    "links_geom_backward_angles": (ci, [vp] * 6 + [ci] + [vp] * 4 + [ci, ci]),
+    "links_flow_pack": (ci, [ci, ci] + [PP] * 8 + [vp]),
+    "links_flow_apply": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
+    "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp]),
+    "links_flow_sample": (ci, [vp, ci, vp, vp, ci, vp]),
+    "links_mpjpe": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]),
+    "links_threshold_counts": (ci, [vp, sz, vp, ci, ci, vp]),
+    "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp]),
+    "links_eval_lift_score": (ci, [vp, vp, ci, vp, ci, cf, vp]),
+    "links_occ_lift": (ci, [vp, vp, vp, ci, cf, vp]),
+    "links_occ_rotate_y": (ci, [vp, vp, ci, vp]),
+    "links_occ_mse": (ci, [vp, ci, vp, vp, ci, ci, cf, vp, vp, vp, ci, ci]),
+}
+# entry points without a stream argument
+PLAIN = {
+    "links_abi_version": (ci, []),
+    "links_device_ok": (ci, []),
+    "links_flow_packed_floats": (sz, [ci, ci]),
+}
+GEMM = {"links_gemm_grouped": (ci, [C.POINTER(GemmProblem), ci, vp])}
+
+ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN) + list(GEMM))
+
+_lib = None
+
+
+class LinksError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    """dlopen + declare prototypes (no device needed)."""
+    if not os.path.exists(path):
+        raise LinksError("CUDA library %s not built: run `python build.py` (there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, list(args) + [vp]
+    for name, (res, args) in list(PLAIN.items()) + list(GEMM.items()):
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, list(args)
+    return L
+
+
+def lib():
+    """The loaded library, verified against a Blackwell device."""
+    global _lib
+    if _lib is None:
+        L = load_library()
+        import torch
+        if not torch.cuda.is_available():
+            raise LinksError("links_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        if not L.links_device_ok():
+            raise LinksError("links_b200 is built for sm_100a (B200) only; current device is %s"
+                             % torch.cuda.get_device_name())
+        _lib = L
+    return _lib
+
+
+_ERR = {-1: "null pointer / bad size", -2: "pointer or leading dimension not 16-byte aligned",
+        -3: "value outside the supported range", -4: "cuTensorMapEncodeTiled unavailable or failed"}
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc < 0:
+        raise ValueError("%s: %s (LINKS_E %d)" % (what, _ERR.get(rc, "argument error"), rc))
+    raise LinksError("%s: CUDA error %d" % (what, rc))

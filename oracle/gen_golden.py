@@ -1,0 +1,257 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own utils (build container only).
+
+Test infrastructure.  Run from the repo root:  ``python -m oracle.gen_golden``.
+
+Imports ``/root/reference/utils/{models_def,helpers,rotation_conversions,metrics_batch,
+metrics}.py`` (with a stub ``pytorch_lightning``: models_def.py:2 imports it and never uses
+it), asserts the oracle restatement reproduces them on seeded inputs, and freezes the
+reference's outputs as small fixtures.  ``/root/reference`` does not exist on the GPU box,
+so only the committed ``.npz`` files travel.  Network weights are not stored (59 MB per
+lifter): fixtures hold the seed, and ``oracle.nets.init_*`` regenerates them bit-exactly
+(torch CPU mt19937 generator).
+
+FrEIA is not importable, so flow fixtures are produced by the (unpinned) restatement and
+are regression vectors plus known-answer checks, not reference outputs.
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                "links-3d-human-pose-estimation_b200"))
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree %s not present (only exists in the build container)" % REF)
+    sys.modules.setdefault("pytorch_lightning", types.ModuleType("pytorch_lightning"))
+    import importlib.util
+    mods = {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # metrics.py:134 `is not 'best'` SyntaxWarning
+        for name in ("models_def", "helpers", "rotation_conversions", "metrics_batch", "metrics"):
+            spec = importlib.util.spec_from_file_location("linksref_" + name, os.path.join(REF, "utils", name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            mods[name] = m
+    return mods
+
+
+def t(a):
+    return a.detach().cpu().numpy()
+
+
+def main():
+    from oracle import flow as OF, geometry as OG, metrics as OM, nets as ON, steps as OS
+    from links_b200.synth import synth_poses, synth_pred_3d
+    ref = import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+
+    # ---------------- networks (models_def.py) ----------------
+    nets = {}
+    for cls, nj, seed in (("Leg_Lifter", 7, 11), ("Torso_Lifter", 10, 12), ("Left_Right_Lifter", 11, 13)):
+        p = ON.init_lifter_params(nj, seed)
+        m = getattr(ref["models_def"], cls)(use_batchnorm=False, num_joints=nj, use_dropout=False, d_rate=0.25)
+        missing = m.load_state_dict(p, strict=False)
+        assert all(".bn" in k for k in missing.missing_keys) and not missing.unexpected_keys
+        x = torch.randn(16, 2 * nj) * 0.15
+        x.requires_grad_(True)
+        xd, xa = m(x)
+        (xd.square().sum() + xa.sum()).backward()
+        pr = OS.params_require_grad(p)
+        x2 = x.detach().clone().requires_grad_(True)
+        od, oa = ON.lifter_forward(x2, pr)
+        (od.square().sum() + oa.sum()).backward()
+        assert torch.equal(od, xd) and torch.equal(oa, xa), cls
+        assert torch.allclose(x2.grad, x.grad, rtol=0, atol=0)
+        gw = m.res_pose2.l1.weight.grad
+        assert torch.allclose(pr["res_pose2.l1.weight"].grad, gw, rtol=1e-6, atol=1e-9)
+        nets[cls + "_seed"] = np.int64(seed)
+        nets[cls + "_x"] = t(x)
+        nets[cls + "_xd"] = t(xd)
+        nets[cls + "_xa"] = t(xa)
+        nets[cls + "_dx"] = t(x.grad)
+        nets[cls + "_dW_res_pose2_l1_sum"] = np.float64(gw.double().sum().item())
+        nets[cls + "_dW_res_pose2_l1_abs"] = np.float64(gw.double().abs().sum().item())
+    for cls, nj, od_, seed in (("Occluded_Limb_Predictor", 14, 9, 21), ("Occluded_Legs_Predictor", 11, 18, 22),
+                               ("Occluded_Torso_Predictor", 7, 30, 23), ("Occluded_Left_Right_Predictor", 11, 18, 24)):
+        p = ON.init_predictor_params(nj, od_, seed)
+        m = getattr(ref["models_def"], cls)(use_batchnorm=False, num_joints=nj)
+        missing = m.load_state_dict(p, strict=False)
+        assert all(".bn" in k for k in missing.missing_keys) and not missing.unexpected_keys
+        x = torch.randn(16, 3 * nj)
+        y = m(x)
+        assert torch.equal(ON.predictor_forward(x, p), y), cls
+        nets[cls + "_seed"] = np.int64(seed)
+        nets[cls + "_x"] = t(x)
+        nets[cls + "_y"] = t(y)
+    np.savez_compressed(os.path.join(OUT, "nets.npz"), **nets)
+
+    # ---------------- index maps (helpers.py) -- integer, bit-exact ----------------
+    H = ref["helpers"]
+    idx = {}
+    B = 6
+    a34 = torch.arange(B * 34, dtype=torch.float32).reshape(B, 34)
+    l, r = H.split_data_left_right(a34)
+    ol, or_ = OG.split_data_left_right(a34)
+    assert torch.equal(l, ol) and torch.equal(r, or_)
+    idx["split_lr_in"], idx["split_lr_left"], idx["split_lr_right"] = t(a34), t(l), t(r)
+    a51 = torch.arange(B * 51, dtype=torch.float32).reshape(B, 3, 17)
+    l3, r3 = H.split_data_left_right_3d(a51)
+    ol3, or3 = OG.split_data_left_right_3d(a51)
+    assert torch.equal(l3, ol3) and torch.equal(r3, or3)
+    idx["split3d_in"], idx["split3d_left"], idx["split3d_right"] = t(a51), t(l3), t(r3)
+    la = torch.arange(B * 11, dtype=torch.float32).reshape(B, 11)
+    ra = 1000 + torch.arange(B * 11, dtype=torch.float32).reshape(B, 11)
+    for ch in ("left", "right"):
+        c = H.combine_left_right_pred_1d(la, ra, ch).reshape(-1, 17)
+        assert torch.equal(c, OG.combine_left_right_1d(la, ra, ch))
+        idx["combine1d_" + ch] = t(c)
+        for dims, fn in ((2, H.combine_left_right_pred_2d), (3, H.combine_left_right_pred_3d)):
+            ll = torch.arange(B * dims * 11, dtype=torch.float32).reshape(B, dims * 11)
+            rr = 5000 + ll
+            c = fn(ll, rr, ch)
+            assert torch.equal(c, OG.combine_left_right_nd(ll, rr, ch, dims))
+            idx["combine%dd_%s" % (dims, ch)] = t(c)
+    idx["combine_la"], idx["combine_ra"] = t(la), t(ra)
+    # occlusion gathers (train_occlusion_models.py:176-191 restated in oracle.steps) on the arange pose
+    tg, inp = OS.occ_targets_inputs(a51)
+    for n in OS.OCC_NAMES:
+        idx["occ_target_" + n] = t(tg[n])
+        idx["occ_input_" + n] = t(inp[n])
+    np.savez_compressed(os.path.join(OUT, "index_maps.npz"), **idx)
+
+    # ---------------- geometry (helpers.py, rotation_conversions.py) ----------------
+    geo = {}
+    ang = torch.randn(32, 3)
+    for conv in ("XYZ", "ZYX", "YXZ", "XZY"):
+        Rr = ref["rotation_conversions"].euler_angles_to_matrix(ang, conv)
+        assert torch.equal(Rr, OG.euler_angles_to_matrix(ang, conv)), conv
+        geo["euler_" + conv] = t(Rr)
+    geo["euler_in"] = t(ang)
+    p3 = torch.randn(32, 51)
+    p3[:, 34:] = p3[:, 34:].abs() + 5.0
+    pp = H.perspective_projection(p3)
+    assert torch.equal(pp, OG.perspective_projection(p3))
+    geo["proj_in"], geo["proj_out"] = t(p3), t(pp)
+    bl = H.get_bone_lengths_all(p3)
+    assert torch.equal(bl, OG.get_bone_lengths_all(p3))
+    geo["bones_out"] = t(bl)
+    noise_in = torch.randn(8, 34)
+    torch.manual_seed(5)
+    ref_noisy = H.add_noise(noise_in, 0.2)
+    torch.manual_seed(5)
+    nz = torch.randn_like(noise_in)
+    assert torch.equal(ref_noisy, OG.add_noise(noise_in, nz, 0.2))
+    raw2d = np.random.RandomState(3).normal(size=(8, 34)) * 100 + 500
+    nh = H.normalize_head(raw2d.copy())
+    assert np.array_equal(nh, OG.normalize_head(raw2d.copy()))
+    nht = H.normalize_head_test(raw2d.copy())
+    assert np.array_equal(nht, OG.normalize_head_test(raw2d.copy()))
+    geo["normhead_in"], geo["normhead_out"], geo["normhead_test_out"] = raw2d, nh, nht
+    np.savez_compressed(os.path.join(OUT, "geometry.npz"), **geo)
+
+    # ---------------- metrics ----------------
+    met = {}
+    p2d, gt = synth_poses(96, seed=7)
+    pred = synth_pred_3d(gt, seed=8, noise_mm=40.0, scale=0.0125, mirror_frac=0.25)
+    gt_t, pred_t = torch.from_numpy(gt), torch.from_numpy(pred)
+    mb = ref["metrics_batch"].Metrics()
+    met["gt"], met["pred"] = gt, pred
+    for nj, rj in ((17, 0), (16, 6)):
+        g, p = gt_t[:, :3 * 17].reshape(-1, 3, 17)[:, :, :nj].reshape(-1, 3 * nj), \
+            pred_t.reshape(-1, 3, 17)[:, :, :nj].reshape(-1, 3 * nj)
+        kw = dict(num_joints=nj, root_joint=rj)
+        for scaling in (True, False):
+            e = mb.mpjpe(g, p, use_scaling=scaling, **kw)
+            assert torch.equal(e, OM.mpjpe(g, p, use_scaling=scaling, **kw))
+            met["mpjpe_j%d_s%d" % (nj, scaling)] = t(e)
+        e = mb.PCK(g, p, **kw)
+        assert torch.equal(e, OM.pck(g, p, **kw))
+        met["pck_j%d" % nj] = t(e)
+        e = mb.AUC(g, p, **kw)
+        assert torch.allclose(e, OM.auc(g, p, **kw), rtol=0, atol=0)
+        met["auc_j%d" % nj] = t(e)
+        ga = mb.get_all(g, p, **kw)
+        oa = OM.get_all(g, p, **kw)
+        for k in ga:
+            assert torch.allclose(ga[k], oa[k], rtol=0, atol=0), k
+            met["getall_%s_j%d" % (k, nj)] = t(ga[k])
+        e = mb.pmpjpe(g, p, num_joints=nj)
+        o = OM.pmpjpe_batch(g, p, num_joints=nj)
+        assert torch.allclose(e, o, rtol=1e-4, atol=1e-3), (e - o).abs().max()  # torch.svd vs linalg.svd
+        met["pmpjpe_batch_j%d" % nj] = t(e)
+    mn = ref["metrics"].Metrics()
+    gt64, pr64 = gt.astype(np.float64), pred.astype(np.float64)
+    for refl in ("best", True, False):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            e = np.array([mn.pmpjpe(gt64[i].reshape(-1, 51), pr64[i].reshape(-1, 51), reflection=refl)
+                          for i in range(gt.shape[0])])
+        o = np.array([OM.pmpjpe_best_np(gt64[i].reshape(-1, 51), pr64[i].reshape(-1, 51), reflection=refl)
+                      for i in range(gt.shape[0])])
+        assert np.allclose(e, o, rtol=0, atol=1e-9), refl
+        met["pmpjpe_np_%s" % refl] = e
+    ob = OM.pmpjpe_best_batch(gt64, pr64)
+    assert np.allclose(ob, met["pmpjpe_np_best"], rtol=0, atol=1e-8)
+    # plain numpy mpjpe (metrics.py:8-33)
+    e = np.array([mn.mpjpe(gt64[i].reshape(-1, 51), pr64[i].reshape(-1, 51)) for i in range(8)])
+    met["mpjpe_np"] = e
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **met)
+
+    # ---------------- steps (oracle-composed from the pinned pieces; flow unpinned) ----------------
+    st = {}
+    B = 8
+    x2d, _ = synth_poses(B, seed=31)
+    x = torch.from_numpy(x2d)
+    g = torch.Generator().manual_seed(77)
+    noise = torch.randn(B, 34, generator=g)
+    eps_x = torch.randn(2 * B, generator=g)
+    u_y = torch.rand(2 * B, generator=g)
+    full_flow = OF.init_flow_params(34, 40, perturb=0.3)
+    u = OS.sample_poses(x, full_flow, noise)
+    st["x"], st["noise"], st["eps_x"], st["u_y"], st["u"] = t(x), t(noise), t(eps_x), t(u_y), t(u)
+    leg, torso = OS.params_require_grad(ON.init_lifter_params(7, 11)), OS.params_require_grad(ON.init_lifter_params(10, 12))
+    lf, tf = OF.init_flow_params(14, 41, perturb=0.3), OF.init_flow_params(20, 42, perturb=0.3)
+    aux = {}
+    out = OS.lt_step(u, leg, torso, lf, tf, eps_x, u_y, aux=aux)
+    out["loss"].backward()
+    for k, v in out.items():
+        st["lt_" + k] = np.float64(v.item())
+    st["lt_rot_2d"], st["lt_pred"] = t(aux["rot_2d"]), t(aux["pred"])
+    st["lt_dW_leg_upscale"] = t(leg["upscale.weight"].grad)
+    st["lt_dW_torso_angles"] = t(torso["angles.weight"].grad)
+    left, right = OS.params_require_grad(ON.init_lifter_params(11, 13)), OS.params_require_grad(ON.init_lifter_params(11, 14))
+    lff, rff = OF.init_flow_params(22, 43, perturb=0.3), OF.init_flow_params(22, 44, perturb=0.3)
+    aux = {}
+    out = OS.lr_step(u, left, right, lff, rff, eps_x, u_y, aux=aux)
+    out["loss"].backward()
+    for k, v in out.items():
+        st["lr_" + k] = np.float64(v.item())
+    st["lr_rot_2d_left"], st["lr_rot_2d_right"] = t(aux["rot_2d_left"]), t(aux["rot_2d_right"])
+    st["lr_dW_left_upscale"] = t(left["upscale.weight"].grad)
+    # flow step (config #1), fp64 twin for the known-answer log-det check is in tests
+    fp = OS.params_require_grad(OF.init_flow_params(34, 40, perturb=0.3))
+    out = OS.flow_step(x, fp, noise)
+    out["loss"].backward()
+    for k, v in out.items():
+        st["flow_" + k] = np.float64(v.item())
+    st["flow_dW_b0_l0"] = t(fp["module_list.0.subnet.0.weight"].grad)
+    z, ld = OF.inn_forward(x, OF.init_flow_params(34, 40, perturb=0.3))
+    st["flow_z"], st["flow_ld"] = t(z), t(ld)
+    np.savez_compressed(os.path.join(OUT, "steps.npz"), **st)
+    print("golden fixtures written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE: build + bind tests/hostsim/_hostsim.so (the product's .cuh kernels compiled for the CPU).
+
+Same argument lists as links_b200._cabi.SIGNATURES without the stream; all pointers are HOST pointers
+(numpy arrays).  Never used by the product.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIMDIR = os.path.join(HERE, "hostsim")
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(ROOT, "links-3d-human-pose-estimation_b200", "csrc")
+SO = os.path.join(SIMDIR, "_hostsim.so")
+_lib = None
+
+
+def _digest():
+    h = hashlib.sha256()
+    files = [os.path.join(SIMDIR, f) for f in ("cuda_shim.h", "hostsim_api.cpp")]
+    files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
+    files.append(os.path.join(ROOT, "include", "links_b200.h"))
+    for f in files:
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def sim():
+    global _lib
+    if _lib is not None:
+        return _lib
+    from links_b200 import _cabi
+    stamp = SO + ".sha256"
+    dig = _digest()
+    if not (os.path.exists(SO) and os.path.exists(stamp) and open(stamp).read() == dig):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-pthread", "-shared", "-fPIC", "-fvisibility=hidden",
+                               "-I" + SIMDIR, "-o", SO, os.path.join(SIMDIR, "hostsim_api.cpp")])
+        open(stamp, "w").write(dig)
+    L = C.CDLL(SO)
+    for name, (res, args) in _cabi.SIGNATURES.items():
+        fn = getattr(L, name.replace("links_", "sim_"))
+        fn.restype, fn.argtypes = res, list(args)
+    L.sim_flow_packed_floats.restype = C.c_size_t
+    L.sim_flow_packed_floats.argtypes = [C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+def ptr(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def bf16_to_f32(a_u16):
+    return (a_u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def f32_to_bf16(a):
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def pack_flow(L, params, C_, n_blocks=8):
+    """FrEIA-layout param dict (torch tensors) -> packed float32 numpy buffer via the sim pack kernel."""
+    keep = []
+    arrs = {k: [] for k in ("subnet.0.weight", "subnet.0.bias", "subnet.2.weight", "subnet.2.bias", "global_scale",
+                            "global_offset", "w_perm", "w_perm_inv")}
+    for k in range(n_blocks):
+        for name in arrs:
+            a = np.ascontiguousarray(params["module_list.%d.%s" % (k, name)].detach().cpu().numpy(), dtype=np.float32)
+            keep.append(a)
+            arrs[name].append(a.ctypes.data)
+    packed = np.zeros(L.sim_flow_packed_floats(C_, n_blocks), dtype=np.float32)
+    def pp(name):
+        return (C.c_void_p * n_blocks)(*arrs[name])
+    rc = L.sim_flow_pack(C_, n_blocks, pp("subnet.0.weight"), pp("subnet.0.bias"), pp("subnet.2.weight"),
+                         pp("subnet.2.bias"), pp("global_scale"), pp("global_offset"), pp("w_perm"),
+                         pp("w_perm_inv"), ptr(packed))
+    assert rc == 0
+    return packed
