@@ -106,10 +106,13 @@ int links_colsum_bf16(const void* G, int ldg, int M, int N, float* out, int accu
 int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
                       void* stream);
 
-/* torch.optim.Adam step with coupled L2 decay (train_leg_torso_lifter.py:111-114), flat buffers. */
+/* torch.optim.Adam step with coupled L2 decay (train_leg_torso_lifter.py:111-114), flat buffers.
+ * The step number t (bias correction) is `step` (>= 1), or, when step_dev != NULL, *step_dev + 1 read on the
+ * device; *step_dev is then incremented after the update, so a captured CUDA graph replays correctly.
+ * Gradients are multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
 int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                    float grad_scale, void* stream);
+                    int* step_dev, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Geometry + losses (train_leg_torso_lifter.py:153-272, train_left_right_lifter.py:150-423)

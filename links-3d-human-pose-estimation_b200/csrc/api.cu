@@ -61,17 +61,16 @@ extern "C" __attribute__((visibility("default"))) int links_cast_weight(const fl
 }
 
 extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                               void* stream) {
+                               float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
+                               float grad_scale, void* stream) {
   LINKS_CHECK_PTR(param); LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(exp_avg); LINKS_CHECK_PTR(exp_avg_sq);
-  if (n == 0 || step < 1) return LINKS_E_RANGE;
-  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
-  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  if (n == 0 || (step_dev == nullptr && step < 1)) return LINKS_E_RANGE;
   const int threads = 256;
   size_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev, step, grad_scale);
+  if (step_dev != nullptr) adam_incr_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev);
   return links_launch_status();
 }
 

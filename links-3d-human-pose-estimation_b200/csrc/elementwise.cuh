@@ -76,7 +76,11 @@ __global__ void cast_weight_kernel(const float* __restrict__ W, int N, int K, __
 //   denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= (lr/(1-b1^t)) * m/denom
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float grad_scale) {
+                            const int* __restrict__ step_dev, int step_host, float grad_scale) {
+  // step number t: host value, or (completed steps on device) + 1 so that a captured CUDA graph replays correctly
+  const int t = step_dev != nullptr ? (*step_dev + 1) : step_host;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(t));
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, static_cast<float>(t)));
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float pi = p[i];
@@ -90,6 +94,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     m[i] = mi;
     v[i] = vi;
   }
+}
+
+__global__ void adam_incr_kernel(int* step_dev) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
 }
 
 }  // namespace links

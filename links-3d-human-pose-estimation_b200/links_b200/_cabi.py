@@ -43,7 +43,7 @@ SIGNATURES = {
     "links_pack_rows": (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, ci]),
     "links_colsum_bf16": (ci, [vp, ci, ci, ci, vp, ci]),
     "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
-    "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, cf]),
+    "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
     "links_geom_loss": (ci, [C.POINTER(GeomMaps)] + [vp] * 10 + [ci] + [vp] * 5 + [ci, ci]),

@@ -1,0 +1,445 @@
+"""Residual-MLP engine: S networks of identical topology run as grouped tcgen05 GEMM launches.
+
+Replaces the forward and autograd-backward of reference utils/models_def.py (res_block :10-39, lifters
+:111-239, occlusion predictors :243-327).  All device buffers are allocated once through PyTorch; every
+operation is a C-ABI launch on the current stream, so a whole step is CUDA-graph capturable.
+
+Data layout (per network s, per pass p):
+  * fp32 master parameters / gradients / Adam moments live in flat buffers (one Adam launch, one all-reduce).
+  * bf16 shadow weights per layer:  W [N, Kp] (A.B^T "TN" operand for forward) and W^T [K, Np] (dgrad operand).
+  * activations are bf16 row-major [M, 1024] plus a transposed copy [1024, ldT] written by the same epilogue;
+    pass 1 and pass 2 write disjoint column ranges of the transposed buffers so one wgrad GEMM per layer
+    contracts over both passes.
+  * per block a [M, 32]-word sign mask of the l2 pre-activation (needed exactly for leaky' in backward).
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import EPI_LEAKY_POST, EPI_LEAKY_PRE, GemmProblem, HEAD_LD, check
+
+WIDTH = 1024
+TOPOLOGY = {
+    # trunk blocks, branches: name -> (blocks, head)
+    "lifter": (["res_common"], {"pose": (["res_pose1", "res_pose2", "res_pose3"], "downscale"),
+                                "angle": (["res_angle1", "res_angle2", "res_angle3"], "angles")}),
+    "predictor": ([], {"pose": (["res_pose1", "res_pose2", "res_pose3"], "downscale")}),
+}
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class _Layer:
+    __slots__ = ("name", "K", "N", "Kp", "Np", "W", "b", "gW", "gb", "Wb", "WbT")
+
+
+class _Net:
+    """Per-network parameter views + bf16 shadows."""
+
+    def __init__(self, layers):
+        self.layers = layers  # dict name -> _Layer
+
+
+class MlpSet:
+    def __init__(self, kind, in_dims, head_dims, max_rows, n_passes=1, device="cuda", train=True,
+                 pass_branches=None):
+        """in_dims[s]: input width of net s; head_dims[s]: dict head name -> width.
+        max_rows: rows per pass; n_passes: forward passes per step sharing weights (1 or 2).
+        pass_branches[p]: branches evaluated in pass p (default: all)."""
+        self.kind = kind
+        self.trunk, self.branches = TOPOLOGY[kind]
+        self.S = len(in_dims)
+        self.M = max_rows
+        self.n_passes = n_passes
+        self.device = torch.device(device)
+        self.train = train
+        self.pass_branches = pass_branches or [list(self.branches) for _ in range(n_passes)]
+        self.ldT = _rup(self.M * n_passes, 8)
+        self.lib = _cabi.lib()
+        dev = self.device
+        # ---- parameter layout
+        names = [("upscale", None)]
+        for blk in self.trunk:
+            names += [(blk + ".l1", None), (blk + ".l2", None)]
+        for br, (blocks, head) in self.branches.items():
+            for blk in blocks:
+                names += [(blk + ".l1", None), (blk + ".l2", None)]
+            names.append((head, br))
+        self.layer_names = [n for n, _ in names]
+        sizes = []
+        for s in range(self.S):
+            for n, br in names:
+                if n == "upscale":
+                    K, N = in_dims[s], WIDTH
+                elif br is not None:
+                    K, N = WIDTH, head_dims[s][n]
+                else:
+                    K, N = WIDTH, WIDTH
+                sizes.append((s, n, K, N))
+        total = sum(K * N + N for _, _, K, N in sizes)
+        self.n_params = total
+        self.master = torch.zeros(total, dtype=torch.float32, device=dev)
+        if train:
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+            self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.nets = []
+        off = 0
+        cur = {}
+        for s, n, K, N in sizes:
+            L = _Layer()
+            L.name, L.K, L.N = n, K, N
+            L.Kp = _rup(K, 64)
+            L.Np = _rup(N, 64)
+            L.W = self.master[off:off + N * K].view(N, K)
+            L.gW = self.grad[off:off + N * K].view(N, K) if train else None
+            off += N * K
+            L.b = self.master[off:off + N]
+            L.gb = self.grad[off:off + N] if train else None
+            off += N
+            L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
+            L.WbT = torch.zeros(K, L.Np, dtype=torch.bfloat16, device=dev) if train else None
+            cur[n] = L
+            if n == names[-1][0]:
+                self.nets.append(_Net(cur))
+                cur = {}
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
+        # ---- activation / gradient workspaces
+        M, ldT = self.M, self.ldT
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.x0 = [[torch.zeros(M, 64, **bf) for _ in range(self.S)] for _ in range(n_passes)]
+        self.x0T = [torch.zeros(in_dims[s], ldT, **bf) for s in range(self.S)] if train else [None] * self.S
+        self.act = []    # act[p][s][name] -> row-major bf16
+        self.actT = [dict() for _ in range(self.S)]  # actT[s][name] -> [1024, ldT] shared by passes
+        self.sign = []   # sign[p][s][blk] -> int32 [M, 32]
+        self.head_out = []  # head_out[p][s][head] -> fp32 [M, HEAD_LD]
+        all_blocks = list(self.trunk) + [b for blocks, _ in self.branches.values() for b in blocks]
+        for p in range(n_passes):
+            act_p, sign_p, head_p = [], [], []
+            for s in range(self.S):
+                d = {"h0": torch.empty(M, WIDTH, **bf)}
+                sg = {}
+                for blk in all_blocks:
+                    d[blk + ".a1"] = torch.empty(M, WIDTH, **bf)
+                    d[blk + ".y"] = torch.empty(M, WIDTH, **bf)
+                    sg[blk] = torch.zeros(M, WIDTH // 32, dtype=torch.int32, device=dev)
+                act_p.append(d)
+                sign_p.append(sg)
+                head_p.append({head: torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev)
+                               for _, head in self.branches.values()})
+            self.act.append(act_p)
+            self.sign.append(sign_p)
+            self.head_out.append(head_p)
+        if train:
+            for s in range(self.S):
+                for name in self.act[0][s]:
+                    self.actT[s][name] = torch.empty(WIDTH, ldT, **bf)
+            # gradients: G[p][s][layer] row-major bf16 [M, N] (heads: [M,64]); GT[s][layer] [N, ldT]; dt per block
+            self.G = [[dict() for _ in range(self.S)] for _ in range(n_passes)]
+            self.GT = [dict() for _ in range(self.S)]
+            self.dt = [[dict() for _ in range(self.S)] for _ in range(n_passes)]
+            self.E = [[torch.empty(M, WIDTH, **bf) for _ in range(self.S)] for _ in range(n_passes)]
+            self.din = [[torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev) for _ in range(self.S)]
+                        for _ in range(n_passes)]   # d/d(input part), fp32 [M, HEAD_LD]
+            heads = [h for _, h in self.branches.values()]
+            for s in range(self.S):
+                for n in self.layer_names:
+                    Nl = self.nets[s].layers[n].N
+                    self.GT[s][n] = torch.zeros(Nl, ldT, **bf)
+                    for p in range(n_passes):
+                        self.G[p][s][n] = torch.zeros(M, 64 if n in heads else WIDTH, **bf)
+                for p in range(n_passes):
+                    for blk in all_blocks:
+                        self.dt[p][s][blk] = torch.empty(M, WIDTH, **bf)
+        self._plans = {}
+
+    # ------------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------------
+    def load_state_dicts(self, dicts):
+        """dicts[s]: reference-style state dict (keys like 'res_pose1.l1.weight'); unused keys ignored."""
+        with torch.no_grad():
+            for s, sd in enumerate(dicts):
+                for n, L in self.nets[s].layers.items():
+                    L.W.copy_(sd[n + ".weight"].to(self.device, torch.float32))
+                    L.b.copy_(sd[n + ".bias"].to(self.device, torch.float32))
+        self.refresh_shadows()
+
+    def state_dict(self, s):
+        out = {}
+        for n, L in self.nets[s].layers.items():
+            out[n + ".weight"] = L.W.detach().clone()
+            out[n + ".bias"] = L.b.detach().clone()
+        return out
+
+    def refresh_shadows(self):
+        st = torch.cuda.current_stream().cuda_stream
+        for net in self.nets:
+            for L in net.layers.values():
+                check(self.lib.links_cast_weight(L.W.data_ptr(), L.N, L.K, L.Wb.data_ptr(), L.Kp,
+                                                 L.WbT.data_ptr() if L.WbT is not None else None, L.Np, st),
+                      "links_cast_weight")
+
+    def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0):
+        st = torch.cuda.current_stream().cuda_stream
+        check(self.lib.links_adam_step(self.master.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.n_params, lr, betas[0], betas[1], eps,
+                                       weight_decay, 0, self.step_dev.data_ptr(), grad_scale, st), "links_adam_step")
+        self.refresh_shadows()
+
+    # ------------------------------------------------------------------------------------------
+    # launch planning
+    # ------------------------------------------------------------------------------------------
+    def _launch(self, problems):
+        """Returns a callable running one grouped launch (<= 8 problems each, split if more)."""
+        chunks = [problems[i:i + _cabi.MAX_GEMM_PROBLEMS] for i in range(0, len(problems), _cabi.MAX_GEMM_PROBLEMS)]
+        arrs = [((GemmProblem * len(c))(*c), len(c)) for c in chunks]
+        fn = self.lib.links_gemm_grouped
+
+        def run():
+            st = torch.cuda.current_stream().cuda_stream
+            for arr, n in arrs:
+                rc = fn(arr, n, st)
+                if rc:
+                    check(rc, "links_gemm_grouped")
+        return run
+
+    @staticmethod
+    def _prob(A, B, M, N, K, lda, ldb, flags=0, bias=None, add0=None, add1=None, ymask=None, bits=None,
+              sign_out=None, mid=None, out=None, outT=None, outT_col0=0, out_f32=None, ld_f32=0):
+        P = GemmProblem()
+        P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb, P.flags = A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb, flags
+        P.bias = bias.data_ptr() if bias is not None else None
+        for name, t in (("add0", add0), ("add1", add1), ("ymask", ymask), ("mid", mid), ("out", out)):
+            if t is not None:
+                setattr(P, name, t.data_ptr())
+                setattr(P, "ld_" + name, t.stride(0))
+        if bits is not None:
+            P.bits, P.ld_bits = bits.data_ptr(), bits.stride(0)
+        if sign_out is not None:
+            P.sign_out, P.ld_sign = sign_out.data_ptr(), sign_out.stride(0)
+        if outT is not None:
+            P.outT, P.ld_outT, P.outT_col0 = outT.data_ptr(), outT.stride(0), outT_col0
+        if out_f32 is not None:
+            P.out_f32, P.ld_f32 = out_f32.data_ptr(), ld_f32 or out_f32.stride(0)
+        return P
+
+    def forward_plan(self, p, rows=None):
+        """Launch list for pass p; inputs are self.x0[p][s] (bf16 [M,64]); outputs self.head_out[p][s]."""
+        key = ("fwd", p, rows)
+        if key in self._plans:
+            return self._plans[key]
+        M = rows or self.M
+        col0 = p * self.M
+        tr = self.train
+        ops = []
+        act = self.act[p]
+        T = lambda s, n: self.actT[s][n] if tr else None
+        nets = self.nets
+        # upscale (no activation, models_def.py:136)
+        ops.append(self._launch([self._prob(self.x0[p][s], nets[s].layers["upscale"].Wb, M, WIDTH, 64, 64, 64,
+                                            bias=nets[s].layers["upscale"].b, out=act[s]["h0"], outT=T(s, "h0"),
+                                            outT_col0=col0) for s in range(self.S)]))
+
+        def block_ops(items):
+            """items: list of (s, blk, xin_name)."""
+            l1 = [self._prob(act[s][xin], nets[s].layers[blk + ".l1"].Wb, M, WIDTH, WIDTH, WIDTH, WIDTH,
+                             flags=EPI_LEAKY_PRE, bias=nets[s].layers[blk + ".l1"].b, out=act[s][blk + ".a1"],
+                             outT=T(s, blk + ".a1"), outT_col0=col0) for s, blk, xin in items]
+            l2 = [self._prob(act[s][blk + ".a1"], nets[s].layers[blk + ".l2"].Wb, M, WIDTH, WIDTH, WIDTH, WIDTH,
+                             flags=EPI_LEAKY_PRE | EPI_LEAKY_POST, bias=nets[s].layers[blk + ".l2"].b,
+                             sign_out=self.sign[p][s][blk] if tr else None, add0=act[s][xin],
+                             out=act[s][blk + ".y"], outT=T(s, blk + ".y"), outT_col0=col0) for s, blk, xin in items]
+            ops.append(self._launch(l1))
+            ops.append(self._launch(l2))
+
+        x = "h0"
+        for blk in self.trunk:
+            block_ops([(s, blk, x) for s in range(self.S)])
+            x = blk + ".y"
+        active = self.pass_branches[p]
+        depth = max(len(self.branches[br][0]) for br in active)
+        xin = {br: x for br in active}
+        for i in range(depth):
+            items = []
+            for br in active:
+                blocks = self.branches[br][0]
+                if i < len(blocks):
+                    items += [(s, blocks[i], xin[br]) for s in range(self.S)]
+            block_ops(items)
+            for br in active:
+                if i < len(self.branches[br][0]):
+                    xin[br] = self.branches[br][0][i] + ".y"
+        heads = []
+        for br in active:
+            head = self.branches[br][1]
+            for s in range(self.S):
+                L = nets[s].layers[head]
+                heads.append(self._prob(act[s][xin[br]], L.Wb, M, L.N, WIDTH, WIDTH, WIDTH, bias=L.b,
+                                        out_f32=self.head_out[p][s][head]))
+        ops.append(self._launch(heads))
+        self._plans[key] = ops
+        return ops
+
+    def backward_plan(self, p, need_input_grad, rows=None):
+        """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64]) and self.GT[s][head] filled by the
+        loss kernels.  Outputs: G/GT of every layer, optionally self.din[p][s] = d/d(input part) fp32."""
+        key = ("bwd", p, need_input_grad, rows)
+        if key in self._plans:
+            return self._plans[key]
+        M = rows or self.M
+        col0 = p * self.M
+        ops = []
+        act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
+        GT = self.GT
+        active = self.pass_branches[p]
+
+        def xin_of(br, i):
+            blocks = self.branches[br][0]
+            if i > 0:
+                return blocks[i - 1]
+            return self.trunk[-1] if self.trunk else None
+
+        # heads: dy_last = G_head . W_head ; masks of the last block of the branch
+        probs = []
+        for br in active:
+            blocks, head = self.branches[br]
+            last = blocks[-1]
+            for s in range(self.S):
+                L = nets[s].layers[head]
+                probs.append(self._prob(G[s][head], L.WbT, M, WIDTH, 64, 64, L.Np, ymask=act[s][last + ".y"],
+                                        mid=dt[s][last], bits=sign[s][last], out=G[s][last + ".l2"],
+                                        outT=GT[s][last + ".l2"], outT_col0=col0))
+        ops.append(self._launch(probs))
+
+        def l2_dgrad(items):
+            ops.append(self._launch([
+                self._prob(G[s][blk + ".l2"], nets[s].layers[blk + ".l2"].WbT, M, WIDTH, WIDTH, WIDTH, WIDTH,
+                           ymask=act[s][blk + ".a1"], out=G[s][blk + ".l1"], outT=GT[s][blk + ".l1"], outT_col0=col0)
+                for s, blk in items]))
+
+        def l1_dgrad(items):
+            """items: (s, blk, prev, mode) -- mode 'mask' (prev is a block), 'raw' (-> E), 'merge' (add E), 'up'."""
+            probs = []
+            for s, blk, prev, mode in items:
+                L = nets[s].layers[blk + ".l1"]
+                kw = dict(add0=dt[s][blk])
+                if mode == "raw":
+                    kw.update(out=self.E[p][s])
+                elif mode == "up":
+                    kw.update(out=G[s]["upscale"], outT=GT[s]["upscale"], outT_col0=col0)
+                else:
+                    if mode == "merge":
+                        kw.update(add1=self.E[p][s])
+                    kw.update(ymask=act[s][prev + ".y"], mid=dt[s][prev], bits=sign[s][prev], out=G[s][prev + ".l2"],
+                              outT=GT[s][prev + ".l2"], outT_col0=col0)
+                probs.append(self._prob(G[s][blk + ".l1"], L.WbT, M, WIDTH, WIDTH, WIDTH, WIDTH, **kw))
+            ops.append(self._launch(probs))
+
+        depth = max(len(self.branches[br][0]) for br in active)
+        for i in range(depth - 1, -1, -1):
+            brs = [br for br in active if i < len(self.branches[br][0])]
+            l2_dgrad([(s, self.branches[br][0][i]) for br in brs for s in range(self.S)])
+            if i > 0:
+                l1_dgrad([(s, self.branches[br][0][i], self.branches[br][0][i - 1], "mask") for br in brs
+                          for s in range(self.S)])
+            else:
+                prev = self.trunk[-1] if self.trunk else None
+                if prev is None:
+                    assert len(brs) == 1
+                    l1_dgrad([(s, self.branches[brs[0]][0][0], None, "up") for s in range(self.S)])
+                elif len(brs) == 1:
+                    l1_dgrad([(s, self.branches[brs[0]][0][0], prev, "mask") for s in range(self.S)])
+                else:
+                    assert len(brs) == 2
+                    l1_dgrad([(s, self.branches[brs[0]][0][0], prev, "raw") for s in range(self.S)])
+                    l1_dgrad([(s, self.branches[brs[1]][0][0], prev, "merge") for s in range(self.S)])
+        for t in range(len(self.trunk) - 1, -1, -1):
+            blk = self.trunk[t]
+            l2_dgrad([(s, blk) for s in range(self.S)])
+            if t > 0:
+                l1_dgrad([(s, blk, self.trunk[t - 1], "mask") for s in range(self.S)])
+            else:
+                l1_dgrad([(s, blk, None, "up") for s in range(self.S)])
+        if need_input_grad:
+            probs = []
+            for s in range(self.S):
+                L = nets[s].layers["upscale"]
+                probs.append(self._prob(G[s]["upscale"], L.WbT, M, L.K, WIDTH, WIDTH, L.Np, out_f32=self.din[p][s]))
+            ops.append(self._launch(probs))
+        self._plans[key] = ops
+        return ops
+
+    def _layer_input(self, name):
+        """Name of the activation feeding layer `name` (or 'x0')."""
+        if name == "upscale":
+            return "x0"
+        for br, (blocks, head) in self.branches.items():
+            if name == head:
+                return blocks[-1] + ".y"
+        blk, l = name.rsplit(".", 1)
+        if l == "l2":
+            return blk + ".a1"
+        if blk in self.trunk:
+            t = self.trunk.index(blk)
+            return "h0" if t == 0 else self.trunk[t - 1] + ".y"
+        for br, (blocks, head) in self.branches.items():
+            if blk in blocks:
+                i = blocks.index(blk)
+                if i > 0:
+                    return blocks[i - 1] + ".y"
+                return self.trunk[-1] + ".y" if self.trunk else "h0"
+        raise KeyError(name)
+
+    def _layer_passes(self, name):
+        """Passes in which layer `name` is evaluated."""
+        if name == "upscale" or name.split(".")[0] in self.trunk:
+            return list(range(self.n_passes))
+        for br, (blocks, head) in self.branches.items():
+            if name == head or name.split(".")[0] in blocks:
+                return [p for p in range(self.n_passes) if br in self.pass_branches[p]]
+        raise KeyError(name)
+
+    def wgrad_plan(self, rows=None):
+        """dW = G^T . X contracted over the rows of every pass that used the layer; db = column sums of G."""
+        key = ("wgrad", rows)
+        if key in self._plans:
+            return self._plans[key]
+        M = rows or self.M
+        assert rows is None or self.n_passes == 1, "partial rows only supported for single-pass sets"
+        ops = []
+        probs = []
+        colsums = []
+        for s in range(self.S):
+            for n in self.layer_names:
+                L = self.nets[s].layers[n]
+                passes = self._layer_passes(n)
+                assert passes == list(range(len(passes))), "passes using a layer must be a prefix"
+                Kc = (len(passes) - 1) * self.M + M
+                xin = self._layer_input(n)
+                XT = self.x0T[s] if xin == "x0" else self.actT[s][xin]
+                probs.append(self._prob(self.GT[s][n], XT, L.N, L.K, Kc, self.ldT, self.ldT, out_f32=L.gW,
+                                        ld_f32=L.K))
+                for i, p in enumerate(passes):
+                    g = self.G[p][s][n]
+                    colsums.append((g.data_ptr(), g.stride(0), M, L.N, L.gb.data_ptr(), 1 if i > 0 else 0))
+        ops.append(self._launch(probs))
+        fn = self.lib.links_colsum_bf16
+
+        def run_colsums():
+            st = torch.cuda.current_stream().cuda_stream
+            for a in colsums:
+                rc = fn(*a, st)
+                if rc:
+                    check(rc, "links_colsum_bf16")
+        ops.append(run_colsums)
+        self._plans[key] = ops
+        return ops
+
+    @staticmethod
+    def run(ops):
+        for op in ops:
+            op()

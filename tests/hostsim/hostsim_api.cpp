@@ -38,9 +38,9 @@ SIM int sim_cast_weight(const float* W, int N, int K, void* Wb, int ldw, void* W
   return 0;
 }
 SIM int sim_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
-                      float wd, int step, float grad_scale) {
-  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel(p, g, m, v, n, lr, b1, b2, eps, wd, bc1, sqrtf(bc2), grad_scale); });
+                      float wd, int step, int* step_dev, float grad_scale) {
+  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale); });
+  if (step_dev) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
   return 0;
 }
 

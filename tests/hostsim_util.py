@@ -66,21 +66,91 @@ def f32_to_bf16(a):
     return (u >> 16).astype(np.uint16)
 
 
-def pack_flow(L, params, C_, n_blocks=8):
-    """FrEIA-layout param dict (torch tensors) -> packed float32 numpy buffer via the sim pack kernel."""
-    keep = []
-    arrs = {k: [] for k in ("subnet.0.weight", "subnet.0.bias", "subnet.2.weight", "subnet.2.bias", "global_scale",
-                            "global_offset", "w_perm", "w_perm_inv")}
-    for k in range(n_blocks):
-        for name in arrs:
-            a = np.ascontiguousarray(params["module_list.%d.%s" % (k, name)].detach().cpu().numpy(), dtype=np.float32)
-            keep.append(a)
-            arrs[name].append(a.ctypes.data)
-    packed = np.zeros(L.sim_flow_packed_floats(C_, n_blocks), dtype=np.float32)
-    def pp(name):
-        return (C.c_void_p * n_blocks)(*arrs[name])
-    rc = L.sim_flow_pack(C_, n_blocks, pp("subnet.0.weight"), pp("subnet.0.bias"), pp("subnet.2.weight"),
-                         pp("subnet.2.bias"), pp("global_scale"), pp("global_offset"), pp("w_perm"),
-                         pp("w_perm_inv"), ptr(packed))
+def pack_flow(backend, params, C_, n_blocks=8):
+    """FrEIA-layout param dict (torch tensors) -> packed float32 numpy buffer via the pack kernel of `backend`."""
+    names = ("subnet.0.weight", "subnet.0.bias", "subnet.2.weight", "subnet.2.bias", "global_scale",
+             "global_offset", "w_perm", "w_perm_inv")
+    host = {n: [np.ascontiguousarray(params["module_list.%d.%s" % (k, n)].detach().cpu().numpy(), dtype=np.float32)
+                for k in range(n_blocks)] for n in names}
+    packed = np.zeros(backend.packed_floats(C_, n_blocks), dtype=np.float32)
+    if backend.name == "sim":
+        tables = [(C.c_void_p * n_blocks)(*[a.ctypes.data for a in host[n]]) for n in names]
+        rc = backend.L.sim_flow_pack(C_, n_blocks, *tables, ptr(packed))
+    else:
+        import torch
+        dev = {n: [torch.from_numpy(a).cuda() for a in host[n]] for n in names}
+        tables = [(C.c_void_p * n_blocks)(*[t.data_ptr() for t in dev[n]]) for n in names]
+        pk = torch.from_numpy(packed).cuda()
+        rc = backend.L.links_flow_pack(C_, n_blocks, *tables, pk.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        packed[...] = pk.cpu().numpy()
     assert rc == 0
     return packed
+
+
+# ------------------------------------------------------------------------------------------------
+# Backends: the same kernel tests run against the CPU simulation ("sim", default suite) and against
+# the real CUDA library through the C ABI ("cuda", `-m gpu`).
+# ------------------------------------------------------------------------------------------------
+class SimBackend:
+    name = "sim"
+
+    def __init__(self):
+        self.L = sim()
+
+    def call(self, fn, *args):
+        conv = [ptr(a) if isinstance(a, np.ndarray) else a for a in args]
+        return getattr(self.L, "sim_" + fn)(*conv)
+
+    def packed_floats(self, C_, nb):
+        return self.L.sim_flow_packed_floats(C_, nb)
+
+
+class CudaBackend:
+    """Marshals numpy arrays through device memory and calls liblinks_b200.so on the current stream."""
+    name = "cuda"
+
+    def __init__(self):
+        from links_b200 import _cabi
+        self.L = _cabi.lib()
+
+    def call(self, fn, *args):
+        import torch
+        dev, conv = [], []
+        for a in args:
+            if isinstance(a, np.ndarray):
+                t = torch.from_numpy(a).cuda()
+                dev.append((a, t))
+                conv.append(t.data_ptr())
+            else:
+                conv.append(a)
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = getattr(self.L, "links_" + fn)(*conv, stream)
+        torch.cuda.synchronize()
+        for a, t in dev:
+            a[...] = t.cpu().numpy()
+        return rc
+
+    def packed_floats(self, C_, nb):
+        return self.L.links_flow_packed_floats(C_, nb)
+
+
+def _make_backend(kind):
+    return SimBackend() if kind == "sim" else CudaBackend()
+
+
+import pytest  # noqa: E402
+
+_backend_cache = {}
+
+
+@pytest.fixture
+def backend(request):
+    kind = request.param
+    if kind not in _backend_cache:
+        _backend_cache[kind] = _make_backend(kind)
+    return _backend_cache[kind]
+
+
+backend_params = pytest.mark.parametrize(
+    "backend", ["sim", pytest.param("cuda", marks=pytest.mark.gpu)], indirect=True)

@@ -1,0 +1,183 @@
+"""GPU parity: lifter / predictor MLP engine and the full LT / LR training steps vs the CPU oracle.
+
+Tolerances: north star = predicted joints and losses within 1e-3 relative (fp32 accumulate, BF16 operands).
+Gradients are not part of that contract; they are checked at BF16-operand accuracy (relative Frobenius error).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_lifter_forward_backward_vs_oracle():
+    from links_b200.mlp import MlpSet
+    from oracle import nets as ON, steps as OS
+    M = 200
+    nj = (7, 10)
+    params = [ON.init_lifter_params(nj[0], 11), ON.init_lifter_params(nj[1], 12)]
+    mlp = MlpSet("lifter", [14, 20], [{"downscale": 7, "angles": 1}, {"downscale": 10, "angles": 1}], M, n_passes=1)
+    mlp.load_state_dicts(params)
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(M, 2 * n, generator=g) * 0.15 for n in nj]
+    lib = mlp.lib
+    st = torch.cuda.current_stream().cuda_stream
+    for s in range(2):
+        idx = torch.arange(2 * nj[s], dtype=torch.int32, device="cuda")
+        xd = xs[s].cuda()
+        assert lib.links_pack_rows(xd.data_ptr(), xd.stride(0), M, idx.data_ptr(), 2 * nj[s], 1, mlp.x0[0][s].data_ptr(),
+                                   mlp.x0T[s].data_ptr(), mlp.ldT, 0, st) == 0
+    mlp.run(mlp.forward_plan(0))
+    torch.cuda.synchronize()
+    # upstream gradients (bf16-representable)
+    ups = []
+    for s in range(2):
+        gd = (torch.randn(M, nj[s], generator=g) * 0.1).bfloat16()
+        ga = (torch.randn(M, 1, generator=g) * 0.1).bfloat16()
+        ups.append((gd, ga))
+        G, GT = mlp.G[0][s], mlp.GT[s]
+        G["downscale"].zero_(); G["angles"].zero_()
+        G["downscale"][:, :nj[s]] = gd.cuda()
+        G["angles"][:, :1] = ga.cuda()
+        GT["downscale"][:, :M] = gd.cuda().t()
+        GT["angles"][:, :M] = ga.cuda().t()
+    mlp.run(mlp.backward_plan(0, need_input_grad=True))
+    mlp.run(mlp.wgrad_plan())
+    torch.cuda.synchronize()
+    for s in range(2):
+        p = OS.params_require_grad(params[s])
+        x = xs[s].clone().requires_grad_(True)
+        xd, xa = ON.lifter_forward(x, p)
+        ((xd * ups[s][0].float()).sum() + (xa * ups[s][1].float()).sum()).backward()
+        got_d = mlp.head_out[0][s]["downscale"][:, :nj[s]].cpu()
+        got_a = mlp.head_out[0][s]["angles"][:, :1].cpu()
+        # depth offsets feed joints as d = 10 + offset: 1e-3 relative on joints == 1e-2 absolute on offsets
+        assert (got_d - xd.detach()).abs().max().item() < 5e-3
+        assert (got_a - xa.detach()).abs().max().item() < 5e-3
+        assert rel_fro(got_d, xd.detach()) < 1.5e-2
+        L = mlp.nets[s].layers
+        for name in ("upscale", "res_common.l1", "res_common.l2", "res_pose2.l1", "res_pose3.l2", "res_angle1.l1",
+                     "res_angle3.l2", "downscale", "angles"):
+            e = rel_fro(L[name].gW.cpu(), p[name + ".weight"].grad)
+            assert e < 4e-2, (name, e)
+            eb = rel_fro(L[name].gb.cpu(), p[name + ".bias"].grad)
+            assert eb < 4e-2, (name, eb)
+        din = mlp.din[0][s][:, :2 * nj[s]].cpu()
+        assert rel_fro(din, x.grad) < 4e-2
+
+
+def test_predictor_forward_vs_golden(golden):
+    """Occluded_*_Predictor forward vs outputs of the reference module (tests/golden/nets.npz)."""
+    from links_b200.mlp import MlpSet
+    from oracle import nets as ON
+    G = golden["nets"]
+    for cls, nj, od in (("Occluded_Limb_Predictor", 14, 9), ("Occluded_Torso_Predictor", 7, 30)):
+        params = ON.init_predictor_params(nj, od, int(G[cls + "_seed"]))
+        x = torch.from_numpy(G[cls + "_x"])
+        M = x.shape[0]
+        mlp = MlpSet("predictor", [3 * nj], [{"downscale": od}], M, n_passes=1, train=False)
+        mlp.load_state_dicts([params])
+        idx = torch.arange(3 * nj, dtype=torch.int32, device="cuda")
+        xd = x.cuda()
+        assert mlp.lib.links_pack_rows(xd.data_ptr(), xd.stride(0), M, idx.data_ptr(), 3 * nj, 1, mlp.x0[0][0].data_ptr(),
+                                       None, 0, 0, torch.cuda.current_stream().cuda_stream) == 0
+        mlp.run(mlp.forward_plan(0))
+        got = mlp.head_out[0][0]["downscale"][:, :od].cpu()
+        ref = torch.from_numpy(G[cls + "_y"])
+        assert rel_fro(got, ref) < 1.5e-2, cls
+
+
+def _make_step(kind, B, seed_off=0):
+    from links_b200.steps import LifterStep
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, nets as ON
+    if kind == "lt":
+        nets = [ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12)]
+        flows = [OF.init_flow_params(14, 41, perturb=0.3), OF.init_flow_params(20, 42, perturb=0.3)]
+    else:
+        nets = [ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)]
+        flows = [OF.init_flow_params(22, 43, perturb=0.3), OF.init_flow_params(22, 44, perturb=0.3)]
+    full = OF.init_flow_params(34, 40, perturb=0.3)
+    step = LifterStep(kind, B, nets, flows, full)
+    x2d, _ = synth_poses(B, seed=31 + seed_off)
+    g = torch.Generator().manual_seed(77 + seed_off)
+    draws = dict(x=torch.from_numpy(x2d), noise=torch.randn(B, 34, generator=g), eps_x=torch.randn(2 * B, generator=g),
+                 u_y=torch.rand(2 * B, generator=g))
+    return step, nets, flows, full, draws
+
+
+def _load(step, d):
+    step.x.copy_(d["x"]); step.noise.copy_(d["noise"]); step.eps_x.copy_(d["eps_x"]); step.u_y.copy_(d["u_y"])
+
+
+@pytest.mark.parametrize("kind", ["lt", "lr"])
+def test_step_matches_golden_fixture(kind, golden):
+    """B = 8 step: same seeds as tests/golden/steps.npz (oracle output frozen in the build container)."""
+    G = golden["steps"]
+    step, nets, flows, full, d = _make_step(kind, 8)
+    np.testing.assert_array_equal(d["x"].numpy(), G["x"])
+    np.testing.assert_array_equal(d["eps_x"].numpy(), G["eps_x"])
+    _load(step, d)
+    step.forward_backward()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(step.u.cpu().numpy(), G["u"], rtol=2e-3, atol=2e-5)
+    got = step.loss_dict()
+    for k, v in got.items():
+        ref = float(G["%s_%s" % (kind, k)])
+        assert abs(v - ref) <= 1e-3 * abs(ref), (k, v, ref)
+    if kind == "lt":
+        np.testing.assert_allclose(step.qfull[0].cpu().numpy(), G["lt_rot_2d"], rtol=1e-3, atol=1e-4)
+        gw = step.mlp.nets[0].layers["upscale"].gW.cpu()
+        assert rel_fro(gw, torch.from_numpy(G["lt_dW_leg_upscale"])) < 5e-2
+        ga = step.mlp.nets[1].layers["angles"].gW.cpu()
+        assert rel_fro(ga, torch.from_numpy(G["lt_dW_torso_angles"])) < 5e-2
+    else:
+        np.testing.assert_allclose(step.qfull[0].cpu().numpy(), G["lr_rot_2d_left"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(step.qfull[1].cpu().numpy(), G["lr_rot_2d_right"], rtol=1e-3, atol=1e-4)
+        gw = step.mlp.nets[0].layers["upscale"].gW.cpu()
+        assert rel_fro(gw, torch.from_numpy(G["lr_dW_left_upscale"])) < 5e-2
+
+
+@pytest.mark.parametrize("kind", ["lt", "lr"])
+def test_step_vs_oracle_with_optimizer(kind):
+    """B = 64 (N = 128): losses / joints after 1 step and losses again after 3 Adam steps vs the oracle."""
+    from oracle import steps as OS
+    B = 64
+    step, nets, flows, full, d = _make_step(kind, B, seed_off=5)
+    pn = [OS.params_require_grad(p) for p in nets]
+    opts = OS.make_adam(pn)
+    fn = OS.lt_step if kind == "lt" else OS.lr_step
+    for it in range(3):
+        _load(step, d)
+        step.step()
+        u = OS.sample_poses(d["x"], full, d["noise"])
+        for o in opts:
+            o.zero_grad()
+        aux = {}
+        out = fn(u, pn[0], pn[1], flows[0], flows[1], d["eps_x"], d["u_y"], aux=aux)
+        out["loss"].backward()
+        got = step.loss_dict()
+        tol = 1e-3 if it == 0 else 5e-3     # after updates the two trajectories differ by BF16-gradient noise
+        for k, v in got.items():
+            ref = out[k].item()
+            assert abs(v - ref) <= tol * abs(ref) + 1e-6, (it, k, v, ref)
+        if it == 0:
+            key = "rot_2d" if kind == "lt" else "rot_2d_left"
+            assert rel_fro(step.qfull[0].cpu(), aux[key].detach()) < 1e-3
+            for s in range(2):
+                for name in ("res_common.l1", "res_pose1.l2", "res_angle2.l1", "downscale", "angles", "upscale"):
+                    e = rel_fro(step.mlp.nets[s].layers[name].gW.cpu(), pn[s][name + ".weight"].grad)
+                    assert e < 6e-2, (s, name, e)
+        for o in opts:
+            o.step()
+    # parameters moved the same way (Adam: +-lr per step per element; compare the update direction statistically)
+    for s in range(2):
+        W0 = nets[s]["res_pose1.l1.weight"]
+        d_gpu = step.mlp.nets[s].layers["res_pose1.l1"].W.cpu() - W0
+        d_ref = pn[s]["res_pose1.l1.weight"].detach() - W0
+        cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
+        assert cos.item() > 0.9, cos.item()

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from hostsim_util import bf16_to_f32, ptr, sim
+from hostsim_util import bf16_to_f32, backend_params
 from links_b200 import maps as MP
 from oracle import geometry as OG
 from oracle import steps as OS
@@ -91,23 +91,24 @@ def oracle_eval(kind, inp, cfg):
 
 
 @pytest.mark.parametrize("kind,N,clamp", [("lt", 10, False), ("lr", 10, False), ("lt", 7, True), ("lr", 6, True)])
-def test_geometry_kernels_match_oracle(kind, N, clamp):
-    L = sim()
+@backend_params
+def test_geometry_kernels_match_oracle(kind, N, clamp, backend):
+    L = backend
     cfg = dict(OS.DEFAULT_CFG)
     inp = make_inputs(kind, N, seed=5 + N, clamp=clamp)
     ref = oracle_eval(kind, inp, cfg)
     m = MP.geom_maps(kind, cfg)
     nj = inp["nj"]
     stats = np.zeros(2, np.float32)
-    assert L.sim_elev_stats(ptr(inp["angs"][0]), ptr(inp["angs"][1]), N, ptr(stats)) == 0
+    assert L.call("elev_stats", inp["angs"][0], inp["angs"][1], N, stats) == 0
     np.testing.assert_allclose(stats, ref["stats"], rtol=2e-5)
 
     # ---- forward
     qp = [np.zeros((N, 2 * nj[p]), np.float32) for p in range(2)]
     qf = [np.zeros((N, 34), np.float32) for _ in range(2)]
-    common = [ptr(inp["u"]), ptr(inp["heads"][0]), ptr(inp["heads"][1]), ptr(inp["angs"][0]), ptr(inp["angs"][1]),
-              ptr(inp["eps"]), ptr(inp["uy"]), ptr(stats)]
-    assert L.sim_geom_forward(C.byref(m), *common, N, ptr(qp[0]), ptr(qp[1]), ptr(qf[0]), ptr(qf[1])) == 0
+    common = [inp["u"], inp["heads"][0], inp["heads"][1], inp["angs"][0], inp["angs"][1],
+              inp["eps"], inp["uy"], stats]
+    assert L.call("geom_forward", C.byref(m), *common, N, qp[0], qp[1], qf[0], qf[1]) == 0
     for p in range(2):
         np.testing.assert_allclose(qp[p], ref["qparts"][p], rtol=2e-4, atol=2e-6)
     for v in range(m.V):
@@ -118,8 +119,8 @@ def test_geometry_kernels_match_oracle(kind, N, clamp):
     sums = np.zeros(4, np.float32)
     g2 = [np.zeros((N, 64), np.uint16) for _ in range(2)]
     g2T = [np.zeros((nj[p], ldT), np.uint16) for p in range(2)]
-    assert L.sim_geom_loss(C.byref(m), *common, ptr(inp["heads2"][0]), ptr(inp["heads2"][1]), N, ptr(sums),
-                           ptr(g2[0]), ptr(g2[1]), ptr(g2T[0]), ptr(g2T[1]), ldT, 3) == 0
+    assert L.call("geom_loss", C.byref(m), *common, inp["heads2"][0], inp["heads2"][1], N, sums,
+                           g2[0], g2[1], g2T[0], g2T[1], ldT, 3) == 0
     npairs = N // 2
     np.testing.assert_allclose(sums[0] / N, ref["L3d"], rtol=3e-5)
     np.testing.assert_allclose(sums[1] / N, ref["rep"], rtol=3e-5)
@@ -136,9 +137,9 @@ def test_geometry_kernels_match_oracle(kind, N, clamp):
     g1 = [np.zeros((N, 64), np.uint16) for _ in range(2)]
     g1T = [np.zeros((nj[p], ldT), np.uint16) for p in range(2)]
     dgam, da, red = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros(2, np.float32)
-    assert L.sim_geom_backward(C.byref(m), *common, ptr(inp["heads2"][0]), ptr(inp["heads2"][1]),
-                               ptr(inp["ext"][0]), ptr(inp["ext"][1]), ptr(inp["ext_l"][0]), ptr(inp["ext_l"][1]), N,
-                               ptr(g1[0]), ptr(g1[1]), ptr(g1T[0]), ptr(g1T[1]), ldT, 0, ptr(dgam), ptr(da), ptr(red)) == 0
+    assert L.call("geom_backward", C.byref(m), *common, inp["heads2"][0], inp["heads2"][1],
+                               inp["ext"][0], inp["ext"][1], inp["ext_l"][0], inp["ext_l"][1], N,
+                               g1[0], g1[1], g1T[0], g1T[1], ldT, 0, dgam, da, red) == 0
     for p in range(2):
         got = bf16_to_f32(g1[p])[:, :nj[p]]
         scale = np.abs(ref["dH"][p]).max()
@@ -148,8 +149,8 @@ def test_geometry_kernels_match_oracle(kind, N, clamp):
     np.testing.assert_allclose(red[1], (da * inp["eps"]).sum(), rtol=1e-4, atol=1e-6)
     ga = [np.zeros((N, 64), np.uint16) for _ in range(2)]
     gaT = [np.zeros((1, ldT), np.uint16) for _ in range(2)]
-    assert L.sim_geom_backward_angles(ptr(inp["angs"][0]), ptr(inp["angs"][1]), ptr(inp["eps"]), ptr(stats), ptr(dgam),
-                                      ptr(red), N, ptr(ga[0]), ptr(ga[1]), ptr(gaT[0]), ptr(gaT[1]), ldT, 0) == 0
+    assert L.call("geom_backward_angles", inp["angs"][0], inp["angs"][1], inp["eps"], stats, dgam,
+                                      red, N, ga[0], ga[1], gaT[0], gaT[1], ldT, 0) == 0
     for p in range(2):
         got = bf16_to_f32(ga[p])[:, 0]
         scale = np.abs(ref["dA"][p]).max()
