@@ -102,6 +102,15 @@ int links_pack_rows(const float* src, int ld_src, int M, const int* idx_dev, int
 /* Column sums of a bf16 matrix: out[n] (+)= sum_m G[m, n]  (bias gradients). */
 int links_colsum_bf16(const void* G, int ldg, int M, int N, float* out, int accumulate, void* stream);
 
+/* The same for up to LINKS_MAX_COLSUM_ITEMS matrices in two launches (all bias gradients of a step). */
+#define LINKS_MAX_COLSUM_ITEMS 96
+typedef struct LinksColsumItem {
+  const void* G;   /* bf16 [M, ldg] */
+  float* out;      /* [N] */
+  int ldg, M, N, accumulate;
+} LinksColsumItem;
+int links_colsum_bf16_batched(const LinksColsumItem* items, int n_items, void* stream);
+
 /* fp32 master weights -> bf16 shadow W[N, Kpad] and W^T[K, Npad] (zero padded). */
 int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
                       void* stream);

@@ -47,6 +47,27 @@ extern "C" __attribute__((visibility("default"))) int links_colsum_bf16(const vo
   return links_launch_status();
 }
 
+extern "C" __attribute__((visibility("default"))) int links_colsum_bf16_batched(const LinksColsumItem* items, int n_items, void* stream) {
+  LINKS_CHECK_PTR(items);
+  if (n_items < 1 || n_items > LINKS_MAX_COLSUM_ITEMS) return LINKS_E_RANGE;
+  ColsumBatch B;
+  memset(&B, 0, sizeof(B));
+  int maxN = 0, maxM = 0;
+  for (int i = 0; i < n_items; ++i) {
+    if (!items[i].G || !items[i].out || items[i].M < 1 || items[i].N < 1) return LINKS_E_ARG;
+    B.it[i] = items[i];
+    if (items[i].N > maxN) maxN = items[i].N;
+    if (items[i].M > maxM) maxM = items[i].M;
+  }
+  B.n = n_items;
+  cudaStream_t s = links_stream(stream);
+  colsum_batched_zero_kernel<<<n_items, 256, 0, s>>>(B);
+  const int rows_per_block = 256;
+  dim3 grid((maxN + 31) / 32, n_items, (maxM + rows_per_block - 1) / rows_per_block);
+  colsum_batched_kernel<<<grid, dim3(32, 8), 0, s>>>(B, rows_per_block);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
                                  void* stream) {
   LINKS_CHECK_PTR(W);

@@ -14,4 +14,5 @@
 #define LINKS_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw[]; \
   type* name = reinterpret_cast<type*>(name##_raw)
 #endif
+#include "../../include/links_b200.h"
 #define LINKS_FULL_MASK 0xffffffffu

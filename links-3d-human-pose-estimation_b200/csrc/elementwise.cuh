@@ -50,6 +50,39 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ G, int ldg,
   }
 }
 
+// Batched variant: one launch for all bias gradients of a step.  grid = (col groups, items, row slabs).
+struct ColsumBatch {
+  LinksColsumItem it[LINKS_MAX_COLSUM_ITEMS];
+  int n;
+};
+__global__ void colsum_batched_zero_kernel(const ColsumBatch B) {
+  const LinksColsumItem& I = B.it[blockIdx.x];
+  if (I.accumulate) return;
+  for (int n = threadIdx.x; n < I.N; n += blockDim.x) I.out[n] = 0.f;
+}
+__global__ void colsum_batched_kernel(const ColsumBatch B, int rows_per_block) {
+  __shared__ float red[8][33];
+  const LinksColsumItem& I = B.it[blockIdx.y];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m0 = blockIdx.z * rows_per_block;
+  if (blockIdx.x * 32 >= I.N || m0 >= I.M) return;     // block-uniform
+  int m1 = m0 + rows_per_block;
+  if (m1 > I.M) m1 = I.M;
+  const __nv_bfloat16* G = static_cast<const __nv_bfloat16*>(I.G);
+  float acc = 0.f;
+  if (n < I.N) {
+    for (int m = m0 + threadIdx.y; m < m1; m += 8) acc += __bfloat162float(G[static_cast<size_t>(m) * I.ldg + n]);
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < I.N) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(I.out + n, s);
+  }
+}
+
 // fp32 W[N,K] -> bf16 Wb[N, ldw] (cols >= K zero) and bf16 WT[K, ldwt] (cols >= N zero), 32x32 smem tiles.
 __global__ void cast_weight_kernel(const float* __restrict__ W, int N, int K, __nv_bfloat16* __restrict__ Wb, int ldw,
                                    __nv_bfloat16* __restrict__ WT, int ldwt) {

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblinks_b200.so")
+LIB_PATH = os.environ.get("LINKS_B200_LIB", os.path.join(_HERE, "_lib", "liblinks_b200.so"))  # env: A/B builds only
 
 HEAD_LD = 32
 KPAD = 64
@@ -31,6 +31,13 @@ class GemmProblem(C.Structure):
                 ("out_f32", vp), ("ld_f32", ci)]
 
 
+class ColsumItem(C.Structure):
+    _fields_ = [("G", vp), ("out", vp), ("ldg", ci), ("M", ci), ("N", ci), ("accumulate", ci)]
+
+
+MAX_COLSUM_ITEMS = 96
+
+
 class GeomMaps(C.Structure):
     _fields_ = [("V", ci), ("n_joints", ci * 2), ("src_net", (ci * 17) * 2), ("col", ci * 17),
                 ("part_net", (ci * 17) * 2), ("part_idx", (ci * 17) * 2), ("bone_rel", cf * 16),
@@ -42,6 +49,7 @@ PP = C.POINTER(vp)
 SIGNATURES = {
     "links_pack_rows": (ci, [vp, ci, ci, vp, ci, ci, vp, vp, ci, ci]),
     "links_colsum_bf16": (ci, [vp, ci, ci, ci, vp, ci]),
+    "links_colsum_bf16_batched": (ci, [C.POINTER(ColsumItem), ci]),
     "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
     "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),

@@ -57,7 +57,10 @@ class MlpSet:
         self.device = torch.device(device)
         self.train = train
         self.pass_branches = pass_branches or [list(self.branches) for _ in range(n_passes)]
-        self.ldT = _rup(self.M * n_passes, 8)
+        # passes write disjoint, 8-aligned column ranges of the transposed buffers (TMA stores need 16-byte aligned
+        # starts); the gap [M, pass_stride) stays zero in every gradient buffer, so wgrad may contract across it
+        self.pass_stride = _rup(self.M, 8)
+        self.ldT = self.pass_stride * n_passes
         self.lib = _cabi.lib()
         dev = self.device
         # ---- parameter layout
@@ -79,8 +82,11 @@ class MlpSet:
                 else:
                     K, N = WIDTH, WIDTH
                 sizes.append((s, n, K, N))
-        total = sum(K * N + N for _, _, K, N in sizes)
-        self.n_params = total
+        # every weight / bias view starts on a 256-byte boundary of the flat buffers: the GEMM epilogue only takes
+        # its vector path for 16-byte aligned operands (a 7x1024+7 head would otherwise misalign everything after it)
+        total = sum(_rup(K * N, 64) + _rup(N, 64) for _, _, K, N in sizes)
+        self.n_params = total      # padded length of the flat buffers (padding stays zero through Adam)
+        self.n_params_real = sum(K * N + N for _, _, K, N in sizes)
         self.master = torch.zeros(total, dtype=torch.float32, device=dev)
         if train:
             self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -96,10 +102,10 @@ class MlpSet:
             L.Np = _rup(N, 64)
             L.W = self.master[off:off + N * K].view(N, K)
             L.gW = self.grad[off:off + N * K].view(N, K) if train else None
-            off += N * K
+            off += _rup(N * K, 64)
             L.b = self.master[off:off + N]
             L.gb = self.grad[off:off + N] if train else None
-            off += N
+            off += _rup(N, 64)
             L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
             L.WbT = torch.zeros(K, L.Np, dtype=torch.bfloat16, device=dev) if train else None
             cur[n] = L
@@ -233,7 +239,7 @@ class MlpSet:
         if key in self._plans:
             return self._plans[key]
         M = rows or self.M
-        col0 = p * self.M
+        col0 = p * self.pass_stride
         tr = self.train
         ops = []
         act = self.act[p]
@@ -291,7 +297,7 @@ class MlpSet:
         if key in self._plans:
             return self._plans[key]
         M = rows or self.M
-        col0 = p * self.M
+        col0 = p * self.pass_stride
         ops = []
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
         GT = self.GT
@@ -418,7 +424,7 @@ class MlpSet:
                 L = self.nets[s].layers[n]
                 passes = self._layer_passes(n)
                 assert passes == list(range(len(passes))), "passes using a layer must be a prefix"
-                Kc = (len(passes) - 1) * self.M + M
+                Kc = (len(passes) - 1) * self.pass_stride + M
                 xin = self._layer_input(n)
                 XT = self.x0T[s] if xin == "x0" else self.actT[s][xin]
                 probs.append(self._prob(self.GT[s][n], XT, L.N, L.K, Kc, self.ldT, self.ldT, out_f32=L.gW,
@@ -427,17 +433,28 @@ class MlpSet:
                     g = self.G[p][s][n]
                     colsums.append((g.data_ptr(), g.stride(0), M, L.N, L.gb.data_ptr(), 1 if i > 0 else 0))
         ops.append(self._launch(probs))
-        fn = self.lib.links_colsum_bf16
+        fn = self.lib.links_colsum_bf16_batched
+        batches = []
+        for i in range(0, len(colsums), _cabi.MAX_COLSUM_ITEMS):
+            chunk = colsums[i:i + _cabi.MAX_COLSUM_ITEMS]
+            arr = (_cabi.ColsumItem * len(chunk))()
+            for j, (g, ldg, Mi, Ni, out, acc) in enumerate(chunk):
+                arr[j].G, arr[j].out, arr[j].ldg, arr[j].M, arr[j].N, arr[j].accumulate = g, out, ldg, Mi, Ni, acc
+            batches.append((arr, len(chunk)))
 
         def run_colsums():
             st = torch.cuda.current_stream().cuda_stream
-            for a in colsums:
-                rc = fn(*a, st)
+            for arr, n in batches:
+                rc = fn(arr, n, st)
                 if rc:
-                    check(rc, "links_colsum_bf16")
+                    check(rc, "links_colsum_bf16_batched")
         ops.append(run_colsums)
         self._plans[key] = ops
         return ops
+
+    def pass_col0(self, p):
+        """Column offset of pass p inside the transposed ([*, ldT]) buffers."""
+        return p * self.pass_stride
 
     @staticmethod
     def run(ops):

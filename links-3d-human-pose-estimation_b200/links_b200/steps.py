@@ -84,7 +84,7 @@ class LifterStep:
     def _pack(self, src, idx, n_idx, p, s):
         m = self.mlp
         check(self.lib.links_pack_rows(src.data_ptr(), src.stride(0), self.N, idx.data_ptr(), n_idx, 1,
-                                       m.x0[p][s].data_ptr(), m.x0T[s].data_ptr(), m.ldT, p * m.M, self._st()),
+                                       m.x0[p][s].data_ptr(), m.x0T[s].data_ptr(), m.ldT, m.pass_col0(p), self._st()),
               "links_pack_rows")
 
     def forward_backward(self):
@@ -113,8 +113,8 @@ class LifterStep:
         g2 = [m.G[1][s]["downscale"] for s in range(2)]
         g2T = [m.GT[s]["downscale"] for s in range(2)]
         check(L.links_geom_loss(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), N, self.scal.data_ptr(),
-                                g2[0].data_ptr(), g2[1].data_ptr(), g2T[0].data_ptr(), g2T[1].data_ptr(), m.ldT, m.M,
-                                self._st()), "links_geom_loss")
+                                g2[0].data_ptr(), g2[1].data_ptr(), g2T[0].data_ptr(), g2T[1].data_ptr(), m.ldT,
+                                m.pass_col0(1), self._st()), "links_geom_loss")
         m.run(m.backward_plan(1, need_input_grad=True))
         g1 = [m.G[0][s]["downscale"] for s in range(2)]
         ga = [m.G[0][s]["angles"] for s in range(2)]

@@ -31,6 +31,17 @@ SIM int sim_colsum_bf16(const void* G, int ldg, int M, int N, float* out, int ac
                   [&] { colsum_bf16_kernel((const bf16*)G, ldg, M, N, out, rpb); });
   return 0;
 }
+SIM int sim_colsum_bf16_batched(const LinksColsumItem* items, int n_items) {
+  ColsumBatch B;
+  memset(&B, 0, sizeof(B));
+  int maxN = 0, maxM = 0;
+  for (int i = 0; i < n_items; ++i) { B.it[i] = items[i]; maxN = std::max(maxN, items[i].N); maxM = std::max(maxM, items[i].M); }
+  B.n = n_items;
+  hostsim::launch(dim3(n_items), dim3(256), 0, [&] { colsum_batched_zero_kernel(B); });
+  const int rpb = 256;
+  hostsim::launch(dim3((maxN + 31) / 32, n_items, (maxM + rpb - 1) / rpb), dim3(32, 8), 0, [&] { colsum_batched_kernel(B, rpb); });
+  return 0;
+}
 SIM int sim_cast_weight(const float* W, int N, int K, void* Wb, int ldw, void* WT, int ldwt) {
   const int kx = ((Wb ? (ldw > K ? ldw : K) : K) + 31) / 32;
   const int ny = ((WT ? (ldwt > N ? ldwt : N) : N) + 31) / 32;

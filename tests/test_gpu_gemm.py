@@ -77,10 +77,14 @@ def test_forward_epilogues_and_transpose():
     # l1-style: leaky(acc + b)
     out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     outT = torch.zeros(N, ldT, device="cuda", dtype=torch.bfloat16)
-    _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE, out=out, outT=outT, outT_col0=5)])
+    _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE, out=out, outT=outT, outT_col0=8)])
     ref = leaky(acc)
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-3)
-    assert torch.equal(outT[:, 5:5 + M], out.t())
+    assert torch.equal(outT[:, 8:8 + M], out.t())
+    assert torch.all(outT[:, :8] == 0)
+    # an unaligned column offset is rejected (TMA stores need 16-byte aligned starts)
+    P = _prob(cabi, A, W, M, N, K, out=out, outT=outT, outT_col0=5)
+    assert L.links_gemm_grouped((cabi.GemmProblem * 1)(P), 1, None) == -2
     # l2-style: leaky(leaky(acc + b) + resid) with the sign mask of (acc + b)
     sign = torch.zeros(M, N // 32, device="cuda", dtype=torch.int32)
     _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE | cabi.EPI_LEAKY_POST, add0=resid,
