@@ -189,6 +189,10 @@ int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, i
 /* nll[m] = 0.5*|z|^2 - log_jac_det, nll_sum += sum_m nll, dx = scale * d(nll)/dx (frozen flow). */
 int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
                           float* nll_sum, float* dx, void* stream);
+/* Vector-Jacobian product of the forward map (z, log_jac_det) = inn(x):
+ * dx = (dz/dx)^T gz + (d log_jac_det/dx)^T gld  (gld may be NULL = 0).  Backs autograd of the FrEIA shim. */
+int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,
+                   const float* gld, float* dx, void* stream);
 /* Sampling block (train_leg_torso_lifter.py:133-142): out = [x ; s], s = inn^-1(z + 0.2*noise*z) with
  * the root joint zeroed; C must be 34.  out is [2M,34]. */
 int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,
@@ -209,7 +213,7 @@ int links_threshold_counts(const float* values, size_t n, const float* threshold
 /* mode 0: metrics_batch.pmpjpe semantics (RMS scale match, R = diag(1,1,det)UV^T);
  * mode 1: metrics.pmpjpe(reflection='best') semantics (optimal scale, reflection allowed). */
 int links_pmpjpe(const float* p_ref, const float* p, int M, int num_joints, int mode, float* per_pose,
-                 double* sum, void* stream);
+                 float* aligned /* [M, 3*num_joints] Procrustes-aligned p, may be NULL */, double* sum, void* stream);
 /* Eval fusion (eval_h36m.py:58-78): lift 2D poses with combined depths, score against GT. */
 int links_eval_lift_score(const float* poses_2d, const float* depth_off, int ld_depth, const float* gt_3d,
                           int M, float depth, double* sums3, void* stream);

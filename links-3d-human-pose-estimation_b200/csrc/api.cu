@@ -276,6 +276,16 @@ extern "C" __attribute__((visibility("default"))) int links_flow_nll_fwdbwd(cons
   return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
 }
 
+extern "C" __attribute__((visibility("default"))) int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,
+                              const float* gld, float* dx, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(gz); LINKS_CHECK_PTR(dx); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = dx; A.gz = gz; A.gld = gld; A.M = M; A.n_blocks = n_blocks;
+  return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
+}
+
 extern "C" __attribute__((visibility("default"))) int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,
                                  float* out, void* stream) {
   LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(noise); LINKS_CHECK_PTR(out); LINKS_CHECK_ALIGN16(packed);
@@ -316,12 +326,12 @@ extern "C" __attribute__((visibility("default"))) int links_threshold_counts(con
 }
 
 extern "C" __attribute__((visibility("default"))) int links_pmpjpe(const float* p_ref, const float* p, int M, int num_joints, int mode, float* per_pose,
-                            double* sum, void* stream) {
+                            float* aligned, double* sum, void* stream) {
   int rc = check_pose_args(p_ref, p, M, num_joints);
   if (rc) return rc;
   if (mode < 0 || mode > 1) return LINKS_E_RANGE;
   pmpjpe_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
-      p_ref, p, M, num_joints, mode, per_pose, sum);
+      p_ref, p, M, num_joints, mode, per_pose, aligned, sum);
   return links_launch_status();
 }
 

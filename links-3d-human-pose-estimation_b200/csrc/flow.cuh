@@ -92,6 +92,8 @@ struct FlowArgs {
   float* ld;            // FWD/REV: [M]
   float* nll_sum;       // NLL_FWDBWD
   float scale;          // NLL_FWDBWD: dx = scale * d nll / dx
+  const float* gz;      // NLL_FWDBWD, optional: general VJP seed d/dz [M, C] (replaces scale * z)
+  const float* gld;     //                       and d/d(log_jac_det) [M] (replaces -scale)
   int M, n_blocks;
 };
 
@@ -395,7 +397,9 @@ __global__ void __launch_bounds__(kFlowWarps * 32) flow_kernel(const FlowArgs A)
     float* d0 = sm + S::off_d0;
     float* d1 = sm + S::off_d1;
     const float* z = state(nb);
-    for (int i = warp; i < C; i += kFlowWarps) d0[lane * S::XS + i] = A.scale * z[lane * S::XS + i];
+    for (int i = warp; i < C; i += kFlowWarps)
+      d0[lane * S::XS + i] = A.gz ? (ok ? A.gz[static_cast<size_t>(row) * C + i] : 0.f) : A.scale * z[lane * S::XS + i];
+    const float glv = A.gz ? ((ok && A.gld) ? A.gld[row] : 0.f) : -A.scale;
     __syncthreads();
     if (warp == 0) {
       float ldt = 0.f;
@@ -411,7 +415,7 @@ __global__ void __launch_bounds__(kFlowWarps * 32) flow_kernel(const FlowArgs A)
     float* din = d0;
     float* dout = d1;
     for (int k = nb - 1; k >= 0; --k) {
-      block_backward<C>(sm, A.packed, k, state(k), din, dout, -A.scale, warp, lane);
+      block_backward<C>(sm, A.packed, k, state(k), din, dout, glv, warp, lane);
       float* t = din; din = dout; dout = t;
     }
     if (ok && A.out) {

@@ -139,7 +139,7 @@ __device__ __forceinline__ void polar_svd3(const float (&A)[3][3], float (&Q)[3]
 }
 
 // ---- PA-MPJPE for one pose.  mode 0: metrics_batch.py:104-159; mode 1: metrics.py:35-171 ('best') ---
-__device__ __forceinline__ float pmpjpe_row(const float* r, const float* p, int J, int mode) {
+__device__ __forceinline__ float pmpjpe_row(const float* r, const float* p, int J, int mode, float* aligned = nullptr) {
   const float invJ = 1.f / static_cast<float>(J);
   float mr[3] = {0.f, 0.f, 0.f}, mp[3] = {0.f, 0.f, 0.f};
   for (int j = 0; j < J; ++j) {
@@ -193,6 +193,7 @@ __device__ __forceinline__ float pmpjpe_row(const float* r, const float* p, int 
     for (int a = 0; a < 3; ++a) {
       const float z = gain * nr * (Q[a][0] * y[0] + Q[a][1] * y[1] + Q[a][2] * y[2]);
       const float e = (r[a * J + j] - mr[a]) - z;
+      if (aligned) aligned[a * J + j] = z + mr[a];
       d2 += e * e;
     }
     acc += sqrtf(d2);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kPosesPerBlock) mpjpe_kernel(
 
 __global__ void __launch_bounds__(kPosesPerBlock) pmpjpe_kernel(
     const float* __restrict__ p_ref, const float* __restrict__ p, int M, int J, int mode,
-    float* __restrict__ per_pose, double* sum) {
+    float* __restrict__ per_pose, float* __restrict__ aligned, double* sum) {
   __shared__ float s_ref[kPosesPerBlock * kRowStride];
   __shared__ float s_p[kPosesPerBlock * kRowStride];
   __shared__ double s_red[2];
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(kPosesPerBlock) pmpjpe_kernel(
   const int t = threadIdx.x;
   float e = 0.f;
   if (t < npos) {
-    e = pmpjpe_row(s_ref + t * kRowStride, s_p + t * kRowStride, J, mode);
+    e = pmpjpe_row(s_ref + t * kRowStride, s_p + t * kRowStride, J, mode,
+                   aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr);
     if (per_pose) per_pose[pose0 + t] = e;
   }
   if (sum != nullptr) {

@@ -61,9 +61,10 @@ SIGNATURES = {
     "links_flow_apply": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
     "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp]),
     "links_flow_sample": (ci, [vp, ci, vp, vp, ci, vp]),
+    "links_flow_vjp": (ci, [vp, ci, ci, vp, ci, vp, vp, vp]),
     "links_mpjpe": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]),
     "links_threshold_counts": (ci, [vp, sz, vp, ci, ci, vp]),
-    "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp]),
+    "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
     "links_eval_lift_score": (ci, [vp, vp, ci, vp, ci, cf, vp]),
     "links_occ_lift": (ci, [vp, vp, vp, ci, cf, vp]),
     "links_occ_rotate_y": (ci, [vp, vp, ci, vp]),

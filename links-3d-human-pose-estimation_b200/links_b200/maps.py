@@ -15,6 +15,9 @@ COMBINE_RIGHT = [(1, 0), (1, 1), (1, 2), (1, 3), (0, 1), (0, 2), (0, 3), (1, 4),
                  (0, 8), (0, 9), (0, 10), (1, 8), (1, 9), (1, 10)]
 COMBINE_LEFT = [(0, 0), (1, 1), (1, 2), (1, 3), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 7),
                 (0, 8), (0, 9), (0, 10), (1, 8), (1, 9), (1, 10)]
+# helpers.py:140-141 (parent, child) of the 16 bones
+BONES = [[0, 1], [1, 2], [2, 3], [0, 4], [4, 5], [5, 6], [0, 7], [7, 8], [8, 9], [9, 10], [8, 11], [11, 12], [12, 13],
+         [8, 14], [14, 15], [15, 16]]
 BONE_REL_H36M = [0.5180581, 1.73711136, 1.72285805, 0.5180552, 1.73710543, 1.72285651, 0.92087518, 0.98792375,
                  0.44812302, 0.44502545, 0.57462, 1.08121276, 0.9651687, 0.57461556, 1.08122523, 0.9651657]
 BONE_REL_MPI = [0.48069107, 1.84637771, 1.49564841, 0.48069107, 1.84301997, 1.4956484, 0.90757932, 0.99706493,

@@ -65,9 +65,9 @@ SIM int sim_threshold_counts(const float* values, size_t n, const float* thr, in
   hostsim::launch(dim3(2), dim3(256), 0, [&] { threshold_counts_kernel(values, n, thr, T, strict, counts); });
   return 0;
 }
-SIM int sim_pmpjpe(const float* r, const float* p, int M, int J, int mode, float* per_pose, double* sum) {
+SIM int sim_pmpjpe(const float* r, const float* p, int M, int J, int mode, float* per_pose, float* aligned, double* sum) {
   hostsim::launch(dim3((M + kPosesPerBlock - 1) / kPosesPerBlock), dim3(kPosesPerBlock), 0,
-                  [&] { pmpjpe_kernel(r, p, M, J, mode, per_pose, sum); });
+                  [&] { pmpjpe_kernel(r, p, M, J, mode, per_pose, aligned, sum); });
   return 0;
 }
 SIM int sim_eval_lift_score(const float* p2d, const float* doff, int ldd, const float* gt, int M, float depth, double* sums3) {
@@ -168,6 +168,12 @@ SIM int sim_flow_nll_fwdbwd(const float* packed, int C, int nb, const float* x, 
   FlowArgs A;
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = nb;
+  return sim_flow_dispatch<FLOW_NLL_FWDBWD>(C, A);
+}
+SIM int sim_flow_vjp(const float* packed, int C, int nb, const float* x, int M, const float* gz, const float* gld, float* dx) {
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = dx; A.gz = gz; A.gld = gld; A.M = M; A.n_blocks = nb;
   return sim_flow_dispatch<FLOW_NLL_FWDBWD>(C, A);
 }
 SIM int sim_flow_sample(const float* packed, int nb, const float* x, const float* noise, int M, float* out) {

@@ -1,0 +1,106 @@
+"""GPU: the drop-in module surface (utils.models_def, FrEIA shim, utils.metrics_batch) vs the oracle / golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_lifter_module_autograd(golden):
+    from oracle import nets as ON
+    from utils.models_def import Leg_Lifter
+    G = golden["nets"]
+    p = ON.init_lifter_params(7, int(G["Leg_Lifter_seed"]))
+    m = Leg_Lifter(use_batchnorm=False, num_joints=7, use_dropout=False, d_rate=0.25).cuda()
+    missing = m.load_state_dict(p, strict=False)
+    assert all(".bn" in k for k in missing.missing_keys)
+    x = torch.from_numpy(G["Leg_Lifter_x"]).cuda().requires_grad_(True)
+    xd, xa = m(x)
+    # forward vs the REFERENCE module's output (fp32): depth offsets within 5e-3 abs (= 5e-4 relative on joints)
+    assert (xd.detach().cpu() - torch.from_numpy(G["Leg_Lifter_xd"])).abs().max() < 5e-3
+    assert (xa.detach().cpu() - torch.from_numpy(G["Leg_Lifter_xa"])).abs().max() < 5e-3
+    (xd.square().sum() + xa.sum()).backward()
+    assert rel_fro(x.grad.cpu(), torch.from_numpy(G["Leg_Lifter_dx"])) < 0.1
+    gw = m.res_pose2.l1.weight.grad
+    assert gw is not None and abs(gw.double().sum().item() - float(G["Leg_Lifter_dW_res_pose2_l1_sum"])) < 0.05 * float(G["Leg_Lifter_dW_res_pose2_l1_abs"])
+    assert m.res_pose1.bn1.weight.grad is None          # unused LayerNorm never receives a gradient
+    # an optimiser step through torch.optim works on the module's own parameters and is picked up next forward
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt.step()
+    xd2, _ = m(x.detach())
+    assert (xd2 - xd.detach()).abs().max() > 0
+    with torch.no_grad():
+        xd3, _ = m(x.detach())
+    assert torch.allclose(xd3, xd2)
+    with pytest.raises(Exception):
+        m(x.detach().cpu())
+
+
+def test_predictor_module(golden):
+    from oracle import nets as ON
+    from utils.models_def import Occluded_Torso_Predictor
+    G = golden["nets"]
+    p = ON.init_predictor_params(7, 30, int(G["Occluded_Torso_Predictor_seed"]))
+    m = Occluded_Torso_Predictor(use_batchnorm=False, num_joints=7).cuda()
+    m.load_state_dict(p, strict=False)
+    y = m(torch.from_numpy(G["Occluded_Torso_Predictor_x"]).cuda())
+    assert rel_fro(y.detach().cpu(), torch.from_numpy(G["Occluded_Torso_Predictor_y"])) < 1.5e-2
+
+
+def test_freia_shim_matches_oracle_and_fixture(golden):
+    import FrEIA.framework as Ff
+    import FrEIA.modules as Fm
+    from oracle import flow as OF
+    from utils.helpers import subnet_fc
+    G = golden["steps"]
+    inn = Ff.SequenceINN(34)
+    for _ in range(8):
+        inn.append(Fm.AllInOneBlock, subnet_constructor=subnet_fc, permute_soft=True)
+    params = OF.init_flow_params(34, 40, perturb=0.3)
+    inn.load_state_dict(params)
+    inn.cuda()
+    for q in inn.parameters():
+        q.requires_grad = False
+    x = torch.from_numpy(G["x"]).cuda().requires_grad_(True)
+    z, ld = inn(x)
+    np.testing.assert_allclose(z.detach().cpu().numpy(), G["flow_z"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(ld.detach().cpu().numpy(), G["flow_ld"], rtol=2e-4, atol=2e-5)
+    nll = (0.5 * torch.sum(z ** 2, 1) - ld).mean()
+    nll.backward()
+    xo = torch.from_numpy(G["x"]).requires_grad_(True)
+    zo, ldo = OF.inn_forward(xo, params)
+    OF.nll(zo, ldo).mean().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xo.grad.numpy(), rtol=2e-3, atol=1e-5)
+    with torch.no_grad():
+        xr, ldr = inn(z.detach(), rev=True)
+    np.testing.assert_allclose(xr.cpu().numpy(), G["x"], rtol=1e-3, atol=2e-5)
+    for q in inn.parameters():
+        q.requires_grad = True
+    with pytest.raises(NotImplementedError):
+        inn(x.detach())
+
+
+def test_metrics_batch_dropin_vs_reference_golden(golden):
+    from utils.metrics_batch import Metrics as mb
+    G = golden["metrics"]
+    gt, pred = torch.from_numpy(G["gt"]).cuda(), torch.from_numpy(G["pred"]).cuda()
+    M = gt.shape[0]
+    for nj, rj in ((17, 0), (16, 6)):
+        g = gt.reshape(M, 3, 17)[:, :, :nj].reshape(M, 3 * nj)
+        p = pred.reshape(M, 3, 17)[:, :, :nj].reshape(M, 3 * nj)
+        kw = dict(num_joints=nj, root_joint=rj)
+        assert (mb().mpjpe(g, p, **kw).cpu().numpy() - G["mpjpe_j%d_s1" % nj]).__abs__().max() < 0.05
+        assert (mb().mpjpe(g, p, use_scaling=False, **kw).cpu().numpy() - G["mpjpe_j%d_s0" % nj]).__abs__().max() < 0.05
+        np.testing.assert_allclose(mb().PCK(g, p, **kw).item(), G["pck_j%d" % nj], rtol=1e-6)
+        np.testing.assert_allclose(mb().AUC(g, p, **kw).item(), G["auc_j%d" % nj], rtol=1e-5)
+        ga = mb().get_all(g, p, **kw)
+        for k in ("MPJPE", "PCK", "AUC", "CPS"):
+            np.testing.assert_allclose(ga[k].item(), G["getall_%s_j%d" % (k, nj)], rtol=2e-5)
+        assert (mb().pmpjpe(g, p, num_joints=nj).cpu().numpy() - G["pmpjpe_batch_j%d" % nj]).__abs__().max() < 0.05
+    assert (mb().pmpjpe_best(gt, pred).cpu().numpy() - G["pmpjpe_np_best"]).__abs__().max() < 0.05
+    al = mb().procrustes(pred.reshape(M, 3, 17), gt.reshape(M, 3, 17))
+    assert al.shape == (M, 3, 17)

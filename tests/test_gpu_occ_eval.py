@@ -1,0 +1,74 @@
+"""GPU parity: occlusion-model training step (train_occlusion_models.py:144-314) and the eval path
+(eval_h36m.py:50-97) vs the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_occlusion_step_vs_oracle():
+    from links_b200.occlusion import OCC_IN, OCC_NAMES, OCC_OUT, OcclusionStep
+    from links_b200.synth import synth_poses
+    from oracle import nets as ON, steps as OS
+    B = 64
+    lifters = [ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12)]
+    preds = {n: ON.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i) for i, n in enumerate(OCC_NAMES)}
+    step = OcclusionStep(B, lifters, preds)
+    x2d, _ = synth_poses(B, seed=9)
+    g = torch.Generator().manual_seed(3)
+    u1, u2 = torch.rand(B, generator=g), torch.rand(B, generator=g)
+    x = torch.from_numpy(x2d)
+    pn = {n: OS.params_require_grad(p) for n, p in preds.items()}
+    opts = OS.make_adam(list(pn.values()))
+    for it in range(2):
+        step.x.copy_(x); step.u_y[0].copy_(u1); step.u_y[1].copy_(u2)
+        step.step()
+        for o in opts:
+            o.zero_grad()
+        ref = OS.occlusion_step(x, lifters[0], lifters[1], pn, u1, u2)
+        ref["loss"].backward()
+        got = step.loss_dict()
+        for k, v in got.items():
+            r = ref[k].item()
+            assert abs(v - r) <= (1e-3 if it == 0 else 5e-3) * abs(r), (it, k, v, r)
+        if it == 0:
+            for s, n in enumerate(OCC_NAMES):
+                for name in ("upscale", "res_pose2.l1", "downscale"):
+                    e = rel_fro(step.mlp.nets[s].layers[name].gW.cpu(), pn[n][name + ".weight"].grad)
+                    assert e < 8e-2, (n, name, e)
+                assert rel_fro(step.mlp.nets[s].layers["downscale"].gb.cpu(), pn[n]["downscale.bias"].grad) < 3e-2
+        for o in opts:
+            o.step()
+
+
+@pytest.mark.parametrize("kind", ["lr", "lt"])
+def test_eval_runner_vs_oracle(kind):
+    from links_b200.occlusion import EvalRunner
+    from links_b200.synth import synth_poses
+    from oracle import metrics as OM, nets as ON, steps as OS
+    n = 3000
+    p2d, gt = synth_poses(n, seed=21)
+    # scale GT to the lifter's unit so the metric is meaningful with random-init weights
+    if kind == "lr":
+        params = [ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)]
+        pred = OS.eval_lr_predict(torch.from_numpy(p2d), params[0], params[1], choice="right")
+    else:
+        params = [ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12)]
+        pred = OS.eval_lt_predict(torch.from_numpy(p2d), params[0], params[1])
+    ref = OS.eval_metrics(torch.from_numpy(gt), pred)
+    ref_batch = OM.pmpjpe_batch(torch.from_numpy(gt), pred, num_joints=17).mean().item()
+    ev = EvalRunner(kind, params, chunk=1024)
+    xd, gd = torch.from_numpy(p2d).cuda(), torch.from_numpy(gt).cuda()
+    for i in range(0, n, 1024):
+        ev.run_chunk(xd[i:i + 1024].contiguous(), gd[i:i + 1024].contiguous())
+    out = ev.result()
+    assert out["count"] == n
+    # north star: MPJPE / PA-MPJPE within 0.05 mm
+    assert abs(out["n_mpjpe"] - ref["n_mpjpe"]) < 0.05, (out, ref)
+    assert abs(out["pa_mpjpe"] - ref["pa_mpjpe"]) < 0.05, (out, ref)
+    assert abs(out["pa_mpjpe_batch"] - ref_batch) < 0.05, (out, ref_batch)

@@ -50,6 +50,16 @@ def test_flow_forward_reverse_nll(Cdim, M, backend):
     np.testing.assert_allclose(nll_sum[0], nll.sum().item(), rtol=1e-4)
     gref = xg.grad.numpy()
     np.testing.assert_allclose(dx, gref, rtol=2e-3, atol=2e-5 * np.abs(gref).max())
+    # general VJP (autograd of the FrEIA shim): arbitrary seeds on z and log_jac_det
+    gz = torch.randn(M, Cdim, generator=g) * 0.3
+    gld = torch.randn(M, generator=g)
+    xg = x.clone().requires_grad_(True)
+    zz, ll = OF.inn_forward(xg, params)
+    ((zz * gz).sum() + (ll * gld).sum()).backward()
+    dx2 = np.zeros((M, Cdim), np.float32)
+    assert L.call("flow_vjp", packed, Cdim, 8, xn, M, np.ascontiguousarray(gz.numpy()), np.ascontiguousarray(gld.numpy()), dx2) == 0
+    gref = xg.grad.numpy()
+    np.testing.assert_allclose(dx2, gref, rtol=2e-3, atol=2e-5 * np.abs(gref).max())
 
 
 @backend_params
@@ -109,12 +119,15 @@ def test_metrics_vs_golden(golden, backend):
         # PA-MPJPE, batch semantics (metrics_batch.py:104-159)
         pa = np.zeros(M, np.float32)
         s = np.zeros(1, np.float64)
-        assert L.call("pmpjpe", g, p, M, nj, 0, pa, s) == 0
+        al = np.zeros((M, 3 * nj), np.float32)
+        assert L.call("pmpjpe", g, p, M, nj, 0, pa, al, s) == 0
+        ref_al = OM.procrustes_batch(torch.from_numpy(p).reshape(M, 3, nj), torch.from_numpy(g).reshape(M, 3, nj))
+        assert np.abs(al - ref_al.reshape(M, -1).numpy()).max() < 0.05
         ref = G["pmpjpe_batch_j%d" % nj]
         assert np.abs(pa - ref).max() < 0.05, np.abs(pa - ref).max()
     # PA-MPJPE 'best' (metrics.py:35-171, the number the scripts report; fp64 numpy reference incl. mirrored poses)
     pa = np.zeros(M, np.float32)
-    assert L.call("pmpjpe", gt, pred, M, 17, 1, pa, None) == 0
+    assert L.call("pmpjpe", gt, pred, M, 17, 1, pa, None, None) == 0
     assert np.abs(pa - G["pmpjpe_np_best"]).max() < 0.05, np.abs(pa - G["pmpjpe_np_best"]).max()
 
 
