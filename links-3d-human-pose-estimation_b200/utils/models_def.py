@@ -42,8 +42,9 @@ class _EngineFn(torch.autograd.Function):
     """y_heads = net(x): forward / dgrad / wgrad through the grouped tcgen05 GEMM plans of a 1-network MlpSet."""
 
     @staticmethod
-    def forward(ctx, module, x, *params):
-        eng = module._engine(x.shape[0], train=torch.is_grad_enabled())
+    def forward(ctx, module, train, x, *params):
+        # grad mode is always off inside Function.forward: the caller decides whether activations are kept
+        eng = module._engine(x.shape[0], train=train)
         module._sync_params(eng)
         M, K = x.shape
         lib = eng.lib
@@ -81,7 +82,7 @@ class _EngineFn(torch.autograd.Function):
             layer, kind = name.rsplit(".", 1)
             L = eng.nets[0].layers[layer]
             grads.append((L.gW if kind == "weight" else L.gb).clone())
-        return (None, gx) + tuple(grads)
+        return (None, None, gx) + tuple(grads)
 
 
 class _EngineModule(nn.Module):
@@ -139,7 +140,8 @@ class _EngineModule(nn.Module):
         sd = dict(self.named_parameters())
         params = [sd[n] for n in self._param_order]
         shape = x.shape
-        out = _EngineFn.apply(self, x.reshape(-1, shape[-1]), *params)
+        train = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        out = _EngineFn.apply(self, train, x.reshape(-1, shape[-1]), *params)
         return out
 
 
