@@ -183,6 +183,10 @@ int links_flow_pack(int C, int n_blocks, const float* const* w0, const float* co
                     const float* const* w2, const float* const* b2, const float* const* gscale,
                     const float* const* goffset, const float* const* wperm, const float* const* wperm_inv,
                     float* packed, void* stream);
+/* Flow batches of >= 48 rows run on the tensor-core kernel (csrc/flow_tc.cuh, 128-row tiles, bf16x3 operands);
+ * smaller ones on the 32-row fp32 SIMT kernel (csrc/flow.cuh).  links_flow_set_simt_only(1) pins the SIMT kernel
+ * (A/B measurements and tests only); returns the previous setting. */
+int links_flow_set_simt_only(int on);
 /* z, log_jac_det = inn(x, rev) for x [M,C] (ld = C). */
 int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, int M, int rev,
                      float* out, float* log_jac_det, void* stream);

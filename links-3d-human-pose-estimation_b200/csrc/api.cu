@@ -4,6 +4,7 @@
 #include "metrics.cuh"
 #include "geom.cuh"
 #include "flow.cuh"
+#include "flow_tc.cuh"
 #include "occ.cuh"
 #include <math.h>
 
@@ -209,7 +210,8 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward_angles
 // ---------------------------------------------------------------------------------------------
 extern "C" __attribute__((visibility("default"))) size_t links_flow_packed_floats(int C, int n_blocks) {
   if (C < 2 || C > 34 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return 0;
-  return static_cast<size_t>(flow_block_floats(C)) * n_blocks;
+  // [SIMT records | tensor-core operand images]
+  return static_cast<size_t>(flow_block_floats(C)) * n_blocks + tc_block_bytes(C) / 4 * n_blocks;
 }
 
 extern "C" __attribute__((visibility("default"))) int links_flow_pack(int C, int n_blocks, const float* const* w0, const float* const* b0,
@@ -227,6 +229,8 @@ extern "C" __attribute__((visibility("default"))) int links_flow_pack(int C, int
   }
   A.packed = packed; A.C = C; A.n_blocks = n_blocks;
   flow_pack_kernel<<<n_blocks, 256, 0, links_stream(stream)>>>(A);
+  flow_tc_pack_kernel<<<n_blocks, 256, 0, links_stream(stream)>>>(
+      A, reinterpret_cast<unsigned char*>(packed + static_cast<size_t>(flow_block_floats(C)) * n_blocks));
   return links_launch_status();
 }
 
@@ -244,16 +248,50 @@ static int launch_flow_c(const FlowArgs& A, cudaStream_t s) {
   return links_launch_status();
 }
 
+// Tensor-core path (128-row tiles) for M >= kFlowTcMinRows; small batches stay on the 32-row SIMT kernel.
+constexpr int kFlowTcMinRows = 48;
+static bool g_flow_force_simt = false;
+
+template <int C, int MODE>
+static int launch_flow_tc_c(const FlowArgs& A, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(flow_tc_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kTcSmemBytes));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = true;
+  }
+  FlowTcArgs T;
+  T.packed = reinterpret_cast<const unsigned char*>(A.packed + static_cast<size_t>(flow_block_floats(C)) * A.n_blocks);
+  T.x = A.x; T.noise = A.noise; T.out = A.out; T.ld = A.ld; T.nll_sum = A.nll_sum; T.scale = A.scale;
+  T.gz = A.gz; T.gld = A.gld; T.M = A.M; T.n_blocks = A.n_blocks;
+  const int blocks = (A.M + kTcRows - 1) / kTcRows;
+  flow_tc_kernel<C, MODE><<<blocks, kTcThreads, kTcSmemBytes, s>>>(T);
+  return links_launch_status();
+}
+
+template <int C, int MODE>
+static int launch_flow_any(const FlowArgs& A, cudaStream_t s) {
+  if (A.M >= kFlowTcMinRows && !g_flow_force_simt) return launch_flow_tc_c<C, MODE>(A, s);
+  return launch_flow_c<C, MODE>(A, s);
+}
+
 template <int MODE>
 static int launch_flow(int C, const FlowArgs& A, cudaStream_t s) {
   switch (C) {
-    case 14: return launch_flow_c<14, MODE>(A, s);
-    case 20: return launch_flow_c<20, MODE>(A, s);
-    case 22: return launch_flow_c<22, MODE>(A, s);
-    case 32: return launch_flow_c<32, MODE>(A, s);
-    case 34: return launch_flow_c<34, MODE>(A, s);
+    case 14: return launch_flow_any<14, MODE>(A, s);
+    case 20: return launch_flow_any<20, MODE>(A, s);
+    case 22: return launch_flow_any<22, MODE>(A, s);
+    case 32: return launch_flow_any<32, MODE>(A, s);
+    case 34: return launch_flow_any<34, MODE>(A, s);
     default: return LINKS_E_RANGE;
   }
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_set_simt_only(int on) {
+  const int prev = g_flow_force_simt ? 1 : 0;
+  g_flow_force_simt = on != 0;
+  return prev;
 }
 
 extern "C" __attribute__((visibility("default"))) int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, int M, int rev, float* out,
@@ -293,7 +331,7 @@ extern "C" __attribute__((visibility("default"))) int links_flow_sample(const fl
   FlowArgs A;
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.noise = noise; A.out = out; A.M = M; A.n_blocks = n_blocks;
-  return launch_flow_c<34, FLOW_SAMPLE>(A, links_stream(stream));
+  return launch_flow_any<34, FLOW_SAMPLE>(A, links_stream(stream));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -75,6 +75,7 @@ PLAIN = {
     "links_abi_version": (ci, []),
     "links_device_ok": (ci, []),
     "links_flow_packed_floats": (sz, [ci, ci]),
+    "links_flow_set_simt_only": (ci, [ci]),
 }
 GEMM = {"links_gemm_grouped": (ci, [C.POINTER(GemmProblem), ci, vp])}
 
