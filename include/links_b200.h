@@ -46,8 +46,11 @@ int links_device_ok(void);
 /* ------------------------------------------------------------------------------------------
  * Grouped GEMM with fused epilogue (tcgen05 / TMEM / TMA).   D = epi(A[M,K] * B[N,K]^T)
  * Replaces every nn.Linear (+LeakyReLU, +residual) of reference utils/models_def.py:10-39,
- * 111-327 in forward, and its autograd backward (dgrad / wgrad).  A and B are bf16, K-major
- * (row-major, K contiguous), accumulate fp32.
+ * 111-327 in forward, and its autograd backward (dgrad / wgrad).  A and B are bf16, accumulate fp32.
+ * Operand layouts: by default K-major (A stored [M, lda], B stored [N, ldb], K contiguous -- nn.Linear's
+ * weight layout for forward).  LINKS_GEMM_A_MN: A is stored [K, lda] (M contiguous); LINKS_GEMM_B_MN: B is
+ * stored [K, ldb] (N contiguous).  dgrad dX = G.W passes W [N_layer, K_layer] as an MN-major B; wgrad
+ * dW = G^T.X passes the row-major G and X as MN-major A and B -- no transposed copies exist anywhere.
  *
  * Epilogue, applied per element in this order (null pointer = step skipped):
  *   v = acc (+ bias[n])
@@ -58,28 +61,29 @@ int links_device_ok(void);
  *   v *= (ymask[m,n] > 0 ? 1 : 0.01)                     [bf16 activation, leaky' of its producer]
  *   mid[m,n] = bf16(v)
  *   v *= (bits(m,n) ? 0.01 : 1)
- *   out[m,n] = bf16(v); outT[n, outT_col0 + m] = bf16(v); out_f32[m,n] (+)= v
+ *   out[m,n] = bf16(v); out_f32[m,n] (+)= v
  * ------------------------------------------------------------------------------------------ */
 #define LINKS_EPI_LEAKY_PRE 1u
 #define LINKS_EPI_LEAKY_POST 2u
 #define LINKS_EPI_RELU_PRE 4u
 #define LINKS_EPI_ACCUM_F32 8u
+#define LINKS_GEMM_A_MN 16u
+#define LINKS_GEMM_B_MN 32u
 
 typedef struct LinksGemmProblem {
-  const void* A;      /* bf16 [M, lda]  */
-  const void* B;      /* bf16 [N, ldb]  */
-  int M, N, K;        /* K = contraction length; lda, ldb >= K, multiples of 8 */
+  const void* A;      /* bf16 [M, lda]  (A_MN: [K, lda]) */
+  const void* B;      /* bf16 [N, ldb]  (B_MN: [K, ldb]) */
+  int M, N, K;        /* K = contraction length; lda, ldb multiples of 8 */
   int lda, ldb;
   uint32_t flags;
-  const float* bias;  /* [N] */
+  const float* bias;  /* [N], 16-byte aligned */
   const void* add0; int ld_add0;   /* bf16 [M, ld] */
   const void* add1; int ld_add1;
   const void* ymask; int ld_ymask; /* bf16 [M, ld] */
   const uint32_t* bits; int ld_bits;   /* [M, ld_bits] words, bit (n & 31) of word n >> 5 */
   uint32_t* sign_out; int ld_sign;
-  void* mid; int ld_mid;           /* bf16 [M, ld] */
-  void* out; int ld_out;           /* bf16 [M, ld] */
-  void* outT; int ld_outT; int outT_col0;  /* bf16 [N, ld], written at columns outT_col0 + m */
+  void* mid; int ld_mid;           /* bf16 [M, ld], ld multiple of 8 */
+  void* out; int ld_out;           /* bf16 [M, ld], ld multiple of 8 */
   float* out_f32; int ld_f32;      /* fp32 [M, ld] */
 } LinksGemmProblem;
 

@@ -14,6 +14,7 @@ KPAD = 64
 MAX_GEMM_PROBLEMS = 8
 
 EPI_LEAKY_PRE, EPI_LEAKY_POST, EPI_RELU_PRE, EPI_ACCUM_F32 = 1, 2, 4, 8
+GEMM_A_MN, GEMM_B_MN = 16, 32
 
 vp = C.c_void_p
 ci = C.c_int
@@ -27,8 +28,7 @@ class GemmProblem(C.Structure):
                 ("add0", vp), ("ld_add0", ci), ("add1", vp), ("ld_add1", ci),
                 ("ymask", vp), ("ld_ymask", ci), ("bits", vp), ("ld_bits", ci),
                 ("sign_out", vp), ("ld_sign", ci), ("mid", vp), ("ld_mid", ci),
-                ("out", vp), ("ld_out", ci), ("outT", vp), ("ld_outT", ci), ("outT_col0", ci),
-                ("out_f32", vp), ("ld_f32", ci)]
+                ("out", vp), ("ld_out", ci), ("out_f32", vp), ("ld_f32", ci)]
 
 
 class ColsumItem(C.Structure):

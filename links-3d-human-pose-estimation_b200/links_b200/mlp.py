@@ -6,10 +6,10 @@ operation is a C-ABI launch on the current stream, so a whole step is CUDA-graph
 
 Data layout (per network s, per pass p):
   * fp32 master parameters / gradients / Adam moments live in flat buffers (one Adam launch, one all-reduce).
-  * bf16 shadow weights per layer:  W [N, Kp] (A.B^T "TN" operand for forward) and W^T [K, Np] (dgrad operand).
-  * activations are bf16 row-major [M, 1024] plus a transposed copy [1024, ldT] written by the same epilogue;
-    pass 1 and pass 2 write disjoint column ranges of the transposed buffers so one wgrad GEMM per layer
-    contracts over both passes.
+  * bf16 shadow weights per layer: W [N, Kp] -- the K-major B operand of forward and, read as an MN-major operand,
+    the B operand of dgrad (no transposed shadow).
+  * activations / gradients are bf16 row-major [n_passes * M, 1024]: pass p owns rows [p*M, (p+1)*M), so one wgrad
+    GEMM per layer contracts over both passes, reading G and X as MN-major operands (no transposed copies).
   * per block a [M, 32]-word sign mask of the l2 pre-activation (needed exactly for leaky' in backward).
 """
 import ctypes as C
@@ -17,7 +17,7 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from ._cabi import EPI_LEAKY_POST, EPI_LEAKY_PRE, GemmProblem, HEAD_LD, check
+from ._cabi import EPI_LEAKY_POST, EPI_LEAKY_PRE, GEMM_A_MN, GEMM_B_MN, GemmProblem, HEAD_LD, check
 
 WIDTH = 1024
 TOPOLOGY = {
@@ -33,7 +33,7 @@ def _rup(x, m):
 
 
 class _Layer:
-    __slots__ = ("name", "K", "N", "Kp", "Np", "W", "b", "gW", "gb", "Wb", "WbT")
+    __slots__ = ("name", "K", "N", "Kp", "Np", "W", "b", "gW", "gb", "Wb")
 
 
 class _Net:
@@ -57,10 +57,6 @@ class MlpSet:
         self.device = torch.device(device)
         self.train = train
         self.pass_branches = pass_branches or [list(self.branches) for _ in range(n_passes)]
-        # passes write disjoint, 8-aligned column ranges of the transposed buffers (TMA stores need 16-byte aligned
-        # starts); the gap [M, pass_stride) stays zero in every gradient buffer, so wgrad may contract across it
-        self.pass_stride = _rup(self.M, 8)
-        self.ldT = self.pass_stride * n_passes
         self.lib = _cabi.lib()
         dev = self.device
         # ---- parameter layout
@@ -107,57 +103,57 @@ class MlpSet:
             L.gb = self.grad[off:off + N] if train else None
             off += _rup(N, 64)
             L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
-            L.WbT = torch.zeros(K, L.Np, dtype=torch.bfloat16, device=dev) if train else None
             cur[n] = L
             if n == names[-1][0]:
                 self.nets.append(_Net(cur))
                 cur = {}
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
         # ---- activation / gradient workspaces
-        M, ldT = self.M, self.ldT
+        M = self.M
+        P_ = n_passes
         bf = dict(dtype=torch.bfloat16, device=dev)
-        self.x0 = [[torch.zeros(M, 64, **bf) for _ in range(self.S)] for _ in range(n_passes)]
-        self.x0T = [torch.zeros(in_dims[s], ldT, **bf) for s in range(self.S)] if train else [None] * self.S
-        self.act = []    # act[p][s][name] -> row-major bf16
-        self.actT = [dict() for _ in range(self.S)]  # actT[s][name] -> [1024, ldT] shared by passes
+
+        def per_pass(t):
+            return [t[p * M:(p + 1) * M] for p in range(P_)]
+        self._x0buf = [torch.zeros(P_ * M, 64, **bf) for _ in range(self.S)]
+        self.x0 = [[per_pass(self._x0buf[s])[p] for s in range(self.S)] for p in range(P_)]
+        self._actbuf = [dict() for _ in range(self.S)]   # [s][name] -> [P*M, 1024]
+        self.act = [[dict() for _ in range(self.S)] for _ in range(P_)]   # act[p][s][name] -> rows of pass p
         self.sign = []   # sign[p][s][blk] -> int32 [M, 32]
         self.head_out = []  # head_out[p][s][head] -> fp32 [M, HEAD_LD]
         all_blocks = list(self.trunk) + [b for blocks, _ in self.branches.values() for b in blocks]
-        for p in range(n_passes):
-            act_p, sign_p, head_p = [], [], []
+        act_names = ["h0"] + [blk + sfx for blk in all_blocks for sfx in (".a1", ".y")]
+        for s in range(self.S):
+            for name in act_names:
+                buf = torch.empty(P_ * M, WIDTH, **bf)
+                self._actbuf[s][name] = buf
+                for p in range(P_):
+                    self.act[p][s][name] = buf[p * M:(p + 1) * M]
+        for p in range(P_):
+            sign_p, head_p = [], []
             for s in range(self.S):
-                d = {"h0": torch.empty(M, WIDTH, **bf)}
-                sg = {}
-                for blk in all_blocks:
-                    d[blk + ".a1"] = torch.empty(M, WIDTH, **bf)
-                    d[blk + ".y"] = torch.empty(M, WIDTH, **bf)
-                    sg[blk] = torch.zeros(M, WIDTH // 32, dtype=torch.int32, device=dev)
-                act_p.append(d)
-                sign_p.append(sg)
+                sign_p.append({blk: torch.zeros(M, WIDTH // 32, dtype=torch.int32, device=dev) for blk in all_blocks}
+                              if train else {})
                 head_p.append({head: torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev)
                                for _, head in self.branches.values()})
-            self.act.append(act_p)
             self.sign.append(sign_p)
             self.head_out.append(head_p)
         if train:
-            for s in range(self.S):
-                for name in self.act[0][s]:
-                    self.actT[s][name] = torch.empty(WIDTH, ldT, **bf)
-            # gradients: G[p][s][layer] row-major bf16 [M, N] (heads: [M,64]); GT[s][layer] [N, ldT]; dt per block
-            self.G = [[dict() for _ in range(self.S)] for _ in range(n_passes)]
-            self.GT = [dict() for _ in range(self.S)]
-            self.dt = [[dict() for _ in range(self.S)] for _ in range(n_passes)]
-            self.E = [[torch.empty(M, WIDTH, **bf) for _ in range(self.S)] for _ in range(n_passes)]
+            # gradients: G[p][s][layer] = rows of pass p of a row-major bf16 [P*M, N] buffer (heads: [P*M, 64]); dt per block
+            self._Gbuf = [dict() for _ in range(self.S)]
+            self.G = [[dict() for _ in range(self.S)] for _ in range(P_)]
+            self.dt = [[dict() for _ in range(self.S)] for _ in range(P_)]
+            self.E = [[torch.empty(M, WIDTH, **bf) for _ in range(self.S)] for _ in range(P_)]
             self.din = [[torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev) for _ in range(self.S)]
-                        for _ in range(n_passes)]   # d/d(input part), fp32 [M, HEAD_LD]
+                        for _ in range(P_)]   # d/d(input part), fp32 [M, HEAD_LD]
             heads = [h for _, h in self.branches.values()]
             for s in range(self.S):
                 for n in self.layer_names:
-                    Nl = self.nets[s].layers[n].N
-                    self.GT[s][n] = torch.zeros(Nl, ldT, **bf)
-                    for p in range(n_passes):
-                        self.G[p][s][n] = torch.zeros(M, 64 if n in heads else WIDTH, **bf)
-                for p in range(n_passes):
+                    buf = torch.zeros(P_ * M, 64 if n in heads else WIDTH, **bf)
+                    self._Gbuf[s][n] = buf
+                    for p in range(P_):
+                        self.G[p][s][n] = buf[p * M:(p + 1) * M]
+                for p in range(P_):
                     for blk in all_blocks:
                         self.dt[p][s][blk] = torch.empty(M, WIDTH, **bf)
         self._plans = {}
@@ -185,8 +181,7 @@ class MlpSet:
         st = torch.cuda.current_stream().cuda_stream
         for net in self.nets:
             for L in net.layers.values():
-                check(self.lib.links_cast_weight(L.W.data_ptr(), L.N, L.K, L.Wb.data_ptr(), L.Kp,
-                                                 L.WbT.data_ptr() if L.WbT is not None else None, L.Np, st),
+                check(self.lib.links_cast_weight(L.W.data_ptr(), L.N, L.K, L.Wb.data_ptr(), L.Kp, None, 0, st),
                       "links_cast_weight")
 
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0):
@@ -215,7 +210,7 @@ class MlpSet:
 
     @staticmethod
     def _prob(A, B, M, N, K, lda, ldb, flags=0, bias=None, add0=None, add1=None, ymask=None, bits=None,
-              sign_out=None, mid=None, out=None, outT=None, outT_col0=0, out_f32=None, ld_f32=0):
+              sign_out=None, mid=None, out=None, out_f32=None, ld_f32=0):
         P = GemmProblem()
         P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb, P.flags = A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb, flags
         P.bias = bias.data_ptr() if bias is not None else None
@@ -227,8 +222,6 @@ class MlpSet:
             P.bits, P.ld_bits = bits.data_ptr(), bits.stride(0)
         if sign_out is not None:
             P.sign_out, P.ld_sign = sign_out.data_ptr(), sign_out.stride(0)
-        if outT is not None:
-            P.outT, P.ld_outT, P.outT_col0 = outT.data_ptr(), outT.stride(0), outT_col0
         if out_f32 is not None:
             P.out_f32, P.ld_f32 = out_f32.data_ptr(), ld_f32 or out_f32.stride(0)
         return P
@@ -239,26 +232,24 @@ class MlpSet:
         if key in self._plans:
             return self._plans[key]
         M = rows or self.M
-        col0 = p * self.pass_stride
         tr = self.train
         ops = []
         act = self.act[p]
-        T = lambda s, n: self.actT[s][n] if tr else None
         nets = self.nets
         # upscale (no activation, models_def.py:136)
         ops.append(self._launch([self._prob(self.x0[p][s], nets[s].layers["upscale"].Wb, M, WIDTH, 64, 64, 64,
-                                            bias=nets[s].layers["upscale"].b, out=act[s]["h0"], outT=T(s, "h0"),
-                                            outT_col0=col0) for s in range(self.S)]))
+                                            bias=nets[s].layers["upscale"].b, out=act[s]["h0"])
+                                 for s in range(self.S)]))
 
         def block_ops(items):
             """items: list of (s, blk, xin_name)."""
             l1 = [self._prob(act[s][xin], nets[s].layers[blk + ".l1"].Wb, M, WIDTH, WIDTH, WIDTH, WIDTH,
-                             flags=EPI_LEAKY_PRE, bias=nets[s].layers[blk + ".l1"].b, out=act[s][blk + ".a1"],
-                             outT=T(s, blk + ".a1"), outT_col0=col0) for s, blk, xin in items]
+                             flags=EPI_LEAKY_PRE, bias=nets[s].layers[blk + ".l1"].b, out=act[s][blk + ".a1"])
+                  for s, blk, xin in items]
             l2 = [self._prob(act[s][blk + ".a1"], nets[s].layers[blk + ".l2"].Wb, M, WIDTH, WIDTH, WIDTH, WIDTH,
                              flags=EPI_LEAKY_PRE | EPI_LEAKY_POST, bias=nets[s].layers[blk + ".l2"].b,
                              sign_out=self.sign[p][s][blk] if tr else None, add0=act[s][xin],
-                             out=act[s][blk + ".y"], outT=T(s, blk + ".y"), outT_col0=col0) for s, blk, xin in items]
+                             out=act[s][blk + ".y"]) for s, blk, xin in items]
             ops.append(self._launch(l1))
             ops.append(self._launch(l2))
 
@@ -291,16 +282,15 @@ class MlpSet:
         return ops
 
     def backward_plan(self, p, need_input_grad, rows=None):
-        """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64]) and self.GT[s][head] filled by the
-        loss kernels.  Outputs: G/GT of every layer, optionally self.din[p][s] = d/d(input part) fp32."""
+        """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64], zero beyond the head width) filled by the
+        loss kernels.  Outputs: G of every layer, optionally self.din[p][s] = d/d(input part) fp32.
+        dX = G . W reads the forward shadow W [N, Kp] as an MN-major B operand."""
         key = ("bwd", p, need_input_grad, rows)
         if key in self._plans:
             return self._plans[key]
         M = rows or self.M
-        col0 = p * self.pass_stride
         ops = []
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
-        GT = self.GT
         active = self.pass_branches[p]
 
         def xin_of(br, i):
@@ -316,15 +306,15 @@ class MlpSet:
             last = blocks[-1]
             for s in range(self.S):
                 L = nets[s].layers[head]
-                probs.append(self._prob(G[s][head], L.WbT, M, WIDTH, 64, 64, L.Np, ymask=act[s][last + ".y"],
-                                        mid=dt[s][last], bits=sign[s][last], out=G[s][last + ".l2"],
-                                        outT=GT[s][last + ".l2"], outT_col0=col0))
+                probs.append(self._prob(G[s][head], L.Wb, M, WIDTH, L.N, 64, L.Kp, flags=GEMM_B_MN,
+                                        ymask=act[s][last + ".y"], mid=dt[s][last], bits=sign[s][last],
+                                        out=G[s][last + ".l2"]))
         ops.append(self._launch(probs))
 
         def l2_dgrad(items):
             ops.append(self._launch([
-                self._prob(G[s][blk + ".l2"], nets[s].layers[blk + ".l2"].WbT, M, WIDTH, WIDTH, WIDTH, WIDTH,
-                           ymask=act[s][blk + ".a1"], out=G[s][blk + ".l1"], outT=GT[s][blk + ".l1"], outT_col0=col0)
+                self._prob(G[s][blk + ".l2"], nets[s].layers[blk + ".l2"].Wb, M, WIDTH, WIDTH, WIDTH, WIDTH,
+                           flags=GEMM_B_MN, ymask=act[s][blk + ".a1"], out=G[s][blk + ".l1"])
                 for s, blk in items]))
 
         def l1_dgrad(items):
@@ -332,17 +322,16 @@ class MlpSet:
             probs = []
             for s, blk, prev, mode in items:
                 L = nets[s].layers[blk + ".l1"]
-                kw = dict(add0=dt[s][blk])
+                kw = dict(add0=dt[s][blk], flags=GEMM_B_MN)
                 if mode == "raw":
                     kw.update(out=self.E[p][s])
                 elif mode == "up":
-                    kw.update(out=G[s]["upscale"], outT=GT[s]["upscale"], outT_col0=col0)
+                    kw.update(out=G[s]["upscale"])
                 else:
                     if mode == "merge":
                         kw.update(add1=self.E[p][s])
-                    kw.update(ymask=act[s][prev + ".y"], mid=dt[s][prev], bits=sign[s][prev], out=G[s][prev + ".l2"],
-                              outT=GT[s][prev + ".l2"], outT_col0=col0)
-                probs.append(self._prob(G[s][blk + ".l1"], L.WbT, M, WIDTH, WIDTH, WIDTH, WIDTH, **kw))
+                    kw.update(ymask=act[s][prev + ".y"], mid=dt[s][prev], bits=sign[s][prev], out=G[s][prev + ".l2"])
+                probs.append(self._prob(G[s][blk + ".l1"], L.Wb, M, WIDTH, WIDTH, WIDTH, WIDTH, **kw))
             ops.append(self._launch(probs))
 
         depth = max(len(self.branches[br][0]) for br in active)
@@ -374,7 +363,8 @@ class MlpSet:
             probs = []
             for s in range(self.S):
                 L = nets[s].layers["upscale"]
-                probs.append(self._prob(G[s]["upscale"], L.WbT, M, L.K, WIDTH, WIDTH, L.Np, out_f32=self.din[p][s]))
+                probs.append(self._prob(G[s]["upscale"], L.Wb, M, L.K, WIDTH, WIDTH, L.Kp, flags=GEMM_B_MN,
+                                        out_f32=self.din[p][s]))
             ops.append(self._launch(probs))
         self._plans[key] = ops
         return ops
@@ -410,7 +400,8 @@ class MlpSet:
         raise KeyError(name)
 
     def wgrad_plan(self, rows=None):
-        """dW = G^T . X contracted over the rows of every pass that used the layer; db = column sums of G."""
+        """dW = G^T . X contracted over the rows of every pass that used the layer (G and X read as MN-major
+        operands straight from their row-major buffers); db = column sums of G."""
         key = ("wgrad", rows)
         if key in self._plans:
             return self._plans[key]
@@ -424,14 +415,13 @@ class MlpSet:
                 L = self.nets[s].layers[n]
                 passes = self._layer_passes(n)
                 assert passes == list(range(len(passes))), "passes using a layer must be a prefix"
-                Kc = (len(passes) - 1) * self.pass_stride + M
+                Kc = (len(passes) - 1) * self.M + M
                 xin = self._layer_input(n)
-                XT = self.x0T[s] if xin == "x0" else self.actT[s][xin]
-                probs.append(self._prob(self.GT[s][n], XT, L.N, L.K, Kc, self.ldT, self.ldT, out_f32=L.gW,
-                                        ld_f32=L.K))
-                for i, p in enumerate(passes):
-                    g = self.G[p][s][n]
-                    colsums.append((g.data_ptr(), g.stride(0), M, L.N, L.gb.data_ptr(), 1 if i > 0 else 0))
+                X = self._x0buf[s] if xin == "x0" else self._actbuf[s][xin]
+                Gb = self._Gbuf[s][n]
+                probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
+                                        out_f32=L.gW, ld_f32=L.K))
+                colsums.append((Gb.data_ptr(), Gb.stride(0), Kc, L.N, L.gb.data_ptr(), 0))
         ops.append(self._launch(probs))
         fn = self.lib.links_colsum_bf16_batched
         batches = []
@@ -451,10 +441,6 @@ class MlpSet:
         ops.append(run_colsums)
         self._plans[key] = ops
         return ops
-
-    def pass_col0(self, p):
-        """Column offset of pass p inside the transposed ([*, ldT]) buffers."""
-        return p * self.pass_stride
 
     @staticmethod
     def run(ops):

@@ -74,7 +74,7 @@ class OcclusionStep:
             for s in range(8):
                 n_idx = self.idx_in[s].numel() // self.period[s]
                 check(L.links_pack_rows(self.pose[r].data_ptr(), 51, B, self.idx_in[s].data_ptr(), n_idx, self.period[s],
-                                        m.x0[r][s].data_ptr(), m.x0T[s].data_ptr(), m.ldT, m.pass_col0(r), st),
+                                        m.x0[r][s].data_ptr(), None, 0, 0, st),
                       "links_pack_rows")
             m.run(m.forward_plan(r))
             for s in range(8):
@@ -82,8 +82,7 @@ class OcclusionStep:
                 pred = m.head_out[r][s]["downscale"]
                 check(L.links_occ_mse(pred.data_ptr(), pred.stride(0), self.pose[r].data_ptr(), self.idx_tgt[s].data_ptr(),
                                       n_out, B, 1.0 / B, self.loss_sums[s:s + 1].data_ptr(),
-                                      m.G[r][s]["downscale"].data_ptr(), m.GT[s]["downscale"].data_ptr(), m.ldT,
-                                      m.pass_col0(r), st), "links_occ_mse")
+                                      m.G[r][s]["downscale"].data_ptr(), None, 0, 0, st), "links_occ_mse")
         for r in range(3):
             m.run(m.backward_plan(r, need_input_grad=False))
         m.run(m.wgrad_plan())

@@ -84,7 +84,7 @@ class LifterStep:
     def _pack(self, src, idx, n_idx, p, s):
         m = self.mlp
         check(self.lib.links_pack_rows(src.data_ptr(), src.stride(0), self.N, idx.data_ptr(), n_idx, 1,
-                                       m.x0[p][s].data_ptr(), m.x0T[s].data_ptr(), m.ldT, m.pass_col0(p), self._st()),
+                                       m.x0[p][s].data_ptr(), None, 0, 0, self._st()),
               "links_pack_rows")
 
     def forward_backward(self):
@@ -111,23 +111,20 @@ class LifterStep:
                                           self.dflow[s])
         m.run(m.forward_plan(1))
         g2 = [m.G[1][s]["downscale"] for s in range(2)]
-        g2T = [m.GT[s]["downscale"] for s in range(2)]
         check(L.links_geom_loss(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), N, self.scal.data_ptr(),
-                                g2[0].data_ptr(), g2[1].data_ptr(), g2T[0].data_ptr(), g2T[1].data_ptr(), m.ldT,
-                                m.pass_col0(1), self._st()), "links_geom_loss")
+                                g2[0].data_ptr(), g2[1].data_ptr(), None, None, 0, 0, self._st()), "links_geom_loss")
         m.run(m.backward_plan(1, need_input_grad=True))
         g1 = [m.G[0][s]["downscale"] for s in range(2)]
         ga = [m.G[0][s]["angles"] for s in range(2)]
         check(L.links_geom_backward(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), self.dflow[0].data_ptr(),
                                     self.dflow[1].data_ptr(), m.din[1][0].data_ptr(), m.din[1][1].data_ptr(), N,
-                                    g1[0].data_ptr(), g1[1].data_ptr(), g2T[0].data_ptr(), g2T[1].data_ptr(), m.ldT, 0,
+                                    g1[0].data_ptr(), g1[1].data_ptr(), None, None, 0, 0,
                                     self.dgamma.data_ptr(), self.da.data_ptr(), self.scal[6:8].data_ptr(), self._st()),
               "links_geom_backward")
-        gaT = [m.GT[s]["angles"] for s in range(2)]
         check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
                                            self.stats.data_ptr(), self.dgamma.data_ptr(), self.scal[6:8].data_ptr(), N,
-                                           ga[0].data_ptr(), ga[1].data_ptr(), gaT[0].data_ptr(), gaT[1].data_ptr(),
-                                           m.ldT, 0, self._st()), "links_geom_backward_angles")
+                                           ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, self._st()),
+              "links_geom_backward_angles")
         m.run(m.backward_plan(0, need_input_grad=False))
         m.run(m.wgrad_plan())
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss

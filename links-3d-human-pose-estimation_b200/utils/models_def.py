@@ -51,8 +51,8 @@ class _EngineFn(torch.autograd.Function):
         st = torch.cuda.current_stream().cuda_stream
         xc = x.detach().contiguous().float()
         idx = module._identity_index(K, x.device)
-        _cabi.check(lib.links_pack_rows(xc.data_ptr(), K, M, idx.data_ptr(), K, 1, eng.x0[0][0].data_ptr(),
-                                        eng.x0T[0].data_ptr() if eng.train else None, eng.ldT, 0, st), "links_pack_rows")
+        _cabi.check(lib.links_pack_rows(xc.data_ptr(), K, M, idx.data_ptr(), K, 1, eng.x0[0][0].data_ptr(), None, 0, 0, st),
+                    "links_pack_rows")
         eng.run(eng.forward_plan(0))
         outs = []
         for head, width in module._heads:
@@ -67,13 +67,10 @@ class _EngineFn(torch.autograd.Function):
         if not eng.train:
             raise _cabi.LinksError("forward ran under no_grad; no activations were kept for backward")
         for (head, width), g in zip(module._heads, gouts):
-            G, GT = eng.G[0][0][head], eng.GT[0][head]
+            G = eng.G[0][0][head]
             G.zero_()
-            GT.zero_()
             if g is not None:
-                gb = g.to(torch.bfloat16)
-                G[:, :width] = gb
-                GT[:, :M] = gb.t()
+                G[:, :width] = g.to(torch.bfloat16)
         eng.run(eng.backward_plan(0, need_input_grad=ctx.need_x))
         eng.run(eng.wgrad_plan())
         gx = eng.din[0][0][:, :K].clone() if ctx.need_x else None

@@ -16,13 +16,11 @@ def _prob(cabi, A, B, M, N, K, **kw):
     P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb = A.data_ptr(), B.data_ptr(), M, N, K, A.stride(0), B.stride(0)
     P.flags = kw.pop("flags", 0)
     for k, v in kw.items():
-        if k in ("ld_f32", "outT_col0"):
+        if k in ("ld_f32",):
             setattr(P, k, v)
         elif v is not None:
             setattr(P, k, v.data_ptr())
-            if k == "outT":
-                P.ld_outT = v.stride(0)
-            elif k == "out_f32":
+            if k == "out_f32":
                 P.ld_f32 = v.stride(0)
             elif k == "sign_out":
                 P.ld_sign = v.stride(0)
@@ -64,7 +62,7 @@ def test_plain_gemm_f32_out(M, N, K):
     torch.testing.assert_close(out, 2 * ref - bias, rtol=2e-4, atol=4e-3)
 
 
-def test_forward_epilogues_and_transpose():
+def test_forward_epilogues():
     cabi, L = _lib()
     M, N, K = 300, 1024, 1024
     g = torch.Generator(device="cuda").manual_seed(1)
@@ -73,18 +71,14 @@ def test_forward_epilogues_and_transpose():
     bias = torch.randn(N, device="cuda", generator=g) * 0.1
     resid = (torch.randn(M, N, device="cuda", generator=g) * 0.3).bfloat16()
     acc = A.float() @ W.float().t() + bias
-    ldT = 312
-    # l1-style: leaky(acc + b)
-    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
-    outT = torch.zeros(N, ldT, device="cuda", dtype=torch.bfloat16)
-    _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE, out=out, outT=outT, outT_col0=8)])
+    # l1-style: leaky(acc + b); the output buffer is wider than N (rows beyond M / columns beyond N stay untouched)
+    big = torch.full((M + 5, N + 8), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = big[:M, :N]
+    _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE, out=out)])
     ref = leaky(acc)
     torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-3)
-    assert torch.equal(outT[:, 8:8 + M], out.t())
-    assert torch.all(outT[:, :8] == 0)
-    # an unaligned column offset is rejected (TMA stores need 16-byte aligned starts)
-    P = _prob(cabi, A, W, M, N, K, out=out, outT=outT, outT_col0=5)
-    assert L.links_gemm_grouped((cabi.GemmProblem * 1)(P), 1, None) == -2
+    assert torch.all(big[M:] == 7.0) and torch.all(big[:, N:] == 7.0)
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     # l2-style: leaky(leaky(acc + b) + resid) with the sign mask of (acc + b)
     sign = torch.zeros(M, N // 32, device="cuda", dtype=torch.int32)
     _run(cabi, L, [_prob(cabi, A, W, M, N, K, bias=bias, flags=cabi.EPI_LEAKY_PRE | cabi.EPI_LEAKY_POST, add0=resid,
@@ -112,14 +106,48 @@ def test_backward_epilogue_masks():
     bits = torch.where(w >= 2 ** 31, w - 2 ** 32, w).to(torch.int32).contiguous()
     mid = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
     out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
-    outT = torch.zeros(N, M, device="cuda", dtype=torch.bfloat16)
-    _run(cabi, L, [_prob(cabi, G, WT, M, N, K, add0=skip, add1=extra, ymask=y, mid=mid, bits=bits, out=out, outT=outT)])
+    _run(cabi, L, [_prob(cabi, G, WT, M, N, K, add0=skip, add1=extra, ymask=y, mid=mid, bits=bits, out=out)])
     v = G.float() @ WT.float().t() + skip.float() + extra.float()
     v = v * torch.where(y.float() > 0, 1.0, 0.01)
     torch.testing.assert_close(mid.float(), v, rtol=1e-2, atol=1e-3)
     v = v * torch.where(bits_bool, 0.01, 1.0)
     torch.testing.assert_close(out.float(), v, rtol=1e-2, atol=1e-3)
-    assert torch.equal(outT, out.t())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 1024), (300, 1024, 11), (2048, 22, 1024), (77, 200, 130)])
+def test_dgrad_mn_major_b(M, N, K):
+    """dX[M, N] = G[M, K] . W[K, N] with W read in place as an MN-major B operand (no transposed shadow)."""
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    ldg, ldw = (K + 63) // 64 * 64, (N + 63) // 64 * 64
+    G = torch.zeros(M, ldg, device="cuda", dtype=torch.bfloat16)
+    G[:, :K] = (torch.randn(M, K, device="cuda", generator=g) * 0.3).bfloat16()
+    W = torch.zeros(K, ldw, device="cuda", dtype=torch.bfloat16)
+    W[:, :N] = (torch.randn(K, N, device="cuda", generator=g) * 0.1).bfloat16()
+    out = torch.full((M, (N + 3) // 4 * 4), float("nan"), device="cuda")
+    P = _prob(cabi, G, W, M, N, K, flags=cabi.GEMM_B_MN, out_f32=out)
+    P.ldb = ldw
+    _run(cabi, L, [P])
+    ref = G[:, :K].float() @ W[:, :N].float()
+    torch.testing.assert_close(out[:, :N], ref, rtol=2e-4, atol=3e-3)
+
+
+@pytest.mark.parametrize("rows,N,K", [(2048, 1024, 1024), (4096, 1024, 1024), (300, 11, 1024), (1000, 1024, 22), (130, 30, 42)])
+def test_wgrad_mn_major_ab(rows, N, K):
+    """dW[N, K] = G[rows, N]^T . X[rows, K]: both operands read in place as MN-major (contraction over rows)."""
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(rows + N + K)
+    ldg, ldx = (N + 63) // 64 * 64, (K + 63) // 64 * 64
+    G = torch.zeros(rows, ldg, device="cuda", dtype=torch.bfloat16)
+    G[:, :N] = (torch.randn(rows, N, device="cuda", generator=g) * 0.1).bfloat16()
+    X = torch.zeros(rows, ldx, device="cuda", dtype=torch.bfloat16)
+    X[:, :K] = (torch.randn(rows, K, device="cuda", generator=g) * 0.3).bfloat16()
+    out = torch.full((N, K), float("nan"), device="cuda")
+    P = _prob(cabi, G, X, N, K, rows, flags=cabi.GEMM_A_MN | cabi.GEMM_B_MN, out_f32=out)
+    P.lda, P.ldb = ldg, ldx
+    _run(cabi, L, [P])
+    ref = G[:, :N].float().t() @ X[:, :K].float()
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=5e-3)
 
 
 def test_grouped_heterogeneous_problems():
