@@ -1,6 +1,8 @@
 // Grouped bf16 GEMM with fused epilogue for sm_100a -- persistent, warp-specialised:
 //   TMA -> shared memory (128B swizzle, 4-stage ring) -> tcgen05.mma (M128 x N256 x K16, fp32 accumulators in TMEM,
-//   two accumulator buffers) -> tcgen05.ld -> fused epilogue -> bf16 slabs staged in shared memory -> TMA stores.
+//   two accumulator buffers) -> tcgen05.ld -> fused epilogue -> 16-byte global stores straight from registers
+//   (each thread owns 32 contiguous columns of one row; staging the tile for TMA stores serialised the epilogue on
+//   the store round trip: measured 9-14 us per tile against a 4.2 us main loop).
 //
 // Replaces every nn.Linear(+LeakyReLU, +residual) of reference utils/models_def.py (forward) and its autograd
 // backward (dgrad, wgrad); see include/links_b200.h for the epilogue contract.
@@ -8,7 +10,7 @@
 // One CTA per SM walks the 128x256 output tiles of all problems of the group (static round-robin).
 //   warp 0      : TMA producer (one elected lane), runs ahead across tile boundaries
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (warp-uniform control flow, one elected lane)
-//   warps 2..9  : epilogue (TMEM lane group = warp % 4, column half = (warp - 2) / 4); the epilogue of tile i overlaps
+//   warps 2..17 : epilogue (TMEM lane group = warp % 4, column quarter = (warp - 2) / 4); the epilogue of tile i overlaps
 //                 the main loop of tile i + 1 through the second accumulator buffer.
 // Operands may be K-major (row-major with the contraction dimension contiguous) or MN-major (contraction dimension
 // strided): dgrad reads W itself as an MN-major B operand and wgrad reads the row-major activations / gradients as
@@ -27,18 +29,17 @@ constexpr int BN = 256;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;     // 4 TMEM lane groups x 4 column quarters: 4 warps per scheduler hide the epilogue's latencies
+constexpr int kChunk = 16;        // accumulator columns per thread per 64-column slab
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccCols = BN;      // fp32 accumulator columns per buffer
 constexpr int kTmemCols = 2 * kAccCols;
 constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
 constexpr uint32_t kStageBytesB = BN * BK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
-constexpr uint32_t kSlabBytes = BM * 64 * 2;     // one 128 x 64 bf16 output slab
 constexpr uint32_t kOffStage = 0;
-constexpr uint32_t kOffOut = kStages * kStageBytes;          // staging: out slab
-constexpr uint32_t kOffMid = kOffOut + kSlabBytes;           // staging: mid slab
-constexpr uint32_t kOffBar = kOffMid + kSlabBytes;
+constexpr uint32_t kOffBias = kStages * kStageBytes;          // 2 x BN floats: bias slice of the tile, per accumulator slot
+constexpr uint32_t kOffBar = kOffBias + 2 * BN * 4;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024 /*align slack*/;
 
 // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]
@@ -47,12 +48,10 @@ enum { GB_FULL = 0, GB_EMPTY = kStages, GB_ACCFULL = 2 * kStages, GB_ACCEMPTY = 
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
-  CUtensorMap tmOut;    // bf16 [M, N] row-major, box 64 x 128, 128B swizzle (TMA store)
-  CUtensorMap tmMid;
   int M, N, K;
   int tile_begin, tiles_m, tiles_n;
   uint32_t flags;
-  int ld_add0, ld_add1, ld_ymask, ld_bits, ld_sign, ld_f32;
+  int ld_add0, ld_add1, ld_ymask, ld_bits, ld_sign, ld_f32, ld_out, ld_mid;
   const float* bias;
   const __nv_bfloat16* add0;
   const __nv_bfloat16* add1;
@@ -60,7 +59,10 @@ struct alignas(64) GemmProblemDev {
   const uint32_t* bits;
   uint32_t* sign_out;
   float* out_f32;
-  int has_out, has_mid;
+  __nv_bfloat16* out;
+  __nv_bfloat16* mid;
+  int vec_ok;           // every present epilogue operand is 16-byte aligned with a vector-friendly leading dimension
+  int epi_mode;         // index into kEpiMask (0 = run-time flags)
 };
 
 struct GemmGroupDev {
@@ -81,6 +83,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn128(uint32_t saddr) {
   return d;
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -93,27 +105,252 @@ __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&o)[8]
   o[4] = bf16_bits_to_f32(q.z & 0xFFFFu); o[5] = bf16_bits_to_f32(q.z >> 16);
   o[6] = bf16_bits_to_f32(q.w & 0xFFFFu); o[7] = bf16_bits_to_f32(q.w >> 16);
 }
-// 8 bf16 values of row-major X[m, n .. n+8) with a column guard (n + 8 may exceed N)
-__device__ __forceinline__ void load8_guard(const __nv_bfloat16* base, int ld, int m, int n, int N, bool vec, float (&o)[8]) {
-  const __nv_bfloat16* p = base + static_cast<size_t>(m) * ld + n;
-  if (vec && n + 8 <= N) { load8_bf16(p, o); return; }
+__device__ __forceinline__ void unpack8_bf16(const uint4& q, float (&o)[8]) {
+  o[0] = bf16_bits_to_f32(q.x & 0xFFFFu); o[1] = bf16_bits_to_f32(q.x >> 16);
+  o[2] = bf16_bits_to_f32(q.y & 0xFFFFu); o[3] = bf16_bits_to_f32(q.y >> 16);
+  o[4] = bf16_bits_to_f32(q.z & 0xFFFFu); o[5] = bf16_bits_to_f32(q.z >> 16);
+  o[6] = bf16_bits_to_f32(q.w & 0xFFFFu); o[7] = bf16_bits_to_f32(q.w >> 16);
+}
+
+// Register-resident copy of one problem's epilogue parameters.
+struct EpiParams {
+  int M, N;
+  uint32_t flags;
+  int vec_ok;
+  int ld_add0, ld_add1, ld_ymask, ld_bits, ld_sign, ld_f32, ld_out, ld_mid;
+  const float* bias;
+  const __nv_bfloat16* add0;
+  const __nv_bfloat16* add1;
+  const __nv_bfloat16* ymask;
+  const uint32_t* bits;
+  uint32_t* sign_out;
+  float* out_f32;
+  __nv_bfloat16* out;
+  __nv_bfloat16* mid;
+};
+
+// Scalar path for one 16-column chunk of row m: N tails and operands that are not 16-byte aligned (heads,
+// upscale dgrad / wgrad).  Same arithmetic, element by element.  n0 is a multiple of 16: the chunk owns one half of
+// a 32-column sign / bits word.
+__device__ __noinline__ void epilogue_chunk_scalar(const EpiParams& E, const uint32_t (&acc)[kChunk], int m, int n0) {
+  const int sh = n0 & 16;
+  uint32_t bits_word = 0;
+  if (E.bits) bits_word = E.bits[static_cast<size_t>(m) * E.ld_bits + (n0 >> 5)] >> sh;
+  uint32_t sign_word = 0;
+#pragma unroll 1
+  for (int i = 0; i < kChunk; ++i) {
+    const int n = n0 + i;
+    if (n >= E.N) break;
+    float v = __uint_as_float(acc[i]);
+    if (E.bias) v += __ldg(E.bias + n);
+    sign_word |= (v > 0.f ? 0u : 1u) << i;
+    if (E.flags & LINKS_EPI_LEAKY_PRE) v = links_leaky(v);
+    if (E.flags & LINKS_EPI_RELU_PRE) v = fmaxf(v, 0.f);
+    if (E.add0) v += __bfloat162float(E.add0[static_cast<size_t>(m) * E.ld_add0 + n]);
+    if (E.add1) v += __bfloat162float(E.add1[static_cast<size_t>(m) * E.ld_add1 + n]);
+    if (E.flags & LINKS_EPI_LEAKY_POST) v = links_leaky(v);
+    if (E.ymask) v *= (__bfloat162float(E.ymask[static_cast<size_t>(m) * E.ld_ymask + n]) > 0.f ? 1.f : 0.01f);
+    if (E.mid) E.mid[static_cast<size_t>(m) * E.ld_mid + n] = __float2bfloat16_rn(v);
+    if (E.bits) v *= ((bits_word >> i) & 1u) ? 0.01f : 1.f;
+    if (E.out) E.out[static_cast<size_t>(m) * E.ld_out + n] = __float2bfloat16_rn(v);
+    if (E.out_f32) {
+      float* p = E.out_f32 + static_cast<size_t>(m) * E.ld_f32 + n;
+      *p = (E.flags & LINKS_EPI_ACCUM_F32) ? *p + v : v;
+    }
+  }
+  if (E.sign_out)
+    reinterpret_cast<unsigned short*>(E.sign_out + static_cast<size_t>(m) * E.ld_sign + (n0 >> 5))[sh >> 4] =
+        static_cast<unsigned short>(sign_word);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue specialisations.  The per-problem combination of epilogue steps is classified on the host into one of a
+// few modes; each mode is a compile-time feature mask so the hot loop is straight-line code (mask 0 = decide
+// everything at run time).  The arithmetic is identical in every mode (see include/links_b200.h).
+// ----------------------------------------------------------------------------------------------
+enum : uint32_t { F_BIAS = 1, F_LPRE = 2, F_RPRE = 4, F_ADD0 = 8, F_ADD1 = 16, F_LPOST = 32, F_YMASK = 64, F_MID = 128,
+                  F_BITS = 256, F_SIGN = 512, F_OUT = 1024, F_F32 = 2048, F_ACC = 4096 };
+__device__ constexpr uint32_t kEpiMask[11] = {
+    0u,
+    F_BIAS | F_OUT,                                             // 1  upscale forward
+    F_BIAS | F_LPRE | F_OUT,                                    // 2  res-block l1 forward
+    F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,        // 3  res-block l2 forward (training)
+    F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT,                 // 4  res-block l2 forward (inference)
+    F_YMASK | F_OUT,                                            // 5  l2 dgrad
+    F_ADD0 | F_OUT,                                             // 6  l1 dgrad into a plain sum
+    F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT,                  // 7  l1 dgrad + masks of the previous block
+    F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,         // 8  l1 dgrad merging two branches
+    F_YMASK | F_MID | F_BITS | F_OUT,                           // 9  head dgrad
+    F_F32,                                                      // 10 wgrad
+};
+
+// One accumulator tile (this thread: row m, columns n_tile + 64*sl .. +16 for sl = 0..3).  The chunk's global
+// operands are fetched one slab ahead of their use, so their latency overlaps the previous slab's arithmetic.
+template <uint32_t F>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& E, uint32_t t_addr, const float* sbias, int m, int n_tile) {
+  constexpr bool kDyn = F == 0u;
+  constexpr int G8 = kChunk / 8;
+  const bool row_ok = m < E.M;
+  const bool has_bias = kDyn ? E.bias != nullptr : (F & F_BIAS) != 0;
+  const bool lpre = kDyn ? (E.flags & LINKS_EPI_LEAKY_PRE) != 0 : (F & F_LPRE) != 0;
+  const bool rpre = kDyn ? (E.flags & LINKS_EPI_RELU_PRE) != 0 : (F & F_RPRE) != 0;
+  const bool has_add0 = kDyn ? E.add0 != nullptr : (F & F_ADD0) != 0;
+  const bool has_add1 = kDyn ? E.add1 != nullptr : (F & F_ADD1) != 0;
+  const bool lpost = kDyn ? (E.flags & LINKS_EPI_LEAKY_POST) != 0 : (F & F_LPOST) != 0;
+  const bool has_y = kDyn ? E.ymask != nullptr : (F & F_YMASK) != 0;
+  const bool has_mid = kDyn ? E.mid != nullptr : (F & F_MID) != 0;
+  const bool has_bits = kDyn ? E.bits != nullptr : (F & F_BITS) != 0;
+  const bool has_sign = kDyn ? E.sign_out != nullptr : (F & F_SIGN) != 0;
+  const bool has_out = kDyn ? E.out != nullptr : (F & F_OUT) != 0;
+  const bool has_f32 = kDyn ? E.out_f32 != nullptr : (F & F_F32) != 0;
+  const bool accum = (E.flags & LINKS_EPI_ACCUM_F32) != 0;
+  const size_t mo = static_cast<size_t>(m);
+  const int sh = n_tile & 16;                                         // which half of the 32-column sign / bits words
+
+  // prefetch registers (no lambdas / early returns here: the arrays must stay in registers)
+  uint4 q0[G8], q1[G8], qy[G8];
+  uint32_t bits_word = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (n + i < N) ? __bfloat162float(p[i]) : 0.f;
+  for (int g = 0; g < G8; ++g) { q0[g] = make_uint4(0, 0, 0, 0); q1[g] = q0[g]; qy[g] = q0[g]; }
+#define LINKS_EPI_PREFETCH(N0)                                                                         \
+  {                                                                                                    \
+    const int pn = (N0);                                                                               \
+    if (row_ok && E.vec_ok && pn + kChunk <= E.N) {                                                    \
+      if (has_add0) {                                                                                  \
+        const uint4* pp = reinterpret_cast<const uint4*>(E.add0 + mo * E.ld_add0 + pn);                \
+        _Pragma("unroll") for (int g = 0; g < G8; ++g) q0[g] = __ldg(pp + g);                          \
+      }                                                                                                \
+      if (has_add1) {                                                                                  \
+        const uint4* pp = reinterpret_cast<const uint4*>(E.add1 + mo * E.ld_add1 + pn);                \
+        _Pragma("unroll") for (int g = 0; g < G8; ++g) q1[g] = __ldg(pp + g);                          \
+      }                                                                                                \
+      if (has_y) {                                                                                     \
+        const uint4* pp = reinterpret_cast<const uint4*>(E.ymask + mo * E.ld_ymask + pn);              \
+        _Pragma("unroll") for (int g = 0; g < G8; ++g) qy[g] = __ldg(pp + g);                          \
+      }                                                                                                \
+      if (has_bits) bits_word = __ldg(E.bits + mo * E.ld_bits + (pn >> 5)) >> sh;                      \
+    }                                                                                                  \
+  }
+  LINKS_EPI_PREFETCH(n_tile)
+#pragma unroll 1
+  for (int sl = 0; sl < BN / 64; ++sl) {
+    const int n0 = n_tile + sl * 64;
+    if ((n0 & ~63) >= E.N) break;                                     // slab start beyond N: uniform over the CTA
+    const bool fast = row_ok && E.vec_ok && (n0 + kChunk <= E.N);
+    uint32_t acc[kChunk];
+    tmem_ld16(t_addr + static_cast<uint32_t>(sl * 64), acc);
+    if (fast) {
+      // move this slab's operands out of the prefetch registers, then fetch the next slab's
+      uint4 c0[G8], c1[G8], cy[G8];
+#pragma unroll
+      for (int g = 0; g < G8; ++g) { c0[g] = q0[g]; c1[g] = q1[g]; cy[g] = qy[g]; }
+      const uint32_t cbits = bits_word;
+      if (sl + 1 < BN / 64) LINKS_EPI_PREFETCH(n0 + 64)
+      uint32_t sign_word = 0;
+      __nv_bfloat16* out_row = has_out ? E.out + mo * E.ld_out + n0 : nullptr;
+      __nv_bfloat16* mid_row = has_mid ? E.mid + mo * E.ld_mid + n0 : nullptr;
+      float* f32_row = has_f32 ? E.out_f32 + mo * E.ld_f32 + n0 : nullptr;
+#pragma unroll
+      for (int g = 0; g < G8; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
+        if (has_bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + sl * 64 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + sl * 64 + g * 8 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (has_sign) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sign_word |= (v[i] > 0.f ? 0u : 1u) << (g * 8 + i);
+        }
+        if (lpre) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);      // == leaky for slope < 1
+        }
+        if (rpre) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (has_add0) {
+          float t[8]; unpack8_bf16(c0[g], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += t[i];
+        }
+        if (has_add1) {
+          float t[8]; unpack8_bf16(c1[g], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += t[i];
+        }
+        if (lpost) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
+        }
+        if (has_y) {
+          float t[8]; unpack8_bf16(cy[g], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = t[i] > 0.f ? v[i] : 0.01f * v[i];
+        }
+        if (has_mid)
+          *reinterpret_cast<uint4*>(mid_row + g * 8) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (has_bits) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = ((cbits >> (g * 8 + i)) & 1u) ? 0.01f * v[i] : v[i];
+        }
+        if (has_out)
+          *reinterpret_cast<uint4*>(out_row + g * 8) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        if (has_f32) {
+          float* p = f32_row + g * 8;
+          float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
+          float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
+          if (accum) {
+            const float4 a0 = *reinterpret_cast<const float4*>(p);
+            const float4 a1 = *reinterpret_cast<const float4*>(p + 4);
+            o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
+            o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+          }
+          *reinterpret_cast<float4*>(p) = o0;
+          *reinterpret_cast<float4*>(p + 4) = o1;
+        }
+      }
+      if (has_sign)
+        reinterpret_cast<unsigned short*>(E.sign_out + mo * E.ld_sign + (n0 >> 5))[sh >> 4] = static_cast<unsigned short>(sign_word);
+    } else {
+      if (row_ok && n0 < E.N) {                                      // tails / unaligned operands
+        // pass COPIES: taking the address of E / acc themselves would pin them in local memory for the fast path too
+        EpiParams Ec = E;
+        uint32_t acc_c[kChunk];
+#pragma unroll
+        for (int i = 0; i < kChunk; ++i) acc_c[i] = acc[i];
+        epilogue_chunk_scalar(Ec, acc_c, m, n0);
+      }
+      if (sl + 1 < BN / 64) LINKS_EPI_PREFETCH(n0 + 64)
+    }
+  }
+#undef LINKS_EPI_PREFETCH
 }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+#ifdef LINKS_GEMM_TRACE
+// debug build only (scratch/trace_gemm.py): per-CTA timestamps of the pipeline phases
+__device__ unsigned long long g_gemm_trace[148 * 16];
+__device__ __forceinline__ void trace_mark(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (blockIdx.x < 148) g_gemm_trace[blockIdx.x * 16 + slot] = t;
+}
+#define TRACE(slot) trace_mark(slot)
+#else
+#define TRACE(slot)
+#endif
 
 struct TileCoord { int pi, tm, tn; };
 __device__ __forceinline__ TileCoord tile_coord(const GemmGroupDev& G, int tile) {
@@ -140,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TRACE(0);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -157,6 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -213,6 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         const uint32_t s = it % kStages, use = it / kStages;
         mbar_wait(bb + (GB_FULL + s) * 8, use & 1u);
         tc_fence_after();
+        if (leader && it == 0) TRACE(2);
         if (leader) {
           const uint32_t sA = sb + kOffStage + s * kStageBytes, sB = sA + kStageBytesA;
           const uint64_t adesc = a_mn ? make_smem_desc_mn128(sA) : make_smem_desc_k128(sA);
@@ -231,139 +471,59 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
   } else {
     // ================= epilogue warps (256 threads) =================
     const int lane_grp = warp & 3;                                    // TMEM lanes 32*lane_grp .. +31
-    const int half = (warp - 2) >> 2;                                 // which 32 columns of each 64-column slab
+    const int quarter = (warp - 2) >> 2;                              // which 16 columns of each 64-column slab
     const int r = lane_grp * 32 + lane;
-    const uint32_t sOut = base + kOffOut, sMid = base + kOffMid;
-    const uint32_t row_off = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128);
     const bool store_thread = threadIdx.x == 64;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord(G, tile);
-      const GemmProblemDev& P = G.p[tc.pi];
-      const int M = P.M, N = P.N;
-      const uint32_t flags = P.flags;
-      const float* bias = P.bias;
-      const __nv_bfloat16* add0 = P.add0; const __nv_bfloat16* add1 = P.add1; const __nv_bfloat16* ymask = P.ymask;
-      const uint32_t* bits = P.bits; uint32_t* sign_out = P.sign_out; float* out_f32 = P.out_f32;
-      const bool has_out = P.has_out != 0, has_mid = P.has_mid != 0;
-      const bool v0 = (P.ld_add0 & 7) == 0, v1 = (P.ld_add1 & 7) == 0, vy = (P.ld_ymask & 7) == 0;
+      // register copy of the problem's epilogue parameters (an indexed constant-bank load per use otherwise)
+      EpiParams E;
+      int mode;
+      {
+        const GemmProblemDev& P = G.p[tc.pi];
+        E.M = P.M; E.N = P.N; E.flags = P.flags; E.vec_ok = P.vec_ok;
+        E.ld_add0 = P.ld_add0; E.ld_add1 = P.ld_add1; E.ld_ymask = P.ld_ymask; E.ld_bits = P.ld_bits; E.ld_sign = P.ld_sign;
+        E.ld_f32 = P.ld_f32; E.ld_out = P.ld_out; E.ld_mid = P.ld_mid;
+        E.bias = P.bias; E.add0 = P.add0; E.add1 = P.add1; E.ymask = P.ymask; E.bits = P.bits; E.sign_out = P.sign_out;
+        E.out_f32 = P.out_f32; E.out = P.out; E.mid = P.mid;
+        mode = P.epi_mode;
+      }
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
-      const int m = tc.tm * BM + r;
-      const bool row_ok = m < M;
+      // stage the tile's bias slice in shared memory (one global round trip per tile instead of one per 8 columns);
+      // slot-indexed double buffer: the readers of this buffer two tiles ago are long past the barrier below
+      float* sbias = reinterpret_cast<float*>(smem_raw + (base + kOffBias - raw)) + slot * BN;
+      {
+        const int t = threadIdx.x - 64, nb = tc.tn * BN + t;
+        if (t < BN) sbias[t] = (E.bias != nullptr && nb < E.N) ? __ldg(E.bias + nb) : 0.f;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
       mbar_wait(bars + (GB_ACCFULL + slot) * 8, acc_use & 1u);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + slot * kAccCols;
-#pragma unroll 1
-      for (int sl = 0; sl < BN / 64; ++sl) {
-        const int n_slab = tc.tn * BN + sl * 64;
-        if (n_slab >= N) break;                                        // uniform over the CTA
-        const int n0 = n_slab + half * 32;
-        uint32_t acc[32];
-        tmem_ld32(t_addr + static_cast<uint32_t>(sl * 64 + half * 32), acc);
-        uint32_t bits_word = 0;
-        if (bits && row_ok && n0 < N) bits_word = bits[static_cast<size_t>(m) * P.ld_bits + (n0 >> 5)];
-        uint32_t sign_word = 0;
-        uint32_t po[16], pm[16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + g * 8;
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
-          if (bias) {
-            if (n + 8 <= N) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) if (n + i < N) v[i] += __ldg(bias + n + i);
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sign_word |= (v[i] > 0.f ? 0u : 1u) << (g * 8 + i);
-          if (flags & LINKS_EPI_LEAKY_PRE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = links_leaky(v[i]);
-          }
-          if (flags & LINKS_EPI_RELU_PRE) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (add0 && row_ok && n < N) {
-            float t[8]; load8_guard(add0, P.ld_add0, m, n, N, v0, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += t[i];
-          }
-          if (add1 && row_ok && n < N) {
-            float t[8]; load8_guard(add1, P.ld_add1, m, n, N, v1, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += t[i];
-          }
-          if (flags & LINKS_EPI_LEAKY_POST) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = links_leaky(v[i]);
-          }
-          if (ymask && row_ok && n < N) {
-            float t[8]; load8_guard(ymask, P.ld_ymask, m, n, N, vy, t);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= (t[i] > 0.f ? 1.f : 0.01f);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pm[g * 4 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          if (bits) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] *= ((bits_word >> (g * 8 + i)) & 1u) ? 0.01f : 1.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) po[g * 4 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          if (out_f32 && row_ok && n < N) {
-            float* p = out_f32 + static_cast<size_t>(m) * P.ld_f32 + n;
-            const bool accum = (flags & LINKS_EPI_ACCUM_F32) != 0;
-            if (n + 8 <= N && (P.ld_f32 & 3) == 0) {
-              float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
-              float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
-              if (accum) {
-                const float4 a0 = *reinterpret_cast<const float4*>(p);
-                const float4 a1 = *reinterpret_cast<const float4*>(p + 4);
-                o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
-                o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
-              }
-              *reinterpret_cast<float4*>(p) = o0;
-              *reinterpret_cast<float4*>(p + 4) = o1;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) if (n + i < N) p[i] = accum ? p[i] + v[i] : v[i];
-            }
-          }
-        }
-        if (sign_out && row_ok && n0 < N) sign_out[static_cast<size_t>(m) * P.ld_sign + (n0 >> 5)] = sign_word;
-        if (has_out || has_mid) {
-          // staging slabs are free once the previous slab's TMA stores have finished reading them
-          if (store_thread) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          epi_bar_sync();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t c_addr = row_off + ((static_cast<uint32_t>(half * 4 + g) ^ static_cast<uint32_t>(r & 7)) << 4);
-            if (has_out) sts128(sOut + c_addr, po[g * 4], po[g * 4 + 1], po[g * 4 + 2], po[g * 4 + 3]);
-            if (has_mid) sts128(sMid + c_addr, pm[g * 4], pm[g * 4 + 1], pm[g * 4 + 2], pm[g * 4 + 3]);
-          }
-          fence_proxy_async_smem();
-          epi_bar_sync();
-          if (store_thread) {
-            if (has_out) tma_store_2d(&P.tmOut, sOut, n_slab, tc.tm * BM);
-            if (has_mid) tma_store_2d(&P.tmMid, sMid, n_slab, tc.tm * BM);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
+      if (store_thread && lt < 3) TRACE(3 + 3 * lt);
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + slot * kAccCols + quarter * kChunk;
+      const int m = tc.tm * BM + r, n_tile = tc.tn * BN + quarter * kChunk;
+      switch (mode) {
+        case 1: epilogue_tile<kEpiMask[1]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 2: epilogue_tile<kEpiMask[2]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 3: epilogue_tile<kEpiMask[3]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 4: epilogue_tile<kEpiMask[4]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 5: epilogue_tile<kEpiMask[5]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 6: epilogue_tile<kEpiMask[6]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 7: epilogue_tile<kEpiMask[7]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 8: epilogue_tile<kEpiMask[8]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 9: epilogue_tile<kEpiMask[9]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        case 10: epilogue_tile<kEpiMask[10]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+        default: epilogue_tile<0u>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
       }
       tc_fence_before();
       mbar_arrive(bars + (GB_ACCEMPTY + slot) * 8);
+      if (store_thread && lt < 3) TRACE(4 + 3 * lt);
     }
-    if (store_thread) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // global writes complete before exit
+    if (store_thread) TRACE(14);
   }
   __syncthreads();
+  if (threadIdx.x == 0) TRACE(15);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -427,21 +587,38 @@ static int build_group(EncodeTiledFn fn, const LinksGemmProblem* problems, int n
     d.tiles_n = (s.N + BN - 1) / BN;
     tiles += d.tiles_m * d.tiles_n;
     d.flags = s.flags;
-    if (s.out) {
-      if (!aligned16(s.out) || (s.ld_out & 7) || s.ld_out < s.N) return LINKS_E_ALIGN;
-      rc = encode_2d(fn, &d.tmOut, s.out, s.M, s.N, s.ld_out, 64, BM);
-      if (rc) return rc;
-      d.has_out = 1;
+    if ((s.out && s.ld_out < s.N) || (s.mid && s.ld_mid < s.N)) return LINKS_E_ALIGN;
+    d.out = static_cast<__nv_bfloat16*>(s.out); d.ld_out = s.ld_out;
+    d.mid = static_cast<__nv_bfloat16*>(s.mid); d.ld_mid = s.ld_mid;
+    bool vec = true;
+    auto chk = [&](const void* p, int ld, int mult) {
+      if (p && (!aligned16(p) || (ld % mult) != 0)) vec = false;
+    };
+    chk(s.bias, 4, 4); chk(s.add0, s.ld_add0, 8); chk(s.add1, s.ld_add1, 8); chk(s.ymask, s.ld_ymask, 8);
+    chk(s.mid, s.ld_mid, 8); chk(s.out, s.ld_out, 8); chk(s.out_f32, s.ld_f32, 4);
+    d.vec_ok = vec ? 1 : 0;
+    {
+      uint32_t f = 0;
+      if (s.bias) f |= F_BIAS;
+      if (s.flags & LINKS_EPI_LEAKY_PRE) f |= F_LPRE;
+      if (s.flags & LINKS_EPI_RELU_PRE) f |= F_RPRE;
+      if (s.add0) f |= F_ADD0;
+      if (s.add1) f |= F_ADD1;
+      if (s.flags & LINKS_EPI_LEAKY_POST) f |= F_LPOST;
+      if (s.ymask) f |= F_YMASK;
+      if (s.mid) f |= F_MID;
+      if (s.bits) f |= F_BITS;
+      if (s.sign_out) f |= F_SIGN;
+      if (s.out) f |= F_OUT;
+      if (s.out_f32) f |= F_F32;
+      static const uint32_t host_masks[11] = {
+          0u, F_BIAS | F_OUT, F_BIAS | F_LPRE | F_OUT, F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,
+          F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT, F_YMASK | F_OUT, F_ADD0 | F_OUT,
+          F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT, F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,
+          F_YMASK | F_MID | F_BITS | F_OUT, F_F32};
+      d.epi_mode = 0;
+      for (int k = 1; k < 11; ++k) if (host_masks[k] == f) d.epi_mode = k;
     }
-    if (s.mid) {
-      if (!aligned16(s.mid) || (s.ld_mid & 7) || s.ld_mid < s.N) return LINKS_E_ALIGN;
-      rc = encode_2d(fn, &d.tmMid, s.mid, s.M, s.N, s.ld_mid, 64, BM);
-      if (rc) return rc;
-      d.has_mid = 1;
-    }
-    if (s.bias && (reinterpret_cast<uintptr_t>(s.bias) & 15u)) return LINKS_E_ALIGN;
-    if (s.out_f32 && (reinterpret_cast<uintptr_t>(s.out_f32) & 15u)) return LINKS_E_ALIGN;
-    if ((s.add0 && !aligned16(s.add0)) || (s.add1 && !aligned16(s.add1)) || (s.ymask && !aligned16(s.ymask))) return LINKS_E_ALIGN;
     d.ld_add0 = s.ld_add0; d.ld_add1 = s.ld_add1; d.ld_ymask = s.ld_ymask; d.ld_bits = s.ld_bits;
     d.ld_sign = s.ld_sign; d.ld_f32 = s.ld_f32;
     d.bias = s.bias;
@@ -478,6 +655,12 @@ static uint64_t hash_bytes(const void* p, size_t n) {
   return h;
 }
 }  // namespace links
+
+#ifdef LINKS_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int links_debug_gemm_trace(unsigned long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, links::g_gemm_trace, sizeof(unsigned long long) * 148 * 16));
+}
+#endif
 
 extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream) {
   using namespace links;
