@@ -1,8 +1,11 @@
 // Grouped bf16 GEMM with fused epilogue for sm_100a -- persistent, warp-specialised:
 //   TMA -> shared memory (128B swizzle, 4-stage ring) -> tcgen05.mma (M128 x N256 x K16, fp32 accumulators in TMEM,
 //   two accumulator buffers) -> tcgen05.ld -> fused epilogue -> 16-byte global stores straight from registers
-//   (each thread owns 32 contiguous columns of one row; staging the tile for TMA stores serialised the epilogue on
-//   the store round trip: measured 9-14 us per tile against a 4.2 us main loop).
+//   Each epilogue warp owns a [32 rows x 64 columns] block of the tile (two passes of 32 columns).  Its bf16 operands /
+//   results cross between the row-per-thread register layout (what tcgen05.ld delivers) and global memory through
+//   private swizzled shared-memory scratch blocks, so every global access of a warp covers whole sectors (8 rows x
+//   64 B per instruction).  Row-per-thread global accesses touch 32 different lines per instruction and made the epilogue
+//   2x slower than the main loop (L1TEX tag-stage bound, measured 8-10 us per tile against 4.2 us of MMA).
 //
 // Replaces every nn.Linear(+LeakyReLU, +residual) of reference utils/models_def.py (forward) and its autograd
 // backward (dgrad, wgrad); see include/links_b200.h for the epilogue contract.
@@ -10,7 +13,7 @@
 // One CTA per SM walks the 128x256 output tiles of all problems of the group (static round-robin).
 //   warp 0      : TMA producer (one elected lane), runs ahead across tile boundaries
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (warp-uniform control flow, one elected lane)
-//   warps 2..17 : epilogue (TMEM lane group = warp % 4, column quarter = (warp - 2) / 4); the epilogue of tile i overlaps
+//   warps 2..17 : epilogue (TMEM lane group = warp % 4, 64-column slab = (warp - 2) / 4); the epilogue of tile i overlaps
 //                 the main loop of tile i + 1 through the second accumulator buffer.
 // Operands may be K-major (row-major with the contraction dimension contiguous) or MN-major (contraction dimension
 // strided): dgrad reads W itself as an MN-major B operand and wgrad reads the row-major activations / gradients as
@@ -28,9 +31,10 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kEpiWarps = 16;     // 4 TMEM lane groups x 4 column quarters: 4 warps per scheduler hide the epilogue's latencies
-constexpr int kChunk = 16;        // accumulator columns per thread per 64-column slab
+constexpr int kChunk = 16;        // accumulator columns per TMEM load / scalar-path chunk
+constexpr int kSlab = 64;         // columns of the [32 rows x 64 cols] block one epilogue warp owns
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccCols = BN;      // fp32 accumulator columns per buffer
 constexpr int kTmemCols = 2 * kAccCols;
@@ -38,7 +42,9 @@ constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
 constexpr uint32_t kStageBytesB = BN * BK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kOffStage = 0;
-constexpr uint32_t kOffBias = kStages * kStageBytes;          // 2 x BN floats: bias slice of the tile, per accumulator slot
+constexpr uint32_t kScratchBytes = 2 * 32 * 64;                // per epilogue warp: operand + output scratch, [32 rows][64 B] each
+constexpr uint32_t kOffScratch = kStages * kStageBytes;
+constexpr uint32_t kOffBias = kOffScratch + kEpiWarps * kScratchBytes;   // 2 x BN floats: bias slice of the tile, per accumulator slot
 constexpr uint32_t kOffBar = kOffBias + 2 * BN * 4;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024 /*align slack*/;
 
@@ -184,12 +190,54 @@ __device__ constexpr uint32_t kEpiMask[11] = {
     F_F32,                                                      // 10 wgrad
 };
 
-// One accumulator tile (this thread: row m, columns n_tile + 64*sl .. +16 for sl = 0..3).  The chunk's global
-// operands are fetched one slab ahead of their use, so their latency overlaps the previous slab's arithmetic.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// scratch addressing: [32 rows][64 B]; 16-byte chunk j (0..3) of row r, XOR-swizzled so that both the row-per-thread
+// and the coalesced (8 rows x 64 B per instruction) access patterns are bank-conflict free
+__device__ __forceinline__ uint32_t scr_addr(uint32_t S, int r, int j) {
+  return S + static_cast<uint32_t>(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+}
+
+// Asynchronous coalesced fetch of a bf16 [32 x 32] block (rows m0.., columns n0..) into a scratch:
+// instruction i moves rows 8i .. 8i+7, 64 contiguous bytes (two full sectors) each.
+__device__ __forceinline__ void block_fetch_async(uint32_t S, const __nv_bfloat16* base, int ld, int m0, int n0, int M, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), j = lane & 3;
+    if (m0 + r < M) cp_async16(scr_addr(S, r, j), base + static_cast<size_t>(m0 + r) * ld + n0 + j * 8);
+  }
+}
+// Coalesced store of a scratch (bf16 [32 x 32]) to global memory.
+__device__ __forceinline__ void block_store(uint32_t S, __nv_bfloat16* base, int ld, int m0, int n0, int M, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = 8 * i + (lane >> 2), j = lane & 3;
+    const uint4 v = lds128(scr_addr(S, r, j));
+    if (m0 + r < M) *reinterpret_cast<uint4*>(base + static_cast<size_t>(m0 + r) * ld + n0 + j * 8) = v;
+  }
+}
+
+constexpr int kHalf = 32;   // columns processed per pass of a warp over its 64-column slab
+
+// One [32 rows x 64 columns] block of an accumulator tile per warp (this thread: row m0 + lane), in two passes of
+// 32 columns.  SA: operand scratch (add0 / add1 / ymask blocks), SB: output scratch (mid / out / fp32 blocks).
+//   t_addr : TMEM address of (lane group, first column of the block);  sbias : bias of the block's 64 columns (smem)
+// The caller has already issued block_fetch_async(SA, add0, ...) for pass 0.
 template <uint32_t F>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& E, uint32_t t_addr, const float* sbias, int m, int n_tile) {
+__device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t SA, uint32_t SB,
+                                               int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
   constexpr bool kDyn = F == 0u;
-  constexpr int G8 = kChunk / 8;
+  const int m = m0 + lane;
   const bool row_ok = m < E.M;
   const bool has_bias = kDyn ? E.bias != nullptr : (F & F_BIAS) != 0;
   const bool lpre = kDyn ? (E.flags & LINKS_EPI_LEAKY_PRE) != 0 : (F & F_LPRE) != 0;
@@ -203,134 +251,158 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& E, uint32_t t_add
   const bool has_sign = kDyn ? E.sign_out != nullptr : (F & F_SIGN) != 0;
   const bool has_out = kDyn ? E.out != nullptr : (F & F_OUT) != 0;
   const bool has_f32 = kDyn ? E.out_f32 != nullptr : (F & F_F32) != 0;
-  const bool accum = (E.flags & LINKS_EPI_ACCUM_F32) != 0;
   const size_t mo = static_cast<size_t>(m);
-  const int sh = n_tile & 16;                                         // which half of the 32-column sign / bits words
+  const bool fast = E.vec_ok && (n_blk + kSlab <= E.N);               // warp-uniform
 
-  // prefetch registers (no lambdas / early returns here: the arrays must stay in registers)
-  uint4 q0[G8], q1[G8], qy[G8];
-  uint32_t bits_word = 0;
-#pragma unroll
-  for (int g = 0; g < G8; ++g) { q0[g] = make_uint4(0, 0, 0, 0); q1[g] = q0[g]; qy[g] = q0[g]; }
-#define LINKS_EPI_PREFETCH(N0)                                                                         \
-  {                                                                                                    \
-    const int pn = (N0);                                                                               \
-    if (row_ok && E.vec_ok && pn + kChunk <= E.N) {                                                    \
-      if (has_add0) {                                                                                  \
-        const uint4* pp = reinterpret_cast<const uint4*>(E.add0 + mo * E.ld_add0 + pn);                \
-        _Pragma("unroll") for (int g = 0; g < G8; ++g) q0[g] = __ldg(pp + g);                          \
-      }                                                                                                \
-      if (has_add1) {                                                                                  \
-        const uint4* pp = reinterpret_cast<const uint4*>(E.add1 + mo * E.ld_add1 + pn);                \
-        _Pragma("unroll") for (int g = 0; g < G8; ++g) q1[g] = __ldg(pp + g);                          \
-      }                                                                                                \
-      if (has_y) {                                                                                     \
-        const uint4* pp = reinterpret_cast<const uint4*>(E.ymask + mo * E.ld_ymask + pn);              \
-        _Pragma("unroll") for (int g = 0; g < G8; ++g) qy[g] = __ldg(pp + g);                          \
-      }                                                                                                \
-      if (has_bits) bits_word = __ldg(E.bits + mo * E.ld_bits + (pn >> 5)) >> sh;                      \
-    }                                                                                                  \
-  }
-  LINKS_EPI_PREFETCH(n_tile)
+  if (!fast) {
+    // tails / unaligned operands: element-wise path straight from TMEM, 16 columns at a time
 #pragma unroll 1
-  for (int sl = 0; sl < BN / 64; ++sl) {
-    const int n0 = n_tile + sl * 64;
-    if ((n0 & ~63) >= E.N) break;                                     // slab start beyond N: uniform over the CTA
-    const bool fast = row_ok && E.vec_ok && (n0 + kChunk <= E.N);
-    uint32_t acc[kChunk];
-    tmem_ld16(t_addr + static_cast<uint32_t>(sl * 64), acc);
-    if (fast) {
-      // move this slab's operands out of the prefetch registers, then fetch the next slab's
-      uint4 c0[G8], c1[G8], cy[G8];
+    for (int c = 0; c < kSlab / kChunk; ++c) {
+      uint32_t acc[kChunk];
+      tmem_ld16(t_addr + static_cast<uint32_t>(c * kChunk), acc);
+      if (row_ok && n_blk + c * kChunk < E.N) {
+        EpiParams Ec = E;                                             // copies: keep E itself in registers
+        epilogue_chunk_scalar(Ec, acc, m, n_blk + c * kChunk);
+      }
+    }
+    tc_fence_before();
+    mbar_arrive(acc_empty_bar);
+    return;
+  }
+
+#pragma unroll 1
+  for (int h = 0; h < kSlab / kHalf; ++h) {
+    const int n0 = n_blk + h * kHalf;
+    // ---- accumulator row -> registers; after the second pass the TMEM buffer is free for the MMA warp
+    float v[kHalf];
 #pragma unroll
-      for (int g = 0; g < G8; ++g) { c0[g] = q0[g]; c1[g] = q1[g]; cy[g] = qy[g]; }
-      const uint32_t cbits = bits_word;
-      if (sl + 1 < BN / 64) LINKS_EPI_PREFETCH(n0 + 64)
-      uint32_t sign_word = 0;
-      __nv_bfloat16* out_row = has_out ? E.out + mo * E.ld_out + n0 : nullptr;
-      __nv_bfloat16* mid_row = has_mid ? E.mid + mo * E.ld_mid + n0 : nullptr;
-      float* f32_row = has_f32 ? E.out_f32 + mo * E.ld_f32 + n0 : nullptr;
+    for (int c = 0; c < kHalf / kChunk; ++c) {
+      uint32_t acc[kChunk];
+      tmem_ld16(t_addr + static_cast<uint32_t>(h * kHalf + c * kChunk), acc);
 #pragma unroll
-      for (int g = 0; g < G8; ++g) {
-        float v[8];
+      for (int i = 0; i < kChunk; ++i) v[c * kChunk + i] = __uint_as_float(acc[i]);
+    }
+    if (h == kSlab / kHalf - 1) {
+      tc_fence_before();
+      mbar_arrive(acc_empty_bar);
+    }
+    uint32_t bits_word = 0;
+    if (has_bits && row_ok) bits_word = __ldg(E.bits + mo * E.ld_bits + (n0 >> 5));
+    if (has_bias) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g * 8 + i]);
-        if (has_bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(sbias + sl * 64 + g * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(sbias + sl * 64 + g * 8 + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (has_sign) {
+      for (int i = 0; i < kHalf; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(sbias + h * kHalf + i);
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+    if (has_sign) {
+      uint32_t sw = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sign_word |= (v[i] > 0.f ? 0u : 1u) << (g * 8 + i);
-        }
-        if (lpre) {
+      for (int i = 0; i < kHalf; ++i) sw |= (v[i] > 0.f ? 0u : 1u) << i;
+      if (row_ok) E.sign_out[mo * E.ld_sign + (n0 >> 5)] = sw;
+    }
+    if (lpre) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);      // == leaky for slope < 1
-        }
-        if (rpre) {
+      for (int i = 0; i < kHalf; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);      // == leaky for slope < 1
+    }
+    if (rpre) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (has_add0) {
-          float t[8]; unpack8_bf16(c0[g], t);
+      for (int i = 0; i < kHalf; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    // bf16 operand blocks: fetched coalesced into scratch SA, read back row-per-thread
+    if (has_add0) {
+      cp_async_wait_all();
+      __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += t[i];
-        }
-        if (has_add1) {
-          float t[8]; unpack8_bf16(c1[g], t);
+      for (int j = 0; j < 4; ++j) {
+        float t[8]; unpack8_bf16(lds128(scr_addr(SA, lane, j)), t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] += t[i];
-        }
-        if (lpost) {
+        for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
+      }
+      __syncwarp();
+    }
+    if (has_add1) {
+      block_fetch_async(SA, E.add1, E.ld_add1, m0, n0, E.M, lane);
+      cp_async_wait_all();
+      __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
-        }
-        if (has_y) {
-          float t[8]; unpack8_bf16(cy[g], t);
+      for (int j = 0; j < 4; ++j) {
+        float t[8]; unpack8_bf16(lds128(scr_addr(SA, lane, j)), t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = t[i] > 0.f ? v[i] : 0.01f * v[i];
-        }
-        if (has_mid)
-          *reinterpret_cast<uint4*>(mid_row + g * 8) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        if (has_bits) {
+        for (int i = 0; i < 8; ++i) v[j * 8 + i] += t[i];
+      }
+      __syncwarp();
+    }
+    if (has_y) block_fetch_async(SA, E.ymask, E.ld_ymask, m0, n0, E.M, lane);   // in flight during the leaky below
+    if (lpost) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = ((cbits >> (g * 8 + i)) & 1u) ? 0.01f * v[i] : v[i];
-        }
-        if (has_out)
-          *reinterpret_cast<uint4*>(out_row + g * 8) =
-              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        if (has_f32) {
-          float* p = f32_row + g * 8;
-          float4 o0 = make_float4(v[0], v[1], v[2], v[3]);
-          float4 o1 = make_float4(v[4], v[5], v[6], v[7]);
-          if (accum) {
-            const float4 a0 = *reinterpret_cast<const float4*>(p);
-            const float4 a1 = *reinterpret_cast<const float4*>(p + 4);
-            o0.x += a0.x; o0.y += a0.y; o0.z += a0.z; o0.w += a0.w;
-            o1.x += a1.x; o1.y += a1.y; o1.z += a1.z; o1.w += a1.w;
+      for (int i = 0; i < kHalf; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
+    }
+    if (has_y) {
+      cp_async_wait_all();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t[8]; unpack8_bf16(lds128(scr_addr(SA, lane, j)), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j * 8 + i] = t[i] > 0.f ? v[j * 8 + i] : 0.01f * v[j * 8 + i];
+      }
+      __syncwarp();
+    }
+    // SA is free: fetch the first operand of the next pass while this pass stores its results
+    if (has_add0 && h + 1 < kSlab / kHalf) block_fetch_async(SA, E.add0, E.ld_add0, m0, n0 + kHalf, E.M, lane);
+    if (has_mid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(scr_addr(SB, lane, j), make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                                pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7])));
+      __syncwarp();
+      block_store(SB, E.mid, E.ld_mid, m0, n0, E.M, lane);
+      __syncwarp();
+    }
+    if (has_bits) {
+#pragma unroll
+      for (int i = 0; i < kHalf; ++i) v[i] = ((bits_word >> i) & 1u) ? 0.01f * v[i] : v[i];
+    }
+    if (has_out) {
+#ifdef LINKS_GEMM_TRACE
+      if (!(E.flags & (1u << 30)))
+#endif
+      {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(scr_addr(SB, lane, j), make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                                  pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7])));
+        __syncwarp();
+        block_store(SB, E.out, E.ld_out, m0, n0, E.M, lane);
+        __syncwarp();
+      }
+    }
+    if (has_f32) {
+      // fp32 [32 x 32] block in two quarters of 16 columns (one scratch row = 16 floats); coalesced read-modify-write
+      const bool accum = (E.flags & LINKS_EPI_ACCUM_F32) != 0;
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(scr_addr(SB, lane, j), make_uint4(__float_as_uint(v[qq * 16 + j * 4]), __float_as_uint(v[qq * 16 + j * 4 + 1]),
+                                                  __float_as_uint(v[qq * 16 + j * 4 + 2]), __float_as_uint(v[qq * 16 + j * 4 + 3])));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + (lane >> 2), j = lane & 3;
+          const uint4 q = lds128(scr_addr(SB, r, j));
+          if (m0 + r < E.M) {
+            float4* p = reinterpret_cast<float4*>(E.out_f32 + static_cast<size_t>(m0 + r) * E.ld_f32 + n0 + qq * 16 + j * 4);
+            float4 o = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+            if (accum) { const float4 a = *p; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+            *p = o;
           }
-          *reinterpret_cast<float4*>(p) = o0;
-          *reinterpret_cast<float4*>(p + 4) = o1;
         }
+        __syncwarp();
       }
-      if (has_sign)
-        reinterpret_cast<unsigned short*>(E.sign_out + mo * E.ld_sign + (n0 >> 5))[sh >> 4] = static_cast<unsigned short>(sign_word);
-    } else {
-      if (row_ok && n0 < E.N) {                                      // tails / unaligned operands
-        // pass COPIES: taking the address of E / acc themselves would pin them in local memory for the fast path too
-        EpiParams Ec = E;
-        uint32_t acc_c[kChunk];
-#pragma unroll
-        for (int i = 0; i < kChunk; ++i) acc_c[i] = acc[i];
-        epilogue_chunk_scalar(Ec, acc_c, m, n0);
-      }
-      if (sl + 1 < BN / 64) LINKS_EPI_PREFETCH(n0 + 64)
     }
   }
-#undef LINKS_EPI_PREFETCH
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -471,9 +543,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
   } else {
     // ================= epilogue warps (256 threads) =================
     const int lane_grp = warp & 3;                                    // TMEM lanes 32*lane_grp .. +31
-    const int quarter = (warp - 2) >> 2;                              // which 16 columns of each 64-column slab
-    const int r = lane_grp * 32 + lane;
+    const int slab = (warp - 2) >> 2;                                 // which 64 columns of the tile
     const bool store_thread = threadIdx.x == 64;
+    const uint32_t S = base + kOffScratch + static_cast<uint32_t>(warp - 2) * kScratchBytes;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord(G, tile);
@@ -490,6 +562,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
         mode = P.epi_mode;
       }
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
+      const int m0 = tc.tm * BM + lane_grp * 32, n0 = tc.tn * BN + slab * kSlab;
+      // first residual operand of this warp's block: fetched while the main loop of the tile is still running
+      if (E.add0 != nullptr && E.vec_ok && n0 + kSlab <= E.N) block_fetch_async(S, E.add0, E.ld_add0, m0, n0, E.M, lane);
       // stage the tile's bias slice in shared memory (one global round trip per tile instead of one per 8 columns);
       // slot-indexed double buffer: the readers of this buffer two tiles ago are long past the barrier below
       float* sbias = reinterpret_cast<float*>(smem_raw + (base + kOffBias - raw)) + slot * BN;
@@ -501,23 +576,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       mbar_wait(bars + (GB_ACCFULL + slot) * 8, acc_use & 1u);
       tc_fence_after();
       if (store_thread && lt < 3) TRACE(3 + 3 * lt);
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + slot * kAccCols + quarter * kChunk;
-      const int m = tc.tm * BM + r, n_tile = tc.tn * BN + quarter * kChunk;
-      switch (mode) {
-        case 1: epilogue_tile<kEpiMask[1]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 2: epilogue_tile<kEpiMask[2]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 3: epilogue_tile<kEpiMask[3]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 4: epilogue_tile<kEpiMask[4]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 5: epilogue_tile<kEpiMask[5]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 6: epilogue_tile<kEpiMask[6]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 7: epilogue_tile<kEpiMask[7]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 8: epilogue_tile<kEpiMask[8]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 9: epilogue_tile<kEpiMask[9]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        case 10: epilogue_tile<kEpiMask[10]>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
-        default: epilogue_tile<0u>(E, t_addr, sbias + quarter * kChunk, m, n_tile); break;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + slot * kAccCols + slab * kSlab;
+      const uint32_t ae = bars + (GB_ACCEMPTY + slot) * 8;
+      if (n0 >= E.N) {
+        // this warp's slab lies entirely beyond N: nothing to do but release the accumulator
+        tc_fence_before();
+        mbar_arrive(ae);
+      } else {
+        const float* sb = sbias + slab * kSlab;
+        switch (mode) {
+          case 1: epilogue_block<kEpiMask[1]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 2: epilogue_block<kEpiMask[2]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 3: epilogue_block<kEpiMask[3]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 4: epilogue_block<kEpiMask[4]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 5: epilogue_block<kEpiMask[5]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 6: epilogue_block<kEpiMask[6]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 7: epilogue_block<kEpiMask[7]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 8: epilogue_block<kEpiMask[8]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 9: epilogue_block<kEpiMask[9]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 10: epilogue_block<kEpiMask[10]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          default: epilogue_block<0u>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+        }
       }
-      tc_fence_before();
-      mbar_arrive(bars + (GB_ACCEMPTY + slot) * 8);
       if (store_thread && lt < 3) TRACE(4 + 3 * lt);
     }
     if (store_thread) TRACE(14);
