@@ -169,7 +169,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from links_b200 import _cabi
-    from links_b200.steps import LifterStep
+    from links_b200.steps import LifterStep, StepGroup
     from links_b200.synth import synth_poses
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,9 +203,14 @@ def run_gpu(args):
         host_losses[0].copy_(lt.losses, non_blocking=True)
         host_losses[1].copy_(lr.losses, non_blocking=True)
 
+    group = StepGroup([lt, lr])      # the two independent lifter steps run as parallel branches of one graph
+
     def one_step():
-        lt.step()
-        lr.step()
+        if args.serial:
+            lt.step()
+            lr.step()
+        else:
+            group.step()
 
     # ---- count launches of one eager step (also serves as warm-up / lazy init)
     upload()
@@ -303,6 +308,8 @@ def run_gpu(args):
                                    "B=%d poses per GPU (N=%d rows), 17 joints" % (B, 2 * B),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                        "cuda_graph": graph is not None,
+                       "branches": "LT and LR steps serial on one stream" if args.serial else
+                                   "LT and LR steps as parallel branches (2 streams) of one CUDA graph",
                        "l2_policy": "no explicit flush: each step streams ~%.1f GB of activations/weights/gradients, "
                                     "far above the 126 MB L2" % (2 * 2048 * 1024 * 2 * 2 * 60 * (B / 1024) / 1e9),
                        "operands": "bf16 operands + bf16-stored activations, fp32 accumulate / master weights / losses",
@@ -336,6 +343,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=256, help="poses per step of the bounded CPU sample")
     ap.add_argument("--impl", default="links_b200", choices=["links_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="run the LT and LR steps back to back on one stream")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

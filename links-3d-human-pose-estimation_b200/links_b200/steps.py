@@ -155,3 +155,44 @@ class LifterStep:
 
     def set_lr(self, lr):
         self.cfg["lr"] = lr
+
+
+class StepGroup:
+    """Independent step objects (e.g. the leg/torso and the left/right lifter steps of one batch) run as parallel
+    branches: step i is issued on its own stream forked from / joined to the caller's stream, so inside one captured
+    CUDA graph the branches overlap -- one branch's few-CTA kernels (flows, geometry, heads) and launch gaps are
+    filled by the other branch's GEMM tiles."""
+
+    def __init__(self, steps):
+        self.steps = list(steps)
+        self.streams = [torch.cuda.Stream() for _ in self.steps[1:]]
+        self.graph = None
+
+    def step(self):
+        main = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(main)
+        for step, st in zip(self.steps[1:], self.streams):
+            with torch.cuda.stream(st):
+                step.step()
+        self.steps[0].step()
+        for st in self.streams:
+            main.wait_stream(st)
+
+    def capture(self, warmup=2):
+        """Capture step() into one CUDA graph (replay with .replay()).  Eager warm-up runs first (lazy inits)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
