@@ -119,6 +119,15 @@ int links_colsum_bf16_batched(const LinksColsumItem* items, int n_items, void* s
 int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
                       void* stream);
 
+/* The same for all layers of a network set in one launch (bf16 shadows W[N, ldw] only). */
+#define LINKS_MAX_CAST_ITEMS 128
+typedef struct LinksCastItem {
+  const float* W;  /* fp32 [N, K] */
+  void* Wb;        /* bf16 [N, ldw], columns >= K are written as zero */
+  int N, K, ldw, pad_;
+} LinksCastItem;
+int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* stream);
+
 /* torch.optim.Adam step with coupled L2 decay (train_leg_torso_lifter.py:111-114), flat buffers.
  * The step number t (bias correction) is `step` (>= 1), or, when step_dev != NULL, *step_dev + 1 read on the
  * device; *step_dev is then incremented after the update, so a captured CUDA graph replays correctly.

@@ -82,6 +82,20 @@ extern "C" __attribute__((visibility("default"))) int links_cast_weight(const fl
   return links_launch_status();
 }
 
+extern "C" __attribute__((visibility("default"))) int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* stream) {
+  LINKS_CHECK_PTR(items);
+  if (n_items < 1 || n_items > LINKS_MAX_CAST_ITEMS) return LINKS_E_RANGE;
+  CastBatch B;
+  memset(&B, 0, sizeof(B));
+  for (int i = 0; i < n_items; ++i) {
+    if (!items[i].W || !items[i].Wb || items[i].N < 1 || items[i].K < 1 || items[i].ldw < items[i].K) return LINKS_E_ARG;
+    B.it[i] = items[i];
+  }
+  B.n = n_items;
+  cast_weight_batched_kernel<<<dim3(64, n_items), 256, 0, links_stream(stream)>>>(B);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
                                float grad_scale, void* stream) {

@@ -104,6 +104,48 @@ __global__ void cast_weight_kernel(const float* __restrict__ W, int N, int K, __
   }
 }
 
+// Batched shadow refresh: all layers of a network set in one launch.  grid = (row-slabs, items); a warp converts rows
+// of fp32 W[N,K] to bf16 Wb[N, ldw] (columns >= K zero) with 8-element vectors when the layout allows.
+struct alignas(16) CastBf8 { __nv_bfloat16 v[8]; };
+struct CastBatch {
+  LinksCastItem it[LINKS_MAX_CAST_ITEMS];
+  int n;
+};
+__global__ void cast_weight_batched_kernel(const CastBatch B) {
+  const LinksCastItem& I = B.it[blockIdx.y];
+  const int N = I.N, K = I.K, ldw = I.ldw;
+  const float* __restrict__ W = I.W;
+  __nv_bfloat16* __restrict__ Wb = static_cast<__nv_bfloat16*>(I.Wb);
+  const bool vec = (K % 8 == 0) && (ldw % 8 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(Wb) & 15u) == 0);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (vec) {
+    const int kv = ldw / 8;
+    const size_t total = static_cast<size_t>(N) * kv;
+    for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+      const int n = static_cast<int>(e / kv), k = static_cast<int>(e - static_cast<size_t>(n) * kv) * 8;
+      CastBf8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = __float2bfloat16_rn(0.f);
+      if (k < K) {
+        const float4 a = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + k);
+        const float4 b = *reinterpret_cast<const float4*>(W + static_cast<size_t>(n) * K + k + 4);
+        o.v[0] = __float2bfloat16_rn(a.x); o.v[1] = __float2bfloat16_rn(a.y);
+        o.v[2] = __float2bfloat16_rn(a.z); o.v[3] = __float2bfloat16_rn(a.w);
+        o.v[4] = __float2bfloat16_rn(b.x); o.v[5] = __float2bfloat16_rn(b.y);
+        o.v[6] = __float2bfloat16_rn(b.z); o.v[7] = __float2bfloat16_rn(b.w);
+      }
+      *reinterpret_cast<CastBf8*>(Wb + static_cast<size_t>(n) * ldw + k) = o;
+    }
+  } else {
+    const size_t total = static_cast<size_t>(N) * ldw;
+    for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+      const int n = static_cast<int>(e / ldw), k = static_cast<int>(e - static_cast<size_t>(n) * ldw);
+      Wb[e] = __float2bfloat16_rn(k < K ? W[static_cast<size_t>(n) * K + k] : 0.f);
+    }
+  }
+}
+
 // torch.optim.Adam (coupled L2 weight decay), same operation order as torch's single-tensor path:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g;
 //   denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= (lr/(1-b1^t)) * m/denom

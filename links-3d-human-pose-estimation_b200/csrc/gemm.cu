@@ -67,6 +67,8 @@ struct alignas(64) GemmProblemDev {
   float* out_f32;
   __nv_bfloat16* out;
   __nv_bfloat16* mid;
+  int a_boxes, b_boxes; // TMA boxes per stage actually needed (MN-major: 64-wide slabs; K-major: 1)
+  uint32_t stage_tx;    // bytes the boxes of one stage deliver (small M / N problems load smaller boxes)
   int vec_ok;           // every present epilogue operand is 16-byte aligned with a vector-friendly leading dimension
   int epi_mode;         // index into kEpiMask (0 = run-time flags)
 };
@@ -135,38 +137,40 @@ struct EpiParams {
   __nv_bfloat16* mid;
 };
 
-// Scalar path for one 16-column chunk of row m: N tails and operands that are not 16-byte aligned (heads,
-// upscale dgrad / wgrad).  Same arithmetic, element by element.  n0 is a multiple of 16: the chunk owns one half of
-// a 32-column sign / bits word.
-__device__ __noinline__ void epilogue_chunk_scalar(const EpiParams& E, const uint32_t (&acc)[kChunk], int m, int n0) {
+// Element-wise path for one 16-column chunk of row m: N tails and operands that are not 16-byte aligned (heads,
+// upscale dgrad / wgrad).  Same arithmetic as the vector path.  Fully inlined on purpose: a noinline helper would pin
+// the parameter block and the accumulators in local memory (measured: ~0.5 us per element).
+__device__ __forceinline__ void epilogue_chunk_scalar(const EpiParams& E, const uint32_t (&acc)[kChunk], const float* sbias16,
+                                                      int m, int n0) {
   const int sh = n0 & 16;
+  const size_t mo = static_cast<size_t>(m);
   uint32_t bits_word = 0;
-  if (E.bits) bits_word = E.bits[static_cast<size_t>(m) * E.ld_bits + (n0 >> 5)] >> sh;
+  if (E.bits) bits_word = __ldg(E.bits + mo * E.ld_bits + (n0 >> 5)) >> sh;
   uint32_t sign_word = 0;
-#pragma unroll 1
+  const bool accum = (E.flags & LINKS_EPI_ACCUM_F32) != 0;
+#pragma unroll
   for (int i = 0; i < kChunk; ++i) {
     const int n = n0 + i;
-    if (n >= E.N) break;
-    float v = __uint_as_float(acc[i]);
-    if (E.bias) v += __ldg(E.bias + n);
-    sign_word |= (v > 0.f ? 0u : 1u) << i;
-    if (E.flags & LINKS_EPI_LEAKY_PRE) v = links_leaky(v);
-    if (E.flags & LINKS_EPI_RELU_PRE) v = fmaxf(v, 0.f);
-    if (E.add0) v += __bfloat162float(E.add0[static_cast<size_t>(m) * E.ld_add0 + n]);
-    if (E.add1) v += __bfloat162float(E.add1[static_cast<size_t>(m) * E.ld_add1 + n]);
-    if (E.flags & LINKS_EPI_LEAKY_POST) v = links_leaky(v);
-    if (E.ymask) v *= (__bfloat162float(E.ymask[static_cast<size_t>(m) * E.ld_ymask + n]) > 0.f ? 1.f : 0.01f);
-    if (E.mid) E.mid[static_cast<size_t>(m) * E.ld_mid + n] = __float2bfloat16_rn(v);
-    if (E.bits) v *= ((bits_word >> i) & 1u) ? 0.01f : 1.f;
-    if (E.out) E.out[static_cast<size_t>(m) * E.ld_out + n] = __float2bfloat16_rn(v);
-    if (E.out_f32) {
-      float* p = E.out_f32 + static_cast<size_t>(m) * E.ld_f32 + n;
-      *p = (E.flags & LINKS_EPI_ACCUM_F32) ? *p + v : v;
+    if (n < E.N) {
+      float v = __uint_as_float(acc[i]) + sbias16[i];                 // staged bias (zero when the problem has none)
+      sign_word |= (v > 0.f ? 0u : 1u) << i;
+      if (E.flags & LINKS_EPI_LEAKY_PRE) v = links_leaky(v);
+      if (E.flags & LINKS_EPI_RELU_PRE) v = fmaxf(v, 0.f);
+      if (E.add0) v += __bfloat162float(E.add0[mo * E.ld_add0 + n]);
+      if (E.add1) v += __bfloat162float(E.add1[mo * E.ld_add1 + n]);
+      if (E.flags & LINKS_EPI_LEAKY_POST) v = links_leaky(v);
+      if (E.ymask) v *= (__bfloat162float(E.ymask[mo * E.ld_ymask + n]) > 0.f ? 1.f : 0.01f);
+      if (E.mid) E.mid[mo * E.ld_mid + n] = __float2bfloat16_rn(v);
+      if (E.bits) v *= ((bits_word >> i) & 1u) ? 0.01f : 1.f;
+      if (E.out) E.out[mo * E.ld_out + n] = __float2bfloat16_rn(v);
+      if (E.out_f32) {
+        float* p = E.out_f32 + mo * E.ld_f32 + n;
+        *p = accum ? *p + v : v;
+      }
     }
   }
   if (E.sign_out)
-    reinterpret_cast<unsigned short*>(E.sign_out + static_cast<size_t>(m) * E.ld_sign + (n0 >> 5))[sh >> 4] =
-        static_cast<unsigned short>(sign_word);
+    reinterpret_cast<unsigned short*>(E.sign_out + mo * E.ld_sign + (n0 >> 5))[sh >> 4] = static_cast<unsigned short>(sign_word);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -260,10 +264,7 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
     for (int c = 0; c < kSlab / kChunk; ++c) {
       uint32_t acc[kChunk];
       tmem_ld16(t_addr + static_cast<uint32_t>(c * kChunk), acc);
-      if (row_ok && n_blk + c * kChunk < E.N) {
-        EpiParams Ec = E;                                             // copies: keep E itself in registers
-        epilogue_chunk_scalar(Ec, acc, m, n_blk + c * kChunk);
-      }
+      if (row_ok && n_blk + c * kChunk < E.N) epilogue_chunk_scalar(E, acc, sbias + c * kChunk, m, n_blk + c * kChunk);
     }
     tc_fence_before();
     mbar_arrive(acc_empty_bar);
@@ -482,19 +483,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
           const uint32_t s = it % kStages, use = it / kStages;
           mbar_wait(bars + (GB_EMPTY + s) * 8, (use & 1u) ^ 1u);
           const uint32_t full = bars + (GB_FULL + s) * 8;
-          mbar_expect_tx(full, kStageBytes);
+          mbar_expect_tx(full, P.stage_tx);
           const uint32_t sA = base + kOffStage + s * kStageBytes, sB = sA + kStageBytesA;
           if (!a_mn) {
             tma_load_2d(sA, &P.tmA, full, kb * BK, tc.tm * BM);
           } else {
 #pragma unroll
-            for (int q = 0; q < BM / 64; ++q) tma_load_2d(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
+            for (int q = 0; q < BM / 64; ++q)
+              if (q < P.a_boxes) tma_load_2d(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
           }
           if (!b_mn) {
             tma_load_2d(sB, &P.tmB, full, kb * BK, tc.tn * BN);
           } else {
 #pragma unroll
-            for (int q = 0; q < BN / 64; ++q) tma_load_2d(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + q * 64, kb * BK);
+            for (int q = 0; q < BN / 64; ++q)
+              if (q < P.b_boxes) tma_load_2d(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + q * 64, kb * BK);
           }
         }
       }
@@ -547,6 +550,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
     const bool store_thread = threadIdx.x == 64;
     const uint32_t S = base + kOffScratch + static_cast<uint32_t>(warp - 2) * kScratchBytes;
     uint32_t lt = 0;
+    const int bias_t = threadIdx.x - 64;
+    float bias_next = 0.f;
+    if (bias_t < BN && static_cast<int>(blockIdx.x) < G.total_tiles) {
+      const TileCoord t0 = tile_coord(G, blockIdx.x);
+      const float* bp = G.p[t0.pi].bias;
+      const int nb = t0.tn * BN + bias_t;
+      if (bp != nullptr && nb < G.p[t0.pi].N) bias_next = __ldg(bp + nb);
+    }
     for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord(G, tile);
       // register copy of the problem's epilogue parameters (an indexed constant-bank load per use otherwise)
@@ -565,14 +576,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       const int m0 = tc.tm * BM + lane_grp * 32, n0 = tc.tn * BN + slab * kSlab;
       // first residual operand of this warp's block: fetched while the main loop of the tile is still running
       if (E.add0 != nullptr && E.vec_ok && n0 + kSlab <= E.N) block_fetch_async(S, E.add0, E.ld_add0, m0, n0, E.M, lane);
-      // stage the tile's bias slice in shared memory (one global round trip per tile instead of one per 8 columns);
-      // slot-indexed double buffer: the readers of this buffer two tiles ago are long past the barrier below
+      // the tile's bias slice lives in shared memory (slot-indexed double buffer); its global load was issued one
+      // tile earlier (bias_next), so only the barrier that publishes it is on the critical path
       float* sbias = reinterpret_cast<float*>(smem_raw + (base + kOffBias - raw)) + slot * BN;
-      {
-        const int t = threadIdx.x - 64, nb = tc.tn * BN + t;
-        if (t < BN) sbias[t] = (E.bias != nullptr && nb < E.N) ? __ldg(E.bias + nb) : 0.f;
-      }
+      if (bias_t < BN) sbias[bias_t] = bias_next;
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      {
+        const int nt = tile + gridDim.x;
+        bias_next = 0.f;
+        if (bias_t < BN && nt < G.total_tiles) {
+          const TileCoord tn2 = tile_coord(G, nt);
+          const float* bp = G.p[tn2.pi].bias;
+          const int nb = tn2.tn * BN + bias_t;
+          if (bp != nullptr && nb < G.p[tn2.pi].N) bias_next = __ldg(bp + nb);
+        }
+      }
       mbar_wait(bars + (GB_ACCFULL + slot) * 8, acc_use & 1u);
       tc_fence_after();
       if (store_thread && lt < 3) TRACE(3 + 3 * lt);
@@ -657,9 +675,14 @@ static int build_group(EncodeTiledFn fn, const LinksGemmProblem* problems, int n
     const bool a_mn = (s.flags & LINKS_GEMM_A_MN) != 0, b_mn = (s.flags & LINKS_GEMM_B_MN) != 0;
     if (!aligned16(s.A) || !aligned16(s.B) || (s.lda & 7) || (s.ldb & 7)) return LINKS_E_ALIGN;
     if (s.lda < (a_mn ? s.M : s.K) || s.ldb < (b_mn ? s.N : s.K)) return LINKS_E_ALIGN;
-    int rc = a_mn ? encode_2d(fn, &d.tmA, s.A, s.K, s.M, s.lda, 64, BK) : encode_2d(fn, &d.tmA, s.A, s.M, s.K, s.lda, BK, BM);
+    // small problems load smaller boxes: rows the MMA never needs are not fetched (or zero-filled) at all
+    const int a_rows = s.M >= BM ? BM : ((s.M + 7) & ~7), b_rows = s.N >= BN ? BN : ((s.N + 15) & ~15);
+    d.a_boxes = a_mn ? (s.M >= BM ? BM / 64 : (s.M + 63) / 64) : 1;
+    d.b_boxes = b_mn ? (s.N >= BN ? BN / 64 : (s.N + 63) / 64) : 1;
+    d.stage_tx = static_cast<uint32_t>((a_mn ? d.a_boxes * 64 : a_rows) * BK * 2 + (b_mn ? d.b_boxes * 64 : b_rows) * BK * 2);
+    int rc = a_mn ? encode_2d(fn, &d.tmA, s.A, s.K, s.M, s.lda, 64, BK) : encode_2d(fn, &d.tmA, s.A, s.M, s.K, s.lda, BK, a_rows);
     if (rc) return rc;
-    rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, BN);
+    rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, b_rows);
     if (rc) return rc;
     d.M = s.M; d.N = s.N; d.K = s.K;
     d.tile_begin = tiles;

@@ -38,6 +38,13 @@ class ColsumItem(C.Structure):
 MAX_COLSUM_ITEMS = 96
 
 
+class CastItem(C.Structure):
+    _fields_ = [("W", vp), ("Wb", vp), ("N", ci), ("K", ci), ("ldw", ci), ("pad_", ci)]
+
+
+MAX_CAST_ITEMS = 128
+
+
 class GeomMaps(C.Structure):
     _fields_ = [("V", ci), ("n_joints", ci * 2), ("src_net", (ci * 17) * 2), ("col", ci * 17),
                 ("part_net", (ci * 17) * 2), ("part_idx", (ci * 17) * 2), ("bone_rel", cf * 16),
@@ -51,6 +58,7 @@ SIGNATURES = {
     "links_colsum_bf16": (ci, [vp, ci, ci, ci, vp, ci]),
     "links_colsum_bf16_batched": (ci, [C.POINTER(ColsumItem), ci]),
     "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
+    "links_cast_weight_batched": (ci, [C.POINTER(CastItem), ci]),
     "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),

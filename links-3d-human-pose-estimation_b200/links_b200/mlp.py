@@ -178,11 +178,19 @@ class MlpSet:
         return out
 
     def refresh_shadows(self):
+        """fp32 master weights -> bf16 shadows, all layers in one launch per 128 layers."""
+        if getattr(self, "_cast_batches", None) is None:
+            items = [(L.W.data_ptr(), L.Wb.data_ptr(), L.N, L.K, L.Kp) for net in self.nets for L in net.layers.values()]
+            self._cast_batches = []
+            for i in range(0, len(items), _cabi.MAX_CAST_ITEMS):
+                chunk = items[i:i + _cabi.MAX_CAST_ITEMS]
+                arr = (_cabi.CastItem * len(chunk))()
+                for j, (w, wb, N, K, ldw) in enumerate(chunk):
+                    arr[j].W, arr[j].Wb, arr[j].N, arr[j].K, arr[j].ldw = w, wb, N, K, ldw
+                self._cast_batches.append((arr, len(chunk)))
         st = torch.cuda.current_stream().cuda_stream
-        for net in self.nets:
-            for L in net.layers.values():
-                check(self.lib.links_cast_weight(L.W.data_ptr(), L.N, L.K, L.Wb.data_ptr(), L.Kp, None, 0, st),
-                      "links_cast_weight")
+        for arr, n in self._cast_batches:
+            check(self.lib.links_cast_weight_batched(arr, n, st), "links_cast_weight_batched")
 
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0):
         st = torch.cuda.current_stream().cuda_stream

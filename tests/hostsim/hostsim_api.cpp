@@ -48,6 +48,14 @@ SIM int sim_cast_weight(const float* W, int N, int K, void* Wb, int ldw, void* W
   hostsim::launch(dim3(kx, ny), dim3(32, 8), 0, [&] { cast_weight_kernel(W, N, K, (bf16*)Wb, ldw, (bf16*)WT, ldwt); });
   return 0;
 }
+SIM int sim_cast_weight_batched(const LinksCastItem* items, int n_items) {
+  CastBatch B;
+  memset(&B, 0, sizeof(B));
+  for (int i = 0; i < n_items; ++i) B.it[i] = items[i];
+  B.n = n_items;
+  hostsim::launch(dim3(2, n_items), dim3(64), 0, [&] { cast_weight_batched_kernel(B); });
+  return 0;
+}
 SIM int sim_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
                       float wd, int step, int* step_dev, float grad_scale) {
   hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale); });
