@@ -76,6 +76,9 @@ class LifterStep:
         self._w = torch.tensor([c["weight_3d"], c["weight_2d"], c["weight_velocity"], c["weight_bl"],
                                 c["weight_likeli"], c["weight_likeli"]], **f32)
         self.graph = None
+        # the two part-flow NLL kernels (few CTAs each, ~0.3 ms) run on forked streams next to the pass-2 GEMMs;
+        # they are joined right before the geometry backward that consumes their input gradients
+        self._flow_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
 
     # ------------------------------------------------------------------------------------------
     def _st(self):
@@ -105,10 +108,15 @@ class LifterStep:
         check(L.links_geom_forward(mp, *common, N, self.qpart[0].data_ptr(), self.qpart[1].data_ptr(),
                                    self.qfull[0].data_ptr(), self.qfull[1].data_ptr(), self._st()), "links_geom_forward")
         self.scal.zero_()
+        main = torch.cuda.current_stream()
+        for s in range(2):
+            fs = self._flow_streams[s]
+            fs.wait_stream(main)
+            with torch.cuda.stream(fs):
+                self.part_flows[s].nll_fwdbwd(self.qpart[s], self.cfg["weight_likeli"] / N, self.scal[4 + s:5 + s],
+                                              self.dflow[s])
         for s in range(2):
             self._pack(self.qpart[s], self.idx_q[s], 2 * self.nj[s], 1, s)
-            self.part_flows[s].nll_fwdbwd(self.qpart[s], self.cfg["weight_likeli"] / N, self.scal[4 + s:5 + s],
-                                          self.dflow[s])
         m.run(m.forward_plan(1))
         g2 = [m.G[1][s]["downscale"] for s in range(2)]
         check(L.links_geom_loss(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), N, self.scal.data_ptr(),
@@ -116,6 +124,8 @@ class LifterStep:
         m.run(m.backward_plan(1, need_input_grad=True))
         g1 = [m.G[0][s]["downscale"] for s in range(2)]
         ga = [m.G[0][s]["angles"] for s in range(2)]
+        for fs in self._flow_streams:
+            main.wait_stream(fs)
         check(L.links_geom_backward(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), self.dflow[0].data_ptr(),
                                     self.dflow[1].data_ptr(), m.din[1][0].data_ptr(), m.din[1][1].data_ptr(), N,
                                     g1[0].data_ptr(), g1[1].data_ptr(), None, None, 0, 0,
