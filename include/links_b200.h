@@ -130,7 +130,8 @@ int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* str
 
 /* torch.optim.Adam step with coupled L2 decay (train_leg_torso_lifter.py:111-114), flat buffers.
  * The step number t (bias correction) is `step` (>= 1), or, when step_dev != NULL, *step_dev + 1 read on the
- * device; *step_dev is then incremented after the update, so a captured CUDA graph replays correctly.
+ * device; *step_dev is then incremented after the update (unless step == -1: used when one optimiser step is issued as
+ * several per-bucket launches), so a captured CUDA graph replays correctly.
  * Gradients are multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
 int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,

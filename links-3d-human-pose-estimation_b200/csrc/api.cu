@@ -106,7 +106,7 @@ extern "C" __attribute__((visibility("default"))) int links_adam_step(float* par
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev, step, grad_scale);
-  if (step_dev != nullptr) adam_incr_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev);
+  if (step_dev != nullptr && step >= 0) adam_incr_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev);
   return links_launch_status();
 }
 

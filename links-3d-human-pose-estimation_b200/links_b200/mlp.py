@@ -68,7 +68,7 @@ class MlpSet:
                 names += [(blk + ".l1", None), (blk + ".l2", None)]
             names.append((head, br))
         self.layer_names = [n for n, _ in names]
-        sizes = []
+        dims = {}
         for s in range(self.S):
             for n, br in names:
                 if n == "upscale":
@@ -77,36 +77,60 @@ class MlpSet:
                     K, N = WIDTH, head_dims[s][n]
                 else:
                     K, N = WIDTH, WIDTH
-                sizes.append((s, n, K, N))
+                dims[(s, n)] = (K, N)
+        # Gradient buckets in the order the backward pass completes them (heads + deepest blocks first, upscale last).
+        # The flat buffers are laid out bucket by bucket (all networks of a bucket adjacent), so a finished bucket is
+        # ONE contiguous range: one all-reduce + one Adam + one shadow-cast launch, issued while backward continues.
+        depth = max(len(blocks) for blocks, _ in self.branches.values())
+        buckets = []
+        for i in range(depth - 1, -1, -1):
+            b = []
+            for br, (blocks, head) in self.branches.items():
+                if i == len(blocks) - 1:
+                    b.append(head)
+                if i < len(blocks):
+                    b += [blocks[i] + ".l2", blocks[i] + ".l1"]
+            buckets.append(b)
+        tail = []
+        for blk in reversed(self.trunk):
+            tail += [blk + ".l2", blk + ".l1"]
+        tail.append("upscale")
+        buckets.append(tail)
+        assert sorted(n for b in buckets for n in b) == sorted(self.layer_names)
+        self.buckets = buckets
         # every weight / bias view starts on a 256-byte boundary of the flat buffers: the GEMM epilogue only takes
         # its vector path for 16-byte aligned operands (a 7x1024+7 head would otherwise misalign everything after it)
-        total = sum(_rup(K * N, 64) + _rup(N, 64) for _, _, K, N in sizes)
+        order = [(s, n) for b in buckets for s in range(self.S) for n in b]
+        total = sum(_rup(K * N, 64) + _rup(N, 64) for K, N in (dims[k] for k in order))
         self.n_params = total      # padded length of the flat buffers (padding stays zero through Adam)
-        self.n_params_real = sum(K * N + N for _, _, K, N in sizes)
+        self.n_params_real = sum(K * N + N for K, N in dims.values())
         self.master = torch.zeros(total, dtype=torch.float32, device=dev)
         if train:
             self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
             self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
             self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.nets = []
+        layers = [dict() for _ in range(self.S)]
+        self.bucket_ranges = []
         off = 0
-        cur = {}
-        for s, n, K, N in sizes:
-            L = _Layer()
-            L.name, L.K, L.N = n, K, N
-            L.Kp = _rup(K, 64)
-            L.Np = _rup(N, 64)
-            L.W = self.master[off:off + N * K].view(N, K)
-            L.gW = self.grad[off:off + N * K].view(N, K) if train else None
-            off += _rup(N * K, 64)
-            L.b = self.master[off:off + N]
-            L.gb = self.grad[off:off + N] if train else None
-            off += _rup(N, 64)
-            L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
-            cur[n] = L
-            if n == names[-1][0]:
-                self.nets.append(_Net(cur))
-                cur = {}
+        for b in buckets:
+            start = off
+            for s in range(self.S):
+                for n in b:
+                    K, N = dims[(s, n)]
+                    L = _Layer()
+                    L.name, L.K, L.N = n, K, N
+                    L.Kp = _rup(K, 64)
+                    L.Np = _rup(N, 64)
+                    L.W = self.master[off:off + N * K].view(N, K)
+                    L.gW = self.grad[off:off + N * K].view(N, K) if train else None
+                    off += _rup(N * K, 64)
+                    L.b = self.master[off:off + N]
+                    L.gb = self.grad[off:off + N] if train else None
+                    off += _rup(N, 64)
+                    L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
+                    layers[s][n] = L
+            self.bucket_ranges.append((start, off))
+        self.nets = [_Net({n: layers[s][n] for n in self.layer_names}) for s in range(self.S)]
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
         # ---- activation / gradient workspaces
         M = self.M
@@ -177,27 +201,40 @@ class MlpSet:
             out[n + ".bias"] = L.b.detach().clone()
         return out
 
-    def refresh_shadows(self):
-        """fp32 master weights -> bf16 shadows, all layers in one launch per 128 layers."""
-        if getattr(self, "_cast_batches", None) is None:
-            items = [(L.W.data_ptr(), L.Wb.data_ptr(), L.N, L.K, L.Kp) for net in self.nets for L in net.layers.values()]
-            self._cast_batches = []
+    def _cast_plan(self, bucket=None):
+        key = ("cast", bucket)
+        if key not in self._plans:
+            names = self.layer_names if bucket is None else self.buckets[bucket]
+            items = [(net.layers[n].W.data_ptr(), net.layers[n].Wb.data_ptr(), net.layers[n].N, net.layers[n].K,
+                      net.layers[n].Kp) for net in self.nets for n in names]
+            batches = []
             for i in range(0, len(items), _cabi.MAX_CAST_ITEMS):
                 chunk = items[i:i + _cabi.MAX_CAST_ITEMS]
                 arr = (_cabi.CastItem * len(chunk))()
                 for j, (w, wb, N, K, ldw) in enumerate(chunk):
                     arr[j].W, arr[j].Wb, arr[j].N, arr[j].K, arr[j].ldw = w, wb, N, K, ldw
-                self._cast_batches.append((arr, len(chunk)))
+                batches.append((arr, len(chunk)))
+            self._plans[key] = batches
+        return self._plans[key]
+
+    def refresh_shadows(self, bucket=None):
+        """fp32 master weights -> bf16 shadows (all layers, or the layers of one gradient bucket), one launch."""
         st = torch.cuda.current_stream().cuda_stream
-        for arr, n in self._cast_batches:
+        for arr, n in self._cast_plan(bucket):
             check(self.lib.links_cast_weight_batched(arr, n, st), "links_cast_weight_batched")
 
-    def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0):
+    def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0, bucket=None,
+                  last=True):
+        """Adam on the whole flat buffer, or on one bucket's contiguous range.  The device-side step counter is
+        advanced by the call with last=True (the other buckets of the same step pass last=False)."""
         st = torch.cuda.current_stream().cuda_stream
-        check(self.lib.links_adam_step(self.master.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
-                                       self.exp_avg_sq.data_ptr(), self.n_params, lr, betas[0], betas[1], eps,
-                                       weight_decay, 0, self.step_dev.data_ptr(), grad_scale, st), "links_adam_step")
-        self.refresh_shadows()
+        a, b = (0, self.n_params) if bucket is None else self.bucket_ranges[bucket]
+        es = 4
+        check(self.lib.links_adam_step(self.master.data_ptr() + a * es, self.grad.data_ptr() + a * es,
+                                       self.exp_avg.data_ptr() + a * es, self.exp_avg_sq.data_ptr() + a * es, b - a, lr,
+                                       betas[0], betas[1], eps, weight_decay, 0 if last else -1, self.step_dev.data_ptr(),
+                                       grad_scale, st), "links_adam_step")
+        self.refresh_shadows(bucket)
 
     # ------------------------------------------------------------------------------------------
     # launch planning
@@ -289,15 +326,23 @@ class MlpSet:
         self._plans[key] = ops
         return ops
 
-    def backward_plan(self, p, need_input_grad, rows=None):
+    def backward_plan(self, p, need_input_grad, rows=None, wgrad=False):
         """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64], zero beyond the head width) filled by the
         loss kernels.  Outputs: G of every layer, optionally self.din[p][s] = d/d(input part) fp32.
         dX = G . W reads the forward shadow W [N, Kp] as an MN-major B operand."""
-        key = ("bwd", p, need_input_grad, rows)
+        """With wgrad=True (the LAST pass to run backward) the weight-gradient GEMMs of a bucket are issued as soon as
+        the dgrad chain has completed its G buffers, each followed by a ("bucket", b) marker: run(plan, on_bucket)
+        calls on_bucket(b) there so the step driver can start the bucket's all-reduce / Adam on another stream."""
+        key = ("bwd", p, need_input_grad, rows, wgrad)
         if key in self._plans:
             return self._plans[key]
         M = rows or self.M
         ops = []
+
+        def bucket_done(b):
+            if wgrad:
+                ops.extend(self._wgrad_ops(b, rows))
+                ops.append(("bucket", b))
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
         active = self.pass_branches[p]
 
@@ -343,6 +388,8 @@ class MlpSet:
             ops.append(self._launch(probs))
 
         depth = max(len(self.branches[br][0]) for br in active)
+        full_depth = max(len(blocks) for blocks, _ in self.branches.values())
+        assert not wgrad or depth == full_depth, "the wgrad pass must run every branch"
         for i in range(depth - 1, -1, -1):
             brs = [br for br in active if i < len(self.branches[br][0])]
             l2_dgrad([(s, self.branches[br][0][i]) for br in brs for s in range(self.S)])
@@ -360,6 +407,9 @@ class MlpSet:
                     assert len(brs) == 2
                     l1_dgrad([(s, self.branches[brs[0]][0][0], prev, "raw") for s in range(self.S)])
                     l1_dgrad([(s, self.branches[brs[1]][0][0], prev, "merge") for s in range(self.S)])
+            # G of level i (and of the heads for the deepest level) is final and the level's weights have been read for
+            # the last time in this step: its bucket may be reduced / updated while the chain continues
+            bucket_done(full_depth - 1 - i)
         for t in range(len(self.trunk) - 1, -1, -1):
             blk = self.trunk[t]
             l2_dgrad([(s, blk) for s in range(self.S)])
@@ -374,6 +424,7 @@ class MlpSet:
                 probs.append(self._prob(G[s]["upscale"], L.Wb, M, L.K, WIDTH, WIDTH, L.Kp, flags=GEMM_B_MN,
                                         out_f32=self.din[p][s]))
             ops.append(self._launch(probs))
+        bucket_done(len(self.buckets) - 1)
         self._plans[key] = ops
         return ops
 
@@ -407,19 +458,14 @@ class MlpSet:
                 return [p for p in range(self.n_passes) if br in self.pass_branches[p]]
         raise KeyError(name)
 
-    def wgrad_plan(self, rows=None):
-        """dW = G^T . X contracted over the rows of every pass that used the layer (G and X read as MN-major
-        operands straight from their row-major buffers); db = column sums of G."""
-        key = ("wgrad", rows)
-        if key in self._plans:
-            return self._plans[key]
+    def _wgrad_ops(self, bucket, rows=None):
+        """dW = G^T . X of one bucket's layers, contracted over the rows of every pass that used the layer (G and X read
+        as MN-major operands straight from their row-major buffers); db = column sums of G."""
         M = rows or self.M
         assert rows is None or self.n_passes == 1, "partial rows only supported for single-pass sets"
-        ops = []
-        probs = []
-        colsums = []
+        probs, colsums = [], []
         for s in range(self.S):
-            for n in self.layer_names:
+            for n in self.buckets[bucket]:
                 L = self.nets[s].layers[n]
                 passes = self._layer_passes(n)
                 assert passes == list(range(len(passes))), "passes using a layer must be a prefix"
@@ -430,7 +476,7 @@ class MlpSet:
                 probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
                                         out_f32=L.gW, ld_f32=L.K))
                 colsums.append((Gb.data_ptr(), Gb.stride(0), Kc, L.N, L.gb.data_ptr(), 0))
-        ops.append(self._launch(probs))
+        ops = [self._launch(probs)]
         fn = self.lib.links_colsum_bf16_batched
         batches = []
         for i in range(0, len(colsums), _cabi.MAX_COLSUM_ITEMS):
@@ -447,10 +493,23 @@ class MlpSet:
                 if rc:
                     check(rc, "links_colsum_bf16_batched")
         ops.append(run_colsums)
-        self._plans[key] = ops
         return ops
 
+    def wgrad_plan(self, rows=None):
+        """All weight / bias gradients (every bucket), for callers that do not interleave them with backward."""
+        key = ("wgrad", rows)
+        if key not in self._plans:
+            ops = []
+            for b in range(len(self.buckets)):
+                ops.extend(self._wgrad_ops(b, rows))
+            self._plans[key] = ops
+        return self._plans[key]
+
     @staticmethod
-    def run(ops):
+    def run(ops, on_bucket=None):
         for op in ops:
-            op()
+            if isinstance(op, tuple):
+                if on_bucket is not None:
+                    on_bucket(op[1])
+            else:
+                op()

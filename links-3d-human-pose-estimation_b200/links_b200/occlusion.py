@@ -19,7 +19,8 @@ OCC_OUT = {n: len(maps.occ_target_index(n)) for n in OCC_NAMES}
 
 
 class OcclusionStep:
-    def __init__(self, batch, lifter_params, predictor_params, cfg=None, device="cuda", process_group=None):
+    def __init__(self, batch, lifter_params, predictor_params, cfg=None, device="cuda", process_group=None,
+                 comm_stream=None):
         """lifter_params: [leg, torso] state dicts; predictor_params: dict OCC_NAMES -> state dict."""
         if batch % 2:
             raise ValueError("split_data_left_right_3d (utils/helpers.py:81-91) needs an even batch")
@@ -51,11 +52,23 @@ class OcclusionStep:
         self.idx_tgt = [torch.tensor(maps.occ_target_index(n), **i32) for n in OCC_NAMES]
         self.loss_sums = torch.zeros(8, **f32)
         self.losses = torch.zeros(9, **f32)
+        self.comm = comm_stream if comm_stream is not None else torch.cuda.Stream(device=dev)
+
+    def _on_bucket(self, b):
+        main = torch.cuda.current_stream()
+        self.comm.wait_stream(main)
+        m = self.mlp
+        with torch.cuda.stream(self.comm):
+            if self.world > 1:
+                a, e = m.bucket_ranges[b]
+                torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+            m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
+                        last=(b == len(m.buckets) - 1))
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream
 
-    def forward_backward(self):
+    def forward_backward(self, fused_optimizer=False):
         L, B, m, lf = self.lib, self.B, self.mlp, self.lifters
         st = self._st()
         for s in range(2):
@@ -83,9 +96,11 @@ class OcclusionStep:
                 check(L.links_occ_mse(pred.data_ptr(), pred.stride(0), self.pose[r].data_ptr(), self.idx_tgt[s].data_ptr(),
                                       n_out, B, 1.0 / B, self.loss_sums[s:s + 1].data_ptr(),
                                       m.G[r][s]["downscale"].data_ptr(), None, 0, 0, st), "links_occ_mse")
-        for r in range(3):
+        for r in range(2):
             m.run(m.backward_plan(r, need_input_grad=False))
-        m.run(m.wgrad_plan())
+        m.run(m.backward_plan(2, need_input_grad=False, wgrad=True), on_bucket=self._on_bucket if fused_optimizer else None)
+        if fused_optimizer:
+            torch.cuda.current_stream().wait_stream(self.comm)
         self.losses[:8] = self.loss_sums / B
         self.losses[8] = self.losses[:8].sum()
 
@@ -95,8 +110,7 @@ class OcclusionStep:
         self.mlp.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world)
 
     def step(self):
-        self.forward_backward()
-        self.optimizer_step()
+        self.forward_backward(fused_optimizer=True)
 
     def loss_dict(self):
         v = self.losses.tolist()

@@ -31,7 +31,7 @@ class LifterStep:
     """kind = 'lt' (Leg_Lifter + Torso_Lifter) or 'lr' (left + right Left_Right_Lifter)."""
 
     def __init__(self, kind, batch, lifter_params, part_flow_params, full_flow_params, cfg=None, device="cuda",
-                 process_group=None):
+                 process_group=None, comm_stream=None):
         self.kind = kind
         self.cfg = dict(DEFAULT_CFG)
         self.cfg.update(cfg or {})
@@ -79,6 +79,10 @@ class LifterStep:
         # the two part-flow NLL kernels (few CTAs each, ~0.3 ms) run on forked streams next to the pass-2 GEMMs;
         # they are joined right before the geometry backward that consumes their input gradients
         self._flow_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        # gradient buckets are all-reduced (NCCL), Adam-updated and re-cast on this stream as soon as the backward
+        # pass has produced them, overlapping the rest of backward.  Steps that run concurrently (StepGroup) must
+        # share ONE comm stream so that every rank issues its collectives in the same order.
+        self.comm = comm_stream if comm_stream is not None else torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------------------------------
     def _st(self):
@@ -90,8 +94,21 @@ class LifterStep:
                                        m.x0[p][s].data_ptr(), None, 0, 0, self._st()),
               "links_pack_rows")
 
-    def forward_backward(self):
-        """Everything of one step up to (and including) the gradients; no optimiser."""
+    def _on_bucket(self, b):
+        """Bucket b of the flat gradient buffer is final: all-reduce + Adam + shadow refresh on the comm stream."""
+        main = torch.cuda.current_stream()
+        self.comm.wait_stream(main)
+        m = self.mlp
+        with torch.cuda.stream(self.comm):
+            if self.world > 1:
+                a, e = m.bucket_ranges[b]
+                torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+            m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
+                        last=(b == len(m.buckets) - 1))
+
+    def forward_backward(self, fused_optimizer=False):
+        """Everything of one step up to (and including) the gradients.  fused_optimizer=True also runs the
+        per-bucket all-reduce / Adam / shadow refresh overlapped with the backward pass (what step() does)."""
         L, m, N = self.lib, self.mlp, self.N
         mp = C.byref(self.maps)
         self.full_flow.sample(self.x, self.noise, self.u)
@@ -135,8 +152,9 @@ class LifterStep:
                                            self.stats.data_ptr(), self.dgamma.data_ptr(), self.scal[6:8].data_ptr(), N,
                                            ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, self._st()),
               "links_geom_backward_angles")
-        m.run(m.backward_plan(0, need_input_grad=False))
-        m.run(m.wgrad_plan())
+        m.run(m.backward_plan(0, need_input_grad=False, wgrad=True), on_bucket=self._on_bucket if fused_optimizer else None)
+        if fused_optimizer:
+            main.wait_stream(self.comm)
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
         t = self.scal[:6] * self._norm
         self.losses[:6] = t
@@ -149,8 +167,7 @@ class LifterStep:
         self.mlp.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world)
 
     def step(self):
-        self.forward_backward()
-        self.optimizer_step()
+        self.forward_backward(fused_optimizer=True)
 
     def loss_dict(self):
         v = self.losses.tolist()
@@ -177,6 +194,10 @@ class StepGroup:
         self.steps = list(steps)
         self.streams = [torch.cuda.Stream() for _ in self.steps[1:]]
         self.graph = None
+        # one comm stream for all branches: collectives are issued (and captured) in one deterministic order on every
+        # rank; two NCCL kernels of one communicator racing on different streams would deadlock
+        for st in self.steps[1:]:
+            st.comm = self.steps[0].comm
 
     def step(self):
         main = torch.cuda.current_stream()
@@ -188,6 +209,7 @@ class StepGroup:
         self.steps[0].step()
         for st in self.streams:
             main.wait_stream(st)
+        main.wait_stream(self.steps[0].comm)
 
     def capture(self, warmup=2):
         """Capture step() into one CUDA graph (replay with .replay()).  Eager warm-up runs first (lazy inits)."""
