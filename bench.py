@@ -212,12 +212,18 @@ def run_gpu(args):
         else:
             group.step()
 
+    def stage(msg):
+        if args.verbose:
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
     # ---- count launches of one eager step (also serves as warm-up / lazy init)
+    stage("built steps")
     upload()
     counter = _cabi.install_launch_counter()
     one_step()
     launches_per_step = counter.stop()
     torch.cuda.synchronize()
+    stage("first eager step done")
 
     # ---- capture the whole step in a CUDA graph (falls back to eager launches if capture is unavailable)
     side = torch.cuda.Stream()
@@ -238,6 +244,7 @@ def run_gpu(args):
                 print("[bench] CUDA graph capture failed (%s); timing eager launches" % e, file=sys.stderr)
             graph = None
     run = (lambda: graph.replay()) if graph is not None else one_step
+    stage("graph captured: %s" % (graph is not None))
 
     def barrier():
         if world > 1:
@@ -265,7 +272,9 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    stage("warm-up done")
     ms_total = timed(run, K)
+    stage("timed region done")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end: pinned host inputs -> H2D, step, losses -> D2H, every step
@@ -330,8 +339,14 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL work; drop them before the communicator goes away.  Tearing the process group down
+        # with captured collectives alive was observed to hang on exit, so leave without running destructors.
+        graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -343,6 +358,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=256, help="poses per step of the bounded CPU sample")
     ap.add_argument("--impl", default="links_b200", choices=["links_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--serial", action="store_true", help="run the LT and LR steps back to back on one stream")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
