@@ -1,0 +1,199 @@
+"""Plain training / evaluation harness behind the drop-in scripts (replaces the pytorch_lightning 1.x harness of the
+reference, which is not installable here -- SURVEY F4): same step order, same optimiser / scheduler settings, same
+checkpoint file names, synthetic data when no dataset pickle is available.
+
+Reference: train_leg_torso_lifter.py:61-121,376-398, train_left_right_lifter.py:59-119,541-560,
+train_occlusion_models.py:81-142,547-570, eval_h36m.py:27-99."""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+from . import init as INIT
+from .occlusion import OCC_IN, OCC_NAMES, OCC_OUT, EvalRunner, OcclusionStep
+from .shard import shard_bounds
+from .steps import LifterStep
+from .synth import synth_poses
+
+LR0, GAMMA = 2e-4, 0.95          # config.learning_rate, ExponentialLR(gamma=0.95) stepped per epoch
+
+
+def add_common_args(p, batch=256, epochs=100):
+    """Flags the reference does not have (the reference's own flags are declared by each script, verbatim)."""
+    g = p.add_argument_group("links_b200 additions")
+    g.add_argument("--synthetic", type=int, default=65536, help="number of synthetic training poses (no dataset is shipped)")
+    g.add_argument("--batch", type=int, default=batch, help="global batch size (reference: config.BATCH_SIZE)")
+    g.add_argument("--epochs", type=int, default=epochs, help="reference: config.N_epochs")
+    g.add_argument("--steps", type=int, default=0, help="stop after this many optimiser steps (0 = run all epochs)")
+    g.add_argument("--seed", type=int, default=0)
+    g.add_argument("--weights-dir", default="models", help="where pretrained flows / lifters are read from and results saved")
+    g.add_argument("--log-every", type=int, default=50)
+    g.add_argument("--no-save", action="store_true")
+    return p
+
+
+def dist_setup():
+    """One process per GPU under torchrun (NCCL over NVLink); single process otherwise."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = torch.distributed.group.WORLD
+    return rank, world, pg
+
+
+def load_state(path, fallback):
+    """Reference checkpoints are plain state dicts (torch.save(module.state_dict())).  Without one, seeded random init."""
+    if os.path.exists(path):
+        return {k: v.float() for k, v in torch.load(path, map_location="cpu").items()}
+    print("[links_b200] %s not found: using seeded random initialisation" % path, file=sys.stderr)
+    return fallback()
+
+
+def save_module_state(module_cls, kwargs, params, path):
+    """Save with the reference's full key set (unused LayerNorm / res_common entries included)."""
+    m = module_cls(**kwargs)
+    m.load_state_dict(params, strict=False)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    torch.save(m.state_dict(), path)
+
+
+class SyntheticLoader:
+    """Epochs of shuffled batches of this rank's shard of a synthetic pose set, staged through pinned host memory."""
+
+    def __init__(self, n, batch_global, rank, world, seed):
+        x2d, gt = synth_poses(n, seed=1234 + seed)
+        b, e = shard_bounds(n, rank, world)
+        self.x = torch.from_numpy(x2d[b:e]).pin_memory()
+        self.gt = torch.from_numpy(gt[b:e])
+        self.batch = batch_global // world
+        if self.batch % 2 or self.batch < 2:
+            raise ValueError("per-rank batch must be even (row pairs / split_data_left_right_3d)")
+        self.gen = torch.Generator().manual_seed(seed * 1000 + rank)
+
+    def __len__(self):
+        return self.x.shape[0] // self.batch
+
+    def __iter__(self):
+        perm = torch.randperm(self.x.shape[0], generator=self.gen)
+        for i in range(len(self)):
+            yield self.x[perm[i * self.batch:(i + 1) * self.batch]].pin_memory()
+
+
+def run_training(step, loader, args, rank, feed):
+    """Epoch loop: feed(step, batch) uploads inputs + draws, step.step() does the rest on the device."""
+    n_steps, t0 = 0, time.time()
+    lr = LR0
+    for epoch in range(args.epochs):
+        step.set_lr(lr)
+        for xb in loader:
+            feed(step, xb)
+            step.step()
+            n_steps += 1
+            if rank == 0 and n_steps % args.log_every == 0:
+                torch.cuda.synchronize()
+                d = step.loss_dict()
+                print("epoch %d step %d  %s  (%.0f poses/s)" % (epoch, n_steps, " ".join("%s=%.5f" % kv for kv in d.items()),
+                                                                n_steps * args.batch / (time.time() - t0)), flush=True)
+            if args.steps and n_steps >= args.steps:
+                torch.cuda.synchronize()
+                return n_steps
+        lr *= GAMMA                                   # training_epoch_end: ExponentialLR.step()
+    torch.cuda.synchronize()
+    return n_steps
+
+
+def lifter_feed(gen_dev):
+    def feed(step, xb):
+        B = xb.shape[0]
+        step.x.copy_(xb, non_blocking=True)
+        step.noise.normal_(generator=gen_dev)        # add_noise eps (utils/helpers.py:298-308)
+        step.eps_x.normal_(generator=gen_dev)        # elevation draw (train_leg_torso_lifter.py:169-171)
+        step.u_y.uniform_(generator=gen_dev)         # azimuth draw (:176)
+        assert B == step.B
+    return feed
+
+
+def train_lifters(kind, args):
+    rank, world, pg = dist_setup()
+    cfg = dict(depth=args.translation, weight_bl=args.bl, weight_2d=args.rep2d, weight_3d=args.rot3d,
+               weight_likeli=args.likelihood, weight_velocity=args.velocity)
+    wd = args.weights_dir
+    if kind == "lt":
+        nj, names = (7, 10), ("leg_lifter.pt", "torso_lifter.pt")
+        flow_files = ("leg_norm_flow.pt", "torso_norm_flow.pt")
+    else:
+        nj, names = (11, 11), ("left_side_lifter_final.pt", "right_side_lifter_final.pt")
+        flow_files = ("left_norm_flow.pt", "right_norm_flow.pt")
+    nets = [INIT.init_lifter_params(n, 11 + i + args.seed) for i, n in enumerate(nj)]
+    flows = [load_state(os.path.join(wd, f), lambda C=2 * n, s=41 + i: INIT.init_flow_params(C, s))
+             for i, (f, n) in enumerate(zip(flow_files, nj))]
+    full = load_state(os.path.join(wd, "full_pose_norm_flow.pt"), lambda: INIT.init_flow_params(34, 40))
+    loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
+    step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
+    gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
+    n = run_training(step, loader, args, rank, lifter_feed(gen_dev))
+    if rank == 0 and not args.no_save:
+        from utils import models_def as MD
+        cls = (MD.Leg_Lifter, MD.Torso_Lifter) if kind == "lt" else (MD.Left_Right_Lifter, MD.Left_Right_Lifter)
+        for s in range(2):
+            save_module_state(cls[s], dict(use_batchnorm=False, num_joints=nj[s], use_dropout=False, d_rate=0.25),
+                              step.mlp.state_dict(s), os.path.join(wd, names[s]))
+    return n, step
+
+
+OCC_FILES = {"left_arm": "left_arm_estimator.pt", "right_arm": "right_arm_estimator.pt", "left_leg": "left_leg_estimator.pt",
+             "right_leg": "right_leg_estimator.pt", "left": "left_side_estimator.pt", "right": "right_side_estimator.pt",
+             "both_legs": "both_legs_estimator.pt", "torso": "torso_estimator.pt"}
+
+
+def train_occlusion(args):
+    rank, world, pg = dist_setup()
+    wd = args.weights_dir
+    lifters = [load_state(os.path.join(wd, "leg_lifter.pt"), lambda: INIT.init_lifter_params(7, 11)),
+               load_state(os.path.join(wd, "torso_lifter.pt"), lambda: INIT.init_lifter_params(10, 12))]
+    preds = {n: INIT.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i + args.seed) for i, n in enumerate(OCC_NAMES)}
+    loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
+    step = OcclusionStep(loader.batch, lifters, preds, cfg=dict(depth=args.translation), process_group=pg)
+    gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
+
+    def feed(st, xb):
+        st.x.copy_(xb, non_blocking=True)
+        st.u_y[0].uniform_(generator=gen_dev)        # Ry augmentation draws (train_occlusion_models.py:213-217,256-260)
+        st.u_y[1].uniform_(generator=gen_dev)
+    n = run_training(step, loader, args, rank, feed)
+    if rank == 0 and not args.no_save:
+        from utils import models_def as MD
+        classes = {"left_arm": MD.Occluded_Limb_Predictor, "right_arm": MD.Occluded_Limb_Predictor,
+                   "left_leg": MD.Occluded_Limb_Predictor, "right_leg": MD.Occluded_Limb_Predictor,
+                   "left": MD.Occluded_Left_Right_Predictor, "right": MD.Occluded_Left_Right_Predictor,
+                   "both_legs": MD.Occluded_Legs_Predictor, "torso": MD.Occluded_Torso_Predictor}
+        for s, name in enumerate(OCC_NAMES):
+            key = name if name in OCC_FILES else name.replace("_side", "")
+            save_module_state(classes[key], dict(use_batchnorm=False, num_joints=OCC_IN[name] // 3), step.mlp.state_dict(s),
+                              os.path.join(wd, "occlusion_model_weights", OCC_FILES[key]))
+    return n, step
+
+
+def evaluate(args):
+    """eval_h36m.py:27-99 on a (sharded) synthetic test set: prints PA-MPJPE ('best') and N-MPJPE."""
+    rank, world, pg = dist_setup()
+    wd = args.weights_dir
+    lifters = [load_state(os.path.join(wd, "left_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 13)),
+               load_state(os.path.join(wd, "right_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 14))]
+    x2d, gt = synth_poses(args.synthetic, seed=4321 + args.seed)
+    b, e = shard_bounds(args.synthetic, rank, world, multiple=1)
+    ev = EvalRunner("lr", lifters, chunk=args.chunk, choice="right", process_group=pg)
+    xs, gs = torch.from_numpy(x2d[b:e]).pin_memory(), torch.from_numpy(gt[b:e]).pin_memory()
+    for i in range(0, e - b, args.chunk):
+        ev.run_chunk(xs[i:i + args.chunk].cuda(non_blocking=True), gs[i:i + args.chunk].cuda(non_blocking=True))
+    out = ev.result()
+    if rank == 0:
+        print("PA-MPJPE: %.4f" % out["pa_mpjpe"])
+        print("N-MPJPE: %.4f" % out["n_mpjpe"])
+    return out

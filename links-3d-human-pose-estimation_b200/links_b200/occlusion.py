@@ -112,6 +112,9 @@ class OcclusionStep:
     def step(self):
         self.forward_backward(fused_optimizer=True)
 
+    def set_lr(self, lr):
+        self.cfg["lr"] = lr
+
     def loss_dict(self):
         v = self.losses.tolist()
         d = {"threed_loss_" + n: v[i] for i, n in enumerate(OCC_NAMES)}
@@ -169,9 +172,8 @@ class EvalRunner:
         self.count += n
 
     def result(self):
-        sums, count = self.sums.clone(), torch.tensor([float(self.count)], dtype=torch.float64, device=self.device)
-        if self.pg is not None:
-            torch.distributed.all_reduce(sums, group=self.pg)
-            torch.distributed.all_reduce(count, group=self.pg)
-        s = (sums / count).tolist()
-        return {"n_mpjpe": s[0], "pa_mpjpe": s[1], "pa_mpjpe_batch": s[2], "count": int(count.item())}
+        """Single final reduction over ranks (per-rank double sums + counts)."""
+        from .shard import reduce_eval_sums
+        s, total = reduce_eval_sums(self.sums.clone(), self.count, self.pg) if self.pg is not None else \
+            ((self.sums / max(self.count, 1)).tolist(), self.count)
+        return {"n_mpjpe": s[0], "pa_mpjpe": s[1], "pa_mpjpe_batch": s[2], "count": total}

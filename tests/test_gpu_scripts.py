@@ -1,0 +1,40 @@
+"""GPU: the drop-in scripts (reference CLI preserved) run end to end on synthetic data: a few optimiser steps, the
+reference's checkpoint file names / key sets, and evaluation from those checkpoints."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "links-3d-human-pose-estimation_b200")
+
+
+def _run(script, *args):
+    env = dict(os.environ, WANDB_MODE="disabled")
+    r = subprocess.run([sys.executable, os.path.join(PKG, script)] + list(args), capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_lifter_scripts_train_save_eval(tmp_path):
+    wd = str(tmp_path)
+    out = _run("train_left_right_lifter.py", "-b", "50", "-t", "10", "--synthetic", "1024", "--batch", "128", "--steps", "6",
+               "--log-every", "3", "--weights-dir", wd)
+    assert "step 6" in out and "loss=" in out
+    sd = torch.load(os.path.join(wd, "left_side_lifter_final.pt"))
+    assert len(sd) == 62 and sd["downscale.weight"].shape == (11, 1024) and "res_pose2.bn1.weight" in sd
+    out = _run("train_leg_torso_lifter.py", "--synthetic", "1024", "--batch", "128", "--steps", "4", "--log-every", "2",
+               "--weights-dir", wd, "-l", "0.5")
+    assert "step 4" in out
+    assert os.path.exists(os.path.join(wd, "leg_lifter.pt")) and os.path.exists(os.path.join(wd, "torso_lifter.pt"))
+    out = _run("eval_h36m.py", "--synthetic", "5000", "--chunk", "2048", "--weights-dir", wd)
+    assert "PA-MPJPE:" in out and "N-MPJPE:" in out
+    out = _run("train_occlusion_models.py", "-n", "26", "--synthetic", "512", "--batch", "64", "--steps", "3", "--log-every", "1",
+               "--weights-dir", wd)
+    assert "step 3" in out
+    sd = torch.load(os.path.join(wd, "occlusion_model_weights", "torso_estimator.pt"))
+    assert len(sd) == 36 and sd["downscale.weight"].shape == (30, 1024)
