@@ -58,7 +58,7 @@ int links_device_ok(void);
  *   LEAKY_PRE : v = v > 0 ? v : 0.01 v      (RELU_PRE : v = max(v, 0))
  *   v += add0[m,n]  ; v += add1[m,n]                     [bf16]
  *   LEAKY_POST: v = v > 0 ? v : 0.01 v
- *   v *= (ymask[m,n] > 0 ? 1 : 0.01)                     [bf16 activation, leaky' of its producer]
+ *   v *= (ymask[m,n] > 0 ? 1 : 0.01)                     [bf16 activation, leaky' of its producer; 0 with YMASK_ZERO]
  *   mid[m,n] = bf16(v)
  *   v *= (bits(m,n) ? 0.01 : 1)
  *   out[m,n] = bf16(v); out_f32[m,n] (+)= v
@@ -69,6 +69,7 @@ int links_device_ok(void);
 #define LINKS_EPI_ACCUM_F32 8u
 #define LINKS_GEMM_A_MN 16u
 #define LINKS_GEMM_B_MN 32u
+#define LINKS_EPI_YMASK_ZERO 64u   /* ymask multiplies by 0 instead of 0.01 where ymask <= 0 (ReLU') */
 
 typedef struct LinksGemmProblem {
   const void* A;      /* bf16 [M, lda]  (A_MN: [K, lda]) */
@@ -207,6 +208,16 @@ int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, i
 /* nll[m] = 0.5*|z|^2 - log_jac_det, nll_sum += sum_m nll, dx = scale * d(nll)/dx (frozen flow). */
 int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
                           float* nll_sum, float* dx, void* stream);
+/* Training a flow (train_full_pose_norm_flow.py:75-98): NLL forward + backward as above, and in addition, per coupling
+ * block k, the operands of the parameter-gradient GEMMs -- ex_x1[k] = subnet input x1 (bf16 [M,64], first c1 columns)
+ * and ex_dsub[k] = d nll / d subnet output (bf16 [M,64], first 2*c2 columns; the caller keeps the padding zero) -- and
+ * the row-reduced gradients of the global affine, d_gscale / d_goffset fp32 [n_blocks, C] (accumulated).  With these
+ *   dW2 = ex_dsub^T . relu(x1 W1^T + b1),  db2 = colsum(ex_dsub),
+ *   dW1 = ((ex_dsub . W2) * relu')^T . x1, db1 = colsum of that,
+ * which the host issues as grouped GEMMs (links_gemm_grouped).  Tensor-core kernel for every M. */
+int links_flow_nll_train(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
+                         float* nll_sum, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale, float* d_goffset,
+                         void* stream);
 /* Vector-Jacobian product of the forward map (z, log_jac_det) = inn(x):
  * dx = (dz/dx)^T gz + (d log_jac_det/dx)^T gld  (gld may be NULL = 0).  Backs autograd of the FrEIA shim. */
 int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,

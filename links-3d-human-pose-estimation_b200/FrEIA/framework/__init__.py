@@ -38,7 +38,7 @@ class SequenceINN(nn.Module):
     """``inn = SequenceINN(C); inn.append(AllInOneBlock, subnet_constructor=..., permute_soft=True)`` ...
     ``z, log_jac_det = inn(x)``, ``x, log_jac_det = inn(z, rev=True)``.  Gradients flow to the *input*
     (frozen flows, as in the lifter trainers); training the flow's own parameters goes through
-    ``links_b200.flowtrain`` (train_full_pose_norm_flow.py drop-in)."""
+    ``links_b200.flowtrain.FlowTrainStep`` (train_full_pose_norm_flow.py drop-in)."""
 
     def __init__(self, *dims, force_tuple_output=False):
         super().__init__()
@@ -83,7 +83,7 @@ class SequenceINN(nn.Module):
         if not x_or_z.is_cuda:
             raise _cabi.LinksError("links_b200 SequenceINN runs on a B200 only (no CPU fallback)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("parameter gradients of the flow are provided by links_b200.flowtrain.FlowTrainer; "
+            raise NotImplementedError("parameter gradients of the flow are provided by links_b200.flowtrain.FlowTrainStep; "
                                       "freeze the flow (requires_grad=False) or wrap the call in torch.no_grad()")
         out, ld = _FlowFn.apply(self, x_or_z, bool(rev))
         return ((out,), ld) if (self.force_tuple_output or force_tuple_output) else (out, ld)

@@ -279,6 +279,7 @@ static int launch_flow_tc_c(const FlowArgs& A, cudaStream_t s) {
   T.packed = reinterpret_cast<const unsigned char*>(A.packed + static_cast<size_t>(flow_block_floats(C)) * A.n_blocks);
   T.x = A.x; T.noise = A.noise; T.out = A.out; T.ld = A.ld; T.nll_sum = A.nll_sum; T.scale = A.scale;
   T.gz = A.gz; T.gld = A.gld; T.M = A.M; T.n_blocks = A.n_blocks;
+  T.ex_x1 = A.ex_x1; T.ex_dsub = A.ex_dsub; T.d_gscale = A.d_gscale; T.d_goffset = A.d_goffset;
   const int blocks = (A.M + kTcRows - 1) / kTcRows;
   flow_tc_kernel<C, MODE><<<blocks, kTcThreads, kTcSmemBytes, s>>>(T);
   return links_launch_status();
@@ -326,6 +327,31 @@ extern "C" __attribute__((visibility("default"))) int links_flow_nll_fwdbwd(cons
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = n_blocks;
   return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
+}
+
+template <int MODE>
+static int launch_flow_tc_only(int C, const FlowArgs& A, cudaStream_t s) {
+  switch (C) {
+    case 14: return launch_flow_tc_c<14, MODE>(A, s);
+    case 20: return launch_flow_tc_c<20, MODE>(A, s);
+    case 22: return launch_flow_tc_c<22, MODE>(A, s);
+    case 32: return launch_flow_tc_c<32, MODE>(A, s);
+    case 34: return launch_flow_tc_c<34, MODE>(A, s);
+    default: return LINKS_E_RANGE;
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int links_flow_nll_train(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
+                                    float* nll_sum, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale,
+                                    float* d_goffset, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(ex_x1); LINKS_CHECK_PTR(ex_dsub);
+  LINKS_CHECK_PTR(d_gscale); LINKS_CHECK_PTR(d_goffset); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = n_blocks;
+  A.ex_x1 = ex_x1; A.ex_dsub = ex_dsub; A.d_gscale = d_gscale; A.d_goffset = d_goffset;
+  return launch_flow_tc_only<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,

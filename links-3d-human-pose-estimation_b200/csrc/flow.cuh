@@ -94,6 +94,10 @@ struct FlowArgs {
   float scale;          // NLL_FWDBWD: dx = scale * d nll / dx
   const float* gz;      // NLL_FWDBWD, optional: general VJP seed d/dz [M, C] (replaces scale * z)
   const float* gld;     //                       and d/d(log_jac_det) [M] (replaces -scale)
+  void* ex_x1;          // flow training exports (tensor-core kernel only, see flow_tc.cuh)
+  void* ex_dsub;
+  float* d_gscale;
+  float* d_goffset;
   int M, n_blocks;
 };
 

@@ -40,8 +40,9 @@ __host__ __device__ constexpr int tc_fw_bytes(int C) { return kTcHc * 128 + 2 * 
 __host__ __device__ constexpr int tc_bw_bytes(int C) {
   return kTcHc * 128 + tc_k3slabs(C) * kTcHc * 128 + 2 * tc_n4p(C) * 128;
 }
-// fp32 tail of a block: b2[2c2] g[C] off[C] logg[1] pad -> WT[C][36] WiT[C][36] Wrow[C][36]
-__host__ __device__ constexpr int tc_tail_hdr(int C) { return tc_rup(2 * flow_c2(C) + 2 * C + 1, 4); }
+// fp32 tail of a block: b2[2c2] g[C] off[C] logg[1] dgfac[C] pad -> WT[C][36] WiT[C][36] Wrow[C][36]
+// (dgfac = d g / d global_scale = 0.1 * sigmoid(0.5 * global_scale), used when the flow itself is trained)
+__host__ __device__ constexpr int tc_tail_hdr(int C) { return tc_rup(2 * flow_c2(C) + 3 * C + 1, 4); }
 __host__ __device__ constexpr int tc_tail_floats(int C) { return tc_tail_hdr(C) + 3 * C * kTcPermLd; }
 __host__ __device__ constexpr size_t tc_block_bytes(int C) {
   return static_cast<size_t>(kTcChunks) * (tc_fw_bytes(C) + tc_bw_bytes(C)) + static_cast<size_t>(tc_tail_floats(C)) * 4;
@@ -159,6 +160,7 @@ __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_pack
   float* g = b2 + 2 * c2;
   float* of = g + C;
   float* logg = of + C;
+  float* dgfac = logg + 1;
   float* WT = T + tc_tail_hdr(C);
   float* WiT = WT + C * kTcPermLd;
   float* Wrow = WiT + C * kTcPermLd;
@@ -172,6 +174,7 @@ __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_pack
     g[i] = gg;
     of[i] = A.go[k][i];
     lg += logf(gg);
+    dgfac[i] = 0.1f / (1.f + expf(-0.5f * x));
   }
   for (int e = threadIdx.x; e < C * kTcPermLd; e += blockDim.x) {
     const int i = e / kTcPermLd, o = e - i * kTcPermLd;
@@ -201,6 +204,13 @@ struct FlowTcArgs {
   float scale;
   const float* gz;
   const float* gld;
+  // flow training (NLL mode, all optional): per-block exports for the parameter-gradient GEMMs and row-reduced
+  // gradients of the global affine.  ex_x1 / ex_dsub: bf16 [n_blocks][M][64] (only the first c1 / 2*c2 columns are
+  // written; the caller keeps the padding zero), d_gscale / d_goffset: fp32 [n_blocks][C], accumulated atomically.
+  void* ex_x1;
+  void* ex_dsub;
+  float* d_gscale;
+  float* d_goffset;
   int M, n_blocks;
 };
 
@@ -243,14 +253,15 @@ __device__ __forceinline__ bool tc_elect_one() {
 }
 
 struct TcTail {
-  const float* b2; const float* g; const float* off; const float* WT; const float* WiT; const float* Wrow; float logg;
+  const float* b2; const float* g; const float* off; const float* dgfac; const float* WT; const float* WiT; const float* Wrow;
+  float logg;
 };
 template <int C>
 __device__ __forceinline__ TcTail tc_tail(const unsigned char* packed, int k) {
   const float* T = reinterpret_cast<const float*>(packed + static_cast<size_t>(k) * tc_block_bytes(C) +
                                                   static_cast<size_t>(kTcChunks) * (tc_fw_bytes(C) + tc_bw_bytes(C)));
   TcTail t;
-  t.b2 = T; t.g = T + 2 * flow_c2(C); t.off = t.g + C; t.logg = __ldg(t.off + C);
+  t.b2 = T; t.g = T + 2 * flow_c2(C); t.off = t.g + C; t.logg = __ldg(t.off + C); t.dgfac = t.off + C + 1;
   t.WT = T + tc_tail_hdr(C); t.WiT = t.WT + C * kTcPermLd; t.Wrow = t.WiT + C * kTcPermLd;
   return t;
 }
@@ -643,11 +654,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
         if (lane == 0 && A.nll_sum) atomicAdd(A.nll_sum, nll);
         for (int k = nb - 1; k >= 0; --k) {
           const TcTail T = tc_tail<C>(A.packed, k);
-          // dy = g * (W^T d)   (d = gradient w.r.t. the block output)
+          // dyg = W^T d, dy = g * dyg   (d = gradient w.r.t. the block output)
 #pragma unroll
           for (int i = 0; i < C; ++i) ys[i] = d[i];
           float dy[C];
           matvec(T.Wrow, dy);
+          float dyg[C];
+          const bool train = A.d_gscale != nullptr;
+          if (train) {
+#pragma unroll
+            for (int i = 0; i < C; ++i) dyg[i] = ok ? dy[i] : 0.f;
+          }
 #pragma unroll
           for (int i = 0; i < C; ++i) dy[i] *= __ldg(T.g + i);
           // reconstruct the block input (x <- input) and the coupling coefficients
@@ -663,6 +680,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
             const float ds = dy2 * x[c1 + c] * e + glv;
             da[c] = ds * 2.f * (1.f - th * th) * 0.1f;
             da[c2 + c] = dy2 * 0.1f;
+          }
+          if (train) {
+            // global affine: out = (y * g + off) W^T, log-det += sum log g  ->  d off = sum_rows dyg,
+            // d g = sum_rows (dyg * y + glv / g), d global_scale = d g * dgfac;  y = (x1, x2 * e^s + t)
+            float* dgs = A.d_gscale + static_cast<size_t>(k) * C;
+            float* dgo = A.d_goffset + static_cast<size_t>(k) * C;
+            const float glv_ok = ok ? glv : 0.f;
+#pragma unroll
+            for (int i = 0; i < C; ++i) {
+              float yv = x[i];
+              if (i >= c1) {
+                const float th = tanhf(a[i - c1]);
+                yv = x[i] * expf(2.f * th) + a[c2 + (i - c1)];
+              }
+              float v_off = dyg[i];
+              float v_g = (dyg[i] * yv + glv_ok / __ldg(T.g + i)) * __ldg(T.dgfac + i);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                v_off += __shfl_xor_sync(0xffffffffu, v_off, o);
+                v_g += __shfl_xor_sync(0xffffffffu, v_g, o);
+              }
+              if (lane == 0) { atomicAdd(dgo + i, v_off); atomicAdd(dgs + i, v_g); }
+            }
+            if (ok) {
+              __nv_bfloat16* ex1 = static_cast<__nv_bfloat16*>(A.ex_x1) + (static_cast<size_t>(k) * A.M + grow) * 64;
+              __nv_bfloat16* exd = static_cast<__nv_bfloat16*>(A.ex_dsub) + (static_cast<size_t>(k) * A.M + grow) * 64;
+#pragma unroll
+              for (int i = 0; i < c1; ++i) ex1[i] = __float2bfloat16_rn(x[i]);
+#pragma unroll
+              for (int i = 0; i < 2 * c2; ++i) exd[i] = __float2bfloat16_rn(da[i]);
+            }
           }
           // backward chain: dx1 = ((da . W2) * relu'(W1 x1 + b1)) . W1
           {

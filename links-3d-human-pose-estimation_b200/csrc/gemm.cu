@@ -159,7 +159,7 @@ __device__ __forceinline__ void epilogue_chunk_scalar(const EpiParams& E, const 
       if (E.add0) v += __bfloat162float(E.add0[mo * E.ld_add0 + n]);
       if (E.add1) v += __bfloat162float(E.add1[mo * E.ld_add1 + n]);
       if (E.flags & LINKS_EPI_LEAKY_POST) v = links_leaky(v);
-      if (E.ymask) v *= (__bfloat162float(E.ymask[mo * E.ld_ymask + n]) > 0.f ? 1.f : 0.01f);
+      if (E.ymask) v *= (__bfloat162float(E.ymask[mo * E.ld_ymask + n]) > 0.f ? 1.f : ((E.flags & LINKS_EPI_YMASK_ZERO) ? 0.f : 0.01f));
       if (E.mid) E.mid[mo * E.ld_mid + n] = __float2bfloat16_rn(v);
       if (E.bits) v *= ((bits_word >> i) & 1u) ? 0.01f : 1.f;
       if (E.out) E.out[mo * E.ld_out + n] = __float2bfloat16_rn(v);
@@ -256,6 +256,7 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
   const bool has_out = kDyn ? E.out != nullptr : (F & F_OUT) != 0;
   const bool has_f32 = kDyn ? E.out_f32 != nullptr : (F & F_F32) != 0;
   const size_t mo = static_cast<size_t>(m);
+  const float yneg = (E.flags & LINKS_EPI_YMASK_ZERO) ? 0.f : 0.01f;  // slope applied where the mask activation is <= 0
   const bool fast = E.vec_ok && (n_blk + kSlab <= E.N);               // warp-uniform
 
   if (!fast) {
@@ -346,7 +347,7 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       for (int j = 0; j < 4; ++j) {
         float t[8]; unpack8_bf16(lds128(scr_addr(SA, lane, j)), t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[j * 8 + i] = t[i] > 0.f ? v[j * 8 + i] : 0.01f * v[j * 8 + i];
+        for (int i = 0; i < 8; ++i) v[j * 8 + i] = t[i] > 0.f ? v[j * 8 + i] : yneg * v[j * 8 + i];
       }
       __syncwarp();
     }

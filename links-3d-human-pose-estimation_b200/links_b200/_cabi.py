@@ -15,6 +15,7 @@ MAX_GEMM_PROBLEMS = 8
 
 EPI_LEAKY_PRE, EPI_LEAKY_POST, EPI_RELU_PRE, EPI_ACCUM_F32 = 1, 2, 4, 8
 GEMM_A_MN, GEMM_B_MN = 16, 32
+EPI_YMASK_ZERO = 64
 
 vp = C.c_void_p
 ci = C.c_int
@@ -70,6 +71,7 @@ SIGNATURES = {
     "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp]),
     "links_flow_sample": (ci, [vp, ci, vp, vp, ci, vp]),
     "links_flow_vjp": (ci, [vp, ci, ci, vp, ci, vp, vp, vp]),
+    "links_flow_nll_train": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
     "links_mpjpe": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]),
     "links_threshold_counts": (ci, [vp, sz, vp, ci, ci, vp]),
     "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),

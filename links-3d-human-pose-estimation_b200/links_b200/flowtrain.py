@@ -1,0 +1,182 @@
+"""Training step of a GLOW / AllInOne normalising flow on the B200 path (reference train_full_pose_norm_flow.py:67-98;
+train_leg_torso_left_right_norm_flow.py:100-198 uses the same step on four part widths).
+
+    z, ld = inn(x);                      dist_2d        = mean(0.5 |z|^2 - ld)                    (:75-78)
+    s = inn^-1(add_noise(z)) (no grad), root joint zeroed                                        (:81-87)
+    z2, ld2 = inn(s);                    dist_2d_sample = mean(0.5 |z2|^2 - ld2)                  (:89-91)
+    loss = dist_2d + dist_2d_sample;  backward;  Adam                                            (:93-98)
+
+Everything that depends on the rows runs in ONE fused tensor-core kernel launch over the stacked rows [x ; s]
+(links_flow_nll_train): forward, NLL, reversible backward, gradients of the global affine, and the per-block operands
+of the parameter-gradient GEMMs.  The weight gradients are then four grouped tcgen05 GEMM launches over the 8 blocks
+(hidden recompute, dgrad with the ReLU mask, two wgrads), bias gradients one batched column-sum launch, Adam one launch
+on the flat parameter buffer, and the packed operand images are rebuilt by links_flow_pack.
+"""
+import ctypes as C
+
+import torch
+
+from . import _cabi
+from ._cabi import EPI_RELU_PRE, EPI_YMASK_ZERO, GEMM_A_MN, GEMM_B_MN, GemmProblem, check
+from .flowpack import FlowPacked
+
+HIDDEN = 1024
+_NAMES = ("subnet.0.weight", "subnet.0.bias", "subnet.2.weight", "subnet.2.bias", "global_scale", "global_offset")
+
+
+def _rup(x, m):
+    return (x + m - 1) // m * m
+
+
+class FlowTrainStep:
+    def __init__(self, C_dim, params, batch, n_blocks=8, lr=2e-4, weight_decay=0.0, device="cuda", process_group=None):
+        """params: FrEIA-layout state dict; batch: rows of x per step (the kernel sees 2*batch rows)."""
+        self.C, self.nb, self.B = C_dim, n_blocks, batch
+        self.M = 2 * batch
+        self.c1, self.c2 = C_dim - C_dim // 2, C_dim // 2
+        self.lr, self.wd = lr, weight_decay
+        self.lib = _cabi.lib()
+        self.device = dev = torch.device(device)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        c1, c2, nb, M = self.c1, self.c2, n_blocks, self.M
+        # ---- flat trainable parameters (w_perm / w_perm_inv are fixed, FrEIA keeps them requires_grad=False)
+        shapes = {"subnet.0.weight": (HIDDEN, c1), "subnet.0.bias": (HIDDEN,), "subnet.2.weight": (2 * c2, HIDDEN),
+                  "subnet.2.bias": (2 * c2,), "global_scale": (1, C_dim), "global_offset": (1, C_dim)}
+        total = sum(_rup(int(torch.tensor(shapes[n]).prod()), 64) for n in _NAMES) * nb
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.master = torch.zeros(total, **f32)
+        self.grad = torch.zeros(total, **f32)
+        self.exp_avg = torch.zeros(total, **f32)
+        self.exp_avg_sq = torch.zeros(total, **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.P, self.Gd = [], []          # per block: name -> view
+        off = 0
+        for k in range(nb):
+            pv, gv = {}, {}
+            for n in _NAMES:
+                numel = int(torch.tensor(shapes[n]).prod())
+                pv[n] = self.master[off:off + numel].view(shapes[n])
+                gv[n] = self.grad[off:off + numel].view(shapes[n])
+                pv[n].copy_(params["module_list.%d.%s" % (k, n)].to(dev, torch.float32))
+                off += _rup(numel, 64)
+            self.P.append(pv)
+            self.Gd.append(gv)
+        self.fixed = {"module_list.%d.%s" % (k, n): params["module_list.%d.%s" % (k, n)].to(dev, torch.float32).contiguous()
+                      for k in range(nb) for n in ("w_perm", "w_perm_inv")}
+        self.flow = FlowPacked(C_dim, self.state_dict(), n_blocks=nb, device=dev)
+        # ---- bf16 operands / workspaces of the parameter-gradient GEMMs
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.W1b = torch.zeros(nb, HIDDEN, 64, **bf)                    # K-major B of the hidden recompute
+        self.W2b = torch.zeros(nb, _rup(2 * c2, 8), HIDDEN, **bf)       # MN-major B of the dgrad
+        self.X1 = torch.zeros(nb, M, 64, **bf)                          # exports (padding stays zero)
+        self.DS = torch.zeros(nb, M, 64, **bf)
+        self.H = torch.empty(nb, M, HIDDEN, **bf)                       # relu(x1 W1^T + b1)
+        self.DP = torch.empty(nb, M, HIDDEN, **bf)                      # (d_sub . W2) * relu'
+        self.x = torch.zeros(batch, C_dim, **f32)
+        self.noise = torch.zeros(batch, C_dim, **f32)
+        self.u = torch.zeros(M, C_dim, **f32)
+        self.nll_sum = torch.zeros(1, **f32)
+        self.loss = torch.zeros(1, **f32)
+        self._refresh_shadows()
+        self._plans = None
+
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self):
+        sd = {}
+        for k in range(self.nb):
+            for n in _NAMES:
+                sd["module_list.%d.%s" % (k, n)] = self.P[k][n]
+        sd.update(self.fixed)
+        return sd
+
+    def _refresh_shadows(self):
+        with torch.no_grad():
+            for k in range(self.nb):
+                self.W1b[k, :, :self.c1] = self.P[k]["subnet.0.weight"]
+                self.W2b[k, :2 * self.c2] = self.P[k]["subnet.2.weight"]
+        self.flow.repack(self.state_dict())
+
+    def _prob(self, A, B, M, N, K, lda, ldb, **kw):
+        P = GemmProblem()
+        P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb = A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb
+        P.flags = kw.pop("flags", 0)
+        for name, t in kw.items():
+            if name == "bias":
+                P.bias = t.data_ptr()
+            elif name == "out_f32":
+                P.out_f32, P.ld_f32 = t.data_ptr(), t.stride(0)
+            else:
+                setattr(P, name, t.data_ptr())
+                setattr(P, "ld_" + name, t.stride(0))
+        return P
+
+    def _build_plans(self):
+        nb, M, c1, c2 = self.nb, self.M, self.c1, self.c2
+        g1 = [self._prob(self.X1[k], self.W1b[k], M, HIDDEN, 64, 64, 64, flags=EPI_RELU_PRE, bias=self.P[k]["subnet.0.bias"],
+                         out=self.H[k]) for k in range(nb)]
+        g2 = [self._prob(self.DS[k], self.W2b[k], M, HIDDEN, 2 * c2, 64, HIDDEN, flags=GEMM_B_MN | EPI_YMASK_ZERO,
+                         ymask=self.H[k], out=self.DP[k]) for k in range(nb)]
+        g3 = [self._prob(self.DS[k], self.H[k], 2 * c2, HIDDEN, M, 64, HIDDEN, flags=GEMM_A_MN | GEMM_B_MN,
+                         out_f32=self.Gd[k]["subnet.2.weight"]) for k in range(nb)]
+        g4 = [self._prob(self.DP[k], self.X1[k], HIDDEN, c1, M, HIDDEN, 64, flags=GEMM_A_MN | GEMM_B_MN,
+                         out_f32=self.Gd[k]["subnet.0.weight"]) for k in range(nb)]
+        gemms = [((GemmProblem * nb)(*g), nb) for g in (g1, g2, g3, g4)]
+        items = []
+        for k in range(nb):
+            items.append((self.DP[k].data_ptr(), HIDDEN, M, HIDDEN, self.Gd[k]["subnet.0.bias"].data_ptr()))
+            items.append((self.DS[k].data_ptr(), 64, M, 2 * c2, self.Gd[k]["subnet.2.bias"].data_ptr()))
+        arr = (_cabi.ColsumItem * len(items))()
+        for j, (g, ldg, Mi, Ni, out) in enumerate(items):
+            arr[j].G, arr[j].out, arr[j].ldg, arr[j].M, arr[j].N, arr[j].accumulate = g, out, ldg, Mi, Ni, 0
+        self._plans = (gemms, (arr, len(items)))
+
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self):
+        L = self.lib
+        st = torch.cuda.current_stream().cuda_stream
+        if self._plans is None:
+            self._build_plans()
+        self.flow.sample(self.x, self.noise, self.u)               # [x ; s], s detached with the root joint zeroed
+        self.nll_sum.zero_()
+        # global-affine gradients are accumulated atomically: clear their slots of the flat gradient buffer
+        for k in range(self.nb):
+            self.Gd[k]["global_scale"].zero_()
+            self.Gd[k]["global_offset"].zero_()
+        # d_gscale / d_goffset live at a fixed stride inside the flat buffer: pass block 0's pointers + use per-block
+        # contiguous staging so the kernel's [n_blocks, C] indexing holds
+        if not hasattr(self, "_dgs"):
+            self._dgs = torch.zeros(self.nb, self.C, dtype=torch.float32, device=self.device)
+            self._dgo = torch.zeros(self.nb, self.C, dtype=torch.float32, device=self.device)
+        self._dgs.zero_()
+        self._dgo.zero_()
+        check(L.links_flow_nll_train(self.flow.packed.data_ptr(), self.C, self.nb, self.u.data_ptr(), self.M, 1.0 / self.B,
+                                     self.nll_sum.data_ptr(), None, self.X1.data_ptr(), self.DS.data_ptr(),
+                                     self._dgs.data_ptr(), self._dgo.data_ptr(), st), "links_flow_nll_train")
+        gemms, (carr, cn) = self._plans
+        for arr, n in gemms:
+            check(L.links_gemm_grouped(arr, n, st), "links_gemm_grouped")
+        check(L.links_colsum_bf16_batched(carr, cn, st), "links_colsum_bf16_batched")
+        for k in range(self.nb):
+            self.Gd[k]["global_scale"].copy_(self._dgs[k:k + 1])
+            self.Gd[k]["global_offset"].copy_(self._dgo[k:k + 1])
+        self.loss.copy_(self.nll_sum / self.B)                      # dist_2d + dist_2d_sample
+
+    def optimizer_step(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+        st = torch.cuda.current_stream().cuda_stream
+        check(self.lib.links_adam_step(self.master.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                       self.exp_avg_sq.data_ptr(), self.master.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0,
+                                       self.step_dev.data_ptr(), 1.0 / self.world, st), "links_adam_step")
+        self._refresh_shadows()
+
+    def step(self):
+        self.forward_backward()
+        self.optimizer_step()
+
+    def set_lr(self, lr):
+        self.lr = lr
+
+    def loss_dict(self):
+        return {"loss": self.loss.item()}

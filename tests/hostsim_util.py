@@ -41,6 +41,8 @@ def sim():
         open(stamp, "w").write(dig)
     L = C.CDLL(SO)
     for name, (res, args) in _cabi.SIGNATURES.items():
+        if name in ("links_flow_nll_train",):      # tensor-core-only entry points have no CPU build
+            continue
         fn = getattr(L, name.replace("links_", "sim_"))
         fn.restype, fn.argtypes = res, list(args)
     L.sim_flow_packed_floats.restype = C.c_size_t

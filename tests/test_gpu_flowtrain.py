@@ -1,0 +1,55 @@
+"""GPU: flow training step (train_full_pose_norm_flow.py:67-98) -- loss, every parameter gradient and the trajectory
+after a few Adam steps vs the oracle's autograd on the FrEIA restatement."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_fro(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_flow_train_step_vs_oracle():
+    from links_b200.flowtrain import FlowTrainStep
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, steps as OS
+    B, C = 96, 34
+    params = OF.init_flow_params(C, 77, perturb=0.3)
+    step = FlowTrainStep(C, params, B)
+    x2d, _ = synth_poses(B, seed=17)
+    g = torch.Generator().manual_seed(5)
+    x, noise = torch.from_numpy(x2d), torch.randn(B, C, generator=g)
+    pn = OS.params_require_grad(params)
+    for k in list(pn):
+        if "w_perm" in k:
+            pn[k].requires_grad_(False)
+    opt = torch.optim.Adam([v for v in pn.values() if v.requires_grad], lr=2e-4, weight_decay=1e-5)
+    step.wd = 1e-5
+    for it in range(3):
+        step.x.copy_(x); step.noise.copy_(noise)
+        step.forward_backward()
+        torch.cuda.synchronize()
+        opt.zero_grad()
+        out = OS.flow_step(x, pn, noise)
+        out["loss"].backward()
+        ref_loss = out["loss"].item()
+        got = step.loss_dict()["loss"]
+        assert abs(got - ref_loss) <= (1e-3 if it == 0 else 5e-3) * abs(ref_loss), (it, got, ref_loss)
+        if it == 0:
+            for k in range(8):
+                for n, tol in (("subnet.0.weight", 4e-2), ("subnet.0.bias", 4e-2), ("subnet.2.weight", 4e-2),
+                               ("subnet.2.bias", 2e-2), ("global_scale", 1e-3), ("global_offset", 1e-3)):
+                    ref = pn["module_list.%d.%s" % (k, n)].grad
+                    e = rel_fro(step.Gd[k][n].cpu(), ref)
+                    assert e < tol, (k, n, e)
+        step.optimizer_step()
+        opt.step()
+    # the two trajectories moved the parameters the same way
+    for n in ("subnet.0.weight", "subnet.2.weight", "global_offset"):
+        key = "module_list.3." + n
+        d_gpu = step.P[3][n].cpu() - params[key]
+        d_ref = pn[key].detach() - params[key]
+        cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
+        assert cos.item() > 0.9, (n, cos.item())

@@ -33,6 +33,11 @@ def test_lifter_scripts_train_save_eval(tmp_path):
     assert os.path.exists(os.path.join(wd, "leg_lifter.pt")) and os.path.exists(os.path.join(wd, "torso_lifter.pt"))
     out = _run("eval_h36m.py", "--synthetic", "5000", "--chunk", "2048", "--weights-dir", wd)
     assert "PA-MPJPE:" in out and "N-MPJPE:" in out
+    out = _run("train_full_pose_norm_flow.py", "-n", "34", "--synthetic", "1024", "--batch", "128", "--steps", "4", "--log-every", "2",
+               "--weights-dir", wd)
+    assert "step 4" in out
+    sd = torch.load(os.path.join(wd, "norm_flow_sampling.pt"))
+    assert len(sd) == 64 and sd["module_list.7.subnet.2.weight"].shape == (34, 1024)
     out = _run("train_occlusion_models.py", "-n", "26", "--synthetic", "512", "--batch", "64", "--steps", "3", "--log-every", "1",
                "--weights-dir", wd)
     assert "step 3" in out
