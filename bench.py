@@ -166,6 +166,15 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # Libraries (NCCL prints its version banner) write to stdout; the contract is ONE JSON line there.  Point fd 1 at
+    # stderr for the whole run and keep the real stdout for the final line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (line + "\n").encode())
+
     import torch
     import torch.distributed as dist
     from links_b200 import _cabi
@@ -337,7 +346,7 @@ def run_gpu(args):
                 "value": args.cpu_batch / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches, 3 timed steps" % args.cpu_batch},
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         # captured graphs hold NCCL work; drop them before the communicator goes away.  Tearing the process group down
         # with captured collectives alive was observed to hang on exit, so leave without running destructors.

@@ -83,6 +83,8 @@ class LifterStep:
         # pass has produced them, overlapping the rest of backward.  Steps that run concurrently (StepGroup) must
         # share ONE comm stream so that every rank issues its collectives in the same order.
         self.comm = comm_stream if comm_stream is not None else torch.cuda.Stream(device=dev)
+        # Adam + shadow refresh of a reduced bucket run on their own stream so the collectives stay back to back
+        self.opt_stream = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------------------------------
     def _st(self):
@@ -97,12 +99,16 @@ class LifterStep:
     def _on_bucket(self, b):
         """Bucket b of the flat gradient buffer is final: all-reduce + Adam + shadow refresh on the comm stream."""
         main = torch.cuda.current_stream()
-        self.comm.wait_stream(main)
         m = self.mlp
-        with torch.cuda.stream(self.comm):
-            if self.world > 1:
+        src = main
+        if self.world > 1:
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
                 a, e = m.bucket_ranges[b]
                 torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+            src = self.comm
+        self.opt_stream.wait_stream(src)
+        with torch.cuda.stream(self.opt_stream):
             m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
                         last=(b == len(m.buckets) - 1))
 
@@ -154,7 +160,7 @@ class LifterStep:
               "links_geom_backward_angles")
         m.run(m.backward_plan(0, need_input_grad=False, wgrad=True), on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
-            main.wait_stream(self.comm)
+            main.wait_stream(self.opt_stream)
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
         t = self.scal[:6] * self._norm
         self.losses[:6] = t
@@ -209,7 +215,8 @@ class StepGroup:
         self.steps[0].step()
         for st in self.streams:
             main.wait_stream(st)
-        main.wait_stream(self.steps[0].comm)
+        for step in self.steps:
+            main.wait_stream(step.opt_stream)
 
     def capture(self, warmup=2):
         """Capture step() into one CUDA graph (replay with .replay()).  Eager warm-up runs first (lazy inits)."""
