@@ -111,6 +111,12 @@ extern "C" __attribute__((visibility("default"))) int links_adam_step(float* par
 }
 
 // ---------------------------------------------------------------------------------------------
+// grid of the row-walking geometry kernels (one warp per row / row pair, kGeomWarps warps per block)
+static int geom_grid(int warps_needed) {
+  const int blocks = (warps_needed + kGeomWarps - 1) / kGeomWarps;
+  return blocks < 148 * 16 ? blocks : 148 * 16;
+}
+
 static int check_maps(const LinksGeomMaps* m) {
   if (!m) return LINKS_E_ARG;
   if (m->V < 1 || m->V > 2) return LINKS_E_RANGE;
@@ -146,7 +152,7 @@ extern "C" __attribute__((visibility("default"))) int links_geom_forward(const L
   A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
   A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
   A.qpart[0] = qpart0; A.qpart[1] = qpart1; A.qfull[0] = q_full0; A.qfull[1] = q_full1;
-  geom_forward_kernel<<<(N + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  geom_forward_kernel<<<geom_grid(N), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -172,7 +178,7 @@ extern "C" __attribute__((visibility("default"))) int links_geom_loss(const Link
   A.g2T[0] = static_cast<__nv_bfloat16*>(g2T_head0); A.g2T[1] = static_cast<__nv_bfloat16*>(g2T_head1);
   A.ldT = ldT; A.colT0 = colT0;
   const int pairs = (N + 1) / 2;
-  geom_lossgrad_kernel<false><<<(pairs + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  geom_lossgrad_kernel<false><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -202,7 +208,7 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
   A.ldT = ldT; A.colT0 = colT0;
   A.dgamma = dgamma_direct; A.da = da; A.red = red;
   const int pairs = (N + 1) / 2;
-  geom_lossgrad_kernel<true><<<(pairs + kGeomWarps - 1) / kGeomWarps, kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  geom_lossgrad_kernel<true><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -375,6 +381,12 @@ extern "C" __attribute__((visibility("default"))) int links_flow_sample(const fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// grid of the chunk-walking metric kernels: at most 8 blocks (of 64 threads, ~27-36 KB shared) per SM
+static int metric_grid(int M) {
+  const int chunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  return chunks < 148 * 8 ? chunks : 148 * 8;
+}
+
 static int check_pose_args(const float* a, const float* b, int M, int J) {
   if (!a || !b) return LINKS_E_ARG;
   if (M < 1 || J < 2 || J > 17) return LINKS_E_RANGE;
@@ -387,7 +399,7 @@ extern "C" __attribute__((visibility("default"))) int links_mpjpe(const float* p
   int rc = check_pose_args(p_ref, p, M, num_joints);
   if (rc) return rc;
   if (root_joint < 0 || root_joint >= num_joints) return LINKS_E_RANGE;
-  mpjpe_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+  mpjpe_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
       p_ref, p, M, num_joints, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
   return links_launch_status();
 }
@@ -408,7 +420,7 @@ extern "C" __attribute__((visibility("default"))) int links_pmpjpe(const float* 
   int rc = check_pose_args(p_ref, p, M, num_joints);
   if (rc) return rc;
   if (mode < 0 || mode > 1) return LINKS_E_RANGE;
-  pmpjpe_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+  pmpjpe_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
       p_ref, p, M, num_joints, mode, per_pose, aligned, sum);
   return links_launch_status();
 }
@@ -419,7 +431,7 @@ extern "C" __attribute__((visibility("default"))) int links_eval_lift_score(cons
   if (rc) return rc;
   LINKS_CHECK_PTR(depth_off); LINKS_CHECK_PTR(sums3);
   if (ld_depth < 17) return LINKS_E_RANGE;
-  eval_lift_score_kernel<<<(M + kPosesPerBlock - 1) / kPosesPerBlock, kPosesPerBlock, 0, links_stream(stream)>>>(
+  eval_lift_score_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
       poses_2d, depth_off, ld_depth, gt_3d, M, depth, sums3);
   return links_launch_status();
 }

@@ -38,6 +38,17 @@ struct GeomArgs {
   float* qfull[2];
 };
 
+// The argument block (index maps, pointers) is copied into shared memory once per block: the maps are indexed by
+// lane, and lane-divergent reads of the kernel-parameter constant bank serialise (one transaction per distinct
+// address) -- together with per-block single-address atomics that made these kernels 10-50x slower than the HBM
+// roofline at large N.  Blocks then walk rows with a grid-stride loop and issue ONE set of atomics at the end.
+__device__ __forceinline__ void stage_args(GeomArgs* dst, const GeomArgs& src) {
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(&src);
+  uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+  for (int i = threadIdx.x; i < static_cast<int>(sizeof(GeomArgs) / 4); i += blockDim.x) d32[i] = s32[i];
+  __syncthreads();
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LINKS_FULL_MASK, v, o);
@@ -173,30 +184,41 @@ __device__ __forceinline__ void row_consistency(const GeomArgs& A, int v, int n,
 // =========================================================================================================
 // forward: projected parts for the flows / pass-2 lifters
 // =========================================================================================================
-__global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const GeomArgs A) {
+__global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const GeomArgs Ap) {
+  __shared__ GeomArgs sA;
+  stage_args(&sA, Ap);
+  const GeomArgs& A = sA;
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * kGeomWarps + (threadIdx.x >> 5);   // one warp per row
-  if (n >= A.N) return;                                          // warp-uniform
-  const float gamma = 0.5f * (A.ang[0][static_cast<size_t>(n) * LINKS_HEAD_LD] + A.ang[1][static_cast<size_t>(n) * LINKS_HEAD_LD]);
-  const float a = -A.stats[0] + A.stats[1] * A.eps_x[n];
-  const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
-  float R[9];
-  make_rotation(a, b, gamma, R);
-  for (int v = 0; v < A.maps.V; ++v) {
-    RowVar s;
-    row_forward(A, v, n, lane, R, s);
-    if (lane < kJ) {
-      if (A.qfull[v]) {
-        A.qfull[v][static_cast<size_t>(n) * 34 + lane] = s.qx;
-        A.qfull[v][static_cast<size_t>(n) * 34 + kJ + lane] = s.qy;
-      }
-      const int p = A.maps.part_net[v][lane];
-      if (p >= 0) {
-        const int nj = A.maps.n_joints[p];
-        const int idx = A.maps.part_idx[v][lane];
-        float* dst = A.qpart[p] + static_cast<size_t>(n) * (2 * nj);
-        dst[idx] = s.qx;
-        dst[nj + idx] = s.qy;
+  // lane-constant map entries
+  int part_net[2], part_idx[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    part_net[v] = lane < kJ ? A.maps.part_net[v][lane] : -1;
+    part_idx[v] = lane < kJ ? A.maps.part_idx[v][lane] : 0;
+  }
+  const int stride = gridDim.x * kGeomWarps;
+  for (int n = blockIdx.x * kGeomWarps + (threadIdx.x >> 5); n < A.N; n += stride) {   // one warp per row
+    const float gamma = 0.5f * (A.ang[0][static_cast<size_t>(n) * LINKS_HEAD_LD] + A.ang[1][static_cast<size_t>(n) * LINKS_HEAD_LD]);
+    const float a = -A.stats[0] + A.stats[1] * A.eps_x[n];
+    const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
+    float R[9];
+    make_rotation(a, b, gamma, R);
+    for (int v = 0; v < A.maps.V; ++v) {
+      RowVar s;
+      row_forward(A, v, n, lane, R, s);
+      if (lane < kJ) {
+        if (A.qfull[v]) {
+          A.qfull[v][static_cast<size_t>(n) * 34 + lane] = s.qx;
+          A.qfull[v][static_cast<size_t>(n) * 34 + kJ + lane] = s.qy;
+        }
+        const int p = part_net[v];
+        if (p >= 0) {
+          const int nj = A.maps.n_joints[p];
+          const int idx = part_idx[v];
+          float* dst = A.qpart[p] + static_cast<size_t>(n) * (2 * nj);
+          dst[idx] = s.qx;
+          dst[nj + idx] = s.qy;
+        }
       }
     }
   }
@@ -207,13 +229,13 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
 // kFull = true : complete backward to the pass-1 heads, d gamma (direct) and d a (runs after it).
 // =========================================================================================================
 template <bool kFull>
-__global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const GeomArgs A) {
+__global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const GeomArgs Ap) {
   __shared__ float s_part[kGeomWarps][6];
+  __shared__ GeomArgs sA;
+  stage_args(&sA, Ap);
+  const GeomArgs& A = sA;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int pair = blockIdx.x * kGeomWarps + warp;
-  const int nA = 2 * pair, nB = 2 * pair + 1;
-  const bool vA = nA < A.N, vB = nB < A.N;                      // warp-uniform
   const bool act = lane < kJ;
   const float invN = 1.f / static_cast<float>(A.N);
   const int npairs = A.N / 2;
@@ -224,7 +246,10 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const Ge
   float sums[4] = {0.f, 0.f, 0.f, 0.f};   // L3d, rep, pair, bl (raw sums, lane-uniform)
   float red_da = 0.f, red_eda = 0.f;
 
-  if (vA) {
+  const int total_pairs = (A.N + 1) / 2;
+  for (int pair = blockIdx.x * kGeomWarps + warp; pair < total_pairs; pair += gridDim.x * kGeomWarps) {
+    const int nA = 2 * pair, nB = 2 * pair + 1;
+    const bool vB = nB < A.N;                                    // warp-uniform
     float R[2][9], gam[2], eps[2];
     int rows[2] = {nA, nB};
     const int nrows = vB ? 2 : 1;

@@ -12,29 +12,17 @@ namespace links {
 
 constexpr int kPosesPerBlock = 64;
 constexpr int kMaxRow = 51;           // 3 * 17
-constexpr int kRowStride = 53;        // odd, >= kMaxRow, so lanes hit distinct banks
+constexpr int kRowStride = 52;        // shared arrays hold kPosesPerBlock rows of up to 51 floats (+ float4 slack)
 
-// Cooperative copy of `count` floats starting at g (16-byte aligned chunk start) into padded shared rows.
-__device__ __forceinline__ void stage_rows(const float* __restrict__ g, size_t count, int row_len, float* s) {
+// Cooperative LINEAR copy of `count` floats starting at g (16-byte aligned chunk start) into shared memory: the
+// shared rows keep the global row length as their stride (51 for 17 joints: odd, so lane = pose reads are bank-conflict
+// free; 34 for the 2D poses: 2-way), which makes staging pure float4 traffic with no per-element index arithmetic.
+__device__ __forceinline__ void stage_rows(const float* __restrict__ g, size_t count, float* s) {
   const size_t n4 = count >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
-  for (size_t i = threadIdx.x; i < n4; i += blockDim.x) {
-    const float4 v = g4[i];
-    const size_t e = i << 2;
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t ee = e + k;
-      const int r = static_cast<int>(ee / row_len);
-      const int c = static_cast<int>(ee - static_cast<size_t>(r) * row_len);
-      s[r * kRowStride + c] = vv[k];
-    }
-  }
-  for (size_t ee = (n4 << 2) + threadIdx.x; ee < count; ee += blockDim.x) {
-    const int r = static_cast<int>(ee / row_len);
-    const int c = static_cast<int>(ee - static_cast<size_t>(r) * row_len);
-    s[r * kRowStride + c] = g[ee];
-  }
+  float4* s4 = reinterpret_cast<float4*>(s);
+  for (size_t i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = g4[i];
+  for (size_t ee = (n4 << 2) + threadIdx.x; ee < count; ee += blockDim.x) s[ee] = g[ee];
 }
 
 __device__ __forceinline__ double block_sum_double(double v, double* sh /*[2]*/) {
@@ -201,30 +189,98 @@ __device__ __forceinline__ float pmpjpe_row(const float* r, const float* p, int 
   return acc * invJ;
 }
 
+// Both PA-MPJPE semantics of one pose from ONE covariance + ONE SVD: the polar factor Q = U V^T is invariant to the
+// positive scale that distinguishes the two normalisations, and the trace scales linearly with it.
+// Returns mode-1 ('best') error in e_best and mode-0 (metrics_batch) error in e_batch.
+__device__ __forceinline__ void pmpjpe_row_both(const float* r, const float* p, int J, float& e_best, float& e_batch) {
+  const float invJ = 1.f / static_cast<float>(J);
+  float mr[3] = {0.f, 0.f, 0.f}, mp[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < J; ++j) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mr[a] += r[a * J + j]; mp[a] += p[a * J + j]; }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) { mr[a] *= invJ; mp[a] *= invJ; }
+  float ssr = 0.f, ssp = 0.f;
+  float A[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  for (int j = 0; j < J; ++j) {
+    float x[3], y[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { x[a] = r[a * J + j] - mr[a]; y[a] = p[a * J + j] - mp[a]; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      ssr += x[a] * x[a];
+      ssp += y[a] * y[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
+    }
+  }
+  const float nr1 = sqrtf(ssr), np1 = sqrtf(ssp);                       // unit Frobenius norm (mode 1)
+  const float nr0 = sqrtf(ssr / (3.f * J)), np0 = sqrtf(ssp / (3.f * J));   // unit RMS (mode 0)
+  const float inv = 1.f / (nr1 * np1);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) A[a][b] *= inv;
+  float Q[3][3], tr;
+  polar_svd3(A, Q, &tr);
+  const float det = Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) +
+                    Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
+  const float g1 = tr * nr1 / np1;      // mode 1: Z = normX * trace * (Y0 / normY) T
+  const float g0 = nr0 / np0;           // mode 0: RMS match, last row of R scaled by det
+  float acc1 = 0.f, acc0 = 0.f;
+  for (int j = 0; j < J; ++j) {
+    float y[3], x[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { y[a] = p[a * J + j] - mp[a]; x[a] = r[a * J + j] - mr[a]; }
+    float d1 = 0.f, d0 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float q = Q[a][0] * y[0] + Q[a][1] * y[1] + Q[a][2] * y[2];
+      const float e1 = x[a] - g1 * q;
+      const float e0 = x[a] - g0 * (a == 2 ? det * q : q);
+      d1 += e1 * e1;
+      d0 += e0 * e0;
+    }
+    acc1 += sqrtf(d1);
+    acc0 += sqrtf(d0);
+  }
+  e_best = acc1 * invJ;
+  e_batch = acc0 * invJ;
+}
+
 // =========================================================================================================
+// All three kernels walk 64-pose chunks with a grid-stride loop (grid = a few blocks per SM) and keep their partial
+// sums in registers: one double atomic per block at the end instead of one per 64 poses (single-address atomics
+// serialise in L2 and dominated the run time at 8 M poses).
 __global__ void __launch_bounds__(kPosesPerBlock) mpjpe_kernel(
     const float* __restrict__ p_ref, const float* __restrict__ p, int M, int J, int root, int use_scaling,
     float* __restrict__ per_pose, float* __restrict__ per_pose_max, float* __restrict__ dist, double* sum) {
-  __shared__ float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ float s_p[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];
   __shared__ double s_red[2];
   const int row_len = 3 * J;
-  const int pose0 = blockIdx.x * kPosesPerBlock;
-  const int npos = min(kPosesPerBlock, M - pose0);
-  stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, row_len, s_ref);
-  stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, row_len, s_p);
-  __syncthreads();
   const int t = threadIdx.x;
-  float e = 0.f;
-  if (t < npos) {
-    float mx;
-    e = mpjpe_row(s_ref + t * kRowStride, s_p + t * kRowStride, J, root, use_scaling,
-                  dist ? dist + static_cast<size_t>(pose0 + t) * J : nullptr, &mx);
-    if (per_pose) per_pose[pose0 + t] = e;
-    if (per_pose_max) per_pose_max[pose0 + t] = mx;
+  const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  double acc = 0.0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int pose0 = chunk * kPosesPerBlock;
+    const int npos = min(kPosesPerBlock, M - pose0);
+    stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_ref);
+    stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_p);
+    __syncthreads();
+    if (t < npos) {
+      float mx;
+      const float e = mpjpe_row(s_ref + t * row_len, s_p + t * row_len, J, root, use_scaling,
+                                dist ? dist + static_cast<size_t>(pose0 + t) * J : nullptr, &mx);
+      if (per_pose) per_pose[pose0 + t] = e;
+      if (per_pose_max) per_pose_max[pose0 + t] = mx;
+      acc += static_cast<double>(e);
+    }
+    __syncthreads();
   }
   if (sum != nullptr) {   // uniform branch
-    const double tot = block_sum_double(static_cast<double>(e), s_red);
+    const double tot = block_sum_double(acc, s_red);
     if (t == 0) atomicAdd(sum, tot);
   }
 }
@@ -232,24 +288,29 @@ __global__ void __launch_bounds__(kPosesPerBlock) mpjpe_kernel(
 __global__ void __launch_bounds__(kPosesPerBlock) pmpjpe_kernel(
     const float* __restrict__ p_ref, const float* __restrict__ p, int M, int J, int mode,
     float* __restrict__ per_pose, float* __restrict__ aligned, double* sum) {
-  __shared__ float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ float s_p[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];
   __shared__ double s_red[2];
   const int row_len = 3 * J;
-  const int pose0 = blockIdx.x * kPosesPerBlock;
-  const int npos = min(kPosesPerBlock, M - pose0);
-  stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, row_len, s_ref);
-  stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, row_len, s_p);
-  __syncthreads();
   const int t = threadIdx.x;
-  float e = 0.f;
-  if (t < npos) {
-    e = pmpjpe_row(s_ref + t * kRowStride, s_p + t * kRowStride, J, mode,
-                   aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr);
-    if (per_pose) per_pose[pose0 + t] = e;
+  const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  double acc = 0.0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int pose0 = chunk * kPosesPerBlock;
+    const int npos = min(kPosesPerBlock, M - pose0);
+    stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_ref);
+    stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_p);
+    __syncthreads();
+    if (t < npos) {
+      const float e = pmpjpe_row(s_ref + t * row_len, s_p + t * row_len, J, mode,
+                                 aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr);
+      if (per_pose) per_pose[pose0 + t] = e;
+      acc += static_cast<double>(e);
+    }
+    __syncthreads();
   }
   if (sum != nullptr) {
-    const double tot = block_sum_double(static_cast<double>(e), s_red);
+    const double tot = block_sum_double(acc, s_red);
     if (t == 0) atomicAdd(sum, tot);
   }
 }
@@ -291,38 +352,46 @@ __global__ void __launch_bounds__(256) threshold_counts_kernel(const float* __re
 __global__ void __launch_bounds__(kPosesPerBlock) eval_lift_score_kernel(
     const float* __restrict__ poses_2d, const float* __restrict__ depth_off, int ld_depth,
     const float* __restrict__ gt, int M, float depth, double* sums3) {
-  __shared__ float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ float s_p[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
+  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];     // per pose: x*d (17), y*d (17), d (17)
+  __shared__ __align__(16) float s_2d[kPosesPerBlock * 34];
   __shared__ double s_red[2];
   const int J = 17;
-  const int pose0 = blockIdx.x * kPosesPerBlock;
-  const int npos = min(kPosesPerBlock, M - pose0);
-  stage_rows(gt + static_cast<size_t>(pose0) * 51, static_cast<size_t>(npos) * 51, 51, s_ref);
-  stage_rows(poses_2d + static_cast<size_t>(pose0) * 34, static_cast<size_t>(npos) * 34, 34, s_p);
-  for (int i = threadIdx.x; i < npos * J; i += blockDim.x) {
-    const int r = i / J, j = i - r * J;
-    s_p[r * kRowStride + 34 + j] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j] + depth;
-  }
-  __syncthreads();
   const int t = threadIdx.x;
-  float e0 = 0.f, e1 = 0.f, e2 = 0.f;
-  if (t < npos) {
-    float* p = s_p + t * kRowStride;
-    for (int j = 0; j < J; ++j) {
-      const float d = p[34 + j];
-      p[j] *= d;
-      p[J + j] *= d;
+  const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int pose0 = chunk * kPosesPerBlock;
+    const int npos = min(kPosesPerBlock, M - pose0);
+    stage_rows(gt + static_cast<size_t>(pose0) * 51, static_cast<size_t>(npos) * 51, s_ref);
+    stage_rows(poses_2d + static_cast<size_t>(pose0) * 34, static_cast<size_t>(npos) * 34, s_2d);
+    for (int i = threadIdx.x; i < npos * J; i += blockDim.x) {
+      const int r = i / J, j = i - r * J;
+      s_p[r * 51 + 34 + j] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j] + depth;
     }
-    const float* r = s_ref + t * kRowStride;
-    e0 = mpjpe_row(r, p, J, 0, 1, nullptr, nullptr);
-    e1 = pmpjpe_row(r, p, J, 1);
-    e2 = pmpjpe_row(r, p, J, 0);
+    __syncthreads();
+    if (t < npos) {
+      float* p = s_p + t * 51;
+      const float* q = s_2d + t * 34;
+      for (int j = 0; j < J; ++j) {
+        const float d = p[34 + j];
+        p[j] = q[j] * d;
+        p[J + j] = q[J + j] * d;
+      }
+      const float* r = s_ref + t * 51;
+      a0 += static_cast<double>(mpjpe_row(r, p, J, 0, 1, nullptr, nullptr));
+      float eb, e0;
+      pmpjpe_row_both(r, p, J, eb, e0);
+      a1 += static_cast<double>(eb);
+      a2 += static_cast<double>(e0);
+    }
+    __syncthreads();
   }
-  const double t0 = block_sum_double(static_cast<double>(e0), s_red);
+  const double t0 = block_sum_double(a0, s_red);
   __syncthreads();
-  const double t1 = block_sum_double(static_cast<double>(e1), s_red);
+  const double t1 = block_sum_double(a1, s_red);
   __syncthreads();
-  const double t2 = block_sum_double(static_cast<double>(e2), s_red);
+  const double t2 = block_sum_double(a2, s_red);
   if (t == 0) {
     atomicAdd(sums3 + 0, t0);
     atomicAdd(sums3 + 1, t1);
