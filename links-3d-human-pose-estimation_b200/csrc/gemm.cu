@@ -10,7 +10,11 @@
 // Replaces every nn.Linear(+LeakyReLU, +residual) of reference utils/models_def.py (forward) and its autograd
 // backward (dgrad, wgrad); see include/links_b200.h for the epilogue contract.
 //
-// One CTA per SM walks the 128x256 output tiles of all problems of the group (static round-robin).
+// One CTA per SM; the two CTAs of a cluster form a tcgen05 CTA PAIR (cta_group::2) that computes a 256x256 output
+// tile: each CTA holds its own 128 rows of A, HALF of the shared B tile and its own 128x256 fp32 accumulator in TMEM;
+// the leader CTA issues one M=256 MMA for both.  Per CTA and k-block that is 16 KB of A + 16 KB of B instead of
+// 16 + 32 KB: 1.5x less TMA traffic from L2 and 1.5x less shared-memory operand traffic -- the two measured limiters
+// of the single-CTA version (steady state ~9 TB/s of L2->SM traffic; isolated main loop at 75 % of the MMA floor).
 //   warp 0      : TMA producer (one elected lane), runs ahead across tile boundaries
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (warp-uniform control flow, one elected lane)
 //   warps 2..17 : epilogue (TMEM lane group = warp % 4, 64-column slab = (warp - 2) / 4); the epilogue of tile i overlaps
@@ -31,7 +35,7 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kEpiWarps = 16;     // 4 TMEM lane groups x 4 column quarters: 4 warps per scheduler hide the epilogue's latencies
 constexpr int kChunk = 16;        // accumulator columns per TMEM load / scalar-path chunk
 constexpr int kSlab = 64;         // columns of the [32 rows x 64 cols] block one epilogue warp owns
@@ -39,13 +43,12 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kAccCols = BN;      // fp32 accumulator columns per buffer
 constexpr int kTmemCols = 2 * kAccCols;
 constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
-constexpr uint32_t kStageBytesB = BN * BK * 2;   // 32 KB
+constexpr uint32_t kStageBytesB = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the pair's B tile
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kOffStage = 0;
-constexpr uint32_t kScratchBytes = 2 * 32 * 64;                // per epilogue warp: operand + output scratch, [32 rows][64 B] each
+constexpr uint32_t kScratchBytes = 2 * 32 * 64 + 256;          // per epilogue warp: operand + output scratch ([32 rows][64 B] each) + 64 bias floats
 constexpr uint32_t kOffScratch = kStages * kStageBytes;
-constexpr uint32_t kOffBias = kOffScratch + kEpiWarps * kScratchBytes;   // 2 x BN floats: bias slice of the tile, per accumulator slot
-constexpr uint32_t kOffBar = kOffBias + 2 * BN * 4;
+constexpr uint32_t kOffBar = kOffScratch + kEpiWarps * kScratchBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024 /*align slack*/;
 
 // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]
@@ -55,7 +58,7 @@ struct alignas(64) GemmProblemDev {
   CUtensorMap tmA;
   CUtensorMap tmB;
   int M, N, K;
-  int tile_begin, tiles_m, tiles_n;
+  int tile_begin, pairs_m, tiles_n;     // scheduling unit: a pair of M-adjacent tiles (one per CTA of the cluster)
   uint32_t flags;
   int ld_add0, ld_add1, ld_ymask, ld_bits, ld_sign, ld_f32, ld_out, ld_mid;
   const float* bias;
@@ -68,6 +71,7 @@ struct alignas(64) GemmProblemDev {
   __nv_bfloat16* out;
   __nv_bfloat16* mid;
   int a_boxes, b_boxes; // TMA boxes per stage actually needed (MN-major: 64-wide slabs; K-major: 1)
+  int b_rows;           // rows of the (K-major) B tile actually loaded per stage, split in two halves across the pair
   uint32_t stage_tx;    // bytes the boxes of one stage deliver (small M / N problems load smaller boxes)
   int vec_ok;           // every present epilogue operand is 16-byte aligned with a vector-friendly leading dimension
   int epi_mode;         // index into kEpiMask (0 = run-time flags)
@@ -76,7 +80,7 @@ struct alignas(64) GemmProblemDev {
 struct GemmGroupDev {
   GemmProblemDev p[LINKS_MAX_GEMM_PROBLEMS];
   int n_problems;
-  int total_tiles;
+  int total_tiles;      // number of pair-tiles
 };
 
 // MN-major operand tile (contraction dimension strided), 128-byte swizzle: each 64-element slab along M/N is
@@ -194,6 +198,15 @@ __device__ constexpr uint32_t kEpiMask[11] = {
     F_F32,                                                      // 10 wgrad
 };
 
+// arrive on the barrier at the same shared offset in CTA `rank` of the cluster.  Relaxed: the TMEM reads are ordered by
+// tcgen05.fence::before_thread_sync; a release would wait for all of the warp's outstanding global stores (ERRBAR, ~9 %).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -268,7 +281,8 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       if (row_ok && n_blk + c * kChunk < E.N) epilogue_chunk_scalar(E, acc, sbias + c * kChunk, m, n_blk + c * kChunk);
     }
     tc_fence_before();
-    mbar_arrive(acc_empty_bar);
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster(acc_empty_bar, 0);
     return;
   }
 
@@ -286,7 +300,8 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
     }
     if (h == kSlab / kHalf - 1) {
       tc_fence_before();
-      mbar_arrive(acc_empty_bar);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_bar, 0);
     }
     uint32_t bits_word = 0;
     if (has_bits && row_ok) bits_word = __ldg(E.bits + mo * E.ld_bits + (n0 >> 5));
@@ -407,6 +422,44 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
   }
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a CTA pair: the data lands in the executing CTA's shared memory, the transaction bytes are signalled on
+// the LEADER CTA's barrier (peer bit of the shared-window address cleared), which is the one the MMA issuer waits on.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// pair MMA: D[256 x N] (128 rows in each CTA's TMEM) += A[256 x 16] * B[N x 16]^T, operands split across the two CTAs
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// pair MMA completion -> arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -434,15 +487,15 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmGroupDev& G, int tile)
   const int local = tile - G.p[pi].tile_begin;
   TileCoord t;
   t.pi = pi;
-  t.tn = local / G.p[pi].tiles_m;          // consecutive tiles share the B (weight) slice
-  t.tm = local - t.tn * G.p[pi].tiles_m;
+  t.tn = local / G.p[pi].pairs_m;          // consecutive pair-tiles share the B (weight) slice
+  t.tm = local - t.tn * G.p[pi].pairs_m;   // pair index along M: the CTA's tile is 2 * tm + cluster rank
   return t;
 }
 
 // ----------------------------------------------------------------------------------------------
 // Kernel
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GemmGroupDev G) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GemmGroupDev G) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // 1024-B aligned (128B swizzle atoms)
@@ -451,22 +504,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
   if (threadIdx.x == 0) TRACE(0);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bars + (GB_FULL + s) * 8, 1);
-      mbar_init(bars + (GB_EMPTY + s) * 8, 1);
+      mbar_init(bars + (GB_EMPTY + s) * 8, 1);     // released by the leader's pair-MMA commit (multicast to both CTAs)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bars + (GB_ACCFULL + s) * 8, 1);
-      mbar_init(bars + (GB_ACCEMPTY + s) * 8, kEpiWarps * 32);
+      mbar_init(bars + (GB_ACCEMPTY + s) * 8, 2 * kEpiWarps);   // leader's copy: one arrival per epilogue warp of BOTH CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(bars + GB_COUNT * 8, kTmemCols);
+  if (warp == 1) tmem_alloc_pair(bars + GB_COUNT * 8, kTmemCols);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                                     // both CTAs' barriers exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) TRACE(1);
@@ -475,42 +530,44 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;   // running k-block index over all tiles of this CTA
-      for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(G, tile);
+      for (int tile = cl_id; tile < G.total_tiles; tile += n_cl) {
+        TileCoord tc = tile_coord(G, tile);
+        tc.tm = 2 * tc.tm + cta_rank;
         const GemmProblemDev& P = G.p[tc.pi];
         const int num_kb = (P.K + BK - 1) / BK;
         const bool a_mn = (P.flags & LINKS_GEMM_A_MN) != 0, b_mn = (P.flags & LINKS_GEMM_B_MN) != 0;
+        const int b_half = P.b_rows >> 1;                 // this CTA's rows (K-major) / columns (MN-major) of the pair's B tile
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % kStages, use = it / kStages;
-          mbar_wait(bars + (GB_EMPTY + s) * 8, (use & 1u) ^ 1u);
+          mbar_wait(bars + (GB_EMPTY + s) * 8, (use & 1u) ^ 1u);        // own slot free (leader's commit reaches both CTAs)
           const uint32_t full = bars + (GB_FULL + s) * 8;
-          mbar_expect_tx(full, P.stage_tx);
+          if (cta_rank == 0) mbar_expect_tx(full, 2u * P.stage_tx);     // the leader's barrier collects both CTAs' bytes
           const uint32_t sA = base + kOffStage + s * kStageBytes, sB = sA + kStageBytesA;
           if (!a_mn) {
-            tma_load_2d(sA, &P.tmA, full, kb * BK, tc.tm * BM);
+            tma_load_2d_pair(sA, &P.tmA, full, kb * BK, tc.tm * BM);
           } else {
 #pragma unroll
             for (int q = 0; q < BM / 64; ++q)
-              if (q < P.a_boxes) tma_load_2d(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
+              if (q < P.a_boxes) tma_load_2d_pair(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
           }
           if (!b_mn) {
-            tma_load_2d(sB, &P.tmB, full, kb * BK, tc.tn * BN);
+            tma_load_2d_pair(sB, &P.tmB, full, kb * BK, tc.tn * BN + cta_rank * b_half);
           } else {
 #pragma unroll
-            for (int q = 0; q < BN / 64; ++q)
-              if (q < P.b_boxes) tma_load_2d(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + q * 64, kb * BK);
+            for (int q = 0; q < BN / 128; ++q)
+              if (q < P.b_boxes) tma_load_2d_pair(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const bool leader = elect_one();
+    const bool leader = elect_one() && cta_rank == 0;     // only the leader CTA issues the pair's MMAs
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t bb = sb + kOffBar;
     uint32_t it = 0, lt = 0;   // k-block counter, local tile counter
-    for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = cl_id; tile < G.total_tiles && cta_rank == 0; tile += n_cl, ++lt) {   // leader CTA only
       const TileCoord tc = tile_coord(G, tile);
       const GemmProblemDev& P = G.p[tc.pi];
       const int num_kb = (P.K + BK - 1) / BK;
@@ -519,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       int n_eff = P.N - tc.tn * BN;
       n_eff = n_eff >= BN ? BN : ((n_eff + 15) & ~15);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
-                             (static_cast<uint32_t>(n_eff >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+                             (static_cast<uint32_t>(n_eff >> 3) << 17) | (static_cast<uint32_t>((2 * BM) >> 4) << 24);
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
       mbar_wait(bb + (GB_ACCEMPTY + slot) * 8, (acc_use & 1u) ^ 1u);     // epilogue has drained this accumulator
       tc_fence_after();
@@ -537,9 +594,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
           const uint32_t a_step = a_mn ? 128u : 2u, b_step = b_mn ? 128u : 2u;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16(d_addr, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(bb + (GB_EMPTY + s) * 8);                          // frees the smem slot when the MMAs retire
-          if (kb == num_kb - 1) umma_commit(bb + (GB_ACCFULL + slot) * 8);
+            umma_bf16_pair(d_addr, adesc + a_step * k, bdesc + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(bb + (GB_EMPTY + s) * 8, 3);                  // frees the slot in BOTH CTAs when the MMAs retire
+          if (kb == num_kb - 1) umma_commit_pair(bb + (GB_ACCFULL + slot) * 8, 3);   // both CTAs' epilogues
         }
         __syncwarp();
       }
@@ -551,16 +608,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
     const bool store_thread = threadIdx.x == 64;
     const uint32_t S = base + kOffScratch + static_cast<uint32_t>(warp - 2) * kScratchBytes;
     uint32_t lt = 0;
-    const int bias_t = threadIdx.x - 64;
-    float bias_next = 0.f;
-    if (bias_t < BN && static_cast<int>(blockIdx.x) < G.total_tiles) {
-      const TileCoord t0 = tile_coord(G, blockIdx.x);
-      const float* bp = G.p[t0.pi].bias;
-      const int nb = t0.tn * BN + bias_t;
-      if (bp != nullptr && nb < G.p[t0.pi].N) bias_next = __ldg(bp + nb);
-    }
-    for (int tile = blockIdx.x; tile < G.total_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord tc = tile_coord(G, tile);
+    // bias of this warp's 64 columns: two floats per lane, loaded one tile ahead, published through the warp's own
+    // scratch (no CTA-wide barrier in the epilogue: the 16 warps run fully decoupled)
+    float* sbias = reinterpret_cast<float*>(smem_raw + (S + 4096u - raw));
+    auto load_bias = [&](int tile_idx, float& b0, float& b1) {
+      b0 = 0.f; b1 = 0.f;
+      if (tile_idx < G.total_tiles) {
+        const TileCoord t0 = tile_coord(G, tile_idx);
+        const float* bp = G.p[t0.pi].bias;
+        const int nb = t0.tn * BN + slab * kSlab + lane;
+        if (bp != nullptr) {
+          if (nb < G.p[t0.pi].N) b0 = __ldg(bp + nb);
+          if (nb + 32 < G.p[t0.pi].N) b1 = __ldg(bp + nb + 32);
+        }
+      }
+    };
+    float bias_n0, bias_n1;
+    load_bias(cl_id, bias_n0, bias_n1);
+    for (int tile = cl_id; tile < G.total_tiles; tile += n_cl, ++lt) {
+      TileCoord tc = tile_coord(G, tile);
+      tc.tm = 2 * tc.tm + cta_rank;
       // register copy of the problem's epilogue parameters (an indexed constant-bank load per use otherwise)
       EpiParams E;
       int mode;
@@ -577,21 +644,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       const int m0 = tc.tm * BM + lane_grp * 32, n0 = tc.tn * BN + slab * kSlab;
       // first residual operand of this warp's block: fetched while the main loop of the tile is still running
       if (E.add0 != nullptr && E.vec_ok && n0 + kSlab <= E.N) block_fetch_async(S, E.add0, E.ld_add0, m0, n0, E.M, lane);
-      // the tile's bias slice lives in shared memory (slot-indexed double buffer); its global load was issued one
-      // tile earlier (bias_next), so only the barrier that publishes it is on the critical path
-      float* sbias = reinterpret_cast<float*>(smem_raw + (base + kOffBias - raw)) + slot * BN;
-      if (bias_t < BN) sbias[bias_t] = bias_next;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      {
-        const int nt = tile + gridDim.x;
-        bias_next = 0.f;
-        if (bias_t < BN && nt < G.total_tiles) {
-          const TileCoord tn2 = tile_coord(G, nt);
-          const float* bp = G.p[tn2.pi].bias;
-          const int nb = tn2.tn * BN + bias_t;
-          if (bp != nullptr && nb < G.p[tn2.pi].N) bias_next = __ldg(bp + nb);
-        }
-      }
+      __syncwarp();                                  // every lane is done reading the previous tile's bias
+      sbias[lane] = bias_n0;
+      sbias[lane + 32] = bias_n1;
+      __syncwarp();
+      load_bias(tile + n_cl, bias_n0, bias_n1);      // next tile's bias: in flight during this tile's epilogue
       mbar_wait(bars + (GB_ACCFULL + slot) * 8, acc_use & 1u);
       tc_fence_after();
       if (store_thread && lt < 3) TRACE(3 + 3 * lt);
@@ -600,9 +657,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
       if (n0 >= E.N) {
         // this warp's slab lies entirely beyond N: nothing to do but release the accumulator
         tc_fence_before();
-        mbar_arrive(ae);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(ae, 0);
       } else {
-        const float* sb = sbias + slab * kSlab;
+        const float* sb = sbias;
         switch (mode) {
           case 1: epilogue_block<kEpiMask[1]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
           case 2: epilogue_block<kEpiMask[2]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
@@ -621,11 +679,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_
     }
     if (store_thread) TRACE(14);
   }
-  __syncthreads();
+  tc_fence_before();
+  cluster_sync_all();                                     // the peer may still multicast into / arrive on this CTA
   if (threadIdx.x == 0) TRACE(15);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_pair(tmem_base, kTmemCols);
   }
 }
 
@@ -679,17 +738,18 @@ static int build_group(EncodeTiledFn fn, const LinksGemmProblem* problems, int n
     // small problems load smaller boxes: rows the MMA never needs are not fetched (or zero-filled) at all
     const int a_rows = s.M >= BM ? BM : ((s.M + 7) & ~7), b_rows = s.N >= BN ? BN : ((s.N + 15) & ~15);
     d.a_boxes = a_mn ? (s.M >= BM ? BM / 64 : (s.M + 63) / 64) : 1;
-    d.b_boxes = b_mn ? (s.N >= BN ? BN / 64 : (s.N + 63) / 64) : 1;
-    d.stage_tx = static_cast<uint32_t>((a_mn ? d.a_boxes * 64 : a_rows) * BK * 2 + (b_mn ? d.b_boxes * 64 : b_rows) * BK * 2);
+    d.b_boxes = b_mn ? (b_rows / 2 + 63) / 64 : 1;       // per CTA: 64-wide slabs covering its half of the B tile
+    d.stage_tx = static_cast<uint32_t>((a_mn ? d.a_boxes * 64 : a_rows) * BK * 2 + (b_mn ? d.b_boxes * 64 : b_rows / 2) * BK * 2);
     int rc = a_mn ? encode_2d(fn, &d.tmA, s.A, s.K, s.M, s.lda, 64, BK) : encode_2d(fn, &d.tmA, s.A, s.M, s.K, s.lda, BK, a_rows);
     if (rc) return rc;
-    rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, b_rows);
+    d.b_rows = b_rows;
+    rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, b_rows / 2);
     if (rc) return rc;
     d.M = s.M; d.N = s.N; d.K = s.K;
     d.tile_begin = tiles;
-    d.tiles_m = (s.M + BM - 1) / BM;
+    d.pairs_m = ((s.M + BM - 1) / BM + 1) / 2;
     d.tiles_n = (s.N + BN - 1) / BN;
-    tiles += d.tiles_m * d.tiles_n;
+    tiles += d.pairs_m * d.tiles_n;
     d.flags = s.flags;
     if ((s.out && s.ld_out < s.N) || (s.mid && s.ld_mid < s.N)) return LINKS_E_ALIGN;
     d.out = static_cast<__nv_bfloat16*>(s.out); d.ld_out = s.ld_out;
@@ -792,7 +852,8 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
     memcpy(ce.key, problems, key_bytes);
     ce.n = n_problems;
   }
-  const int grid = ce.G.total_tiles < g_num_sms ? ce.G.total_tiles : g_num_sms;
+  const int max_cl = g_num_sms / 2;
+  const int grid = 2 * (ce.G.total_tiles < max_cl ? ce.G.total_tiles : max_cl);   // clusters of 2 CTAs
   gemm_grouped_kernel<<<grid, kThreads, kSmemBytes, links_stream(stream)>>>(ce.G);
   return links_launch_status();
 }
