@@ -525,6 +525,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   if (threadIdx.x == 0) TRACE(1);
+  // Programmatic dependent launch: everything above (barriers, TMEM, cluster handshake) overlapped the tail of the
+  // previous kernel in the stream; from here on this grid reads what that kernel wrote.  Let our own successor be
+  // scheduled as soon as SMs free up -- it will wait at the same point for this grid to finish.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -811,6 +816,7 @@ constexpr int kCacheSize = 1024;
 static CacheEntry* g_cache = nullptr;
 static std::mutex g_cache_mu;
 static int g_num_sms = 0;
+static bool g_gemm_pdl = true;   // programmatic dependent launch between consecutive GEMM launches (env LINKS_GEMM_PDL=0 disables)
 
 static uint64_t hash_bytes(const void* p, size_t n) {
   const unsigned char* b = static_cast<const unsigned char*>(p);
@@ -839,6 +845,8 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return static_cast<int>(e);
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return static_cast<int>(e);
     g_num_sms = sms;
+    const char* pdl = getenv("LINKS_GEMM_PDL");
+    if (pdl != nullptr && pdl[0] == '0') g_gemm_pdl = false;
   }
   const size_t key_bytes = sizeof(LinksGemmProblem) * static_cast<size_t>(n_problems);
   const uint64_t h = hash_bytes(problems, key_bytes);
@@ -854,6 +862,18 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
   }
   const int max_cl = g_num_sms / 2;
   const int grid = 2 * (ce.G.total_tiles < max_cl ? ce.G.total_tiles : max_cl);   // clusters of 2 CTAs
-  gemm_grouped_kernel<<<grid, kThreads, kSmemBytes, links_stream(stream)>>>(ce.G);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = links_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_gemm_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_grouped_kernel, ce.G);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return links_launch_status();
 }
