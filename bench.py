@@ -310,6 +310,10 @@ def run_gpu(args):
         gemm_only()
     ms_gemm = timed(gemm_only, K) / K
     peaks = load_peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
     gemm_flops = (gemm_flops_per_pose("lt") + gemm_flops_per_pose("lr")) * B
     achieved = gemm_flops / (ms_gemm * 1e-3) / 1e12
 
@@ -337,7 +341,11 @@ def run_gpu(args):
             "gpu_launches": launches_per_step * K,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                         "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+                         "traffic_note": "mean dram read+write bytes per GEMM launch from the ncu --set full capture in "
+                                         "profiles/ (B=1024 config); algorithmic operand bytes of a 4-problem launch: 24 MB",
+                         "flops_per_launch": gemm_flops / n_gemm_launches,
+                         "us_per_launch": ms_gemm * 1e3 / n_gemm_launches,
                          "kernel": "links::gemm_grouped_kernel (tcgen05/TMEM/TMA), %d launches per step timed in "
                                    "isolation" % n_gemm_launches,
                          "ms_per_step_gemm_only": ms_gemm, "flops_per_step": gemm_flops,
