@@ -187,11 +187,22 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     pg = None
     if world > 1:
+        # the all-reduce kernels overlap the backward GEMMs: keep them on a few SMs and keep the GEMM grid off those
+        if args.nccl_ctas > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(args.nccl_ctas))
+            os.environ.setdefault("NCCL_MIN_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
+        if args.gemm_ctas > 0:
+            _cabi.lib().links_gemm_set_max_ctas(args.gemm_ctas)
     B = args.batch
     nets, flows, full = make_weights()
-    steps = {k: LifterStep(k, B, nets[k], flows[k], full, process_group=pg) for k in ("lt", "lr")}
+    # one communicator per branch: the LT and LR all-reduces are independent and may run concurrently
+    pgs = {"lt": pg, "lr": pg}
+    if world > 1 and not args.shared_comm:
+        pgs["lr"] = dist.new_group(ranks=list(range(world)), backend="nccl")
+    cfg = {"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets}
+    steps = {k: LifterStep(k, B, nets[k], flows[k], full, cfg=cfg, process_group=pgs[k]) for k in ("lt", "lr")}
     lt, lr = steps["lt"], steps["lr"]
 
     # ---- inputs: per-rank shard of the global batch, pinned on the host for the e2e arm
@@ -336,6 +347,7 @@ def run_gpu(args):
                                     "far above the 126 MB L2" % (2 * 2048 * 1024 * 2 * 2 * 60 * (B / 1024) / 1e9),
                        "operands": "bf16 operands + bf16-stored activations, fp32 accumulate / master weights / losses",
                        "elevation_stats": "local shard" if world > 1 else "global",
+                       "grad_allreduce": ("%s buckets over NCCL, overlapped with backward" % args.grad_comm) if world > 1 else "none",
                        "final_losses": final_losses},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches_per_step * K,
@@ -376,6 +388,12 @@ def main():
     ap.add_argument("--impl", default="links_b200", choices=["links_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--dp-buckets", type=int, default=2, help="gradient buckets per network set under data parallelism")
+    ap.add_argument("--shared-comm", action="store_true", help="one NCCL communicator for both branches")
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="CTAs (SMs) the NCCL all-reduce kernels may use (0: NCCL default)")
+    ap.add_argument("--gemm-ctas", type=int, default=-1, help="GEMM grid cap under data parallelism (<= 0: no cap)")
+    ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"],
+                    help="dtype of the data-parallel gradient all-reduce (bf16 = compressed buckets)")
     ap.add_argument("--serial", action="store_true", help="run the LT and LR steps back to back on one stream")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -89,6 +89,9 @@ typedef struct LinksGemmProblem {
 } LinksGemmProblem;
 
 int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream);
+/* Cap the persistent grid of links_gemm_grouped at n CTAs (0 = one per SM).  Data-parallel runs leave a few SMs free so
+ * that the concurrently running NCCL all-reduce kernels never push GEMM CTAs into a second wave.  Returns the old cap. */
+int links_gemm_set_max_ctas(int n);
 
 /* ------------------------------------------------------------------------------------------
  * Operand packing / reductions around the GEMMs
@@ -137,6 +140,13 @@ int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* str
 int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     int* step_dev, float grad_scale, void* stream);
+
+/* Data-parallel gradient compression: grad_bf16[i] = bf16(grad[i]) before the NCCL all-reduce (half the NVLink
+ * bytes), and the Adam step that consumes the reduced bf16 gradients directly (same arithmetic otherwise). */
+int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream);
+int links_adam_step_g16(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, size_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        int* step_dev, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Geometry + losses (train_leg_torso_lifter.py:153-272, train_left_right_lifter.py:150-423)

@@ -96,17 +96,41 @@ extern "C" __attribute__((visibility("default"))) int links_cast_weight_batched(
   return links_launch_status();
 }
 
-extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
-                               float grad_scale, void* stream) {
+template <typename GradT>
+static int adam_launch(float* param, const GradT* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int step, int* step_dev, float grad_scale, void* stream) {
   LINKS_CHECK_PTR(param); LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(exp_avg); LINKS_CHECK_PTR(exp_avg_sq);
   if (n == 0 || (step_dev == nullptr && step < 1)) return LINKS_E_RANGE;
   const int threads = 256;
   size_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  adam_kernel<<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
+  adam_kernel<GradT><<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
       param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev, step, grad_scale);
   if (step_dev != nullptr && step >= 0) adam_incr_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
+                               float grad_scale, void* stream) {
+  return adam_launch<float>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev,
+                            grad_scale, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int links_adam_step_g16(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, size_t n,
+                                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                   int* step_dev, float grad_scale, void* stream) {
+  return adam_launch<__nv_bfloat16>(param, static_cast<const __nv_bfloat16*>(grad_bf16), exp_avg, exp_avg_sq, n, lr, beta1,
+                                    beta2, eps, weight_decay, step, step_dev, grad_scale, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream) {
+  LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(grad_bf16);
+  if (n == 0) return LINKS_E_RANGE;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  grad_compress_bf16_kernel<<<static_cast<int>(blocks), 256, 0, links_stream(stream)>>>(
+      grad, static_cast<__nv_bfloat16*>(grad_bf16), n);
   return links_launch_status();
 }
 

@@ -149,7 +149,18 @@ __global__ void cast_weight_batched_kernel(const CastBatch B) {
 // torch.optim.Adam (coupled L2 weight decay), same operation order as torch's single-tensor path:
 //   g += wd*p; m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g;
 //   denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= (lr/(1-b1^t)) * m/denom
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+__device__ __forceinline__ float links_grad_load(const float* g, size_t i) { return g[i]; }
+__device__ __forceinline__ float links_grad_load(const __nv_bfloat16* g, size_t i) { return __bfloat162float(g[i]); }
+
+// fp32 gradients -> bf16 (gradient compression for the data-parallel all-reduce: half the NVLink bytes)
+__global__ void grad_compress_bf16_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16_rn(g[i]);
+}
+
+template <typename GradT>
+__global__ void adam_kernel(float* __restrict__ p, const GradT* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
                             const int* __restrict__ step_dev, int step_host, float grad_scale) {
   // step number t: host value, or (completed steps on device) + 1 so that a captured CUDA graph replays correctly
@@ -159,7 +170,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float pi = p[i];
-    float gi = g[i] * grad_scale;
+    float gi = links_grad_load(g, i) * grad_scale;
     gi = gi + wd * pi;
     const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // torch: exp_avg.lerp_(grad, 1-beta1)
     const float vi = v[i] * b2 + (1.f - b2) * gi * gi;         // torch: mul_(beta2).addcmul_(g, g, 1-beta2)

@@ -816,6 +816,7 @@ constexpr int kCacheSize = 1024;
 static CacheEntry* g_cache = nullptr;
 static std::mutex g_cache_mu;
 static int g_num_sms = 0;
+static int g_gemm_max_ctas = 0;  // 0 = all SMs; data-parallel runs leave a few SMs to the NCCL kernels (links_gemm_set_max_ctas)
 static bool g_gemm_pdl = true;   // programmatic dependent launch between consecutive GEMM launches (env LINKS_GEMM_PDL=0 disables)
 
 static uint64_t hash_bytes(const void* p, size_t n) {
@@ -825,6 +826,12 @@ static uint64_t hash_bytes(const void* p, size_t n) {
   return h;
 }
 }  // namespace links
+
+extern "C" __attribute__((visibility("default"))) int links_gemm_set_max_ctas(int n) {
+  const int prev = links::g_gemm_max_ctas;
+  links::g_gemm_max_ctas = n < 0 ? 0 : n;
+  return prev;
+}
 
 #ifdef LINKS_GEMM_TRACE
 extern "C" __attribute__((visibility("default"))) int links_debug_gemm_trace(unsigned long long* host_out) {
@@ -860,7 +867,7 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
     memcpy(ce.key, problems, key_bytes);
     ce.n = n_problems;
   }
-  const int max_cl = g_num_sms / 2;
+  const int max_cl = (g_gemm_max_ctas > 0 && g_gemm_max_ctas < g_num_sms ? g_gemm_max_ctas : g_num_sms) / 2;
   const int grid = 2 * (ce.G.total_tiles < max_cl ? ce.G.total_tiles : max_cl);   // clusters of 2 CTAs
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

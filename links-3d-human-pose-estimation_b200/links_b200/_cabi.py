@@ -61,6 +61,8 @@ SIGNATURES = {
     "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
     "links_cast_weight_batched": (ci, [C.POINTER(CastItem), ci]),
     "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
+    "links_adam_step_g16": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
+    "links_grad_compress_bf16": (ci, [vp, vp, sz]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
     "links_geom_loss": (ci, [C.POINTER(GeomMaps)] + [vp] * 10 + [ci] + [vp] * 5 + [ci, ci]),
@@ -86,6 +88,7 @@ PLAIN = {
     "links_device_ok": (ci, []),
     "links_flow_packed_floats": (sz, [ci, ci]),
     "links_flow_set_simt_only": (ci, [ci]),
+    "links_gemm_set_max_ctas": (ci, [ci]),
 }
 GEMM = {"links_gemm_grouped": (ci, [C.POINTER(GemmProblem), ci, vp])}
 

@@ -45,7 +45,7 @@ class _Net:
 
 class MlpSet:
     def __init__(self, kind, in_dims, head_dims, max_rows, n_passes=1, device="cuda", train=True,
-                 pass_branches=None):
+                 pass_branches=None, max_buckets=None):
         """in_dims[s]: input width of net s; head_dims[s]: dict head name -> width.
         max_rows: rows per pass; n_passes: forward passes per step sharing weights (1 or 2).
         pass_branches[p]: branches evaluated in pass p (default: all)."""
@@ -97,6 +97,16 @@ class MlpSet:
         tail.append("upscale")
         buckets.append(tail)
         assert sorted(n for b in buckets for n in b) == sorted(self.layer_names)
+        # fewer, larger buckets for latency-bound collectives (8 ranks: ~50-100 us fixed cost per all-reduce): merge
+        # neighbours in completion order until at most max_buckets remain
+        levels = [[i] for i in range(len(buckets))]
+        self._n_levels = len(buckets)
+        while max_buckets is not None and len(buckets) > max(1, max_buckets):
+            sizes = [len(b) for b in buckets]
+            i = min(range(len(buckets) - 1), key=lambda k: sizes[k] + sizes[k + 1])
+            buckets[i:i + 2] = [buckets[i] + buckets[i + 1]]
+            levels[i:i + 2] = [levels[i] + levels[i + 1]]
+        self._bucket_levels = levels
         self.buckets = buckets
         # every weight / bias view starts on a 256-byte boundary of the flat buffers: the GEMM epilogue only takes
         # its vector path for 16-byte aligned operands (a 7x1024+7 head would otherwise misalign everything after it)
@@ -223,17 +233,28 @@ class MlpSet:
         for arr, n in self._cast_plan(bucket):
             check(self.lib.links_cast_weight_batched(arr, n, st), "links_cast_weight_batched")
 
+    def compress_grads(self, bucket):
+        """fp32 gradients of one bucket -> the bf16 communication buffer; returns the bf16 view to all-reduce."""
+        if getattr(self, "grad16", None) is None:
+            self.grad16 = torch.zeros(self.n_params, dtype=torch.bfloat16, device=self.device)
+        a, b = self.bucket_ranges[bucket]
+        st = torch.cuda.current_stream().cuda_stream
+        check(self.lib.links_grad_compress_bf16(self.grad.data_ptr() + 4 * a, self.grad16.data_ptr() + 2 * a, b - a, st),
+              "links_grad_compress_bf16")
+        return self.grad16[a:b]
+
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0, bucket=None,
-                  last=True):
+                  last=True, grads_bf16=False):
         """Adam on the whole flat buffer, or on one bucket's contiguous range.  The device-side step counter is
         advanced by the call with last=True (the other buckets of the same step pass last=False)."""
         st = torch.cuda.current_stream().cuda_stream
         a, b = (0, self.n_params) if bucket is None else self.bucket_ranges[bucket]
         es = 4
-        check(self.lib.links_adam_step(self.master.data_ptr() + a * es, self.grad.data_ptr() + a * es,
-                                       self.exp_avg.data_ptr() + a * es, self.exp_avg_sq.data_ptr() + a * es, b - a, lr,
-                                       betas[0], betas[1], eps, weight_decay, 0 if last else -1, self.step_dev.data_ptr(),
-                                       grad_scale, st), "links_adam_step")
+        fn = self.lib.links_adam_step_g16 if grads_bf16 else self.lib.links_adam_step
+        gptr = self.grad16.data_ptr() + 2 * a if grads_bf16 else self.grad.data_ptr() + a * es
+        check(fn(self.master.data_ptr() + a * es, gptr, self.exp_avg.data_ptr() + a * es,
+                 self.exp_avg_sq.data_ptr() + a * es, b - a, lr, betas[0], betas[1], eps, weight_decay,
+                 0 if last else -1, self.step_dev.data_ptr(), grad_scale, st), "links_adam_step")
         self.refresh_shadows(bucket)
 
     # ------------------------------------------------------------------------------------------
@@ -339,10 +360,20 @@ class MlpSet:
         M = rows or self.M
         ops = []
 
-        def bucket_done(b):
-            if wgrad:
-                ops.extend(self._wgrad_ops(b, rows))
-                ops.append(("bucket", b))
+        done = set()
+
+        def bucket_done(level):
+            """`level` indexes the un-merged completion order (deepest branch level = 0 ... trunk + upscale = last); the
+            bucket that contains it is issued once its LAST level has been reached."""
+            if not wgrad:
+                return
+            done.add(level)
+            for b, members in enumerate(self._bucket_levels):
+                if b not in self._issued and all(l in done for l in members):
+                    self._issued.add(b)
+                    ops.extend(self._wgrad_ops(b, rows))
+                    ops.append(("bucket", b))
+        self._issued = set()
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
         active = self.pass_branches[p]
 
@@ -424,7 +455,7 @@ class MlpSet:
                 probs.append(self._prob(G[s]["upscale"], L.Wb, M, L.K, WIDTH, WIDTH, L.Kp, flags=GEMM_B_MN,
                                         out_f32=self.din[p][s]))
             ops.append(self._launch(probs))
-        bucket_done(len(self.buckets) - 1)
+        bucket_done(self._n_levels - 1)
         self._plans[key] = ops
         return ops
 

@@ -60,10 +60,14 @@ class OcclusionStep:
         m = self.mlp
         with torch.cuda.stream(self.comm):
             if self.world > 1:
-                a, e = m.bucket_ranges[b]
-                torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+                if self.cfg.get("grad_comm", "bf16") == "bf16":
+                    torch.distributed.all_reduce(m.compress_grads(b), group=self.pg)     # half the NVLink bytes
+                else:
+                    a, e = m.bucket_ranges[b]
+                    torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
             m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
-                        last=(b == len(m.buckets) - 1))
+                        last=(b == len(m.buckets) - 1),
+                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"))
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream

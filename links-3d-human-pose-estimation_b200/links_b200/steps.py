@@ -47,7 +47,8 @@ class LifterStep:
         nj = [len(j) for j in self.joints]
         self.nj = nj
         self.mlp = MlpSet("lifter", [2 * n for n in nj], [{"downscale": n, "angles": 1} for n in nj], self.N,
-                          n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]])
+                          n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]],
+                          max_buckets=self.cfg.get("dp_buckets") if self.world > 1 else None)
         self.mlp.load_state_dicts(lifter_params)
         self.part_flows = [FlowPacked(2 * nj[s], part_flow_params[s], device=dev) for s in range(2)]
         self.full_flow = FlowPacked(34, full_flow_params, device=dev)
@@ -104,13 +105,17 @@ class LifterStep:
         if self.world > 1:
             self.comm.wait_stream(main)
             with torch.cuda.stream(self.comm):
-                a, e = m.bucket_ranges[b]
-                torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+                if self.cfg.get("grad_comm", "bf16") == "bf16":
+                    torch.distributed.all_reduce(m.compress_grads(b), group=self.pg)     # half the NVLink bytes
+                else:
+                    a, e = m.bucket_ranges[b]
+                    torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
             src = self.comm
         self.opt_stream.wait_stream(src)
         with torch.cuda.stream(self.opt_stream):
             m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
-                        last=(b == len(m.buckets) - 1))
+                        last=(b == len(m.buckets) - 1),
+                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"))
 
     def forward_backward(self, fused_optimizer=False):
         """Everything of one step up to (and including) the gradients.  fused_optimizer=True also runs the
@@ -200,10 +205,17 @@ class StepGroup:
         self.steps = list(steps)
         self.streams = [torch.cuda.Stream() for _ in self.steps[1:]]
         self.graph = None
-        # one comm stream for all branches: collectives are issued (and captured) in one deterministic order on every
-        # rank; two NCCL kernels of one communicator racing on different streams would deadlock
-        for st in self.steps[1:]:
-            st.comm = self.steps[0].comm
+        # Branches that share a communicator must share ONE comm stream: collectives are then issued (and captured) in
+        # one deterministic order on every rank -- two NCCL kernels of one communicator racing on different streams
+        # would deadlock.  Branches with their own process group (own communicator) keep their own comm stream and
+        # their all-reduces run concurrently.
+        by_pg = {}
+        for st in self.steps:
+            key = id(st.pg)
+            if key in by_pg:
+                st.comm = by_pg[key].comm
+            else:
+                by_pg[key] = st
 
     def step(self):
         main = torch.cuda.current_stream()
