@@ -176,7 +176,8 @@ extern "C" __attribute__((visibility("default"))) int links_geom_forward(const L
   A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
   A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
   A.qpart[0] = qpart0; A.qpart[1] = qpart1; A.qfull[0] = q_full0; A.qfull[1] = q_full1;
-  geom_forward_kernel<<<geom_grid(N), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  if (maps->V == 1) geom_forward_kernel<1><<<geom_grid((N + 1) / 2), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  else geom_forward_kernel<2><<<geom_grid((N + 1) / 2), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -202,7 +203,8 @@ extern "C" __attribute__((visibility("default"))) int links_geom_loss(const Link
   A.g2T[0] = static_cast<__nv_bfloat16*>(g2T_head0); A.g2T[1] = static_cast<__nv_bfloat16*>(g2T_head1);
   A.ldT = ldT; A.colT0 = colT0;
   const int pairs = (N + 1) / 2;
-  geom_lossgrad_kernel<false><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  if (maps->V == 1) geom_lossgrad_kernel<false, 1><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  else geom_lossgrad_kernel<false, 2><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -232,7 +234,8 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
   A.ldT = ldT; A.colT0 = colT0;
   A.dgamma = dgamma_direct; A.da = da; A.red = red;
   const int pairs = (N + 1) / 2;
-  geom_lossgrad_kernel<true><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  if (maps->V == 1) geom_lossgrad_kernel<true, 1><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  else geom_lossgrad_kernel<true, 2><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -406,9 +409,9 @@ extern "C" __attribute__((visibility("default"))) int links_flow_sample(const fl
 
 // ---------------------------------------------------------------------------------------------
 // grid of the chunk-walking metric kernels: at most 8 blocks (of 64 threads, ~27-36 KB shared) per SM
-static int metric_grid(int M) {
+static int metric_grid(int M, int blocks_per_sm) {
   const int chunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
-  return chunks < 148 * 8 ? chunks : 148 * 8;
+  return chunks < 148 * blocks_per_sm ? chunks : 148 * blocks_per_sm;
 }
 
 static int check_pose_args(const float* a, const float* b, int M, int J) {
@@ -423,8 +426,23 @@ extern "C" __attribute__((visibility("default"))) int links_mpjpe(const float* p
   int rc = check_pose_args(p_ref, p, M, num_joints);
   if (rc) return rc;
   if (root_joint < 0 || root_joint >= num_joints) return LINKS_E_RANGE;
-  mpjpe_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
-      p_ref, p, M, num_joints, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
+  // light math per pose: two staging buffers keep the next chunk in flight (52 KB of shared memory -> 4 blocks per SM)
+  const int grid = metric_grid(M, 4);
+  cudaStream_t s = links_stream(stream);
+  constexpr size_t smem = metric_smem_bytes(2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(mpjpe_kernel<17, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(mpjpe_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(mpjpe_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr_done = true;
+  }
+  if (num_joints == 17)
+    mpjpe_kernel<17, 2><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, 17, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
+  else if (num_joints == 16)
+    mpjpe_kernel<16, 2><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, 16, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
+  else
+    mpjpe_kernel<0, 2><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, num_joints, root_joint, use_scaling, per_pose, per_pose_max, dist, sum);
   return links_launch_status();
 }
 
@@ -444,8 +462,16 @@ extern "C" __attribute__((visibility("default"))) int links_pmpjpe(const float* 
   int rc = check_pose_args(p_ref, p, M, num_joints);
   if (rc) return rc;
   if (mode < 0 || mode > 1) return LINKS_E_RANGE;
-  pmpjpe_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
-      p_ref, p, M, num_joints, mode, per_pose, aligned, sum);
+  // SVD-heavy: one staging buffer, more resident blocks to hide the dependent chains
+  const int grid = metric_grid(M, 6);
+  cudaStream_t s = links_stream(stream);
+  constexpr size_t smem = metric_smem_bytes(1);
+  if (num_joints == 17)
+    pmpjpe_kernel<17, 1><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, 17, mode, per_pose, aligned, sum);
+  else if (num_joints == 16)
+    pmpjpe_kernel<16, 1><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, 16, mode, per_pose, aligned, sum);
+  else
+    pmpjpe_kernel<0, 1><<<grid, kPosesPerBlock, smem, s>>>(p_ref, p, M, num_joints, mode, per_pose, aligned, sum);
   return links_launch_status();
 }
 
@@ -455,7 +481,7 @@ extern "C" __attribute__((visibility("default"))) int links_eval_lift_score(cons
   if (rc) return rc;
   LINKS_CHECK_PTR(depth_off); LINKS_CHECK_PTR(sums3);
   if (ld_depth < 17) return LINKS_E_RANGE;
-  eval_lift_score_kernel<<<metric_grid(M), kPosesPerBlock, 0, links_stream(stream)>>>(
+  eval_lift_score_kernel<<<metric_grid(M, 5), kPosesPerBlock, 0, links_stream(stream)>>>(
       poses_2d, depth_off, ld_depth, gt_3d, M, depth, sums3);
   return links_launch_status();
 }

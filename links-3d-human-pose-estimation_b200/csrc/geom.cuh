@@ -2,9 +2,14 @@
 // Reference: train_leg_torso_lifter.py:153-272 (V = 1 pose variant) and train_left_right_lifter.py:150-423
 // (V = 2 variants: 'left' / 'right' choice of combine_left_right_pred_1d, utils/helpers.py:40-53).
 //
-// Mapping: one warp per consecutive row pair (2k, 2k+1) -- the pairwise deformation loss (:250-254) couples
-// exactly those rows; lane j < 17 owns joint j; per-row reductions are warp shuffles.  Nothing but the
-// network outputs is read: P, R, Q, q are recomputed from (u, depth heads, angle heads, eps_x, u_y, stats).
+// Mapping: one warp per consecutive row pair (2k, 2k+1) -- the pairwise deformation loss (:250-254) couples exactly
+// those rows.  Lanes 0-15 own row 2k, lanes 16-31 row 2k+1; lane s of a half owns joint s+1 AND bone s (whose child is
+// joint s+1).  The root joint needs no lane: after root-centring (:188-192) its lifted, rotated, re-lifted and
+// back-rotated positions are identically zero, its depth offset is forced to 0 (:183) so it receives no gradient, and
+// its only loss contribution is the constant |u_root| of the reprojection term.  Per-row reductions are 4-step
+// half-warp shuffles, the pair exchange is one xor-16 shuffle, the three sin/cos pairs of a row are evaluated by three
+// different lanes in one call.  Nothing but the network outputs is read: P, R, Q, q are recomputed from
+// (u, depth heads, angle heads, eps_x, u_y, stats).
 #pragma once
 #include "devdefs.cuh"
 
@@ -40,8 +45,7 @@ struct GeomArgs {
 
 // The argument block (index maps, pointers) is copied into shared memory once per block: the maps are indexed by
 // lane, and lane-divergent reads of the kernel-parameter constant bank serialise (one transaction per distinct
-// address) -- together with per-block single-address atomics that made these kernels 10-50x slower than the HBM
-// roofline at large N.  Blocks then walk rows with a grid-stride loop and issue ONE set of atomics at the end.
+// address).  Blocks walk row pairs with a grid-stride loop and issue ONE set of atomics at the end.
 __device__ __forceinline__ void stage_args(GeomArgs* dst, const GeomArgs& src) {
   const uint32_t* s32 = reinterpret_cast<const uint32_t*>(&src);
   uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
@@ -54,6 +58,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LINKS_FULL_MASK, v, o);
   return v;
 }
+// sum over the 16 lanes of a half-warp (every lane of the half receives it)
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(LINKS_FULL_MASK, v, o);
+  return v;
+}
+
+// 1/x by the hardware approximation (<= 2 ulp): the projections divide by depths ~ 10, far from its range limits
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }
 
 struct Vec3 { float x, y, z; };
 __device__ __forceinline__ Vec3 shfl3(Vec3 v, int src) {
@@ -78,104 +91,140 @@ __device__ __forceinline__ Vec3 matT_vec(const float (&R)[9], Vec3 p) {  // R^T 
   return q;
 }
 
-// R = Rx(a) @ (Ry(b) @ Rx(g))   (utils/rotation_conversions.py:11-36; train_leg_torso_lifter.py:159-181)
-__device__ __forceinline__ void make_rotation(float a, float b, float g, float (&R)[9]) {
-  float sa, ca, sb, cb, sg, cg;
-  sincosf(a, &sa, &ca);
-  sincosf(b, &sb, &cb);
-  sincosf(g, &sg, &cg);
+// bone table (utils/helpers.py:140-141): bone b joins parent kBoneParent[b] and child b+1 (4 bits per entry);
+// bit j of kHasNextBone: joint j is the parent of bone j; joint 8 is also the parent of bones 10 and 13, the root
+// of bones 0, 3 and 6.
+constexpr unsigned long long kBoneParent = 0xfe8cb89870540210ull;
+constexpr unsigned kHasNextBone = 0xdbb6u;
+
+// Lane-constant indexing state (one joint, one bone).
+struct LaneMaps {
+  int lane, sub, hbase, j;     // j = sub + 1
+  int net[2], col;             // depth-head source of joint j per variant
+  int pnet[2], pidx[2];        // which part (flow / pass-2 lifter input) receives joint j per variant, and where
+  int parent_src;              // lane holding the parent joint of bone `sub`
+  bool parent_is_root, has_next;
+  float crel;                  // bone_rel[sub]
+};
+__device__ __forceinline__ void lane_maps(const GeomArgs& A, LaneMaps& m) {
+  m.lane = threadIdx.x & 31;
+  m.sub = m.lane & 15;
+  m.hbase = m.lane & 16;
+  m.j = m.sub + 1;
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    m.net[v] = A.maps.src_net[v][m.j];
+    m.pnet[v] = A.maps.part_net[v][m.j];
+    m.pidx[v] = A.maps.part_idx[v][m.j];
+  }
+  m.col = A.maps.col[m.j];
+  const int parent = static_cast<int>((kBoneParent >> (4 * m.sub)) & 15ull);
+  m.parent_is_root = parent == 0;
+  m.parent_src = m.hbase | (parent > 0 ? parent - 1 : 0);
+  m.has_next = (kHasNextBone >> m.j) & 1u;
+  m.crel = A.maps.bone_rel[m.sub];
+}
+
+// R = Rx(a) @ (Ry(b) @ Rx(g))   (utils/rotation_conversions.py:11-36; train_leg_torso_lifter.py:159-181).
+// Lanes 0, 1, 2 of each half evaluate sincos(a), sincos(b), sincos(g) in one call; the results are broadcast.
+__device__ __forceinline__ void make_rotation(const LaneMaps& m, float a, float b, float g, float (&R)[9]) {
+  const int k = m.sub % 3;
+  const float arg = k == 0 ? a : (k == 1 ? b : g);
+  float s, c;
+  sincosf(arg, &s, &c);
+  const float sa = __shfl_sync(LINKS_FULL_MASK, s, m.hbase), ca = __shfl_sync(LINKS_FULL_MASK, c, m.hbase);
+  const float sb = __shfl_sync(LINKS_FULL_MASK, s, m.hbase | 1), cb = __shfl_sync(LINKS_FULL_MASK, c, m.hbase | 1);
+  const float sg = __shfl_sync(LINKS_FULL_MASK, s, m.hbase | 2), cg = __shfl_sync(LINKS_FULL_MASK, c, m.hbase | 2);
   R[0] = cb;       R[1] = sb * sg;                 R[2] = sb * cg;
   R[3] = sa * sb;  R[4] = ca * cg - sa * cb * sg;  R[5] = -ca * sg - sa * cb * cg;
   R[6] = -ca * sb; R[7] = sa * cg + ca * cb * sg;  R[8] = -sa * sg + ca * cb * cg;
 }
 
+// Per-row inputs shared by all variants.
+struct RowIn {
+  size_t n;
+  float ux, uy;        // this lane's 2D joint
+  float u0x, u0y;      // root joint
+  float gamma, eps;
+  float R[9];
+};
+__device__ __forceinline__ void load_row(const GeomArgs& A, const LaneMaps& m, int n, RowIn& r) {
+  r.n = static_cast<size_t>(n);
+  const float* u = A.u + r.n * 34;
+  r.ux = u[m.j];
+  r.uy = u[kJ + m.j];
+  r.u0x = u[0];
+  r.u0y = u[kJ];
+  r.gamma = 0.5f * (A.ang[0][r.n * LINKS_HEAD_LD] + A.ang[1][r.n * LINKS_HEAD_LD]);
+  r.eps = A.eps_x[n];
+  const float a = -A.stats[0] + A.stats[1] * r.eps;
+  const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
+  make_rotation(m, a, b, r.gamma, r.R);
+}
+
 // Per-lane state of one (row, variant).
 struct RowVar {
-  float ux, uy;      // input 2D joint
   float mask;        // 1 where depth not clamped (:186)
   float d;           // clamped depth
   Vec3 P;            // root-centred lifted joint (:188-192)
   Vec3 Q;            // rotated joint (:195)
-  float zq, qx, qy;  // projection (:198-199)
+  float izq, qx, qy; // projection (:198-199); izq = 1 / (Q.z + depth)
   // pass-2 side
   float mask2, d2;
   Vec3 P2;           // re-lifted joint (:235-238)
   Vec3 F;            // Q - P2
   float L3d;
   Vec3 S;            // R^T P2 (:242)
-  float zs, rx, ry;
+  float izs, rx, ry; // izs = 1 / (S.z + depth)
+  // bones
+  Vec3 e;            // P_parent - P_child of this lane's bone
+  float bl_len, bl_imean, bl_rho;   // bone length, 1 / mean bone length, their ratio
 };
 
-// bone table (utils/helpers.py:140-141) as lane-indexed lookups
-__device__ __forceinline__ int bone_i(int b) {
-  const int t[16] = {0, 1, 2, 0, 4, 5, 0, 7, 8, 9, 8, 11, 12, 8, 14, 15};
-  return t[b & 15];
-}
-__device__ __forceinline__ int bone_j(int b) {
-  const int t[16] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
-  return t[b & 15];
-}
-
-__device__ __forceinline__ void row_forward(const GeomArgs& A, int v, int n, int lane, const float (&R)[9], RowVar& s) {
-  const bool act = lane < kJ;
-  const int j = act ? lane : 0;
+__device__ __forceinline__ void row_forward(const GeomArgs& A, const LaneMaps& m, int v, const RowIn& r, RowVar& s) {
   const float D = A.maps.depth;
-  s.ux = act ? A.u[static_cast<size_t>(n) * 34 + j] : 0.f;
-  s.uy = act ? A.u[static_cast<size_t>(n) * 34 + kJ + j] : 0.f;
-  float delta = 0.f;
-  if (act && j != 0) delta = A.head[A.maps.src_net[v][j]][static_cast<size_t>(n) * LINKS_HEAD_LD + A.maps.col[j]];
-  float d = delta + D;
+  const float d0 = D < 1.0f ? 1.0f : D;                   // root depth: offset forced to 0 (:183), then clamped
+  float d = A.head[m.net[v]][r.n * LINKS_HEAD_LD + m.col] + D;
   s.mask = (d < 1.0f) ? 0.f : 1.f;
   d = (d < 1.0f) ? 1.0f : d;
   s.d = d;
-  Vec3 T;
-  T.x = s.ux * d; T.y = s.uy * d; T.z = d;
-  const Vec3 T0 = shfl3(T, 0);
-  s.P.x = act ? T.x - T0.x : 0.f;
-  s.P.y = act ? T.y - T0.y : 0.f;
-  s.P.z = act ? T.z - T0.z : 0.f;
-  s.Q = mat_vec(R, s.P);
-  s.zq = s.Q.z + D;
-  s.qx = s.Q.x / s.zq;
-  s.qy = s.Q.y / s.zq;
+  s.P.x = r.ux * d - r.u0x * d0;
+  s.P.y = r.uy * d - r.u0y * d0;
+  s.P.z = d - d0;
+  s.Q = mat_vec(r.R, s.P);
+  s.izq = fast_rcp(s.Q.z + D);
+  s.qx = s.Q.x * s.izq;
+  s.qy = s.Q.y * s.izq;
 }
 
-// pass-2 quantities and the per-row loss terms.  Returns (L3d, rep_rot, bl_prior) via out[3].
-__device__ __forceinline__ void row_consistency(const GeomArgs& A, int v, int n, int lane, const float (&R)[9],
-                                                RowVar& s, float (&out)[3], float& bl_mean, float& bl_len,
-                                                float& bl_rho) {
-  const bool act = lane < kJ;
-  const int j = act ? lane : 0;
+// pass-2 quantities and the per-row loss terms (L3d, rep_rot, bl_prior) via out[3] (uniform over the half-warp).
+__device__ __forceinline__ void row_consistency(const GeomArgs& A, const LaneMaps& m, int v, const RowIn& r, RowVar& s,
+                                                float (&out)[3]) {
   const float D = A.maps.depth;
-  float delta2 = 0.f;
-  if (act && j != 0) delta2 = A.head2[A.maps.src_net[v][j]][static_cast<size_t>(n) * LINKS_HEAD_LD + A.maps.col[j]];
-  float d2 = delta2 + D;
+  const float d0 = D < 1.0f ? 1.0f : D;
+  float d2 = A.head2[m.net[v]][r.n * LINKS_HEAD_LD + m.col] + D;
   s.mask2 = (d2 < 1.0f) ? 0.f : 1.f;
   d2 = (d2 < 1.0f) ? 1.0f : d2;
   s.d2 = d2;
-  Vec3 T;
-  T.x = s.qx * d2; T.y = s.qy * d2; T.z = d2;
-  const Vec3 T0 = shfl3(T, 0);
-  s.P2.x = act ? T.x - T0.x : 0.f;
-  s.P2.y = act ? T.y - T0.y : 0.f;
-  s.P2.z = act ? T.z - T0.z : 0.f;
+  // the root projects to (0, 0): its re-lifted position is (0, 0, d0)
+  s.P2.x = s.qx * d2;
+  s.P2.y = s.qy * d2;
+  s.P2.z = d2 - d0;
   s.F.x = s.Q.x - s.P2.x; s.F.y = s.Q.y - s.P2.y; s.F.z = s.Q.z - s.P2.z;
-  s.L3d = sqrtf(warp_sum(s.F.x * s.F.x + s.F.y * s.F.y + s.F.z * s.F.z));
-  s.S = matT_vec(R, s.P2);
-  s.zs = s.S.z + D;
-  s.rx = s.S.x / s.zs;
-  s.ry = s.S.y / s.zs;
-  const float rep = warp_sum(act ? fabsf(s.rx - s.ux) + fabsf(s.ry - s.uy) : 0.f);
-  // bone lengths: lane b < 16 owns bone b
-  const bool bact = lane < 16;
-  const Vec3 Pi = shfl3(s.P, bone_i(lane));
-  const Vec3 Pj = shfl3(s.P, bone_j(lane));
-  const float ex = Pi.x - Pj.x, ey = Pi.y - Pj.y, ez = Pi.z - Pj.z;
-  bl_len = bact ? sqrtf(ex * ex + ey * ey + ez * ez) : 0.f;
-  bl_mean = warp_sum(bl_len) * (1.f / 16.f);
-  bl_rho = bl_len / bl_mean;
-  const float c = A.maps.bone_rel[lane & 15];
-  const float bl = warp_sum(bact ? (c - bl_rho) * (c - bl_rho) : 0.f);
+  s.L3d = sqrtf(half_sum(s.F.x * s.F.x + s.F.y * s.F.y + s.F.z * s.F.z));
+  s.S = matT_vec(r.R, s.P2);
+  s.izs = fast_rcp(s.S.z + D);
+  s.rx = s.S.x * s.izs;
+  s.ry = s.S.y * s.izs;
+  const float rep = half_sum(fabsf(s.rx - r.ux) + fabsf(s.ry - r.uy)) + (fabsf(r.u0x) + fabsf(r.u0y));
+  // bone lengths: this lane's bone joins its joint (child) to the parent joint
+  Vec3 Pp = shfl3(s.P, m.parent_src);
+  if (m.parent_is_root) { Pp.x = 0.f; Pp.y = 0.f; Pp.z = 0.f; }
+  s.e.x = Pp.x - s.P.x; s.e.y = Pp.y - s.P.y; s.e.z = Pp.z - s.P.z;
+  s.bl_len = sqrtf(s.e.x * s.e.x + s.e.y * s.e.y + s.e.z * s.e.z);
+  s.bl_imean = fast_rcp(half_sum(s.bl_len) * (1.f / 16.f));
+  s.bl_rho = s.bl_len * s.bl_imean;
+  const float bl = half_sum((m.crel - s.bl_rho) * (m.crel - s.bl_rho));
   out[0] = s.L3d;
   out[1] = rep;
   out[2] = bl;
@@ -184,40 +233,46 @@ __device__ __forceinline__ void row_consistency(const GeomArgs& A, int v, int n,
 // =========================================================================================================
 // forward: projected parts for the flows / pass-2 lifters
 // =========================================================================================================
+template <int V>
 __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const GeomArgs Ap) {
   __shared__ GeomArgs sA;
   stage_args(&sA, Ap);
   const GeomArgs& A = sA;
-  const int lane = threadIdx.x & 31;
-  // lane-constant map entries
-  int part_net[2], part_idx[2];
-#pragma unroll
-  for (int v = 0; v < 2; ++v) {
-    part_net[v] = lane < kJ ? A.maps.part_net[v][lane] : -1;
-    part_idx[v] = lane < kJ ? A.maps.part_idx[v][lane] : 0;
-  }
+  LaneMaps m;
+  lane_maps(A, m);
+  const int half = m.lane >> 4;
+  const int npairs = (A.N + 1) / 2;
   const int stride = gridDim.x * kGeomWarps;
-  for (int n = blockIdx.x * kGeomWarps + (threadIdx.x >> 5); n < A.N; n += stride) {   // one warp per row
-    const float gamma = 0.5f * (A.ang[0][static_cast<size_t>(n) * LINKS_HEAD_LD] + A.ang[1][static_cast<size_t>(n) * LINKS_HEAD_LD]);
-    const float a = -A.stats[0] + A.stats[1] * A.eps_x[n];
-    const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
-    float R[9];
-    make_rotation(a, b, gamma, R);
-    for (int v = 0; v < A.maps.V; ++v) {
+  for (int pair = blockIdx.x * kGeomWarps + (threadIdx.x >> 5); pair < npairs; pair += stride) {
+    const int n_own = 2 * pair + half;
+    const bool valid = n_own < A.N;              // uniform over the half-warp
+    RowIn r;
+    load_row(A, m, valid ? n_own : 2 * pair, r);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
       RowVar s;
-      row_forward(A, v, n, lane, R, s);
-      if (lane < kJ) {
-        if (A.qfull[v]) {
-          A.qfull[v][static_cast<size_t>(n) * 34 + lane] = s.qx;
-          A.qfull[v][static_cast<size_t>(n) * 34 + kJ + lane] = s.qy;
-        }
-        const int p = part_net[v];
-        if (p >= 0) {
-          const int nj = A.maps.n_joints[p];
-          const int idx = part_idx[v];
-          float* dst = A.qpart[p] + static_cast<size_t>(n) * (2 * nj);
-          dst[idx] = s.qx;
-          dst[nj + idx] = s.qy;
+      row_forward(A, m, v, r, s);
+      if (!valid) continue;
+      if (A.qfull[v]) {
+        float* qf = A.qfull[v] + r.n * 34;
+        qf[m.j] = s.qx;
+        qf[kJ + m.j] = s.qy;
+        if (m.sub == 0) { qf[0] = 0.f; qf[kJ] = 0.f; }          // root: projects to (0, 0)
+      }
+      const int p = m.pnet[v];
+      if (p >= 0) {
+        const int nj = A.maps.n_joints[p];
+        float* dst = A.qpart[p] + r.n * (2 * nj);
+        dst[m.pidx[v]] = s.qx;
+        dst[nj + m.pidx[v]] = s.qy;
+      }
+      if (m.sub == 0) {
+        const int p0 = A.maps.part_net[v][0];
+        if (p0 >= 0) {
+          const int nj = A.maps.n_joints[p0];
+          float* dst = A.qpart[p0] + r.n * (2 * nj);
+          dst[A.maps.part_idx[v][0]] = 0.f;
+          dst[nj + A.maps.part_idx[v][0]] = 0.f;
         }
       }
     }
@@ -227,195 +282,170 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
 // =========================================================================================================
 // losses + gradients.  kFull = false: loss sums and d/d(pass-2 heads) only (runs before the pass-2 backward);
 // kFull = true : complete backward to the pass-1 heads, d gamma (direct) and d a (runs after it).
+// V (number of pose variants, = maps.V) is a template parameter so that the variant loop unrolls: the per-variant lane
+// maps stay in registers and every shuffle sits in straight-line, provably convergent code.
 // =========================================================================================================
-template <bool kFull>
+template <bool kFull, int V>
 __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const GeomArgs Ap) {
   __shared__ float s_part[kGeomWarps][6];
   __shared__ GeomArgs sA;
   stage_args(&sA, Ap);
   const GeomArgs& A = sA;
-  const int lane = threadIdx.x & 31;
+  LaneMaps m;
+  lane_maps(A, m);
+  const int lane = m.lane;
   const int warp = threadIdx.x >> 5;
-  const bool act = lane < kJ;
+  const int half = lane >> 4;
   const float invN = 1.f / static_cast<float>(A.N);
   const int npairs = A.N / 2;
   const float c3d = A.maps.w_3d * invN, c2d = A.maps.w_2d * invN, cbl = A.maps.w_bl * invN;
   const float cv = npairs > 0 ? A.maps.w_vel / static_cast<float>(npairs) : 0.f;
-  const float D = A.maps.depth;
+  // which depth heads ever feed this lane's joint / the root joint (-> which gradient columns this lane writes)
+  bool feeds[2] = {false, false}, feeds_root[2] = {false, false};
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      feeds[net] = feeds[net] || m.net[v] == net;
+      feeds_root[net] = feeds_root[net] || A.maps.src_net[v][0] == net;
+    }
+  }
+  const int col_root = A.maps.col[0];
 
-  float sums[4] = {0.f, 0.f, 0.f, 0.f};   // L3d, rep, pair, bl (raw sums, lane-uniform)
+  float sums[4] = {0.f, 0.f, 0.f, 0.f};   // L3d, rep, pair, bl (raw sums of this half-warp's rows)
   float red_da = 0.f, red_eda = 0.f;
 
   const int total_pairs = (A.N + 1) / 2;
   for (int pair = blockIdx.x * kGeomWarps + warp; pair < total_pairs; pair += gridDim.x * kGeomWarps) {
-    const int nA = 2 * pair, nB = 2 * pair + 1;
-    const bool vB = nB < A.N;                                    // warp-uniform
-    float R[2][9], gam[2], eps[2];
-    int rows[2] = {nA, nB};
-    const int nrows = vB ? 2 : 1;
-    #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (r >= nrows) break;
-      const int n = rows[r];
-      gam[r] = 0.5f * (A.ang[0][static_cast<size_t>(n) * LINKS_HEAD_LD] + A.ang[1][static_cast<size_t>(n) * LINKS_HEAD_LD]);
-      eps[r] = A.eps_x[n];
-      const float a = -A.stats[0] + A.stats[1] * eps[r];
-      const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
-      make_rotation(a, b, gam[r], R[r]);
-    }
-    float dR[2][9];
+    const bool vB = 2 * pair + 1 < A.N;                           // warp-uniform: the pair is complete
+    const bool valid = half == 0 || vB;                           // uniform over the half-warp
+    RowIn r;
+    load_row(A, m, valid ? 2 * pair + half : 2 * pair, r);
+    float dRm[9];                                                 // lane-partial d/dR
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int k = 0; k < 9; ++k) dR[r][k] = 0.f;
-    float g1acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // [row][net] d/d(pass-1 head) for this lane's column
-    float g2acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k = 0; k < 9; ++k) dRm[k] = 0.f;
+    float g1acc[2] = {0.f, 0.f};   // [net] d/d(pass-1 head) for this lane's column
+    float g2acc[2] = {0.f, 0.f};
 
-    for (int v = 0; v < A.maps.V; ++v) {
-      RowVar s[2];
-      float bl_mean[2], bl_len[2], bl_rho[2];
-      #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (r >= nrows) break;
-        float o[3];
-        row_forward(A, v, rows[r], lane, R[r], s[r]);
-        row_consistency(A, v, rows[r], lane, R[r], s[r], o, bl_mean[r], bl_len[r], bl_rho[r]);
-        sums[0] += o[0]; sums[1] += o[1]; sums[3] += o[2];
-      }
-      // pairwise deformation (:250-254)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      RowVar t;
+      float o[3];
+      row_forward(A, m, v, r, t);
+      row_consistency(A, m, v, r, t, o);
+      if (valid) { sums[0] += o[0]; sums[1] += o[1]; sums[3] += o[2]; }
+      // pairwise deformation (:250-254): E = (P - P') - (S - S'), ' = the other row of the pair
       Vec3 E; E.x = E.y = E.z = 0.f;
       float pnorm = 0.f;
-      if (vB) {
-        E.x = (s[0].P.x - s[1].P.x) - (s[0].S.x - s[1].S.x);
-        E.y = (s[0].P.y - s[1].P.y) - (s[0].S.y - s[1].S.y);
-        E.z = (s[0].P.z - s[1].P.z) - (s[0].S.z - s[1].S.z);
-        pnorm = sqrtf(warp_sum(E.x * E.x + E.y * E.y + E.z * E.z));
-        sums[2] += pnorm;
+      {
+        Vec3 dPS; dPS.x = t.P.x - t.S.x; dPS.y = t.P.y - t.S.y; dPS.z = t.P.z - t.S.z;
+        const float ox = __shfl_xor_sync(LINKS_FULL_MASK, dPS.x, 16);
+        const float oy = __shfl_xor_sync(LINKS_FULL_MASK, dPS.y, 16);
+        const float oz = __shfl_xor_sync(LINKS_FULL_MASK, dPS.z, 16);
+        if (vB) { E.x = dPS.x - ox; E.y = dPS.y - oy; E.z = dPS.z - oz; }
+        pnorm = sqrtf(half_sum(E.x * E.x + E.y * E.y + E.z * E.z));
+        if (half == 0) sums[2] += pnorm;
       }
       const float ge = pnorm > 0.f ? cv / pnorm : 0.f;
-      #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (r >= nrows) break;
-        RowVar& t = s[r];
-        const float sgn = r == 0 ? 1.f : -1.f;
-        // ---- d/dS: reprojection L1 (:247) + pair term
-        const float drx = act ? c2d * ((t.rx > t.ux) ? 1.f : ((t.rx < t.ux) ? -1.f : 0.f)) : 0.f;
-        const float dry = act ? c2d * ((t.ry > t.uy) ? 1.f : ((t.ry < t.uy) ? -1.f : 0.f)) : 0.f;
-        Vec3 dS;
-        dS.x = drx / t.zs - sgn * ge * E.x;
-        dS.y = dry / t.zs - sgn * ge * E.y;
-        dS.z = -(drx * t.rx + dry * t.ry) / t.zs - sgn * ge * E.z;
-        // ---- d/dP2 = R dS - c3d F / L3d
-        const float g3 = t.L3d > 0.f ? c3d / t.L3d : 0.f;
-        Vec3 dP2 = mat_vec(R[r], dS);
-        dP2.x -= g3 * t.F.x; dP2.y -= g3 * t.F.y; dP2.z -= g3 * t.F.z;
-        if (!act) { dP2.x = dP2.y = dP2.z = 0.f; }
-        // root centring: dT_j = dP2_j - [j==0] sum_i dP2_i
-        const float sx = warp_sum(dP2.x), sy = warp_sum(dP2.y), sz = warp_sum(dP2.z);
-        Vec3 dT2 = dP2;
-        if (lane == 0) { dT2.x -= sx; dT2.y -= sy; dT2.z -= sz; }
-        const float dd2 = dT2.x * t.qx + dT2.y * t.qy + dT2.z;
-        const float ddelta2 = (act && lane != 0) ? t.mask2 * dd2 : 0.f;
-        const int net = A.maps.src_net[v][act ? lane : 0];
-        g2acc[r][0] += net == 0 ? ddelta2 : 0.f;
-        g2acc[r][1] += net == 1 ? ddelta2 : 0.f;
-        if (kFull) {
-          // ---- d/dq: through P2 = (q d2) and the external consumers (flows, pass-2 lifters)
-          float dqx = dT2.x * t.d2, dqy = dT2.y * t.d2;
-          const int p = act ? A.maps.part_net[v][lane] : -1;
-          if (p >= 0) {
-            const int nj = A.maps.n_joints[p];
-            const int idx = A.maps.part_idx[v][lane];
-            const size_t n = rows[r];
-            dqx += A.dflow[p][n * (2 * nj) + idx] + A.dlift[p][n * LINKS_HEAD_LD + idx];
-            dqy += A.dflow[p][n * (2 * nj) + nj + idx] + A.dlift[p][n * LINKS_HEAD_LD + nj + idx];
-          }
-          // ---- d/dQ
-          Vec3 dQ;
-          dQ.x = g3 * t.F.x + dqx / t.zq;
-          dQ.y = g3 * t.F.y + dqy / t.zq;
-          dQ.z = g3 * t.F.z - (dqx * t.qx + dqy * t.qy) / t.zq;
-          if (!act) { dQ.x = dQ.y = dQ.z = 0.f; }
-          // ---- d/dP = R^T dQ + pair + bones
-          Vec3 dP = matT_vec(R[r], dQ);
-          dP.x += sgn * ge * E.x; dP.y += sgn * ge * E.y; dP.z += sgn * ge * E.z;
-          {
-            const bool bact = lane < 16;
-            const float c = A.maps.bone_rel[lane & 15];
-            const float h = bact ? -2.f * (c - bl_rho[r]) * cbl : 0.f;
-            const float hl = warp_sum(h * bl_len[r]);
-            const float dl = bact ? h / bl_mean[r] - hl / (16.f * bl_mean[r] * bl_mean[r]) : 0.f;
-            const Vec3 Pi = shfl3(t.P, bone_i(lane));
-            const Vec3 Pj = shfl3(t.P, bone_j(lane));
-            const float w = (bact && bl_len[r] > 0.f) ? dl / bl_len[r] : 0.f;
-            Vec3 dv;
-            dv.x = w * (Pi.x - Pj.x); dv.y = w * (Pi.y - Pj.y); dv.z = w * (Pi.z - Pj.z);
+      // ---- d/dS: reprojection L1 (:247) + pair term
+      const float drx = c2d * ((t.rx > r.ux) ? 1.f : ((t.rx < r.ux) ? -1.f : 0.f));
+      const float dry = c2d * ((t.ry > r.uy) ? 1.f : ((t.ry < r.uy) ? -1.f : 0.f));
+      Vec3 dS;
+      dS.x = drx * t.izs - ge * E.x;
+      dS.y = dry * t.izs - ge * E.y;
+      dS.z = -(drx * t.rx + dry * t.ry) * t.izs - ge * E.z;
+      // ---- d/dP2 = R dS - c3d F / L3d   (root centring only feeds the root's own, constant, depth)
+      const float g3 = t.L3d > 0.f ? c3d / t.L3d : 0.f;
+      Vec3 dP2 = mat_vec(r.R, dS);
+      dP2.x -= g3 * t.F.x; dP2.y -= g3 * t.F.y; dP2.z -= g3 * t.F.z;
+      const float ddelta2 = t.mask2 * (dP2.x * t.qx + dP2.y * t.qy + dP2.z);
+      const int net = m.net[v];
+      g2acc[0] += net == 0 ? ddelta2 : 0.f;
+      g2acc[1] += net == 1 ? ddelta2 : 0.f;
+      if (kFull) {
+        // ---- d/dq: through P2 = (q d2) and the external consumers (flows, pass-2 lifters)
+        float dqx = dP2.x * t.d2, dqy = dP2.y * t.d2;
+        const int p = m.pnet[v];
+        if (p >= 0) {
+          const int nj = A.maps.n_joints[p];
+          const int idx = m.pidx[v];
+          dqx += A.dflow[p][r.n * (2 * nj) + idx] + A.dlift[p][r.n * LINKS_HEAD_LD + idx];
+          dqy += A.dflow[p][r.n * (2 * nj) + nj + idx] + A.dlift[p][r.n * LINKS_HEAD_LD + nj + idx];
+        }
+        // ---- d/dQ
+        Vec3 dQ;
+        dQ.x = g3 * t.F.x + dqx * t.izq;
+        dQ.y = g3 * t.F.y + dqy * t.izq;
+        dQ.z = g3 * t.F.z - (dqx * t.qx + dqy * t.qy) * t.izq;
+        // ---- d/dP = R^T dQ + pair + bones
+        Vec3 dP = matT_vec(r.R, dQ);
+        dP.x += ge * E.x; dP.y += ge * E.y; dP.z += ge * E.z;
+        {
+          const float h = -2.f * (m.crel - t.bl_rho) * cbl;
+          const float hl = half_sum(h * t.bl_len);
+          const float dl = (h - hl * (1.f / 16.f) * t.bl_imean) * t.bl_imean;
+          const float w = t.bl_len > 0.f ? dl * fast_rcp(t.bl_len) : 0.f;
+          Vec3 dv;                                   // d/d(P_parent) of this lane's bone; d/d(P_child) = -dv
+          dv.x = w * t.e.x; dv.y = w * t.e.y; dv.z = w * t.e.z;
+          dP.x -= dv.x; dP.y -= dv.y; dP.z -= dv.z;
+          const Vec3 nx = shfl3(dv, lane + 1);       // bone j (child j+1) lives in the next lane
+          if (m.has_next) { dP.x += nx.x; dP.y += nx.y; dP.z += nx.z; }
+          const Vec3 b10 = shfl3(dv, m.hbase | 10), b13 = shfl3(dv, m.hbase | 13);
+          if (m.j == 8) { dP.x += b10.x + b13.x; dP.y += b10.y + b13.y; dP.z += b10.z + b13.z; }
+        }
+        // ---- d/dR from Q = R P and S = R^T P2 (lane-partial; reduced once per row below)
+        const float dq3[3] = {dQ.x, dQ.y, dQ.z}, p3[3] = {t.P.x, t.P.y, t.P.z};
+        const float p23[3] = {t.P2.x, t.P2.y, t.P2.z}, ds3[3] = {dS.x, dS.y, dS.z};
 #pragma unroll
-            for (int bb = 0; bb < 16; ++bb) {
-              const Vec3 x = shfl3(dv, bb);
-              if (lane == bone_i(bb)) { dP.x += x.x; dP.y += x.y; dP.z += x.z; }
-              if (lane == bone_j(bb)) { dP.x -= x.x; dP.y -= x.y; dP.z -= x.z; }
-            }
-          }
-          if (!act) { dP.x = dP.y = dP.z = 0.f; }
-          // ---- d/dR from Q = R P and S = R^T P2
-          const float dq3[3] = {dQ.x, dQ.y, dQ.z}, p3[3] = {t.P.x, t.P.y, t.P.z};
-          const float p23[3] = {t.P2.x, t.P2.y, t.P2.z}, ds3[3] = {dS.x, dS.y, dS.z};
+        for (int ra = 0; ra < 3; ++ra)
 #pragma unroll
-          for (int ra = 0; ra < 3; ++ra)
+          for (int cb = 0; cb < 3; ++cb) dRm[ra * 3 + cb] += dq3[ra] * p3[cb] + p23[ra] * ds3[cb];
+        // ---- lift
+        const float ddelta = t.mask * (dP.x * r.ux + dP.y * r.uy + dP.z);
+        g1acc[0] += net == 0 ? ddelta : 0.f;
+        g1acc[1] += net == 1 ? ddelta : 0.f;
+      }
+    }
+    // ---- write head gradients (lane -> column col[j] of every net that feeds joint j in some variant; the root's
+    //      columns receive zeros)
+    if (valid) {
 #pragma unroll
-            for (int cb = 0; cb < 3; ++cb)
-              dR[r][ra * 3 + cb] += warp_sum(act ? dq3[ra] * p3[cb] + p23[ra] * ds3[cb] : 0.f);
-          // ---- root centring + lift
-          const float px = warp_sum(dP.x), py = warp_sum(dP.y), pz = warp_sum(dP.z);
-          Vec3 dT = dP;
-          if (lane == 0) { dT.x -= px; dT.y -= py; dT.z -= pz; }
-          const float dd = dT.x * t.ux + dT.y * t.uy + dT.z;
-          const float ddelta = (act && lane != 0) ? t.mask * dd : 0.f;
-          g1acc[r][0] += net == 0 ? ddelta : 0.f;
-          g1acc[r][1] += net == 1 ? ddelta : 0.f;
+      for (int net = 0; net < 2; ++net) {
+        __nv_bfloat16* g = kFull ? A.g1[net] : A.g2[net];
+        __nv_bfloat16* gT = kFull ? A.g1T[net] : A.g2T[net];
+        if (feeds[net]) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(kFull ? g1acc[net] : g2acc[net]);
+          g[r.n * 64 + m.col] = h;
+          if (gT) gT[static_cast<size_t>(m.col) * A.ldT + A.colT0 + r.n] = h;
+        }
+        if (m.sub == 0 && feeds_root[net]) {
+          const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+          g[r.n * 64 + col_root] = z;
+          if (gT) gT[static_cast<size_t>(col_root) * A.ldT + A.colT0 + r.n] = z;
         }
       }
     }
-    // ---- write head gradients (lane j -> column col[j] of every net that feeds joint j in some variant)
-    #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (r >= nrows) break;
-      const size_t n = rows[r];
-      if (act) {
-        const int c = A.maps.col[lane];
-        bool feeds[2] = {false, false};
-        for (int v = 0; v < A.maps.V; ++v) feeds[A.maps.src_net[v][lane]] = true;
-#pragma unroll
-        for (int net = 0; net < 2; ++net) {
-          if (!feeds[net]) continue;
-          if (!kFull) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(g2acc[r][net]);
-            A.g2[net][n * 64 + c] = h;
-            if (A.g2T[net]) A.g2T[net][static_cast<size_t>(c) * A.ldT + A.colT0 + n] = h;
-          } else {
-            const __nv_bfloat16 h = __float2bfloat16_rn(g1acc[r][net]);
-            A.g1[net][n * 64 + c] = h;
-            if (A.g1T[net]) A.g1T[net][static_cast<size_t>(c) * A.ldT + A.colT0 + n] = h;
-          }
-        }
-      }
-      if (kFull) {
-        const float* Rr = R[r];
-        const float* d = dR[r];
-        // dR/da: row1' = -row2, row2' = row1 ; dR/dgamma: col1' = col2, col2' = -col1
-        const float dav = -(d[3] * Rr[6] + d[4] * Rr[7] + d[5] * Rr[8]) + (d[6] * Rr[3] + d[7] * Rr[4] + d[8] * Rr[5]);
-        const float dgv = (d[1] * Rr[2] + d[4] * Rr[5] + d[7] * Rr[8]) - (d[2] * Rr[1] + d[5] * Rr[4] + d[8] * Rr[7]);
-        if (lane == 0) {
-          A.da[n] = dav;
-          A.dgamma[n] = dgv;
+    if (kFull) {
+      const float* Rr = r.R;
+      const float* d = dRm;
+      // dR/da: row1' = -row2, row2' = row1 ; dR/dgamma: col1' = col2, col2' = -col1
+      const float dav = half_sum(-(d[3] * Rr[6] + d[4] * Rr[7] + d[5] * Rr[8]) + (d[6] * Rr[3] + d[7] * Rr[4] + d[8] * Rr[5]));
+      const float dgv = half_sum((d[1] * Rr[2] + d[4] * Rr[5] + d[7] * Rr[8]) - (d[2] * Rr[1] + d[5] * Rr[4] + d[8] * Rr[7]));
+      if (valid) {
+        if (m.sub == 0) {
+          A.da[r.n] = dav;
+          A.dgamma[r.n] = dgv;
         }
         red_da += dav;
-        red_eda += eps[r] * dav;
+        red_eda += r.eps * dav;
       }
     }
   }
-  // ---- block reduction of the scalar sums
+  // ---- block reduction of the scalar sums (values are uniform over each half-warp: add the two halves)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sums[k] += __shfl_xor_sync(LINKS_FULL_MASK, sums[k], 16);
+  red_da += __shfl_xor_sync(LINKS_FULL_MASK, red_da, 16);
+  red_eda += __shfl_xor_sync(LINKS_FULL_MASK, red_eda, 16);
   if (lane == 0) {
     s_part[warp][0] = sums[0]; s_part[warp][1] = sums[1]; s_part[warp][2] = sums[2]; s_part[warp][3] = sums[3];
     s_part[warp][4] = red_da;  s_part[warp][5] = red_eda;

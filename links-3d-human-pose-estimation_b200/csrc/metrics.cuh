@@ -2,28 +2,21 @@
 // in-register 3x3 one-sided Jacobi SVD.  Replaces reference utils/metrics_batch.py:8-159 and the per-pose
 // numpy loop around utils/metrics.py:35-171 (eval_h36m.py:83-93).
 //
-// Layout: a block of 64 threads owns 64 consecutive poses.  Their rows are one contiguous chunk of HBM
-// (64*3J floats per tensor) that is staged into shared memory with coalesced float4 loads; afterwards each
-// thread works on its own pose out of shared memory (row stride odd -> conflict free) entirely in registers.
+// Layout: a block of 64 threads owns 64 consecutive poses.  Their rows are one contiguous chunk of HBM per tensor that
+// the bulk-copy engine drops into shared memory (stage.cuh; the next chunk is in flight while this one is scored);
+// each thread then pulls its own pose into registers ONCE (row stride odd -> conflict free; even strides are read in
+// a per-thread rotated joint order, which every formula here is invariant to) and does all math there.
 #pragma once
 #include "devdefs.cuh"
+#include "stage.cuh"
 
 namespace links {
 
 constexpr int kPosesPerBlock = 64;
 constexpr int kMaxRow = 51;           // 3 * 17
-constexpr int kRowStride = 52;        // shared arrays hold kPosesPerBlock rows of up to 51 floats (+ float4 slack)
-
-// Cooperative LINEAR copy of `count` floats starting at g (16-byte aligned chunk start) into shared memory: the
-// shared rows keep the global row length as their stride (51 for 17 joints: odd, so lane = pose reads are bank-conflict
-// free; 34 for the 2D poses: 2-way), which makes staging pure float4 traffic with no per-element index arithmetic.
-__device__ __forceinline__ void stage_rows(const float* __restrict__ g, size_t count, float* s) {
-  const size_t n4 = count >> 2;
-  const float4* g4 = reinterpret_cast<const float4*>(g);
-  float4* s4 = reinterpret_cast<float4*>(s);
-  for (size_t i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = g4[i];
-  for (size_t ee = (n4 << 2) + threadIdx.x; ee < count; ee += blockDim.x) s[ee] = g[ee];
-}
+constexpr int kRowStride = 52;        // static shared arrays hold kPosesPerBlock rows of up to 51 floats (+ slack)
+constexpr int kChunkFloats = kPosesPerBlock * kMaxRow;      // one staged tensor chunk (13 056 B, a multiple of 128)
+constexpr size_t metric_smem_bytes(int stages) { return static_cast<size_t>(2) * stages * kChunkFloats * sizeof(float); }
 
 __device__ __forceinline__ double block_sum_double(double v, double* sh /*[2]*/) {
   // 64 threads = 2 warps
@@ -34,30 +27,73 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh /*[2]*/)
   return sh[0] + sh[1];
 }
 
-// ---- MPJPE (metrics_batch.py:8-24) for the pose in shared rows r (ref) and p (pred) --------------------
-// Returns mean joint distance; optionally writes joint distances and the max.
-__device__ __forceinline__ float mpjpe_row(const float* r, const float* p, int J, int root, int use_scaling,
-                                           float* dist_out, float* max_out) {
-  const float rx = r[root], ry = r[J + root], rz = r[2 * J + root];
-  const float px = p[root], py = p[J + root], pz = p[2 * J + root];
+// A pose held in registers: c[a][k] = coordinate a of joint slot k.  JT = compile-time joint count (full unroll;
+// JT = 0: runtime count <= 17, arrays sized for 17).  Slot k holds joint (k + rot) mod J.
+template <int JT>
+struct PoseRegs {
+  static constexpr int kCap = JT ? JT : 17;
+  float c[3][kCap];
+};
+
+template <int JT>
+__device__ __forceinline__ int slot_joint(int k, int rot, int J) {
+  int j = k + rot;
+  if (JT == 16) return j & 15;
+  return j >= J ? j - J : j;
+}
+
+// rot = 0 when the shared row stride (3J floats) is odd; otherwise the thread index (mod J) so that the 32 lanes of
+// a warp hit 32 different banks.
+template <int JT>
+__device__ __forceinline__ int lane_rotation(int J) {
+  if (JT != 0 && ((3 * JT) & 1)) return 0;
+  if ((3 * J) & 1) return 0;
+  return JT == 16 ? (threadIdx.x & 15) : static_cast<int>(threadIdx.x % static_cast<unsigned>(J));
+}
+
+template <int JT>
+__device__ __forceinline__ void load_pose(const float* row, int J, int rot, PoseRegs<JT>& P) {
+#pragma unroll
+  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    if (JT == 0 && k >= J) break;
+    const int j = rot ? slot_joint<JT>(k, rot, J) : k;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) P.c[a][k] = row[a * J + j];
+  }
+}
+
+// ---- MPJPE (metrics_batch.py:8-24): mean joint distance after root-centring (+ optional norm matching) ----------
+template <int JT>
+__device__ __forceinline__ float mpjpe_regs(const PoseRegs<JT>& R, const PoseRegs<JT>& P, const float (&r0)[3],
+                                            const float (&p0)[3], int J, int rot, int use_scaling, float* dist_out,
+                                            float* max_out) {
   float scale = 1.f;
   if (use_scaling) {
     float sp = 0.f, sr = 0.f;
-    for (int j = 0; j < J; ++j) {
-      const float ax = p[j] - px, ay = p[J + j] - py, az = p[2 * J + j] - pz;
-      const float bx = r[j] - rx, by = r[J + j] - ry, bz = r[2 * J + j] - rz;
-      sp += ax * ax + ay * ay + az * az;
-      sr += bx * bx + by * by + bz * bz;
+#pragma unroll
+    for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+      if (JT == 0 && k >= J) break;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float x = P.c[a][k] - p0[a], y = R.c[a][k] - r0[a];
+        sp += x * x;
+        sr += y * y;
+      }
     }
     scale = sqrtf(sr) / sqrtf(sp);
   }
   float acc = 0.f, mx = 0.f;
-  for (int j = 0; j < J; ++j) {
-    const float dx = (p[j] - px) * scale - (r[j] - rx);
-    const float dy = (p[J + j] - py) * scale - (r[J + j] - ry);
-    const float dz = (p[2 * J + j] - pz) * scale - (r[2 * J + j] - rz);
-    const float d = sqrtf(dx * dx + dy * dy + dz * dz);
-    if (dist_out) dist_out[j] = d;
+#pragma unroll
+  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    if (JT == 0 && k >= J) break;
+    float d2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float e = (P.c[a][k] - p0[a]) * scale - (R.c[a][k] - r0[a]);
+      d2 += e * e;
+    }
+    const float d = sqrtf(d2);
+    if (dist_out) dist_out[rot ? slot_joint<JT>(k, rot, J) : k] = d;
     acc += d;
     mx = fmaxf(mx, d);
   }
@@ -66,11 +102,12 @@ __device__ __forceinline__ float mpjpe_row(const float* r, const float* p, int J
 }
 
 // ---- 3x3 one-sided Jacobi SVD -> polar factor Q = U V^T and sum of singular values ----------------------
-__device__ __forceinline__ void jacobi_rotate(float (&B)[3][3], float (&V)[3][3], int p, int q) {
+// Returns false when columns p, q are already orthogonal to working precision (no rotation applied).
+__device__ __forceinline__ bool jacobi_rotate(float (&B)[3][3], float (&V)[3][3], int p, int q) {
   const float alpha = B[0][p] * B[0][p] + B[1][p] * B[1][p] + B[2][p] * B[2][p];
   const float beta = B[0][q] * B[0][q] + B[1][q] * B[1][q] + B[2][q] * B[2][q];
   const float gamma = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
-  if (fabsf(gamma) <= 1e-30f || fabsf(gamma) <= 1e-9f * sqrtf(alpha * beta)) return;
+  if (fabsf(gamma) <= 1e-30f || gamma * gamma <= 1e-13f * (alpha * beta)) return false;
   const float zeta = (beta - alpha) / (2.f * gamma);
   const float t = (zeta >= 0.f ? 1.f : -1.f) / (fabsf(zeta) + sqrtf(1.f + zeta * zeta));
   const float c = rsqrtf(1.f + t * t);
@@ -84,6 +121,7 @@ __device__ __forceinline__ void jacobi_rotate(float (&B)[3][3], float (&V)[3][3]
     V[i][p] = c * vp - s * vq;
     V[i][q] = s * vp + c * vq;
   }
+  return true;
 }
 
 __device__ __forceinline__ void polar_svd3(const float (&A)[3][3], float (&Q)[3][3], float* sum_sigma) {
@@ -93,10 +131,11 @@ __device__ __forceinline__ void polar_svd3(const float (&A)[3][3], float (&Q)[3]
 #pragma unroll
     for (int j = 0; j < 3; ++j) { B[i][j] = A[i][j]; V[i][j] = (i == j) ? 1.f : 0.f; }
 #pragma unroll 1
-  for (int sweep = 0; sweep < 8; ++sweep) {
-    jacobi_rotate(B, V, 0, 1);
-    jacobi_rotate(B, V, 0, 2);
-    jacobi_rotate(B, V, 1, 2);
+  for (int sweep = 0; sweep < 8; ++sweep) {   // quadratic convergence: 3-5 sweeps in practice
+    bool any = jacobi_rotate(B, V, 0, 1);
+    any |= jacobi_rotate(B, V, 0, 2);
+    any |= jacobi_rotate(B, V, 1, 2);
+    if (!any) break;
   }
   float sig[3];
 #pragma unroll
@@ -126,87 +165,40 @@ __device__ __forceinline__ void polar_svd3(const float (&A)[3][3], float (&Q)[3]
   *sum_sigma = sig[0] + sig[1] + sig[2];
 }
 
-// ---- PA-MPJPE for one pose.  mode 0: metrics_batch.py:104-159; mode 1: metrics.py:35-171 ('best') ---
-__device__ __forceinline__ float pmpjpe_row(const float* r, const float* p, int J, int mode, float* aligned = nullptr) {
-  const float invJ = 1.f / static_cast<float>(J);
-  float mr[3] = {0.f, 0.f, 0.f}, mp[3] = {0.f, 0.f, 0.f};
-  for (int j = 0; j < J; ++j) {
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { mr[a] += r[a * J + j]; mp[a] += p[a * J + j]; }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { mr[a] *= invJ; mp[a] *= invJ; }
-  float ssr = 0.f, ssp = 0.f;
-  float A[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  for (int j = 0; j < J; ++j) {
-    float x[3], y[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { x[a] = r[a * J + j] - mr[a]; y[a] = p[a * J + j] - mp[a]; }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      ssr += x[a] * x[a];
-      ssp += y[a] * y[a];
-#pragma unroll
-      for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
-    }
-  }
-  // normalise: mode 1 -> unit Frobenius norm; mode 0 -> unit RMS (the common factor cancels in Q)
-  const float nr = mode == 1 ? sqrtf(ssr) : sqrtf(ssr / (3.f * J));
-  const float np = mode == 1 ? sqrtf(ssp) : sqrtf(ssp / (3.f * J));
-  const float inv = 1.f / (nr * np);
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 3; ++b) A[a][b] *= inv;
-  float Q[3][3], tr;
-  polar_svd3(A, Q, &tr);
-  float gain = 1.f;
-  if (mode == 1) {
-    gain = tr;   // optimal scale: Z = normX * trace * Y0 T + muX
-  } else {
-    // R = diag(1,1,det(UV^T)) @ (U V^T): scale the last ROW (metrics_batch.py:145-147)
-    const float det = Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) +
-                      Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
-#pragma unroll
-    for (int b = 0; b < 3; ++b) Q[2][b] *= det;
-  }
-  float acc = 0.f;
-  const float invp = 1.f / np;
-  for (int j = 0; j < J; ++j) {
-    float y[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a) y[a] = (p[a * J + j] - mp[a]) * invp;
-    float d2 = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const float z = gain * nr * (Q[a][0] * y[0] + Q[a][1] * y[1] + Q[a][2] * y[2]);
-      const float e = (r[a * J + j] - mr[a]) - z;
-      if (aligned) aligned[a * J + j] = z + mr[a];
-      d2 += e * e;
-    }
-    acc += sqrtf(d2);
-  }
-  return acc * invJ;
-}
-
-// Both PA-MPJPE semantics of one pose from ONE covariance + ONE SVD: the polar factor Q = U V^T is invariant to the
+// ---- PA-MPJPE.  ONE covariance + ONE SVD serve both semantics: the polar factor Q = U V^T is invariant to the
 // positive scale that distinguishes the two normalisations, and the trace scales linearly with it.
-// Returns mode-1 ('best') error in e_best and mode-0 (metrics_batch) error in e_batch.
-__device__ __forceinline__ void pmpjpe_row_both(const float* r, const float* p, int J, float& e_best, float& e_batch) {
+//   mode 0 (e_batch): metrics_batch.py:104-159 -- unit-RMS normalisation, R = diag(1,1,det) (U V^T), RMS match
+//   mode 1 (e_best) : metrics.py:35-171 'best'  -- unit Frobenius norm, reflection allowed, optimal scale
+// Split in two phases so that the 2 x 3J pose registers are dead while the SVD runs (the kernels re-read the pose
+// from shared memory for phase 2).
+struct PaFit {
+  float mr[3], mp[3];   // means over joints
+  float Q[3][3];        // polar factor
+  float det;            // det(Q)
+  float g1, g0;         // gains of mode 1 / mode 0
+};
+
+template <int JT>
+__device__ __forceinline__ void pa_fit(const PoseRegs<JT>& R, const PoseRegs<JT>& P, int J, PaFit& f) {
   const float invJ = 1.f / static_cast<float>(J);
-  float mr[3] = {0.f, 0.f, 0.f}, mp[3] = {0.f, 0.f, 0.f};
-  for (int j = 0; j < J; ++j) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { mr[a] += r[a * J + j]; mp[a] += p[a * J + j]; }
+  for (int a = 0; a < 3; ++a) { f.mr[a] = 0.f; f.mp[a] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    if (JT == 0 && k >= J) break;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { f.mr[a] += R.c[a][k]; f.mp[a] += P.c[a][k]; }
   }
 #pragma unroll
-  for (int a = 0; a < 3; ++a) { mr[a] *= invJ; mp[a] *= invJ; }
+  for (int a = 0; a < 3; ++a) { f.mr[a] *= invJ; f.mp[a] *= invJ; }
   float ssr = 0.f, ssp = 0.f;
   float A[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-  for (int j = 0; j < J; ++j) {
+#pragma unroll
+  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    if (JT == 0 && k >= J) break;
     float x[3], y[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { x[a] = r[a * J + j] - mr[a]; y[a] = p[a * J + j] - mp[a]; }
+    for (int a = 0; a < 3; ++a) { x[a] = R.c[a][k] - f.mr[a]; y[a] = P.c[a][k] - f.mp[a]; }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       ssr += x[a] * x[a];
@@ -215,100 +207,170 @@ __device__ __forceinline__ void pmpjpe_row_both(const float* r, const float* p, 
       for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
     }
   }
-  const float nr1 = sqrtf(ssr), np1 = sqrtf(ssp);                       // unit Frobenius norm (mode 1)
+  const float nr1 = sqrtf(ssr), np1 = sqrtf(ssp);                           // unit Frobenius norm (mode 1)
   const float nr0 = sqrtf(ssr / (3.f * J)), np0 = sqrtf(ssp / (3.f * J));   // unit RMS (mode 0)
   const float inv = 1.f / (nr1 * np1);
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int b = 0; b < 3; ++b) A[a][b] *= inv;
-  float Q[3][3], tr;
-  polar_svd3(A, Q, &tr);
-  const float det = Q[0][0] * (Q[1][1] * Q[2][2] - Q[1][2] * Q[2][1]) - Q[0][1] * (Q[1][0] * Q[2][2] - Q[1][2] * Q[2][0]) +
-                    Q[0][2] * (Q[1][0] * Q[2][1] - Q[1][1] * Q[2][0]);
-  const float g1 = tr * nr1 / np1;      // mode 1: Z = normX * trace * (Y0 / normY) T
-  const float g0 = nr0 / np0;           // mode 0: RMS match, last row of R scaled by det
+  float tr;
+  polar_svd3(A, f.Q, &tr);
+  f.det = f.Q[0][0] * (f.Q[1][1] * f.Q[2][2] - f.Q[1][2] * f.Q[2][1]) -
+          f.Q[0][1] * (f.Q[1][0] * f.Q[2][2] - f.Q[1][2] * f.Q[2][0]) +
+          f.Q[0][2] * (f.Q[1][0] * f.Q[2][1] - f.Q[1][1] * f.Q[2][0]);
+  f.g1 = tr * nr1 / np1;      // mode 1: Z = normX * trace * (Y0 / normY) T
+  f.g0 = nr0 / np0;           // mode 0: RMS match, last ROW of R scaled by det (metrics_batch.py:145-147)
+}
+
+// aligned (optional, natural joint order) receives the mode-`amode` aligned pose.
+template <int JT>
+__device__ __forceinline__ void pa_errors(const PoseRegs<JT>& R, const PoseRegs<JT>& P, int J, int rot, const PaFit& f,
+                                          float& e_best, float& e_batch, float* aligned, int amode) {
   float acc1 = 0.f, acc0 = 0.f;
-  for (int j = 0; j < J; ++j) {
+#pragma unroll
+  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    if (JT == 0 && k >= J) break;
     float y[3], x[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { y[a] = p[a * J + j] - mp[a]; x[a] = r[a * J + j] - mr[a]; }
+    for (int a = 0; a < 3; ++a) { y[a] = P.c[a][k] - f.mp[a]; x[a] = R.c[a][k] - f.mr[a]; }
     float d1 = 0.f, d0 = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      const float q = Q[a][0] * y[0] + Q[a][1] * y[1] + Q[a][2] * y[2];
-      const float e1 = x[a] - g1 * q;
-      const float e0 = x[a] - g0 * (a == 2 ? det * q : q);
+      const float q = f.Q[a][0] * y[0] + f.Q[a][1] * y[1] + f.Q[a][2] * y[2];
+      const float z1 = f.g1 * q;
+      const float z0 = f.g0 * (a == 2 ? f.det * q : q);
+      if (aligned) aligned[a * J + (rot ? slot_joint<JT>(k, rot, J) : k)] = (amode == 1 ? z1 : z0) + f.mr[a];
+      const float e1 = x[a] - z1, e0 = x[a] - z0;
       d1 += e1 * e1;
       d0 += e0 * e0;
     }
     acc1 += sqrtf(d1);
     acc0 += sqrtf(d0);
   }
+  const float invJ = 1.f / static_cast<float>(J);
   e_best = acc1 * invJ;
   e_batch = acc0 * invJ;
 }
 
+// Compiler barrier: forces the second read of a staged pose to be a real shared-memory load instead of keeping the
+// first copy alive in registers across the SVD.
+__device__ __forceinline__ void forget_registers() { asm volatile("" ::: "memory"); }
+
 // =========================================================================================================
-// All three kernels walk 64-pose chunks with a grid-stride loop (grid = a few blocks per SM) and keep their partial
-// sums in registers: one double atomic per block at the end instead of one per 64 poses (single-address atomics
-// serialise in L2 and dominated the run time at 8 M poses).
+// All kernels walk 64-pose chunks with a grid-stride loop (grid = a few blocks per SM) and keep their partial sums in
+// registers: one double atomic per block at the end instead of one per 64 poses (single-address atomics serialise in
+// L2 and dominated the run time at 8 M poses).
+template <int JT, int kStages>
 __global__ void __launch_bounds__(kPosesPerBlock) mpjpe_kernel(
-    const float* __restrict__ p_ref, const float* __restrict__ p, int M, int J, int root, int use_scaling,
+    const float* __restrict__ p_ref, const float* __restrict__ p, int M, int Jr, int root, int use_scaling,
     float* __restrict__ per_pose, float* __restrict__ per_pose_max, float* __restrict__ dist, double* sum) {
-  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];
+  LINKS_DYN_SMEM(float, s_dyn);                        // [2 tensors][kStages][kChunkFloats]
+  float* const s_ref = s_dyn;
+  float* const s_p = s_dyn + kStages * kChunkFloats;
+  __shared__ __align__(8) uint64_t s_bar[kStages];
   __shared__ double s_red[2];
+  const int J = JT ? JT : Jr;
   const int row_len = 3 * J;
   const int t = threadIdx.x;
   const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  const int rot = lane_rotation<JT>(J);
+  const bool bulk_ok = ((kPosesPerBlock * row_len) & 3) == 0;
   double acc = 0.0;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int pose0 = chunk * kPosesPerBlock;
-    const int npos = min(kPosesPerBlock, M - pose0);
-    stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_ref);
-    stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_p);
-    __syncthreads();
-    if (t < npos) {
-      float mx;
-      const float e = mpjpe_row(s_ref + t * row_len, s_p + t * row_len, J, root, use_scaling,
-                                dist ? dist + static_cast<size_t>(pose0 + t) * J : nullptr, &mx);
-      if (per_pose) per_pose[pose0 + t] = e;
-      if (per_pose_max) per_pose_max[pose0 + t] = mx;
-      acc += static_cast<double>(e);
-    }
-    __syncthreads();
-  }
+  stage_bars_init(s_bar, kStages);
+  chunk_pipeline<kStages>(
+      nchunks, s_bar,
+      [&](int chunk, int st) {
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        const StageReq rq[2] = {
+            {s_ref + st * kChunkFloats, p_ref + static_cast<size_t>(pose0) * row_len, static_cast<uint32_t>(npos * row_len)},
+            {s_p + st * kChunkFloats, p + static_cast<size_t>(pose0) * row_len, static_cast<uint32_t>(npos * row_len)}};
+        const bool bulk = bulk_ok && npos == kPosesPerBlock;
+        stage_issue(rq, s_bar + st, bulk);
+        return bulk;
+      },
+      [&](int chunk, int st) {
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        if (t < npos) {
+          const float* rr = s_ref + st * kChunkFloats + t * row_len;
+          const float* pp = s_p + st * kChunkFloats + t * row_len;
+          PoseRegs<JT> R, P;
+          load_pose<JT>(rr, J, rot, R);
+          load_pose<JT>(pp, J, rot, P);
+          const float r0[3] = {rr[root], rr[J + root], rr[2 * J + root]};
+          const float p0[3] = {pp[root], pp[J + root], pp[2 * J + root]};
+          float mx;
+          const float e = mpjpe_regs<JT>(R, P, r0, p0, J, rot, use_scaling,
+                                         dist ? dist + static_cast<size_t>(pose0 + t) * J : nullptr, &mx);
+          if (per_pose) per_pose[pose0 + t] = e;
+          if (per_pose_max) per_pose_max[pose0 + t] = mx;
+          acc += static_cast<double>(e);
+        }
+      });
   if (sum != nullptr) {   // uniform branch
     const double tot = block_sum_double(acc, s_red);
     if (t == 0) atomicAdd(sum, tot);
   }
 }
 
-__global__ void __launch_bounds__(kPosesPerBlock) pmpjpe_kernel(
-    const float* __restrict__ p_ref, const float* __restrict__ p, int M, int J, int mode,
+template <int JT, int kStages>
+__global__ void __launch_bounds__(kPosesPerBlock, 8) pmpjpe_kernel(
+    const float* __restrict__ p_ref, const float* __restrict__ p, int M, int Jr, int mode,
     float* __restrict__ per_pose, float* __restrict__ aligned, double* sum) {
-  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];
+  LINKS_DYN_SMEM(float, s_dyn);                        // [2 tensors][kStages][kChunkFloats]
+  float* const s_ref = s_dyn;
+  float* const s_p = s_dyn + kStages * kChunkFloats;
+  __shared__ __align__(8) uint64_t s_bar[kStages];
   __shared__ double s_red[2];
+  const int J = JT ? JT : Jr;
   const int row_len = 3 * J;
   const int t = threadIdx.x;
   const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  const int rot = lane_rotation<JT>(J);
+  const bool bulk_ok = ((kPosesPerBlock * row_len) & 3) == 0;
   double acc = 0.0;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int pose0 = chunk * kPosesPerBlock;
-    const int npos = min(kPosesPerBlock, M - pose0);
-    stage_rows(p_ref + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_ref);
-    stage_rows(p + static_cast<size_t>(pose0) * row_len, static_cast<size_t>(npos) * row_len, s_p);
-    __syncthreads();
-    if (t < npos) {
-      const float e = pmpjpe_row(s_ref + t * row_len, s_p + t * row_len, J, mode,
-                                 aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr);
-      if (per_pose) per_pose[pose0 + t] = e;
-      acc += static_cast<double>(e);
-    }
-    __syncthreads();
-  }
+  stage_bars_init(s_bar, kStages);
+  chunk_pipeline<kStages>(
+      nchunks, s_bar,
+      [&](int chunk, int st) {
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        const StageReq rq[2] = {
+            {s_ref + st * kChunkFloats, p_ref + static_cast<size_t>(pose0) * row_len, static_cast<uint32_t>(npos * row_len)},
+            {s_p + st * kChunkFloats, p + static_cast<size_t>(pose0) * row_len, static_cast<uint32_t>(npos * row_len)}};
+        const bool bulk = bulk_ok && npos == kPosesPerBlock;
+        stage_issue(rq, s_bar + st, bulk);
+        return bulk;
+      },
+      [&](int chunk, int st) {
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        if (t < npos) {
+          const float* rr = s_ref + st * kChunkFloats + t * row_len;
+          const float* pp = s_p + st * kChunkFloats + t * row_len;
+          PaFit fit;
+          {
+            PoseRegs<JT> R, P;
+            load_pose<JT>(rr, J, rot, R);
+            load_pose<JT>(pp, J, rot, P);
+            pa_fit<JT>(R, P, J, fit);
+          }
+          forget_registers();
+          float eb, e0;
+          {
+            PoseRegs<JT> R, P;
+            load_pose<JT>(rr, J, rot, R);
+            load_pose<JT>(pp, J, rot, P);
+            pa_errors<JT>(R, P, J, rot, fit, eb, e0,
+                          aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr, mode);
+          }
+          const float e = mode == 1 ? eb : e0;
+          if (per_pose) per_pose[pose0 + t] = e;
+          acc += static_cast<double>(e);
+        }
+      });
   if (sum != nullptr) {
     const double tot = block_sum_double(acc, s_red);
     if (t == 0) atomicAdd(sum, tot);
@@ -349,44 +411,100 @@ __global__ void __launch_bounds__(256) threshold_counts_kernel(const float* __re
 
 // Eval fusion (eval_h36m.py:58-97): pred = [x*d, y*d, d] with d = depth_off + depth (no clamp, not centred);
 // sums3 += (sum N-MPJPE(root 0, scaled), sum PA-MPJPE 'best', sum PA-MPJPE batch).  J = 17.
-__global__ void __launch_bounds__(kPosesPerBlock) eval_lift_score_kernel(
+// The depth rows (17 of ld_depth floats used) are bulk-copied whole and compacted to stride 17 in shared memory.
+constexpr int kEvalMaxLd = 32;
+__global__ void __launch_bounds__(kPosesPerBlock, 6) eval_lift_score_kernel(
     const float* __restrict__ poses_2d, const float* __restrict__ depth_off, int ld_depth,
     const float* __restrict__ gt, int M, float depth, double* sums3) {
-  __shared__ __align__(16) float s_ref[kPosesPerBlock * kRowStride];
-  __shared__ __align__(16) float s_p[kPosesPerBlock * kRowStride];     // per pose: x*d (17), y*d (17), d (17)
-  __shared__ __align__(16) float s_2d[kPosesPerBlock * 34];
+  __shared__ __align__(128) float s_ref[kPosesPerBlock * kRowStride];
+  __shared__ __align__(128) float s_2d[kPosesPerBlock * 34];
+  __shared__ __align__(128) float s_draw[kPosesPerBlock * kEvalMaxLd];
+  __shared__ __align__(16) float s_d[kPosesPerBlock * 17];
+  __shared__ __align__(8) uint64_t s_bar[1];
   __shared__ double s_red[2];
-  const int J = 17;
+  constexpr int J = 17;
   const int t = threadIdx.x;
   const int nchunks = (M + kPosesPerBlock - 1) / kPosesPerBlock;
+  const bool depth_bulk = ld_depth <= kEvalMaxLd && (ld_depth & 3) == 0 &&
+                          (reinterpret_cast<uintptr_t>(depth_off) & 15u) == 0;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int pose0 = chunk * kPosesPerBlock;
-    const int npos = min(kPosesPerBlock, M - pose0);
-    stage_rows(gt + static_cast<size_t>(pose0) * 51, static_cast<size_t>(npos) * 51, s_ref);
-    stage_rows(poses_2d + static_cast<size_t>(pose0) * 34, static_cast<size_t>(npos) * 34, s_2d);
-    for (int i = threadIdx.x; i < npos * J; i += blockDim.x) {
-      const int r = i / J, j = i - r * J;
-      s_p[r * 51 + 34 + j] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j] + depth;
-    }
-    __syncthreads();
-    if (t < npos) {
-      float* p = s_p + t * 51;
-      const float* q = s_2d + t * 34;
-      for (int j = 0; j < J; ++j) {
-        const float d = p[34 + j];
-        p[j] = q[j] * d;
-        p[J + j] = q[J + j] * d;
-      }
-      const float* r = s_ref + t * 51;
-      a0 += static_cast<double>(mpjpe_row(r, p, J, 0, 1, nullptr, nullptr));
-      float eb, e0;
-      pmpjpe_row_both(r, p, J, eb, e0);
-      a1 += static_cast<double>(eb);
-      a2 += static_cast<double>(e0);
-    }
-    __syncthreads();
-  }
+  stage_bars_init(s_bar, 1);
+  chunk_pipeline<1>(
+      nchunks, s_bar,
+      [&](int chunk, int st) {
+        (void)st;
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        const bool bulk = npos == kPosesPerBlock && depth_bulk;
+        if (bulk) {
+          const StageReq rq[3] = {
+              {s_ref, gt + static_cast<size_t>(pose0) * 51, static_cast<uint32_t>(npos * 51)},
+              {s_2d, poses_2d + static_cast<size_t>(pose0) * 34, static_cast<uint32_t>(npos * 34)},
+              {s_draw, depth_off + static_cast<size_t>(pose0) * ld_depth, static_cast<uint32_t>(npos * ld_depth)}};
+          stage_issue(rq, s_bar, true);
+        } else {
+          const StageReq rq[2] = {
+              {s_ref, gt + static_cast<size_t>(pose0) * 51, static_cast<uint32_t>(npos * 51)},
+              {s_2d, poses_2d + static_cast<size_t>(pose0) * 34, static_cast<uint32_t>(npos * 34)}};
+          stage_issue(rq, s_bar, false);
+          for (int i = threadIdx.x; i < npos * J; i += blockDim.x) {
+            const int r = i / J, j = i - r * J;
+            s_d[i] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j];
+          }
+        }
+        return bulk;
+      },
+      [&](int chunk, int st) {
+        (void)st;
+        const int pose0 = chunk * kPosesPerBlock;
+        const int npos = min(kPosesPerBlock, M - pose0);
+        if (npos == kPosesPerBlock && depth_bulk) {     // block-uniform
+          for (int i = threadIdx.x; i < kPosesPerBlock * J; i += blockDim.x) {
+            const int r = i / J, j = i - r * J;
+            s_d[i] = s_draw[r * ld_depth + j];
+          }
+          __syncthreads();
+        }
+        if (t < npos) {
+          const float* q = s_2d + t * 34;
+          const float* dd = s_d + t * J;
+          auto lift = [&](PoseRegs<17>& P) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+              const float d = dd[j] + depth;
+              P.c[0][j] = q[j] * d;
+              P.c[1][j] = q[J + j] * d;
+              P.c[2][j] = d;
+            }
+          };
+          PaFit fit;
+          {
+            PoseRegs<17> R, P;
+            load_pose<17>(s_ref + t * 51, J, 0, R);
+            lift(P);
+            const float r0[3] = {R.c[0][0], R.c[1][0], R.c[2][0]};
+            const float p0[3] = {P.c[0][0], P.c[1][0], P.c[2][0]};
+            a0 += static_cast<double>(mpjpe_regs<17>(R, P, r0, p0, J, 0, 1, nullptr, nullptr));
+          }
+          forget_registers();
+          {
+            PoseRegs<17> R, P;
+            load_pose<17>(s_ref + t * 51, J, 0, R);
+            lift(P);
+            pa_fit<17>(R, P, J, fit);
+          }
+          forget_registers();
+          {
+            PoseRegs<17> R, P;
+            load_pose<17>(s_ref + t * 51, J, 0, R);
+            lift(P);
+            float eb, e0;
+            pa_errors<17>(R, P, J, 0, fit, eb, e0, nullptr, 0);
+            a1 += static_cast<double>(eb);
+            a2 += static_cast<double>(e0);
+          }
+        }
+      });
   const double t0 = block_sum_double(a0, s_red);
   __syncthreads();
   const double t1 = block_sum_double(a1, s_red);

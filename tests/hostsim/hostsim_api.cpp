@@ -76,8 +76,12 @@ SIM int sim_grad_compress_bf16(const float* g, void* out, size_t n) {
 
 SIM int sim_mpjpe(const float* r, const float* p, int M, int J, int root, int scaling, float* per_pose, float* per_max,
                   float* dist, double* sum) {
-  hostsim::launch(dim3((M + kPosesPerBlock - 1) / kPosesPerBlock), dim3(kPosesPerBlock), 0,
-                  [&] { mpjpe_kernel(r, p, M, J, root, scaling, per_pose, per_max, dist, sum); });
+  hostsim::launch(dim3(std::min((M + kPosesPerBlock - 1) / kPosesPerBlock, 2)), dim3(kPosesPerBlock), metric_smem_bytes(2),
+                  [&] {
+                    if (J == 17) mpjpe_kernel<17, 2>(r, p, M, J, root, scaling, per_pose, per_max, dist, sum);
+                    else if (J == 16) mpjpe_kernel<16, 2>(r, p, M, J, root, scaling, per_pose, per_max, dist, sum);
+                    else mpjpe_kernel<0, 2>(r, p, M, J, root, scaling, per_pose, per_max, dist, sum);
+                  });
   return 0;
 }
 SIM int sim_threshold_counts(const float* values, size_t n, const float* thr, int T, int strict, unsigned long long* counts) {
@@ -85,12 +89,16 @@ SIM int sim_threshold_counts(const float* values, size_t n, const float* thr, in
   return 0;
 }
 SIM int sim_pmpjpe(const float* r, const float* p, int M, int J, int mode, float* per_pose, float* aligned, double* sum) {
-  hostsim::launch(dim3((M + kPosesPerBlock - 1) / kPosesPerBlock), dim3(kPosesPerBlock), 0,
-                  [&] { pmpjpe_kernel(r, p, M, J, mode, per_pose, aligned, sum); });
+  hostsim::launch(dim3(std::min((M + kPosesPerBlock - 1) / kPosesPerBlock, 2)), dim3(kPosesPerBlock), metric_smem_bytes(1),
+                  [&] {
+                    if (J == 17) pmpjpe_kernel<17, 1>(r, p, M, J, mode, per_pose, aligned, sum);
+                    else if (J == 16) pmpjpe_kernel<16, 1>(r, p, M, J, mode, per_pose, aligned, sum);
+                    else pmpjpe_kernel<0, 1>(r, p, M, J, mode, per_pose, aligned, sum);
+                  });
   return 0;
 }
 SIM int sim_eval_lift_score(const float* p2d, const float* doff, int ldd, const float* gt, int M, float depth, double* sums3) {
-  hostsim::launch(dim3((M + kPosesPerBlock - 1) / kPosesPerBlock), dim3(kPosesPerBlock), 0,
+  hostsim::launch(dim3(std::min((M + kPosesPerBlock - 1) / kPosesPerBlock, 2)), dim3(kPosesPerBlock), 0,
                   [&] { eval_lift_score_kernel(p2d, doff, ldd, gt, M, depth, sums3); });
   return 0;
 }
@@ -112,7 +120,7 @@ SIM int sim_geom_forward(const LinksGeomMaps* maps, const float* u, const float*
                          float* qp1, float* qf0, float* qf1) {
   GeomArgs A = base_args(maps, u, h0, h1, a0, a1, eps, uy, stats, N);
   A.qpart[0] = qp0; A.qpart[1] = qp1; A.qfull[0] = qf0; A.qfull[1] = qf1;
-  hostsim::launch(dim3((N + kGeomWarps - 1) / kGeomWarps), dim3(kGeomWarps * 32), 0, [&] { geom_forward_kernel(A); });
+  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_forward_kernel<1>(A); else geom_forward_kernel<2>(A); });   // grid-stride over row pairs
   return 0;
 }
 SIM int sim_geom_loss(const LinksGeomMaps* maps, const float* u, const float* h0, const float* h1, const float* a0,
@@ -123,7 +131,8 @@ SIM int sim_geom_loss(const LinksGeomMaps* maps, const float* u, const float* h0
   A.head2[0] = h20; A.head2[1] = h21; A.loss_sums = loss_sums;
   A.g2[0] = (bf16*)g20; A.g2[1] = (bf16*)g21; A.g2T[0] = (bf16*)g2T0; A.g2T[1] = (bf16*)g2T1; A.ldT = ldT; A.colT0 = colT0;
   const int pairs = (N + 1) / 2;
-  hostsim::launch(dim3((pairs + kGeomWarps - 1) / kGeomWarps), dim3(kGeomWarps * 32), 0, [&] { geom_lossgrad_kernel<false>(A); });
+  (void)pairs;
+  hostsim::launch(dim3(1), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<false, 1>(A); else geom_lossgrad_kernel<false, 2>(A); });
   return 0;
 }
 SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float* h0, const float* h1, const float* a0,
@@ -137,7 +146,8 @@ SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float
   A.g1[0] = (bf16*)g10; A.g1[1] = (bf16*)g11; A.g1T[0] = (bf16*)g1T0; A.g1T[1] = (bf16*)g1T1; A.ldT = ldT; A.colT0 = colT0;
   A.dgamma = dgamma; A.da = da; A.red = red;
   const int pairs = (N + 1) / 2;
-  hostsim::launch(dim3((pairs + kGeomWarps - 1) / kGeomWarps), dim3(kGeomWarps * 32), 0, [&] { geom_lossgrad_kernel<true>(A); });
+  (void)pairs;
+  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<true, 1>(A); else geom_lossgrad_kernel<true, 2>(A); });
   return 0;
 }
 SIM int sim_geom_backward_angles(const float* a0, const float* a1, const float* eps, const float* stats, const float* dgamma,

@@ -131,10 +131,45 @@ def test_metrics_vs_golden(golden, backend):
     assert np.abs(pa - G["pmpjpe_np_best"]).max() < 0.05, np.abs(pa - G["pmpjpe_np_best"]).max()
 
 
+@pytest.mark.parametrize("nj,rj", [(17, 0), (16, 6), (12, 3)])
+@backend_params
+def test_metrics_multichunk(nj, rj, backend):
+    """Several 64-pose chunks per block + a ragged tail: exercises the staging pipeline (bulk copies on the GPU,
+    cooperative copies in the host simulation) and the rotated joint order used for even row strides."""
+    L = backend
+    M = 64 * 7 + 13
+    _, gt = synth_poses(M, seed=21)
+    pred = synth_pred_3d(gt, seed=22)
+    g = np.ascontiguousarray(gt.reshape(M, 3, 17)[:, :, :nj].reshape(M, 3 * nj))
+    p = np.ascontiguousarray(pred.reshape(M, 3, 17)[:, :, :nj].reshape(M, 3 * nj))
+    gt_t, p_t = torch.from_numpy(g), torch.from_numpy(p)
+    for scaling in (1, 0):
+        per = np.zeros(M, np.float32); mx = np.zeros(M, np.float32); dist = np.zeros((M, nj), np.float32)
+        s = np.zeros(1, np.float64)
+        assert L.call("mpjpe", g, p, M, nj, rj, scaling, per, mx, dist, s) == 0
+        ref = OM.mpjpe(gt_t, p_t, use_scaling=bool(scaling), root_joint=rj, num_joints=nj).numpy()
+        assert np.abs(per - ref).max() < 0.05
+        np.testing.assert_allclose(per, ref, rtol=3e-5)
+        np.testing.assert_allclose(per, dist.mean(1), rtol=1e-5)
+        np.testing.assert_allclose(mx, dist.max(1))
+        np.testing.assert_allclose(s[0], ref.astype(np.float64).sum(), rtol=1e-6)
+    pa = np.zeros(M, np.float32); al = np.zeros((M, 3 * nj), np.float32); s = np.zeros(1, np.float64)
+    assert L.call("pmpjpe", g, p, M, nj, 0, pa, al, s) == 0
+    ref = OM.pmpjpe_batch(gt_t, p_t, num_joints=nj).numpy()
+    assert np.abs(pa - ref).max() < 0.05, np.abs(pa - ref).max()
+    ref_al = OM.procrustes_batch(p_t.reshape(M, 3, nj), gt_t.reshape(M, 3, nj)).reshape(M, -1).numpy()
+    assert np.abs(al - ref_al).max() < 0.05
+    np.testing.assert_allclose(s[0], ref.astype(np.float64).sum(), rtol=1e-5)
+    if nj == 17:
+        pa1 = np.zeros(M, np.float32)
+        assert L.call("pmpjpe", g, p, M, nj, 1, pa1, None, None) == 0
+        assert np.abs(pa1 - OM.pmpjpe_best_batch(g, p)).max() < 0.05
+
+
 @backend_params
 def test_eval_lift_score_fused(backend):
     L = backend
-    M = 70
+    M = 64 * 5 + 6
     p2d, gt = synth_poses(M, seed=11)
     rng = np.random.RandomState(0)
     doff = np.zeros((M, 32), np.float32)
