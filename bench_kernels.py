@@ -19,6 +19,8 @@ from links_b200.occlusion import EvalRunner  # noqa: E402
 
 
 def timed(fn, reps=10, warm=3):
+    reps = int(os.environ.get("LINKS_BK_REPS", reps))       # 1 / 0 for an ncu capture of one launch per kernel
+    warm = int(os.environ.get("LINKS_BK_WARM", warm))
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()

@@ -29,8 +29,12 @@ def _rup(x, m):
 
 
 class FlowTrainStep:
-    def __init__(self, C_dim, params, batch, n_blocks=8, lr=2e-4, weight_decay=0.0, device="cuda", process_group=None):
-        """params: FrEIA-layout state dict; batch: rows of x per step (the kernel sees 2*batch rows)."""
+    def __init__(self, C_dim, params, batch, n_blocks=8, lr=2e-4, weight_decay=0.0, device="cuda", process_group=None,
+                 external_rows=False):
+        """params: FrEIA-layout state dict; batch: rows of x per step (the kernel sees 2*batch rows).
+        external_rows: the caller fills self.u ([2*batch, C] = [data rows ; sampled rows]) itself instead of the flow
+        drawing samples from its own inverse (the part-flow trainer samples from a frozen full-pose flow)."""
+        self.external_rows = external_rows
         self.C, self.nb, self.B = C_dim, n_blocks, batch
         self.M = 2 * batch
         self.c1, self.c2 = C_dim - C_dim // 2, C_dim // 2
@@ -137,7 +141,8 @@ class FlowTrainStep:
         st = torch.cuda.current_stream().cuda_stream
         if self._plans is None:
             self._build_plans()
-        self.flow.sample(self.x, self.noise, self.u)               # [x ; s], s detached with the root joint zeroed
+        if not self.external_rows:
+            self.flow.sample(self.x, self.noise, self.u)           # [x ; s], s detached with the root joint zeroed
         self.nll_sum.zero_()
         # global-affine gradients are accumulated atomically: clear their slots of the flat gradient buffer
         for k in range(self.nb):
@@ -180,3 +185,56 @@ class FlowTrainStep:
 
     def loss_dict(self):
         return {"loss": self.loss.item()}
+
+
+class PartFlowTrainer:
+    """Joint training step of the four part flows (reference train_leg_torso_left_right_norm_flow.py:100-198).
+
+        parts of the data              -> NLL under the leg / torso / left / right flows           (:108-127)
+        s = full_inn^-1(add_noise(full_inn(x))) (frozen full-pose flow, no grad), root zeroed       (:130-141)
+        parts of s                     -> NLL under the same four flows                            (:144-161)
+        loss = sum of the eight means; four independent Adam(wd 1e-5) steps                         (:163-174)
+
+    The four flows share nothing but their input rows, so each runs its FlowTrainStep (one fused tensor-core launch over
+    the stacked rows [data ; samples] + the parameter-gradient GEMMs + Adam) on its own stream."""
+
+    NAMES = ("legs", "torso", "left", "right")
+
+    def __init__(self, full_params, part_params, batch, lr=2e-4, weight_decay=1e-5, device="cuda", process_group=None):
+        """full_params: frozen 34-d sampler; part_params: dict NAMES -> FrEIA-layout state dict."""
+        from . import maps
+        self.B = batch
+        self.device = dev = torch.device(device)
+        self.sampler = FlowPacked(34, full_params, device=dev)
+        joints = {"legs": maps.LEG_JOINTS, "torso": maps.TORSO_JOINTS, "left": maps.LEFT_JOINTS, "right": maps.RIGHT_JOINTS}
+        self.index = {n: torch.tensor(maps.part_index(joints[n]), dtype=torch.long, device=dev) for n in self.NAMES}
+        self.steps = {n: FlowTrainStep(2 * len(joints[n]), part_params[n], batch, lr=lr, weight_decay=weight_decay, device=dev,
+                                       process_group=process_group, external_rows=True) for n in self.NAMES}
+        self.streams = {n: torch.cuda.Stream(device=dev) for n in self.NAMES}
+        self.x = torch.zeros(batch, 34, dtype=torch.float32, device=dev)
+        self.noise = torch.zeros(batch, 34, dtype=torch.float32, device=dev)
+        self.u = torch.zeros(2 * batch, 34, dtype=torch.float32, device=dev)
+
+    def step(self):
+        main = torch.cuda.current_stream()
+        self.sampler.sample(self.x, self.noise, self.u)            # [x ; s]
+        for n in self.NAMES:
+            st, side = self.steps[n], self.streams[n]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                torch.index_select(self.u, 1, self.index[n], out=st.u)     # integer gather (utils/helpers.py:55-65)
+                st.step()
+        for n in self.NAMES:
+            main.wait_stream(self.streams[n])
+
+    def set_lr(self, lr):
+        for st in self.steps.values():
+            st.set_lr(lr)
+
+    def loss_dict(self):
+        d = {"dist_2d_" + n: self.steps[n].loss.item() for n in self.NAMES}      # data + sample NLL of each flow
+        d["loss"] = sum(d.values())
+        return d
+
+    def state_dict(self, name):
+        return self.steps[name].state_dict()

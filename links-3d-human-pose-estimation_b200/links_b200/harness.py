@@ -31,6 +31,7 @@ def add_common_args(p, batch=256, epochs=100):
     g.add_argument("--weights-dir", default="models", help="where pretrained flows / lifters are read from and results saved")
     g.add_argument("--log-every", type=int, default=50)
     g.add_argument("--no-save", action="store_true")
+    g.add_argument("--val", type=int, default=0, help="synthetic validation poses scored at every epoch end (0 = off)")
     return p
 
 
@@ -85,7 +86,39 @@ class SyntheticLoader:
             yield self.x[perm[i * self.batch:(i + 1) * self.batch]].pin_memory()
 
 
-def run_training(step, loader, args, rank, feed):
+class Validator:
+    """Epoch-end validation on the device (reference validation_step, train_leg_torso_lifter.py:286-337 /
+    train_left_right_lifter.py:437-520): lift the validation poses with the CURRENT lifters, then PA-MPJPE ('best'),
+    scale-matched MPJPE, PCK@150 and AUC.  The reference scores PA-MPJPE with a per-pose numpy loop on the host; here
+    the whole validation set is one fused lift+score pass per chunk plus two threshold-count launches."""
+
+    def __init__(self, kind, step, n_val, seed, depth, rank, world, pg, chunk=16384):
+        x2d, gt = synth_poses(n_val, seed=4321 + seed)
+        b, e = shard_bounds(n_val, rank, world, multiple=1)
+        dev = step.device
+        self.x, self.gt = torch.from_numpy(x2d[b:e]).to(dev), torch.from_numpy(gt[b:e]).to(dev)
+        self.step, self.pg, self.world = step, pg, world
+        self.chunk = min(chunk, max(e - b, 1))
+        self.ev = EvalRunner(kind, [step.mlp.state_dict(s) for s in range(2)], chunk=self.chunk, depth=depth,
+                             choice="right", process_group=pg)
+
+    def run(self):
+        from utils.metrics_batch import Metrics as mb
+        self.ev.load_lifters([self.step.mlp.state_dict(s) for s in range(2)])
+        self.ev.reset()
+        preds = [self.ev.run_chunk(self.x[i:i + self.chunk], self.gt[i:i + self.chunk], want_pred=True)
+                 for i in range(0, self.x.shape[0], self.chunk)]
+        pred = torch.cat(preds, dim=0)
+        out = self.ev.result()
+        extra = torch.stack((mb().PCK(self.gt, pred, num_joints=17, root_joint=0).float(),
+                             mb().AUC(self.gt, pred, num_joints=17, root_joint=0).float()))
+        if self.world > 1:                       # equal shards: the mean of the per-rank ratios is the global ratio
+            torch.distributed.all_reduce(extra, group=self.pg)
+            extra /= self.world
+        return {"pa": out["pa_mpjpe"], "mpjpe_scaled": out["n_mpjpe"], "pck": extra[0].item(), "auc": extra[1].item()}
+
+
+def run_training(step, loader, args, rank, feed, validator=None):
     """Epoch loop: feed(step, batch) uploads inputs + draws, step.step() does the rest on the device."""
     n_steps, t0 = 0, time.time()
     lr = LR0
@@ -101,8 +134,13 @@ def run_training(step, loader, args, rank, feed):
                 print("epoch %d step %d  %s  (%.0f poses/s)" % (epoch, n_steps, " ".join("%s=%.5f" % kv for kv in d.items()),
                                                                 n_steps * args.batch / (time.time() - t0)), flush=True)
             if args.steps and n_steps >= args.steps:
-                torch.cuda.synchronize()
-                return n_steps
+                break
+        if validator is not None:
+            v = validator.run()
+            if rank == 0:
+                print("epoch %d validation  %s" % (epoch, " ".join("%s=%.4f" % kv for kv in v.items())), flush=True)
+        if args.steps and n_steps >= args.steps:
+            break
         lr *= GAMMA                                   # training_epoch_end: ExponentialLR.step()
     torch.cuda.synchronize()
     return n_steps
@@ -137,7 +175,8 @@ def train_lifters(kind, args):
     loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
     step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
-    n = run_training(step, loader, args, rank, lifter_feed(gen_dev))
+    validator = Validator(kind, step, args.val, args.seed, args.translation, rank, world, pg) if args.val else None
+    n = run_training(step, loader, args, rank, lifter_feed(gen_dev), validator)
     if rank == 0 and not args.no_save:
         from utils import models_def as MD
         cls = (MD.Leg_Lifter, MD.Torso_Lifter) if kind == "lt" else (MD.Left_Right_Lifter, MD.Left_Right_Lifter)

@@ -157,8 +157,13 @@ class EvalRunner:
         self.sums.zero_()
         self.count = 0
 
-    def run_chunk(self, poses_2d, gt_3d):
-        """poses_2d [n,34], gt_3d [n,51] device fp32 tensors, n <= chunk."""
+    def load_lifters(self, lifter_params):
+        """Swap in new lifter weights (epoch-end validation of a model that is still training)."""
+        self.mlp.load_state_dicts(lifter_params)
+
+    def run_chunk(self, poses_2d, gt_3d, want_pred=False):
+        """poses_2d [n,34], gt_3d [n,51] device fp32 tensors, n <= chunk.  want_pred: also return the lifted poses
+        [n,51] (eval_h36m.py:60-66; validation PCK / AUC need them)."""
         n = poses_2d.shape[0]
         L, m = self.lib, self.mlp
         st = torch.cuda.current_stream().cuda_stream
@@ -174,6 +179,10 @@ class EvalRunner:
         check(L.links_eval_lift_score(poses_2d.data_ptr(), self.depth_off.data_ptr(), 32, gt_3d.data_ptr(), n, self.depth,
                                       self.sums.data_ptr(), st), "links_eval_lift_score")
         self.count += n
+        if want_pred:
+            dd = (d + self.depth)
+            return torch.cat((poses_2d[:, :17] * dd, poses_2d[:, 17:] * dd, dd), dim=1)
+        return None
 
     def result(self):
         """Single final reduction over ranks (per-rank double sums + counts)."""

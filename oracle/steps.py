@@ -277,3 +277,25 @@ def params_require_grad(p, flag=True):
 def make_adam(param_dicts, lr=2e-4, weight_decay=1e-5):
     """train_leg_torso_lifter.py:111-114 -- one Adam per network."""
     return [torch.optim.Adam(list(p.values()), lr=lr, weight_decay=weight_decay) for p in param_dicts]
+
+
+def part_flow_step(x, full_params, part_params, noise):
+    """train_leg_torso_left_right_norm_flow.py:100-166.  part_params: dict legs/torso/left/right -> flow params.
+    Returns the eight NLL means and their sum."""
+    def parts(p):
+        left, right = G.split_data_left_right(p)
+        r = p.reshape(-1, 2, 17)
+        return {"legs": r[:, :, :7].reshape(-1, 14), "torso": r[:, :, 7:].reshape(-1, 20), "left": left, "right": right}
+    with torch.no_grad():
+        z, _ = F.inn_forward(x, full_params)
+        s, _ = F.inn_forward(G.add_noise(z, noise, 0.2), full_params, rev=True)
+        s = s.reshape(-1, 2, 17).clone()
+        s[:, :, [0]] = 0.0
+        s = s.reshape(-1, x.shape[1])
+    out = {}
+    for tag, rows in (("", parts(x)), ("_sample", parts(s))):
+        for n, inp in rows.items():
+            zz, ld = F.inn_forward(inp, part_params[n])
+            out["dist_2d_%s%s" % (n, tag)] = F.nll(zz, ld).mean()
+    out["loss"] = sum(out.values())
+    return out

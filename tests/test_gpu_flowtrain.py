@@ -53,3 +53,33 @@ def test_flow_train_step_vs_oracle():
         d_ref = pn[key].detach() - params[key]
         cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
         assert cos.item() > 0.9, (n, cos.item())
+
+
+def test_part_flow_trainer_vs_oracle():
+    """train_leg_torso_left_right_norm_flow.py:100-174: four part flows on data + samples of the frozen full flow."""
+    from links_b200.flowtrain import PartFlowTrainer
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, steps as OS
+    B = 64
+    full = OF.init_flow_params(34, 40, perturb=0.3)
+    width = {"legs": 14, "torso": 20, "left": 22, "right": 22}
+    parts = {n: OF.init_flow_params(width[n], 60 + i, perturb=0.3) for i, n in enumerate(PartFlowTrainer.NAMES)}
+    tr = PartFlowTrainer(full, parts, B)
+    x2d, _ = synth_poses(B, seed=23)
+    g = torch.Generator().manual_seed(9)
+    x, noise = torch.from_numpy(x2d), torch.randn(B, 34, generator=g)
+    pn = {n: OS.params_require_grad(parts[n]) for n in parts}
+    ref = OS.part_flow_step(x, full, pn, noise)
+    ref["loss"].backward()
+    tr.x.copy_(x); tr.noise.copy_(noise)
+    for st in tr.steps.values():        # forward/backward only, keep the parameters for the gradient comparison
+        st.optimizer_step = lambda: None
+    tr.step()
+    torch.cuda.synchronize()
+    got = tr.loss_dict()
+    for n in PartFlowTrainer.NAMES:
+        r = (ref["dist_2d_" + n] + ref["dist_2d_%s_sample" % n]).item()
+        assert abs(got["dist_2d_" + n] - r) <= 1e-3 * abs(r), (n, got["dist_2d_" + n], r)
+        e = rel_fro(tr.steps[n].Gd[2]["subnet.2.weight"].cpu(), pn[n]["module_list.2.subnet.2.weight"].grad)
+        assert e < 4e-2, (n, e)
+    assert abs(got["loss"] - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())

@@ -28,8 +28,8 @@ def test_lifter_scripts_train_save_eval(tmp_path):
     sd = torch.load(os.path.join(wd, "left_side_lifter_final.pt"))
     assert len(sd) == 62 and sd["downscale.weight"].shape == (11, 1024) and "res_pose2.bn1.weight" in sd
     out = _run("train_leg_torso_lifter.py", "--synthetic", "1024", "--batch", "128", "--steps", "4", "--log-every", "2",
-               "--weights-dir", wd, "-l", "0.5")
-    assert "step 4" in out
+               "--weights-dir", wd, "-l", "0.5", "--val", "777")
+    assert "step 4" in out and "validation" in out and "pck=" in out
     assert os.path.exists(os.path.join(wd, "leg_lifter.pt")) and os.path.exists(os.path.join(wd, "torso_lifter.pt"))
     out = _run("eval_h36m.py", "--synthetic", "5000", "--chunk", "2048", "--weights-dir", wd)
     assert "PA-MPJPE:" in out and "N-MPJPE:" in out
@@ -43,3 +43,8 @@ def test_lifter_scripts_train_save_eval(tmp_path):
     assert "step 3" in out
     sd = torch.load(os.path.join(wd, "occlusion_model_weights", "torso_estimator.pt"))
     assert len(sd) == 36 and sd["downscale.weight"].shape == (30, 1024)
+    out = _run("train_leg_torso_left_right_norm_flow.py", "-l", "22", "--synthetic", "512", "--batch", "64", "--steps", "3",
+               "--log-every", "1", "--weights-dir", wd)
+    assert "step 3" in out and "dist_2d_torso=" in out
+    sd = torch.load(os.path.join(wd, "mpi_norm_flow_legs_2.pt"))
+    assert len(sd) == 64 and sd["module_list.0.subnet.2.weight"].shape == (14, 1024)
