@@ -463,7 +463,7 @@ extern "C" __attribute__((visibility("default"))) int links_pmpjpe(const float* 
   if (rc) return rc;
   if (mode < 0 || mode > 1) return LINKS_E_RANGE;
   // SVD-heavy: one staging buffer, more resident blocks to hide the dependent chains
-  const int grid = metric_grid(M, 6);
+  const int grid = metric_grid(M, 8);
   cudaStream_t s = links_stream(stream);
   constexpr size_t smem = metric_smem_bytes(1);
   if (num_joints == 17)
@@ -481,7 +481,7 @@ extern "C" __attribute__((visibility("default"))) int links_eval_lift_score(cons
   if (rc) return rc;
   LINKS_CHECK_PTR(depth_off); LINKS_CHECK_PTR(sums3);
   if (ld_depth < 17) return LINKS_E_RANGE;
-  eval_lift_score_kernel<<<metric_grid(M, 5), kPosesPerBlock, 0, links_stream(stream)>>>(
+  eval_lift_score_kernel<<<metric_grid(M, 6), kPosesPerBlock, 0, links_stream(stream)>>>(
       poses_2d, depth_off, ld_depth, gt_3d, M, depth, sums3);
   return links_launch_status();
 }

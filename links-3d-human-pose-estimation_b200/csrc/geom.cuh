@@ -140,6 +140,48 @@ __device__ __forceinline__ void make_rotation(const LaneMaps& m, float a, float 
   R[6] = -ca * sb; R[7] = sa * cg + ca * cb * sg;  R[8] = -sa * sg + ca * cb * cg;
 }
 
+// Everything a lane reads from global memory for one row: loaded one grid-stride iteration AHEAD of its use so that
+// the load latency hides behind the math of the current row pair (these kernels run a few hundred dependent
+// instructions per pair on few resident warps).  kLevel: 0 forward, 1 + pass-2 heads, 2 + external d/dq.
+template <int V, int kLevel>
+struct RawRow {
+  int n;
+  float ux, uy, u0x, u0y;      // this lane's 2D joint, root joint
+  float ang0, ang1, eps, uyaw;
+  float delta[V];              // pass-1 depth-head output of this lane's joint, per variant
+  float delta2[V];             // pass-2 depth-head output
+  float xqx[V], xqy[V];        // external d/d(projected joint): flow + pass-2 lifter input gradients
+};
+template <int V, int kLevel>
+__device__ __forceinline__ void load_raw(const GeomArgs& A, const LaneMaps& m, int n, RawRow<V, kLevel>& w) {
+  w.n = n;
+  const size_t nn = static_cast<size_t>(n);
+  const float* u = A.u + nn * 34;
+  w.ux = u[m.j];
+  w.uy = u[kJ + m.j];
+  w.u0x = u[0];
+  w.u0y = u[kJ];
+  w.ang0 = A.ang[0][nn * LINKS_HEAD_LD];
+  w.ang1 = A.ang[1][nn * LINKS_HEAD_LD];
+  w.eps = A.eps_x[n];
+  w.uyaw = A.u_y[n];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    w.delta[v] = A.head[m.net[v]][nn * LINKS_HEAD_LD + m.col];
+    w.delta2[v] = 0.f; w.xqx[v] = 0.f; w.xqy[v] = 0.f;
+    if (kLevel >= 1) w.delta2[v] = A.head2[m.net[v]][nn * LINKS_HEAD_LD + m.col];
+    if (kLevel >= 2) {
+      const int p = m.pnet[v];
+      if (p >= 0) {
+        const int nj = A.maps.n_joints[p];
+        const int idx = m.pidx[v];
+        w.xqx[v] = A.dflow[p][nn * (2 * nj) + idx] + A.dlift[p][nn * LINKS_HEAD_LD + idx];
+        w.xqy[v] = A.dflow[p][nn * (2 * nj) + nj + idx] + A.dlift[p][nn * LINKS_HEAD_LD + nj + idx];
+      }
+    }
+  }
+}
+
 // Per-row inputs shared by all variants.
 struct RowIn {
   size_t n;
@@ -148,17 +190,14 @@ struct RowIn {
   float gamma, eps;
   float R[9];
 };
-__device__ __forceinline__ void load_row(const GeomArgs& A, const LaneMaps& m, int n, RowIn& r) {
-  r.n = static_cast<size_t>(n);
-  const float* u = A.u + r.n * 34;
-  r.ux = u[m.j];
-  r.uy = u[kJ + m.j];
-  r.u0x = u[0];
-  r.u0y = u[kJ];
-  r.gamma = 0.5f * (A.ang[0][r.n * LINKS_HEAD_LD] + A.ang[1][r.n * LINKS_HEAD_LD]);
-  r.eps = A.eps_x[n];
+template <int V, int kLevel>
+__device__ __forceinline__ void derive_row(const GeomArgs& A, const LaneMaps& m, const RawRow<V, kLevel>& w, RowIn& r) {
+  r.n = static_cast<size_t>(w.n);
+  r.ux = w.ux; r.uy = w.uy; r.u0x = w.u0x; r.u0y = w.u0y;
+  r.gamma = 0.5f * (w.ang0 + w.ang1);
+  r.eps = w.eps;
   const float a = -A.stats[0] + A.stats[1] * r.eps;
-  const float b = (A.u_y[n] - 0.5f) * (1.99f * 3.14159265358979323846f);
+  const float b = (w.uyaw - 0.5f) * (1.99f * 3.14159265358979323846f);
   make_rotation(m, a, b, r.gamma, r.R);
 }
 
@@ -181,10 +220,10 @@ struct RowVar {
   float bl_len, bl_imean, bl_rho;   // bone length, 1 / mean bone length, their ratio
 };
 
-__device__ __forceinline__ void row_forward(const GeomArgs& A, const LaneMaps& m, int v, const RowIn& r, RowVar& s) {
+__device__ __forceinline__ void row_forward(const GeomArgs& A, float delta, const RowIn& r, RowVar& s) {
   const float D = A.maps.depth;
   const float d0 = D < 1.0f ? 1.0f : D;                   // root depth: offset forced to 0 (:183), then clamped
-  float d = A.head[m.net[v]][r.n * LINKS_HEAD_LD + m.col] + D;
+  float d = delta + D;
   s.mask = (d < 1.0f) ? 0.f : 1.f;
   d = (d < 1.0f) ? 1.0f : d;
   s.d = d;
@@ -198,11 +237,11 @@ __device__ __forceinline__ void row_forward(const GeomArgs& A, const LaneMaps& m
 }
 
 // pass-2 quantities and the per-row loss terms (L3d, rep_rot, bl_prior) via out[3] (uniform over the half-warp).
-__device__ __forceinline__ void row_consistency(const GeomArgs& A, const LaneMaps& m, int v, const RowIn& r, RowVar& s,
-                                                float (&out)[3]) {
+__device__ __forceinline__ void row_consistency(const GeomArgs& A, const LaneMaps& m, float delta2, const RowIn& r,
+                                                RowVar& s, float (&out)[3]) {
   const float D = A.maps.depth;
   const float d0 = D < 1.0f ? 1.0f : D;
-  float d2 = A.head2[m.net[v]][r.n * LINKS_HEAD_LD + m.col] + D;
+  float d2 = delta2 + D;
   s.mask2 = (d2 < 1.0f) ? 0.f : 1.f;
   d2 = (d2 < 1.0f) ? 1.0f : d2;
   s.d2 = d2;
@@ -243,15 +282,19 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
   const int half = m.lane >> 4;
   const int npairs = (A.N + 1) / 2;
   const int stride = gridDim.x * kGeomWarps;
-  for (int pair = blockIdx.x * kGeomWarps + (threadIdx.x >> 5); pair < npairs; pair += stride) {
-    const int n_own = 2 * pair + half;
-    const bool valid = n_own < A.N;              // uniform over the half-warp
+  int pair = blockIdx.x * kGeomWarps + (threadIdx.x >> 5);
+  RawRow<V, 0> raw, raw_next;
+  if (pair < npairs) load_raw(A, m, 2 * pair + half < A.N ? 2 * pair + half : 2 * pair, raw);
+  for (; pair < npairs; pair += stride, raw = raw_next) {
+    const int nxt = pair + stride;
+    if (nxt < npairs) load_raw(A, m, 2 * nxt + half < A.N ? 2 * nxt + half : 2 * nxt, raw_next);
+    const bool valid = 2 * pair + half < A.N;    // uniform over the half-warp
     RowIn r;
-    load_row(A, m, valid ? n_own : 2 * pair, r);
+    derive_row(A, m, raw, r);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       RowVar s;
-      row_forward(A, m, v, r, s);
+      row_forward(A, raw.delta[v], r, s);
       if (!valid) continue;
       if (A.qfull[v]) {
         float* qf = A.qfull[v] + r.n * 34;
@@ -316,11 +359,17 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const Ge
   float red_da = 0.f, red_eda = 0.f;
 
   const int total_pairs = (A.N + 1) / 2;
-  for (int pair = blockIdx.x * kGeomWarps + warp; pair < total_pairs; pair += gridDim.x * kGeomWarps) {
+  const int stride = gridDim.x * kGeomWarps;
+  int pair = blockIdx.x * kGeomWarps + warp;
+  RawRow<V, kFull ? 2 : 1> raw, raw_next;
+  if (pair < total_pairs) load_raw(A, m, 2 * pair + half < A.N ? 2 * pair + half : 2 * pair, raw);
+  for (; pair < total_pairs; pair += stride, raw = raw_next) {
+    const int nxt = pair + stride;
+    if (nxt < total_pairs) load_raw(A, m, 2 * nxt + half < A.N ? 2 * nxt + half : 2 * nxt, raw_next);
     const bool vB = 2 * pair + 1 < A.N;                           // warp-uniform: the pair is complete
     const bool valid = half == 0 || vB;                           // uniform over the half-warp
     RowIn r;
-    load_row(A, m, valid ? 2 * pair + half : 2 * pair, r);
+    derive_row(A, m, raw, r);
     float dRm[9];                                                 // lane-partial d/dR
 #pragma unroll
     for (int k = 0; k < 9; ++k) dRm[k] = 0.f;
@@ -331,8 +380,8 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const Ge
     for (int v = 0; v < V; ++v) {
       RowVar t;
       float o[3];
-      row_forward(A, m, v, r, t);
-      row_consistency(A, m, v, r, t, o);
+      row_forward(A, raw.delta[v], r, t);
+      row_consistency(A, m, raw.delta2[v], r, t, o);
       if (valid) { sums[0] += o[0]; sums[1] += o[1]; sums[3] += o[2]; }
       // pairwise deformation (:250-254): E = (P - P') - (S - S'), ' = the other row of the pair
       Vec3 E; E.x = E.y = E.z = 0.f;
@@ -364,14 +413,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const Ge
       g2acc[1] += net == 1 ? ddelta2 : 0.f;
       if (kFull) {
         // ---- d/dq: through P2 = (q d2) and the external consumers (flows, pass-2 lifters)
-        float dqx = dP2.x * t.d2, dqy = dP2.y * t.d2;
-        const int p = m.pnet[v];
-        if (p >= 0) {
-          const int nj = A.maps.n_joints[p];
-          const int idx = m.pidx[v];
-          dqx += A.dflow[p][r.n * (2 * nj) + idx] + A.dlift[p][r.n * LINKS_HEAD_LD + idx];
-          dqy += A.dflow[p][r.n * (2 * nj) + nj + idx] + A.dlift[p][r.n * LINKS_HEAD_LD + nj + idx];
-        }
+        const float dqx = dP2.x * t.d2 + raw.xqx[v], dqy = dP2.y * t.d2 + raw.xqy[v];
         // ---- d/dQ
         Vec3 dQ;
         dQ.x = g3 * t.F.x + dqx * t.izq;

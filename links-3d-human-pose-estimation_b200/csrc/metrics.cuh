@@ -270,10 +270,11 @@ __device__ __forceinline__ void pa_fit(const PoseRegs<JT>& R, const PoseRegs<JT>
   f.g0 = nr0 / np0;           // mode 0: RMS match, last ROW of R scaled by det (metrics_batch.py:145-147)
 }
 
-// aligned (optional, natural joint order) receives the mode-`amode` aligned pose.
-template <int JT>
+// WANT: bit 0 -> e_batch (mode 0), bit 1 -> e_best (mode 1).  aligned (optional, natural joint order) receives the
+// aligned pose of the single requested mode.
+template <int JT, int WANT>
 __device__ __forceinline__ void pa_errors(const PoseRegs<JT>& R, const PoseRegs<JT>& P, int J, int rot, const PaFit& f,
-                                          float& e_best, float& e_batch, float* aligned, int amode) {
+                                          float& e_best, float& e_batch, float* aligned) {
   float acc1 = 0.f, acc0 = 0.f;
 #pragma unroll
   for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
@@ -285,15 +286,21 @@ __device__ __forceinline__ void pa_errors(const PoseRegs<JT>& R, const PoseRegs<
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
       const float q = f.Q[a][0] * y[0] + f.Q[a][1] * y[1] + f.Q[a][2] * y[2];
-      const float z1 = f.g1 * q;
-      const float z0 = f.g0 * (a == 2 ? f.det * q : q);
-      if (aligned) aligned[a * J + (rot ? slot_joint<JT>(k, rot, J) : k)] = (amode == 1 ? z1 : z0) + f.mr[a];
-      const float e1 = x[a] - z1, e0 = x[a] - z0;
-      d1 += e1 * e1;
-      d0 += e0 * e0;
+      if (WANT & 2) {
+        const float z1 = f.g1 * q;
+        if (WANT == 2 && aligned) aligned[a * J + (rot ? slot_joint<JT>(k, rot, J) : k)] = z1 + f.mr[a];
+        const float e1 = x[a] - z1;
+        d1 += e1 * e1;
+      }
+      if (WANT & 1) {
+        const float z0 = f.g0 * (a == 2 ? f.det * q : q);
+        if (WANT == 1 && aligned) aligned[a * J + (rot ? slot_joint<JT>(k, rot, J) : k)] = z0 + f.mr[a];
+        const float e0 = x[a] - z0;
+        d0 += e0 * e0;
+      }
     }
-    acc1 += sqrtf(d1);
-    acc0 += sqrtf(d0);
+    if (WANT & 2) acc1 += sqrtf(d1);
+    if (WANT & 1) acc0 += sqrtf(d0);
   }
   const float invJ = 1.f / static_cast<float>(J);
   e_best = acc1 * invJ;
@@ -410,8 +417,9 @@ __global__ void __launch_bounds__(kPosesPerBlock, 8) pmpjpe_kernel(
             PoseRegs<JT> R, P;
             load_pose<JT>(rr, J, rot, R);
             load_pose<JT>(pp, J, rot, P);
-            pa_errors<JT>(R, P, J, rot, fit, eb, e0,
-                          aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr, mode);
+            float* al = aligned ? aligned + static_cast<size_t>(pose0 + t) * row_len : nullptr;
+            if (mode == 1) pa_errors<JT, 2>(R, P, J, rot, fit, eb, e0, al);     // block-uniform
+            else pa_errors<JT, 1>(R, P, J, rot, fit, eb, e0, al);
           }
           const float e = mode == 1 ? eb : e0;
           if (per_pose) per_pose[pose0 + t] = e;
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(kPosesPerBlock, 6) eval_lift_score_kernel(
             load_pose<17>(s_ref + t * 51, J, 0, R);
             lift(P);
             float eb, e0;
-            pa_errors<17>(R, P, J, 0, fit, eb, e0, nullptr, 0);
+            pa_errors<17, 3>(R, P, J, 0, fit, eb, e0, nullptr);
             a1 += static_cast<double>(eb);
             a2 += static_cast<double>(e0);
           }
