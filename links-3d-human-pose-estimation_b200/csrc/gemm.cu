@@ -46,7 +46,7 @@ constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
 constexpr uint32_t kStageBytesB = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the pair's B tile
 constexpr uint32_t kStageBytes = kStageBytesA + kStageBytesB;
 constexpr uint32_t kOffStage = 0;
-constexpr uint32_t kScratchBytes = 2 * 32 * 64 + 256;          // per epilogue warp: operand + output scratch ([32 rows][64 B] each) + 64 bias floats
+constexpr uint32_t kScratchBytes = 2 * 32 * 64 + 256 + 64;     // per epilogue warp: two operand/output scratches ([32 rows][64 B] each) + 64 bias floats + next-tile operand descriptor
 constexpr uint32_t kOffScratch = kStages * kStageBytes;
 constexpr uint32_t kOffBar = kOffScratch + kEpiWarps * kScratchBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024 /*align slack*/;
@@ -211,6 +211,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// all but the most recently committed group have landed
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -246,13 +249,34 @@ __device__ __forceinline__ void block_store(uint32_t S, __nv_bfloat16* base, int
 
 constexpr int kHalf = 32;   // columns processed per pass of a warp over its 64-column slab
 
+// The operand block that is fetched AHEAD of its use: add0 when the problem has one, else ymask.  The descriptor of the
+// warp's NEXT tile lives in the warp's scratch (32 bytes, written by lane 0 at the start of a tile) rather than in
+// registers: it is warp-uniform, needed only at the two refill points, and keeping it live across a pass cost spills.
+struct PrimaryOp {
+  const __nv_bfloat16* p;
+  int ld, M, m0, n0;
+  int ok;             // present, 16-byte aligned and the warp's 64-column slab lies fully inside N (the vector path)
+  int pad;
+};
+static_assert(sizeof(PrimaryOp) == 32, "PrimaryOp slot");
+__device__ __forceinline__ void prefetch_primary(const PrimaryOp* slot, uint32_t S, int h, int lane) {
+  const uint4 a = *reinterpret_cast<const uint4*>(slot);              // p, ld, M
+  const uint4 b = *(reinterpret_cast<const uint4*>(slot) + 1);        // m0, n0, ok
+  if (b.z != 0u) {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32));
+    block_fetch_async(S, p, static_cast<int>(a.z), static_cast<int>(b.x), static_cast<int>(b.y) + h * 32, static_cast<int>(a.w), lane);
+  }
+  cp_async_commit();                      // one group per pass, empty or not: keeps the wait_group arithmetic uniform
+}
+
 // One [32 rows x 64 columns] block of an accumulator tile per warp (this thread: row m0 + lane), in two passes of
-// 32 columns.  SA: operand scratch (add0 / add1 / ymask blocks), SB: output scratch (mid / out / fp32 blocks).
+// 32 columns.  Pass h owns scratch S0 + 2048 h: it holds the pass's primary operand (cp.async group committed TWO passes
+// earlier, i.e. a full pass of work ahead), then any secondary operand, then stages the pass's outputs for the
+// coalesced stores, and is finally refilled with the primary operand of the same pass of the warp's NEXT tile.
 //   t_addr : TMEM address of (lane group, first column of the block);  sbias : bias of the block's 64 columns (smem)
-// The caller has already issued block_fetch_async(SA, add0, ...) for pass 0.
 template <uint32_t F>
-__device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t SA, uint32_t SB,
-                                               int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
+__device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
+                                               const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
   constexpr bool kDyn = F == 0u;
   const int m = m0 + lane;
   const bool row_ok = m < E.M;
@@ -283,12 +307,17 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(acc_empty_bar, 0);
+    prefetch_primary(nxt, S0, 0, lane);
+    prefetch_primary(nxt, S0 + 2048u, 1, lane);
     return;
   }
 
+  const bool y_primary = has_y && !has_add0;     // ymask is the operand fetched ahead when there is no add0
+  uint32_t sign_prev = 0;
 #pragma unroll 1
   for (int h = 0; h < kSlab / kHalf; ++h) {
     const int n0 = n_blk + h * kHalf;
+    const uint32_t SA = S0 + static_cast<uint32_t>(h) * 2048u, SB = SA;
     // ---- accumulator row -> registers; after the second pass the TMEM buffer is free for the MMA warp
     float v[kHalf];
 #pragma unroll
@@ -316,7 +345,14 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       uint32_t sw = 0;
 #pragma unroll
       for (int i = 0; i < kHalf; ++i) sw |= (v[i] > 0.f ? 0u : 1u) << i;
-      if (row_ok) E.sign_out[mo * E.ld_sign + (n0 >> 5)] = sw;
+      // both passes' words of a row are adjacent: one 8-byte store per row instead of two 4-byte ones (each is a
+      // separate 32-byte sector per lane -- the row-per-thread pattern the L1 tag stage serialises)
+      if ((E.ld_sign & 1) == 0) {
+        if (h == 1 && row_ok) *reinterpret_cast<uint2*>(E.sign_out + mo * E.ld_sign + (n_blk >> 5)) = make_uint2(sign_prev, sw);
+        sign_prev = sw;
+      } else if (row_ok) {
+        E.sign_out[mo * E.ld_sign + (n0 >> 5)] = sw;
+      }
     }
     if (lpre) {
 #pragma unroll
@@ -328,7 +364,7 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
     }
     // bf16 operand blocks: fetched coalesced into scratch SA, read back row-per-thread
     if (has_add0) {
-      cp_async_wait_all();
+      cp_async_wait_but_one();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -350,13 +386,13 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       }
       __syncwarp();
     }
-    if (has_y) block_fetch_async(SA, E.ymask, E.ld_ymask, m0, n0, E.M, lane);   // in flight during the leaky below
+    if (has_y && !y_primary) block_fetch_async(SA, E.ymask, E.ld_ymask, m0, n0, E.M, lane);   // in flight during the leaky below
     if (lpost) {
 #pragma unroll
       for (int i = 0; i < kHalf; ++i) v[i] = fmaxf(v[i], 0.01f * v[i]);
     }
     if (has_y) {
-      cp_async_wait_all();
+      if (y_primary) cp_async_wait_but_one(); else cp_async_wait_all();
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -366,8 +402,6 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       }
       __syncwarp();
     }
-    // SA is free: fetch the first operand of the next pass while this pass stores its results
-    if (has_add0 && h + 1 < kSlab / kHalf) block_fetch_async(SA, E.add0, E.ld_add0, m0, n0 + kHalf, E.M, lane);
     if (has_mid) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -419,7 +453,17 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
         __syncwarp();
       }
     }
+    // this pass's scratch is free again: refill it with the primary operand of the same pass of the next tile
+    prefetch_primary(nxt, SA, h, lane);
   }
+}
+
+// Run-time-flag variant (rare combinations, e.g. the flow-training GEMMs) kept OUT of line: inlined next to the
+// specialised modes its register demand made the compiler spill state that is live across the mode switch in every
+// mode.  The caller passes copies, so only those copies are pinned in local memory.
+__device__ __noinline__ void epilogue_block_dyn(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
+                                                const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
+  epilogue_block<0u>(E, t_addr, sbias, S0, nxt, m0, n_blk, lane, acc_empty_bar);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -630,6 +674,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
     };
     float bias_n0, bias_n1;
     load_bias(cl_id, bias_n0, bias_n1);
+    // primary operand (add0, else ymask) of a tile's two passes for this warp -> the warp's descriptor slot
+    PrimaryOp* const nxt = reinterpret_cast<PrimaryOp*>(smem_raw + (S + 4096u + 256u - raw));
+    auto publish_primary = [&](int tile_idx) {
+      if (lane == 0) {
+        PrimaryOp o;
+        o.p = nullptr; o.ld = 0; o.M = 0; o.m0 = 0; o.n0 = 0; o.ok = 0; o.pad = 0;
+        if (tile_idx < G.total_tiles) {
+          TileCoord t0 = tile_coord(G, tile_idx);
+          const GemmProblemDev& P = G.p[t0.pi];
+          o.p = P.add0 != nullptr ? P.add0 : P.ymask;
+          o.ld = P.add0 != nullptr ? P.ld_add0 : P.ld_ymask;
+          o.M = P.M;
+          o.m0 = (2 * t0.tm + cta_rank) * BM + lane_grp * 32;
+          o.n0 = t0.tn * BN + slab * kSlab;
+          o.ok = (o.p != nullptr && P.vec_ok && o.n0 + kSlab <= P.N) ? 1 : 0;
+        }
+        *nxt = o;
+      }
+      __syncwarp();
+    };
+    publish_primary(cl_id);                                  // in flight while the first main loop runs
+    prefetch_primary(nxt, S, 0, lane);
+    prefetch_primary(nxt, S + 2048u, 1, lane);
     for (int tile = cl_id; tile < G.total_tiles; tile += n_cl, ++lt) {
       TileCoord tc = tile_coord(G, tile);
       tc.tm = 2 * tc.tm + cta_rank;
@@ -647,9 +714,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
       }
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
       const int m0 = tc.tm * BM + lane_grp * 32, n0 = tc.tn * BN + slab * kSlab;
-      // first residual operand of this warp's block: fetched while the main loop of the tile is still running
-      if (E.add0 != nullptr && E.vec_ok && n0 + kSlab <= E.N) block_fetch_async(S, E.add0, E.ld_add0, m0, n0, E.M, lane);
-      __syncwarp();                                  // every lane is done reading the previous tile's bias
+      __syncwarp();                                  // every lane is done with the previous tile's bias and descriptor
+      publish_primary(tile + n_cl);
       sbias[lane] = bias_n0;
       sbias[lane + 32] = bias_n1;
       __syncwarp();
@@ -664,20 +730,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ae, 0);
+        prefetch_primary(nxt, S, 0, lane);
+        prefetch_primary(nxt, S + 2048u, 1, lane);
       } else {
         const float* sb = sbias;
         switch (mode) {
-          case 1: epilogue_block<kEpiMask[1]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 2: epilogue_block<kEpiMask[2]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 3: epilogue_block<kEpiMask[3]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 4: epilogue_block<kEpiMask[4]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 5: epilogue_block<kEpiMask[5]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 6: epilogue_block<kEpiMask[6]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 7: epilogue_block<kEpiMask[7]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 8: epilogue_block<kEpiMask[8]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 9: epilogue_block<kEpiMask[9]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          case 10: epilogue_block<kEpiMask[10]>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
-          default: epilogue_block<0u>(E, t_addr, sb, S, S + 2048u, m0, n0, lane, ae); break;
+          case 1: epilogue_block<kEpiMask[1]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 2: epilogue_block<kEpiMask[2]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 3: epilogue_block<kEpiMask[3]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 4: epilogue_block<kEpiMask[4]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 5: epilogue_block<kEpiMask[5]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 6: epilogue_block<kEpiMask[6]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 7: epilogue_block<kEpiMask[7]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 8: epilogue_block<kEpiMask[8]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 9: epilogue_block<kEpiMask[9]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 10: epilogue_block<kEpiMask[10]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          default: {
+            const EpiParams Ed = E;
+            epilogue_block_dyn(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae);
+            break;
+          }
         }
       }
       if (store_thread && lt < 3) TRACE(4 + 3 * lt);

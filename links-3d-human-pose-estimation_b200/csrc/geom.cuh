@@ -282,12 +282,18 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
   const int half = m.lane >> 4;
   const int npairs = (A.N + 1) / 2;
   const int stride = gridDim.x * kGeomWarps;
-  int pair = blockIdx.x * kGeomWarps + (threadIdx.x >> 5);
+  // The loop bounds depend on blockIdx only (block-uniform trip count): the compiler can then prove that the warp is
+  // converged at every shuffle and emits plain SHFLs; a warp past the end works on a clamped row with writes masked.
+  const int warp = threadIdx.x >> 5;
+  auto row_of = [&](int pr) {                    // row this half-warp reads for pair `pr` (clamped to a valid row)
+    const int n = 2 * pr + half;
+    return n < A.N ? n : A.N - 1;
+  };
   RawRow<V, 0> raw, raw_next;
-  if (pair < npairs) load_raw(A, m, 2 * pair + half < A.N ? 2 * pair + half : 2 * pair, raw);
-  for (; pair < npairs; pair += stride, raw = raw_next) {
-    const int nxt = pair + stride;
-    if (nxt < npairs) load_raw(A, m, 2 * nxt + half < A.N ? 2 * nxt + half : 2 * nxt, raw_next);
+  load_raw(A, m, row_of(blockIdx.x * kGeomWarps + warp), raw);
+  for (int base = blockIdx.x * kGeomWarps; base < npairs; base += stride, raw = raw_next) {
+    const int pair = base + warp;
+    if (base + stride < npairs) load_raw(A, m, row_of(pair + stride), raw_next);
     const bool valid = 2 * pair + half < A.N;    // uniform over the half-warp
     RowIn r;
     derive_row(A, m, raw, r);
@@ -360,14 +366,18 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const Ge
 
   const int total_pairs = (A.N + 1) / 2;
   const int stride = gridDim.x * kGeomWarps;
-  int pair = blockIdx.x * kGeomWarps + warp;
+  // block-uniform trip count (see geom_forward_kernel): shuffles sit in provably convergent code
+  auto row_of = [&](int pr) {
+    const int n = 2 * pr + half;
+    return n < A.N ? n : A.N - 1;
+  };
   RawRow<V, kFull ? 2 : 1> raw, raw_next;
-  if (pair < total_pairs) load_raw(A, m, 2 * pair + half < A.N ? 2 * pair + half : 2 * pair, raw);
-  for (; pair < total_pairs; pair += stride, raw = raw_next) {
-    const int nxt = pair + stride;
-    if (nxt < total_pairs) load_raw(A, m, 2 * nxt + half < A.N ? 2 * nxt + half : 2 * nxt, raw_next);
+  load_raw(A, m, row_of(blockIdx.x * kGeomWarps + warp), raw);
+  for (int base = blockIdx.x * kGeomWarps; base < total_pairs; base += stride, raw = raw_next) {
+    const int pair = base + warp;
+    if (base + stride < total_pairs) load_raw(A, m, row_of(pair + stride), raw_next);
     const bool vB = 2 * pair + 1 < A.N;                           // warp-uniform: the pair is complete
-    const bool valid = half == 0 || vB;                           // uniform over the half-warp
+    const bool valid = 2 * pair + half < A.N;                     // uniform over the half-warp
     RowIn r;
     derive_row(A, m, raw, r);
     float dRm[9];                                                 // lane-partial d/dR
