@@ -17,7 +17,7 @@
 // of the single-CTA version (steady state ~9 TB/s of L2->SM traffic; isolated main loop at 75 % of the MMA floor).
 //   warp 0      : TMA producer (one elected lane), runs ahead across tile boundaries
 //   warp 1      : TMEM allocator + tcgen05.mma issuer (warp-uniform control flow, one elected lane)
-//   warps 2..17 : epilogue (TMEM lane group = warp % 4, 64-column slab = (warp - 2) / 4); the epilogue of tile i overlaps
+//   warps 4..19 : epilogue (TMEM lane group = warp % 4, 64-column slab = (warp - 4) / 4; warps 2-3 idle, see setmaxnreg); the epilogue of tile i overlaps
 //                 the main loop of tile i + 1 through the second accumulator buffer.
 // Operands may be K-major (row-major with the contraction dimension contiguous) or MN-major (contraction dimension
 // strided): dgrad reads W itself as an MN-major B operand and wgrad reads the row-major activations / gradients as
@@ -39,7 +39,11 @@ constexpr int kStages = 4;
 constexpr int kEpiWarps = 16;     // 4 TMEM lane groups x 4 column quarters: 4 warps per scheduler hide the epilogue's latencies
 constexpr int kChunk = 16;        // accumulator columns per TMEM load / scalar-path chunk
 constexpr int kSlab = 64;         // columns of the [32 rows x 64 cols] block one epilogue warp owns
-constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kFirstEpiWarp = 4;  // warpgroup 0 = {TMA producer, MMA issuer, 2 idle warps}; warpgroups 1-4 = epilogue
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
+// setmaxnreg budget: 128 threads x kRegsCtl + 512 threads x kRegsEpi <= 64 K registers, and per scheduler partition
+// (one control warp + four epilogue warps) 32 x (kRegsCtl + 4 kRegsEpi) <= 16 K.  The kernel is compiled for 96.
+constexpr int kRegsCtl = 32, kRegsEpi = 112;
 constexpr int kAccCols = BN;      // fp32 accumulator columns per buffer
 constexpr int kTmemCols = 2 * kAccCols;
 constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
@@ -575,6 +579,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+  if (warp < kFirstEpiWarp) {
+    // the control warpgroup hands registers to the epilogue warpgroups (whose 32-column accumulator slice, operand
+    // conversion and store staging did not fit 96 registers without spills).  The two register budgets must not meet
+    // again before the end of the kernel: ptxas compiles code after a join for the smaller one.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsCtl));
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
@@ -650,12 +659,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
         __syncwarp();
       }
     }
+  }
   } else {
-    // ================= epilogue warps (256 threads) =================
+    // ================= epilogue warps (512 threads) =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     const int lane_grp = warp & 3;                                    // TMEM lanes 32*lane_grp .. +31
-    const int slab = (warp - 2) >> 2;                                 // which 64 columns of the tile
-    const bool store_thread = threadIdx.x == 64;
-    const uint32_t S = base + kOffScratch + static_cast<uint32_t>(warp - 2) * kScratchBytes;
+    const int slab = (warp - kFirstEpiWarp) >> 2;                                 // which 64 columns of the tile
+    const bool store_thread = threadIdx.x == kFirstEpiWarp * 32;
+    const uint32_t S = base + kOffScratch + static_cast<uint32_t>(warp - kFirstEpiWarp) * kScratchBytes;
     uint32_t lt = 0;
     // bias of this warp's 64 columns: two floats per lane, loaded one tile ahead, published through the warp's own
     // scratch (no CTA-wide barrier in the epilogue: the 16 warps run fully decoupled)
