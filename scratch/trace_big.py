@@ -1,6 +1,6 @@
 """Debug: steady-state tile period vs epilogue duration of the grouped GEMM at large M (trace build)."""
 import os, sys, ctypes as C
-os.environ["LINKS_B200_LIB"] = os.path.join(os.getcwd(), "scratch/tracelib/liblinks_b200.so")
+os.environ.setdefault("LINKS_B200_LIB", os.path.join(os.getcwd(), "scratch/tracelib/liblinks_b200.so"))
 sys.path[:0] = [os.getcwd(), os.path.join(os.getcwd(), "links-3d-human-pose-estimation_b200")]
 import numpy as np, torch
 from links_b200 import _cabi
@@ -21,6 +21,15 @@ def run(M, N, K, nprob, kind):
             kw.update(add0=resid, sign_out=sign, flags=_cabi.EPI_LEAKY_PRE | _cabi.EPI_LEAKY_POST); keep += [resid, sign]
         elif kind == "l1":
             kw.update(flags=_cabi.EPI_LEAKY_PRE)
+        elif kind in ("d5", "d7"):
+            del kw["bias"]
+            ym = (torch.randn(M, N, device="cuda") * 0.3).bfloat16(); keep.append(ym)
+            kw.update(ymask=ym)
+            if kind == "d7":
+                a0 = (torch.randn(M, N, device="cuda") * 0.3).bfloat16(); mid = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+                bits = torch.randint(0, 2 ** 31 - 1, (M, N // 32), device="cuda", dtype=torch.int32)
+                keep += [a0, mid, bits]
+                kw.update(add0=a0, mid=mid, bits=bits)
         keep += [A, W, out, bias]
         probs.append(prob(A, W, M, N, K, **kw))
     arr = (_cabi.GemmProblem * nprob)(*probs)
@@ -48,5 +57,5 @@ def run(M, N, K, nprob, kind):
     print("   setup %.2f  first_full %.2f  t0_accfull %.2f | tile period (t2-t1 accfull) mean %.2f min %.2f max %.2f | epilogue(t0) %.2f epilogue(t1) %.2f (warp 2 only)" %
           (rel[:, 1].mean(), rel[::2, 2].mean(), rel[:, 3].mean(), per.mean(), per.min(), per.max(), epi0.mean(), epi1.mean()))
 
-for M, nprob, kind in ((16384, 4, "l2"), (16384, 4, "l1"), (16384, 4, "plain"), (8192, 2, "l2"), (2048, 4, "l2"), (2048, 2, "l2")):
+for M, nprob, kind in ((16384, 4, "l2"), (16384, 4, "d5"), (16384, 4, "d7"), (16384, 4, "plain"), (2048, 4, "l2"), (2048, 4, "d7"), (2048, 2, "l2")):
     run(M, 1024, 1024, nprob, kind)
