@@ -14,7 +14,7 @@ def read_rows(path):
 def short(name):
     for key in ("gemm_grouped_kernel", "flow_tc_kernel", "flow_tc_pack", "geom_lossgrad_kernel", "geom_forward_kernel",
                 "geom_backward_angles", "elev_stats", "adam_kernel", "colsum_batched_zero", "colsum_batched", "cast_weight_batched",
-                "pack_rows", "grad_compress", "mpjpe_kernel", "pmpjpe_kernel", "eval_lift_score", "occ_"):
+                "pack_rows", "grad_compress", "pmpjpe_kernel", "mpjpe_kernel", "eval_lift_score", "occ_"):
         if key in name:
             if key in ("flow_tc_kernel", "geom_lossgrad_kernel") and "<" in name:
                 return key + name[name.index("<"):name.index(">") + 1]
