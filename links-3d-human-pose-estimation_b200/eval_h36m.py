@@ -10,6 +10,7 @@ from links_b200.harness import evaluate  # noqa: E402
 parser = argparse.ArgumentParser(description="evaluate the left/right lifters")
 g = parser.add_argument_group("links_b200 additions")
 g.add_argument("--synthetic", type=int, default=1_000_000, help="number of synthetic test poses (no dataset is shipped)")
+g.add_argument("--datafile", default=None, help="dataset pickle in the reference's format; subjects S9 / S11 are evaluated")
 g.add_argument("--chunk", type=int, default=65536)
 g.add_argument("--seed", type=int, default=0)
 g.add_argument("--weights-dir", default="models")

@@ -13,6 +13,7 @@ import torch
 
 from . import init as INIT
 from .occlusion import OCC_IN, OCC_NAMES, OCC_OUT, EvalRunner, OcclusionStep
+from .data import ArrayLoader, DevicePrefetcher, loader_from_dataset
 from .shard import shard_bounds
 from .steps import LifterStep
 from .synth import synth_poses
@@ -31,6 +32,8 @@ def add_common_args(p, batch=256, epochs=100):
     g.add_argument("--weights-dir", default="models", help="where pretrained flows / lifters are read from and results saved")
     g.add_argument("--log-every", type=int, default=50)
     g.add_argument("--no-save", action="store_true")
+    g.add_argument("--datafile", default=None, help="dataset pickle in the reference's format ({subject: {poses_2d, poses_3d}})")
+    g.add_argument("--dataset", default="h36m", choices=["h36m", "mpi"], help="which dataset class reads --datafile")
     g.add_argument("--val", type=int, default=0, help="synthetic validation poses scored at every epoch end (0 = off)")
     return p
 
@@ -64,26 +67,26 @@ def save_module_state(module_cls, kwargs, params, path):
     torch.save(m.state_dict(), path)
 
 
-class SyntheticLoader:
+class SyntheticLoader(ArrayLoader):
     """Epochs of shuffled batches of this rank's shard of a synthetic pose set, staged through pinned host memory."""
 
     def __init__(self, n, batch_global, rank, world, seed):
         x2d, gt = synth_poses(n, seed=1234 + seed)
-        b, e = shard_bounds(n, rank, world)
-        self.x = torch.from_numpy(x2d[b:e]).pin_memory()
-        self.gt = torch.from_numpy(gt[b:e])
-        self.batch = batch_global // world
-        if self.batch % 2 or self.batch < 2:
-            raise ValueError("per-rank batch must be even (row pairs / split_data_left_right_3d)")
-        self.gen = torch.Generator().manual_seed(seed * 1000 + rank)
+        super().__init__(x2d, gt, batch_global, rank, world, seed)
 
-    def __len__(self):
-        return self.x.shape[0] // self.batch
 
-    def __iter__(self):
-        perm = torch.randperm(self.x.shape[0], generator=self.gen)
-        for i in range(len(self)):
-            yield self.x[perm[i * self.batch:(i + 1) * self.batch]].pin_memory()
+def make_loader(args, rank, world):
+    """The reference's dataset pickle when --datafile is given (H36M_Data / MPI_INF_3DHP_Dataset with normalize_head and
+    ground-truth 2D, as train_leg_torso_lifter.py:376-386 builds it), otherwise synthetic poses."""
+    if getattr(args, "datafile", None):
+        from utils.helpers import normalize_head
+        if args.dataset == "mpi":
+            from utils.mpi_inf_3dhp_dataset_class import MPI_INF_3DHP_Dataset as DS
+        else:
+            from utils.h36m_dataset_class import H36M_Data as DS
+        ds = DS(args.datafile, train=True, normalize_func=normalize_head, get_2dgt=True)
+        return loader_from_dataset(ds, args.batch, rank, world, args.seed)
+    return SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
 
 
 class Validator:
@@ -124,7 +127,7 @@ def run_training(step, loader, args, rank, feed, validator=None):
     lr = LR0
     for epoch in range(args.epochs):
         step.set_lr(lr)
-        for xb in loader:
+        for xb in DevicePrefetcher(loader, step.device):     # batch i+1 crosses PCIe while step i runs
             feed(step, xb)
             step.step()
             n_steps += 1
@@ -172,7 +175,7 @@ def train_lifters(kind, args):
     flows = [load_state(os.path.join(wd, f), lambda C=2 * n, s=41 + i: INIT.init_flow_params(C, s))
              for i, (f, n) in enumerate(zip(flow_files, nj))]
     full = load_state(os.path.join(wd, "full_pose_norm_flow.pt"), lambda: INIT.init_flow_params(34, 40))
-    loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
+    loader = make_loader(args, rank, world)
     step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
     validator = Validator(kind, step, args.val, args.seed, args.translation, rank, world, pg) if args.val else None
@@ -197,7 +200,7 @@ def train_occlusion(args):
     lifters = [load_state(os.path.join(wd, "leg_lifter.pt"), lambda: INIT.init_lifter_params(7, 11)),
                load_state(os.path.join(wd, "torso_lifter.pt"), lambda: INIT.init_lifter_params(10, 12))]
     preds = {n: INIT.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i + args.seed) for i, n in enumerate(OCC_NAMES)}
-    loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
+    loader = make_loader(args, rank, world)
     step = OcclusionStep(loader.batch, lifters, preds, cfg=dict(depth=args.translation), process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
 
@@ -225,8 +228,14 @@ def evaluate(args):
     wd = args.weights_dir
     lifters = [load_state(os.path.join(wd, "left_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 13)),
                load_state(os.path.join(wd, "right_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 14))]
-    x2d, gt = synth_poses(args.synthetic, seed=4321 + args.seed)
-    b, e = shard_bounds(args.synthetic, rank, world, multiple=1)
+    if getattr(args, "datafile", None):          # eval_h36m.py:41: test subjects, fixed-scale normalisation
+        from utils.h36m_dataset_class import H36M_Data
+        from utils.helpers import normalize_head_test
+        ds = H36M_Data(args.datafile, train=False, normalize_func=normalize_head_test, get_2dgt=True, subjects=['S9', 'S11'])
+        x2d, gt = ds.data["poses_2d"].astype("float32"), ds.data["poses_3d"].astype("float32")
+    else:
+        x2d, gt = synth_poses(args.synthetic, seed=4321 + args.seed)
+    b, e = shard_bounds(x2d.shape[0], rank, world, multiple=1)
     ev = EvalRunner("lr", lifters, chunk=args.chunk, choice="right", process_group=pg)
     xs, gs = torch.from_numpy(x2d[b:e]).pin_memory(), torch.from_numpy(gt[b:e]).pin_memory()
     for i in range(0, e - b, args.chunk):

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch  # noqa: E402
 from links_b200 import init as INIT  # noqa: E402
 from links_b200.flowtrain import FlowTrainStep  # noqa: E402
-from links_b200.harness import GAMMA, LR0, SyntheticLoader, add_common_args, dist_setup  # noqa: E402
+from links_b200.harness import GAMMA, LR0, add_common_args, dist_setup, make_loader  # noqa: E402
 
 parser = argparse.ArgumentParser(description='Train 2D INN')
 parser.add_argument("-n", "--num_keypoints", help="number of keypoints", type=int, default=34)
@@ -22,7 +22,7 @@ if __name__ == "__main__":
         raise NotImplementedError("the sampling block zeroes the root joint of a 17-joint pose (reference :84-86)")
     rank, world, pg = dist_setup()
     params = INIT.init_flow_params(34, 40 + args.seed, perturb=0.0)
-    loader = SyntheticLoader(args.synthetic, args.batch, rank, world, args.seed)
+    loader = make_loader(args, rank, world)
     step = FlowTrainStep(34, params, loader.batch, lr=LR0, weight_decay=1e-5, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
     n_steps, lr, t0 = 0, LR0, time.time()

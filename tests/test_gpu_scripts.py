@@ -48,3 +48,25 @@ def test_lifter_scripts_train_save_eval(tmp_path):
     assert "step 3" in out and "dist_2d_torso=" in out
     sd = torch.load(os.path.join(wd, "mpi_norm_flow_legs_2.pt"))
     assert len(sd) == 64 and sd["module_list.0.subnet.2.weight"].shape == (14, 1024)
+
+
+def test_scripts_on_a_dataset_pickle(tmp_path):
+    """--datafile: the reference's pickle layout -> dataset drop-in -> sharded loader -> device prefetcher -> step."""
+    import pickle
+    import numpy as np
+    sys.path.insert(0, PKG)
+    from links_b200.synth import synth_poses
+    data = {}
+    for i, s in enumerate(['S1', 'S5', 'S6', 'S7', 'S8', 'S9', 'S11']):
+        x2d, gt = synth_poses(300, seed=50 + i)
+        data[s] = {"poses_2d": np.ascontiguousarray(x2d.reshape(-1, 2, 17).transpose(0, 2, 1)) * 1000.0,
+                   "poses_3d": np.ascontiguousarray(gt.reshape(-1, 3, 17).transpose(0, 2, 1)).astype(np.float64)}
+    path = str(tmp_path / "h36m_like.pkl")
+    with open(path, "wb") as f:
+        pickle.dump(data, f)
+    wd = str(tmp_path)
+    out = _run("train_left_right_lifter.py", "--datafile", path, "--batch", "128", "--steps", "5", "--log-every", "5",
+               "--weights-dir", wd)
+    assert "step 5" in out and "loss=" in out
+    out = _run("eval_h36m.py", "--datafile", path, "--chunk", "1024", "--weights-dir", wd)
+    assert "PA-MPJPE:" in out and "N-MPJPE:" in out
