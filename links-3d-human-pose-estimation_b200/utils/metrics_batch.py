@@ -9,7 +9,8 @@ from links_b200 import _cabi
 def _prep(t, num_joints):
     if not t.is_cuda:
         raise _cabi.LinksError("links_b200 metrics run on a B200 only (no CPU fallback)")
-    return t.reshape(-1, 3 * num_joints).contiguous().float()
+    t = t.reshape(-1, 3 * num_joints).contiguous().float()
+    return t.clone() if t.data_ptr() % 16 else t      # the kernels stream 16-byte aligned chunks (views may start anywhere)
 
 
 def _st():

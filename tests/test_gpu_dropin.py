@@ -104,3 +104,6 @@ def test_metrics_batch_dropin_vs_reference_golden(golden):
     assert (mb().pmpjpe_best(gt, pred).cpu().numpy() - G["pmpjpe_np_best"]).__abs__().max() < 0.05
     al = mb().procrustes(pred.reshape(M, 3, 17), gt.reshape(M, 3, 17))
     assert al.shape == (M, 3, 17)
+    # views that do not start on a 16-byte boundary (row 1 of a [M,51] tensor) are accepted like any other tensor
+    assert torch.equal(mb().mpjpe(gt[1:], pred[1:], num_joints=17, root_joint=0), mb().mpjpe(gt, pred, num_joints=17, root_joint=0)[1:])
+    assert torch.allclose(mb().pmpjpe_best(gt[1:], pred[1:]), mb().pmpjpe_best(gt, pred)[1:], atol=1e-4)

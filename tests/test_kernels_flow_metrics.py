@@ -173,20 +173,21 @@ def test_metrics_multichunk(nj, rj, backend):
         assert np.abs(pa1 - OM.pmpjpe_best_batch(g, p2)).max() < 0.05
 
 
+@pytest.mark.parametrize("ldd", [32, 20, 17])     # 17: rows are not 16-byte multiples -> the non-bulk staging path
 @backend_params
-def test_eval_lift_score_fused(backend):
+def test_eval_lift_score_fused(ldd, backend):
     L = backend
     M = 64 * 5 + 6
     p2d, gt = synth_poses(M, seed=11)
     rng = np.random.RandomState(0)
-    doff = np.zeros((M, 32), np.float32)
+    doff = np.zeros((M, ldd), np.float32)
     doff[:, :17] = rng.normal(size=(M, 17)) * 0.3
     doff[:, 0] = 0
     pred = OG.lift(torch.from_numpy(p2d), torch.from_numpy(doff[:, :17] + 10.0)).reshape(-1, 51)
     ref = OS.eval_metrics(torch.from_numpy(gt), pred)
     pab = OM.pmpjpe_batch(torch.from_numpy(gt), pred, num_joints=17).mean().item()
     sums = np.zeros(3, np.float64)
-    assert L.call("eval_lift_score", p2d, doff, 32, gt, M, 10.0, sums) == 0
+    assert L.call("eval_lift_score", p2d, doff, ldd, gt, M, 10.0, sums) == 0
     assert abs(sums[0] / M - ref["n_mpjpe"]) < 0.05
     assert abs(sums[1] / M - ref["pa_mpjpe"]) < 0.05
     assert abs(sums[2] / M - pab) < 0.05
