@@ -47,7 +47,54 @@ def t(a):
     return a.detach().cpu().numpy()
 
 
+def helpers_extra(ref):
+    """Outputs of the reference's remaining utils/helpers.py functions (the ones no step body calls but a user of the
+    module may: alternative splits, occluded-pose assembly, part bone lengths, fixed-scale normalisers, part
+    projections, latent interpolation, occlusion masks) on seeded inputs -> tests/golden/helpers_extra.npz."""
+    import random
+    H = ref["helpers"]
+    g = torch.Generator().manual_seed(123)
+    out = {}
+    a34 = torch.randn(6, 34, generator=g)
+    out["a34"] = t(a34)
+    l, r = H.split_data_left_right_v2(a34)
+    out["split_v2_left"], out["split_v2_right"] = t(l), t(r)
+    ln, rn = H.split_data_left_right_numpy(a34.numpy())
+    out["split_np_left"], out["split_np_right"] = ln, rn
+    a68 = torch.randn(4, 68, generator=g)
+    out["a68"] = t(a68)
+    l, r = H.temporal_split_data_left_right(a68)
+    out["split_temporal_left"], out["split_temporal_right"] = t(l), t(r)
+    occ, vis = torch.randn(5, 18, generator=g), torch.randn(5, 33, generator=g)
+    out["occ_part"], out["vis_part"] = t(occ), t(vis)
+    for side in ("right", "left"):
+        out["combine_occluded_" + side] = t(H.combine_left_right_occluded_3d(occ, vis, side))
+    legs, lr = torch.randn(5, 21, generator=g), torch.randn(5, 33, generator=g)
+    out["legs3d"], out["lr3d"] = t(legs), t(lr)
+    out["bones_legs"] = t(H.get_bone_lengths_legs(legs))
+    out["bones_left_right"] = t(H.get_bone_lengths_left_right(lr))
+    raw2d = np.random.RandomState(9).normal(size=(7, 34)) * 120 + 400
+    out["raw2d"] = raw2d
+    for fn in ("normalize_head_test_mpi_chest", "normalize_head_test_mpi_vnect", "normalize_head_test_temporal"):
+        out[fn] = getattr(H, fn)(raw2d.copy())
+    lat = torch.randn(8, 34, generator=g)
+    out["latent"] = t(lat)
+    out["interp_0.3"] = t(H.interpolate_gaussian_batch(lat, 0.3))
+    for fn, w in (("perspective_projection_legs", 21), ("perspective_projection_torso", 30),
+                  ("perspective_projection_left_right", 33)):
+        p = torch.randn(5, w, generator=g)
+        p[:, 2 * w // 3:] = p[:, 2 * w // 3:].abs() + 4.0
+        out[fn + "_in"], out[fn + "_out"] = t(p), t(getattr(H, fn)(p))
+    random.seed(77)
+    out["occlusion_create"] = t(H.occlusion_create(a34))
+    np.savez_compressed(os.path.join(OUT, "helpers_extra.npz"), **out)
+    print("helpers_extra.npz written (%d arrays)" % len(out))
+
+
 def main():
+    if "--only-helpers-extra" in sys.argv:        # added later: does not disturb the RNG streams of the other fixtures
+        helpers_extra(import_reference())
+        return
     from oracle import flow as OF, geometry as OG, metrics as OM, nets as ON, steps as OS
     from links_b200.synth import synth_poses, synth_pred_3d
     ref = import_reference()
@@ -248,6 +295,7 @@ def main():
     z, ld = OF.inn_forward(x, OF.init_flow_params(34, 40, perturb=0.3))
     st["flow_z"], st["flow_ld"] = t(z), t(ld)
     np.savez_compressed(os.path.join(OUT, "steps.npz"), **st)
+    helpers_extra(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -130,3 +130,31 @@ def test_dropin_state_dict_contract():
     assert torch.allclose(w @ w.t(), torch.eye(34), atol=1e-5)
     with pytest.raises(NotImplementedError):
         Leg_Lifter(use_batchnorm=True)
+
+
+def test_remaining_helpers_match_reference(golden):
+    """utils/helpers.py functions no step body calls (alternative splits, occluded-pose assembly, part bone lengths,
+    fixed-scale normalisers, part projections, latent interpolation, occlusion masks) against outputs of the reference
+    itself (tests/golden/helpers_extra.npz, oracle/gen_golden.py::helpers_extra)."""
+    import random
+    G = golden["helpers_extra"]
+    a34 = torch.from_numpy(G["a34"])
+    l, r = H.split_data_left_right_v2(a34)
+    assert np.array_equal(l.numpy(), G["split_v2_left"]) and np.array_equal(r.numpy(), G["split_v2_right"])
+    ln, rn = H.split_data_left_right_numpy(G["a34"])
+    assert np.array_equal(ln, G["split_np_left"]) and np.array_equal(rn, G["split_np_right"])
+    l, r = H.temporal_split_data_left_right(torch.from_numpy(G["a68"]))
+    assert np.array_equal(l.numpy(), G["split_temporal_left"]) and np.array_equal(r.numpy(), G["split_temporal_right"])
+    occ, vis = torch.from_numpy(G["occ_part"]), torch.from_numpy(G["vis_part"])
+    for side in ("right", "left"):
+        assert np.array_equal(H.combine_left_right_occluded_3d(occ, vis, side).numpy(), G["combine_occluded_" + side])
+    np.testing.assert_allclose(H.get_bone_lengths_legs(torch.from_numpy(G["legs3d"])).numpy(), G["bones_legs"], rtol=1e-6)
+    np.testing.assert_allclose(H.get_bone_lengths_left_right(torch.from_numpy(G["lr3d"])).numpy(), G["bones_left_right"],
+                               rtol=1e-6)
+    for fn in ("normalize_head_test_mpi_chest", "normalize_head_test_mpi_vnect", "normalize_head_test_temporal"):
+        np.testing.assert_allclose(getattr(H, fn)(G["raw2d"].copy()), G[fn], rtol=1e-14)
+    np.testing.assert_array_equal(H.interpolate_gaussian_batch(torch.from_numpy(G["latent"]), 0.3).numpy(), G["interp_0.3"])
+    for fn in ("perspective_projection_legs", "perspective_projection_torso", "perspective_projection_left_right"):
+        np.testing.assert_array_equal(getattr(H, fn)(torch.from_numpy(G[fn + "_in"])).numpy(), G[fn + "_out"])
+    random.seed(77)
+    np.testing.assert_array_equal(H.occlusion_create(a34).numpy(), G["occlusion_create"])
