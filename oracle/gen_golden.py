@@ -91,7 +91,37 @@ def helpers_extra(ref):
     print("helpers_extra.npz written (%d arrays)" % len(out))
 
 
+MODULE_CASES = [("PoseDiscriminator", dict(num_joints=16)), ("DepthAngleEstimator", dict(num_joints=16)),
+                ("Leg_Lifter", dict(num_joints=7, d_rate=0.25)), ("Torso_Lifter", dict(num_joints=10, d_rate=0.25)),
+                ("Left_Right_Lifter", dict(num_joints=11, d_rate=0.25)), ("Occluded_Limb_Predictor", dict(num_joints=14)),
+                ("Occluded_Legs_Predictor", dict(num_joints=10)), ("Occluded_Torso_Predictor", dict(num_joints=7)),
+                ("Occluded_Left_Right_Predictor", dict(num_joints=11)), ("res_block", dict())]
+
+
+def module_contract(ref):
+    """state_dict key names + shapes, constructor signatures and default arguments of every class in the reference's
+    utils/models_def.py -> tests/golden/module_contract.json (the drop-in boundary)."""
+    import inspect
+    import json
+    M = ref["models_def"]
+    out = {}
+    for name, kw in MODULE_CASES:
+        cls = getattr(M, name)
+        sig = inspect.signature(cls.__init__)
+        mod = cls(use_batchnorm=False, **kw)
+        out[name] = {"kwargs": kw,
+                     "signature": [[p.name, None if p.default is inspect._empty else p.default]
+                                   for p in list(sig.parameters.values())[1:]],
+                     "state_dict": [[k, list(v.shape)] for k, v in mod.state_dict().items()]}
+    with open(os.path.join(OUT, "module_contract.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("module_contract.json written (%d classes)" % len(out))
+
+
 def main():
+    if "--only-module-contract" in sys.argv:
+        module_contract(import_reference())
+        return
     if "--only-helpers-extra" in sys.argv:        # added later: does not disturb the RNG streams of the other fixtures
         helpers_extra(import_reference())
         return
@@ -296,6 +326,7 @@ def main():
     st["flow_z"], st["flow_ld"] = t(z), t(ld)
     np.savez_compressed(os.path.join(OUT, "steps.npz"), **st)
     helpers_extra(ref)
+    module_contract(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -158,3 +158,24 @@ def test_remaining_helpers_match_reference(golden):
         np.testing.assert_array_equal(getattr(H, fn)(torch.from_numpy(G[fn + "_in"])).numpy(), G[fn + "_out"])
     random.seed(77)
     np.testing.assert_array_equal(H.occlusion_create(a34).numpy(), G["occlusion_create"])
+
+
+def test_module_contract_matches_reference():
+    """Every class of the reference's utils/models_def.py: constructor parameter names / defaults and state_dict key
+    names / order / shapes of the drop-in equal the reference's (tests/golden/module_contract.json, written by
+    oracle/gen_golden.py::module_contract from the reference itself)."""
+    import inspect
+    import json
+    import os
+    from utils import models_def as MD
+    with open(os.path.join(os.path.dirname(__file__), "golden", "module_contract.json")) as f:
+        G = json.load(f)
+    assert len(G) == 10
+    for name, spec in G.items():
+        cls = getattr(MD, name)
+        sig = [[p.name, None if p.default is inspect._empty else p.default]
+               for p in list(inspect.signature(cls.__init__).parameters.values())[1:]]
+        assert sig == spec["signature"], (name, sig, spec["signature"])
+        sd = cls(use_batchnorm=False, **spec["kwargs"]).state_dict()
+        got = [[k, list(v.shape)] for k, v in sd.items()]
+        assert got == spec["state_dict"], (name, [a for a, b in zip(got, spec["state_dict"]) if a != b][:3])
