@@ -118,7 +118,33 @@ def module_contract(ref):
     print("module_contract.json written (%d classes)" % len(out))
 
 
+def cli_contract():
+    """Command-line flags of the reference's scripts (option strings, type, default), read from their argparse
+    sections with the ast module (the scripts cannot be imported: module-level parse_args / wandb / .cuda()) ->
+    tests/golden/cli_contract.json."""
+    import ast
+    import json
+    out = {}
+    for script in ("train_leg_torso_lifter.py", "train_left_right_lifter.py", "train_occlusion_models.py",
+                   "train_full_pose_norm_flow.py", "train_leg_torso_left_right_norm_flow.py", "eval_h36m.py"):
+        tree = ast.parse(open(os.path.join(REF, script)).read())
+        flags = []
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
+                opts = [a.value for a in node.args if isinstance(a, ast.Constant)]
+                kw = {k.arg: (k.value.id if isinstance(k.value, ast.Name) else ast.literal_eval(k.value)) for k in node.keywords
+                      if k.arg in ("type", "default")}
+                flags.append({"options": opts, "type": kw.get("type"), "default": kw.get("default")})
+        out[script] = flags
+    with open(os.path.join(OUT, "cli_contract.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("cli_contract.json written:", {k: len(v) for k, v in out.items()})
+
+
 def main():
+    if "--only-cli-contract" in sys.argv:
+        cli_contract()
+        return
     if "--only-module-contract" in sys.argv:
         module_contract(import_reference())
         return
@@ -327,6 +353,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "steps.npz"), **st)
     helpers_extra(ref)
     module_contract(ref)
+    cli_contract()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
