@@ -44,3 +44,41 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+def header_prototypes():
+    """name -> list of parameter declarations of every function prototype in include/links_b200.h."""
+    src = open(os.path.join(ROOT, "include", "links_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"\b(?:int|size_t)\s+(links_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = [p.strip() for p in m.group(2).split(",") if p.strip() and p.strip() != "void"]
+        out[m.group(1)] = params
+    return out
+
+
+def test_python_binding_matches_header_prototypes():
+    """The ctypes table (links_b200/_cabi.py) declares every entry point with as many arguments as the header, with
+    pointers where the header has pointers and scalars where it has scalars."""
+    import ctypes as C
+    from links_b200 import _cabi
+    protos = header_prototypes()
+    table = {n: list(a) + [C.c_void_p] for n, (_, a) in _cabi.SIGNATURES.items()}       # + stream
+    table.update({n: list(a) for n, (_, a) in list(_cabi.PLAIN.items()) + list(_cabi.GEMM.items())})
+    assert set(protos) == set(table)
+    for name, params in protos.items():
+        args = table[name]
+        assert len(args) == len(params), (name, params, args)
+        for decl, ct in zip(params, args):
+            is_ptr_decl = "*" in decl
+            is_ptr_ct = ct is C.c_void_p or hasattr(ct, "contents") or getattr(ct, "_type_", None) == "P" or \
+                (isinstance(ct, type) and issubclass(ct, C._Pointer))
+            assert is_ptr_decl == is_ptr_ct, (name, decl, ct)
+            if not is_ptr_decl:
+                if re.match(r"(const\s+)?float\b", decl):
+                    assert ct is C.c_float, (name, decl, ct)
+                elif re.match(r"(const\s+)?size_t\b", decl):
+                    assert ct is C.c_size_t, (name, decl, ct)
+                else:
+                    assert ct in (C.c_int, C.c_uint), (name, decl, ct)
