@@ -12,7 +12,6 @@ of the parameter-gradient GEMMs.  The weight gradients are then four grouped tcg
 (hidden recompute, dgrad with the ReLU mask, two wgrads), bias gradients one batched column-sum launch, Adam one launch
 on the flat parameter buffer, and the packed operand images are rebuilt by links_flow_pack.
 """
-import ctypes as C
 
 import torch
 

@@ -4,7 +4,6 @@ checkpoint file names, synthetic data when no dataset pickle is available.
 
 Reference: train_leg_torso_lifter.py:61-121,376-398, train_left_right_lifter.py:59-119,541-560,
 train_occlusion_models.py:81-142,547-570, eval_h36m.py:27-99."""
-import argparse
 import os
 import sys
 import time

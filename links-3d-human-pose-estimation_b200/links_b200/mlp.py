@@ -12,7 +12,6 @@ Data layout (per network s, per pass p):
     GEMM per layer contracts over both passes, reading G and X as MN-major operands (no transposed copies).
   * per block a [M, 32]-word sign mask of the l2 pre-activation (needed exactly for leaky' in backward).
 """
-import ctypes as C
 
 import torch
 

@@ -19,7 +19,7 @@ import ctypes as C
 import torch
 
 from . import _cabi, maps
-from ._cabi import HEAD_LD, check
+from ._cabi import check
 from .flowpack import FlowPacked
 from .mlp import MlpSet
 
