@@ -207,7 +207,29 @@ def train_occlusion(args):
         st.x.copy_(xb, non_blocking=True)
         st.u_y[0].uniform_(generator=gen_dev)        # Ry augmentation draws (train_occlusion_models.py:213-217,256-260)
         st.u_y[1].uniform_(generator=gen_dev)
-    n = run_training(step, loader, args, rank, feed)
+    validator = None
+    if args.val:                                # validation_step of the occlusion script (:316-509), on the device
+        from .occ_assembly import OcclusionValidator
+        lr = [load_state(os.path.join(wd, "left_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 13)),
+              load_state(os.path.join(wd, "right_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 14))]
+        ov = OcclusionValidator.from_params({"legs": lifters[0], "torso": lifters[1], "left": lr[0], "right": lr[1]},
+                                            {n: step.mlp.state_dict(s) for s, n in enumerate(OCC_NAMES)},
+                                            depth=args.translation, device=step.device)
+        x2d, gt = synth_poses(args.val, seed=4321 + args.seed)
+        b, e = shard_bounds(args.val, rank, world, multiple=1)
+        vx, vg = torch.from_numpy(x2d[b:e]).to(step.device), torch.from_numpy(gt[b:e]).to(step.device)
+
+        class _V:
+            def run(self_inner):
+                ov.load_predictors({n: step.mlp.state_dict(s) for s, n in enumerate(OCC_NAMES)})
+                out = ov.run(vx, vg)
+                if world > 1:                   # equal shards: mean of the per-rank means
+                    t = torch.tensor(list(out.values()), dtype=torch.float64, device=step.device)
+                    torch.distributed.all_reduce(t, group=pg)
+                    out = dict(zip(out, (t / world).tolist()))
+                return out
+        validator = _V()
+    n = run_training(step, loader, args, rank, feed, validator)
     if rank == 0 and not args.no_save:
         from utils import models_def as MD
         classes = {"left_arm": MD.Occluded_Limb_Predictor, "right_arm": MD.Occluded_Limb_Predictor,

@@ -141,7 +141,28 @@ def cli_contract():
     print("cli_contract.json written:", {k: len(v) for k, v in out.items()})
 
 
+def script_functions():
+    """Module-level helper functions that live inside the (non-importable) scripts: the FunctionDef is cut out of the
+    script's AST and executed on its own, so the golden outputs still come from the reference's code ->
+    tests/golden/script_funcs.npz.  Currently: combine_pose_and_limb (train_occlusion_models.py:67-78)."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "train_occlusion_models.py")).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "combine_pose_and_limb"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "train_occlusion_models.py", "exec"), ns)
+    pose = torch.arange(5 * 42, dtype=torch.float32).reshape(5, 42)
+    limb = 1000 + torch.arange(5 * 9, dtype=torch.float32).reshape(5, 9)
+    out = {"pose": t(pose), "limb": t(limb)}
+    for which in ("ll", "rl", "la", "ra"):
+        out["combine_" + which] = t(ns["combine_pose_and_limb"](pose, limb, which))
+    np.savez_compressed(os.path.join(OUT, "script_funcs.npz"), **out)
+    print("script_funcs.npz written")
+
+
 def main():
+    if "--only-script-functions" in sys.argv:
+        script_functions()
+        return
     if "--only-cli-contract" in sys.argv:
         cli_contract()
         return
@@ -354,6 +375,7 @@ def main():
     helpers_extra(ref)
     module_contract(ref)
     cli_contract()
+    script_functions()
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

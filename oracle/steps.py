@@ -299,3 +299,58 @@ def part_flow_step(x, full_params, part_params, noise):
             out["dist_2d_%s%s" % (n, tag)] = F.nll(zz, ld).mean()
     out["loss"] = sum(out.values())
     return out
+
+
+def occ_validation_poses(poses_2d, legs_pred, torso_pred, left_pred, right_pred, predictors, depth=10.0):
+    """train_occlusion_models.py:327-398 (validation_step up to the eight camera-frame poses), written out case by case
+    like the script.  predictors: dict name -> callable([M,3k]) -> [M,3(17-k)].  Returns (inputs, full poses)."""
+    left_split, right_split = G.split_data_left_right(poses_2d)
+    legs_split = poses_2d.reshape(-1, 2, 17)[:, :, :7].reshape(-1, 14)
+    torso_split = poses_2d.reshape(-1, 2, 17)[:, :, 7:].reshape(-1, 20)
+    left_pred, right_pred = left_pred.clone(), right_pred.clone()
+    left_pred[:, 0] = 0.0
+    right_pred[:, 0] = 0.0
+    left_pred, right_pred = left_pred + depth, right_pred + depth
+    pred_lt = torch.cat((legs_pred, torso_pred), dim=1).clone()
+    pred_lt[:, 0] = 0.0
+    pred_lt = pred_lt + depth
+
+    def lift(split, d, k):
+        return torch.cat(((split.reshape(-1, 2, k) * d.reshape(-1, 1, k)).reshape(-1, 2 * k), d), dim=1).reshape(-1, 3, k)
+    legs3, torso3 = lift(legs_split, pred_lt[:, :7], 7), lift(torso_split, pred_lt[:, 7:], 10)
+    left3, right3 = lift(left_split, left_pred, 11), lift(right_split, right_pred, 11)
+    torso3 = torso3 - legs3[:, :, [0]]
+    legs3 = legs3 - legs3[:, :, [0]]
+    left3 = left3 - left3[:, :, [0]]
+    right3 = right3 - right3[:, :, [0]]
+    inp = {"la": torch.cat((legs3, right3[:, :, 4:]), dim=2).reshape(-1, 42),
+           "ra": torch.cat((legs3, left3[:, :, 4:]), dim=2).reshape(-1, 42),
+           "ll": torch.cat((right3[:, :, :4], torso3), dim=2).reshape(-1, 42),
+           "rl": torch.cat((left3[:, :, :4], torso3), dim=2).reshape(-1, 42),
+           "torso": legs3.reshape(-1, 21),
+           "legs": torch.cat((legs3[:, :, [0]], torso3), dim=2).reshape(-1, 33),
+           "right": left3.reshape(-1, 33),           # no_right_side
+           "left": right3.reshape(-1, 33)}           # no_left_side
+    name = {"la": "left_arm", "ra": "right_arm", "ll": "left_leg", "rl": "right_leg", "torso": "torso",
+            "legs": "both_legs", "left": "left_side", "right": "right_side"}
+    out = {k: predictors[name[k]](v) for k, v in inp.items()}
+
+    def limb(pose, l, which):                         # combine_pose_and_limb, :67-78
+        l, pose = l.reshape(-1, 3, 3), pose.reshape(-1, 3, 14)
+        cut = {"ll": 4, "rl": 1, "la": 11, "ra": 14}[which]
+        return torch.cat((pose[:, :, :cut], l, pose[:, :, cut:]), dim=2).reshape(-1, 51)
+    full = {k: limb(inp[k], out[k], k) for k in ("la", "ra", "ll", "rl")}
+    full["torso"] = torch.cat((inp["torso"].reshape(-1, 3, 7), out["torso"].reshape(-1, 3, 10)), dim=2).reshape(-1, 51)
+    il = inp["legs"].reshape(-1, 3, 11)
+    full["legs"] = torch.cat((il[:, :, :1], out["legs"].reshape(-1, 3, 6), il[:, :, 1:]), dim=2).reshape(-1, 51)
+    for side in ("left", "right"):                    # utils/helpers.py:121-136
+        o, v = out[side].reshape(-1, 3, 6), inp[side].reshape(-1, 3, 11)
+        if side == "right":
+            cols = [v[:, :, 0], o[:, :, 0], o[:, :, 1], o[:, :, 2]] + [v[:, :, i] for i in range(1, 11)] + \
+                   [o[:, :, 3], o[:, :, 4], o[:, :, 5]]
+        else:
+            cols = [v[:, :, 0], v[:, :, 1], v[:, :, 2], v[:, :, 3], o[:, :, 0], o[:, :, 1], o[:, :, 2], v[:, :, 4], v[:, :, 5],
+                    v[:, :, 6], v[:, :, 7], o[:, :, 3], o[:, :, 4], o[:, :, 5], v[:, :, 8], v[:, :, 9], v[:, :, 10]]
+        full[side] = torch.stack(cols, dim=2).reshape(-1, 51)
+    glob = {k: torch.cat((p[:, :34], p[:, 34:51] + depth), dim=1) for k, p in full.items()}
+    return inp, glob

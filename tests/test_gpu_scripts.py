@@ -70,3 +70,11 @@ def test_scripts_on_a_dataset_pickle(tmp_path):
     assert "step 5" in out and "loss=" in out
     out = _run("eval_h36m.py", "--datafile", path, "--chunk", "1024", "--weights-dir", wd)
     assert "PA-MPJPE:" in out and "N-MPJPE:" in out
+
+
+@pytest.mark.skipif(os.environ.get("LINKS_UNVALIDATED") != "1",
+                    reason="written after this round's GPU budget was spent: first GPU run pending (set LINKS_UNVALIDATED=1)")
+def test_occlusion_script_with_validation(tmp_path):
+    out = _run("train_occlusion_models.py", "-n", "26", "--synthetic", "512", "--batch", "64", "--steps", "3", "--log-every", "1",
+               "--weights-dir", str(tmp_path), "--val", "300", "--no-save")
+    assert "step 3" in out and "validation" in out and "pa_torso=" in out
