@@ -159,7 +159,36 @@ def script_functions():
     print("script_funcs.npz written")
 
 
+def metrics_np_extra(ref):
+    """utils/metrics.py (the per-pose numpy class) beyond what metrics.npz holds: mpjpe flag combinations, PCK, and the
+    full (d, Z, tform) output of procrustes for every scaling / reflection setting -> tests/golden/metrics_np_extra.npz."""
+    from links_b200.synth import synth_poses, synth_pred_3d
+    m = ref["metrics"].Metrics()
+    _, gt = synth_poses(6, seed=71)
+    pred = synth_pred_3d(gt, seed=72, noise_mm=35.0, scale=0.013, mirror_frac=0.5)
+    gt, pred = gt.astype(np.float64), pred.astype(np.float64)
+    out = {"gt": gt, "pred": pred}
+    for sc in (False, True):
+        for ma in (False, True):
+            out["mpjpe_s%d_m%d" % (sc, ma)] = np.array([m.mpjpe(gt[i:i + 1], pred[i:i + 1], scale=sc, mean_align=ma)
+                                                         for i in range(6)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for refl in (False, True, "best"):
+            out["pck_%s" % refl] = np.array([m.PCK(gt[i:i + 1], pred[i:i + 1], reflection=refl) for i in range(6)])
+            for scaling in (True, False):
+                d, Z, tf = m.procrustes(gt[0].reshape(3, 17).T, pred[0].reshape(3, 17).T, scaling=scaling, reflection=refl)
+                tag = "proc_%s_%d_" % (refl, scaling)
+                out[tag + "d"], out[tag + "Z"] = np.float64(d), Z
+                out[tag + "rot"], out[tag + "scale"], out[tag + "trans"] = tf["rotation"], np.float64(tf["scale"]), tf["translation"]
+    np.savez_compressed(os.path.join(OUT, "metrics_np_extra.npz"), **out)
+    print("metrics_np_extra.npz written (%d arrays)" % len(out))
+
+
 def main():
+    if "--only-metrics-np-extra" in sys.argv:
+        metrics_np_extra(import_reference())
+        return
     if "--only-script-functions" in sys.argv:
         script_functions()
         return
@@ -376,6 +405,7 @@ def main():
     module_contract(ref)
     cli_contract()
     script_functions()
+    metrics_np_extra(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

@@ -179,3 +179,30 @@ def test_module_contract_matches_reference():
         sd = cls(use_batchnorm=False, **spec["kwargs"]).state_dict()
         got = [[k, list(v.shape)] for k, v in sd.items()]
         assert got == spec["state_dict"], (name, [a for a, b in zip(got, spec["state_dict"]) if a != b][:3])
+
+
+def test_numpy_metrics_full_surface_matches_reference(golden):
+    """utils/metrics.py drop-in: every flag combination of mpjpe, PCK, and the complete (d, Z, tform) output of
+    procrustes for all scaling / reflection settings, against the reference's outputs (metrics_np_extra.npz)."""
+    import warnings
+    from utils.metrics import Metrics
+    G = golden["metrics_np_extra"]
+    m = Metrics()
+    gt, pred = G["gt"], G["pred"]
+    for sc in (False, True):
+        for ma in (False, True):
+            got = np.array([m.mpjpe(gt[i:i + 1], pred[i:i + 1], scale=sc, mean_align=ma) for i in range(6)])
+            np.testing.assert_allclose(got, G["mpjpe_s%d_m%d" % (sc, ma)], rtol=1e-12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for refl in (False, True, "best"):
+            got = np.array([m.PCK(gt[i:i + 1], pred[i:i + 1], reflection=refl) for i in range(6)])
+            np.testing.assert_allclose(got, G["pck_%s" % refl], rtol=1e-10)
+            for scaling in (True, False):
+                d, Z, tf = m.procrustes(gt[0].reshape(3, 17).T, pred[0].reshape(3, 17).T, scaling=scaling, reflection=refl)
+                tag = "proc_%s_%d_" % (refl, scaling)
+                np.testing.assert_allclose(d, G[tag + "d"], rtol=1e-9)
+                np.testing.assert_allclose(Z, G[tag + "Z"], rtol=1e-9, atol=1e-9)
+                np.testing.assert_allclose(tf["rotation"], G[tag + "rot"], rtol=1e-9, atol=1e-12)
+                np.testing.assert_allclose(tf["scale"], G[tag + "scale"], rtol=1e-9)
+                np.testing.assert_allclose(tf["translation"], G[tag + "trans"], rtol=1e-9, atol=1e-9)
