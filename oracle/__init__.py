@@ -23,5 +23,11 @@ Rules (tier contract, item 3):
     autograd Jacobian, identity-at-init) anchor it.
   * The step bodies live inside non-importable scripts (module-level argparse /
     wandb / torch.load); ``oracle/steps.py`` restates them line range by line range
-    on top of the pinned pieces.
+    on top of the pinned pieces -- and is itself pinned against the reference's OWN
+    step code: ``gen_golden.py::reference_training_steps`` cuts ``training_step`` /
+    ``validation_step`` (and ``combine_pose_and_limb``) out of each script's AST and
+    executes them in the build container on a stand-in ``self`` that carries the
+    reference's networks, the only substitution being the oracle flow in place of the
+    absent FrEIA modules (``tests/golden/ref_steps.npz``,
+    ``tests/test_oracle_steps_pinned.py``: losses to 2e-5, gradients to 2e-4).
 """

@@ -185,7 +185,166 @@ def metrics_np_extra(ref):
     print("metrics_np_extra.npz written (%d arrays)" % len(out))
 
 
+def reference_training_steps(ref):
+    """Run the reference's OWN training_step code: the method is cut out of each script's AST (the scripts themselves
+    cannot be imported) and executed on a stand-in `self` that carries the reference's networks (utils/models_def.py,
+    importable) and -- the one substitution -- the oracle flow in place of the absent FrEIA modules.  Losses and a few
+    gradients go to tests/golden/ref_steps.npz; tests/test_oracle_steps_pinned.py replays the same seeded inputs through
+    oracle/steps.py.  RNG: the step draws randn_like(z) [B,34], normal(0,1) [N,1], rand [N,1] in that order (occlusion:
+    rand [B,1] twice); the test re-seeds and draws the same sequence."""
+    import ast
+    from types import SimpleNamespace
+    from oracle import flow as OF, nets as ON, steps as OS
+    from links_b200.synth import synth_poses
+    H, M, RC = ref["helpers"], ref["models_def"], ref["rotation_conversions"]
+
+    def method(script, cls_name, name):
+        tree = ast.parse(open(os.path.join(REF, script)).read())
+        cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == cls_name][0]
+        fn = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+        ns = {k: getattr(H, k) for k in dir(H) if not k.startswith("_")}
+        ns.update(torch=torch, np=np, euler_angles_to_matrix=RC.euler_angles_to_matrix, SimpleNamespace=SimpleNamespace)
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), script, "exec"), ns)
+        return ns
+
+    class Flow:
+        def __init__(self, params):
+            self.p = params
+
+        def __call__(self, x, rev=False):
+            return OF.inn_forward(x, self.p, rev=rev)
+
+    class Opt:
+        def zero_grad(self):
+            pass
+
+        def step(self):
+            pass
+
+    def module(cls, nj, params):
+        m = getattr(M, cls)(use_batchnorm=False, num_joints=nj, use_dropout=False, d_rate=0.25)
+        m.load_state_dict(params, strict=False)
+        return m
+
+    def base_self(n_opt):
+        return SimpleNamespace(optimizers=lambda: [Opt() for _ in range(n_opt)], device=torch.device("cpu"),
+                               manual_backward=lambda loss: loss.backward(), losses=SimpleNamespace(), log=lambda *a, **k: None,
+                               losses_mean=SimpleNamespace())
+
+    cfg = SimpleNamespace(use_elevation=True, depth=10.0, weight_bl=50.0, weight_2d=1.0, weight_3d=1.0, weight_likeli=1.0,
+                          weight_velocity=1.0)
+    out = {}
+    B = 16
+    x2d, _ = synth_poses(B, seed=91)
+    x = torch.from_numpy(x2d)
+    out["x"] = x2d
+    full = OF.init_flow_params(34, 40, perturb=0.3)
+    cuda_orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # the step bodies call .cuda() on CPU tensors
+    try:
+        # ---- leg / torso step (train_leg_torso_lifter.py:123-284)
+        ns = method("train_leg_torso_lifter.py", "LitLifter", "training_step")
+        ns["config"] = cfg
+        leg, torso = ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12)
+        s = base_self(2)
+        s.full_inn_2d, s.leg_inn_2d, s.torso_inn_2d = Flow(full), Flow(OF.init_flow_params(14, 41, perturb=0.3)), \
+            Flow(OF.init_flow_params(20, 42, perturb=0.3))
+        s.legs_lifter, s.torso_lifter = module("Leg_Lifter", 7, leg), module("Torso_Lifter", 10, torso)
+        from oracle import geometry as OG
+        s.bone_relations_mean = torch.tensor(OG.BONE_REL_MPI, dtype=torch.float32)
+        torch.manual_seed(1001)
+        ns["training_step"](s, {"p2d_gt": x.clone()}, 0)
+        for k, v in s.losses.__dict__.items():
+            out["lt_" + k] = np.float64(v.item())
+        out["lt_dW_leg_upscale"] = t(s.legs_lifter.upscale.weight.grad)
+        out["lt_dW_torso_angles"] = t(s.torso_lifter.angles.weight.grad)
+        # ---- left / right step (train_left_right_lifter.py:121-435)
+        ns = method("train_left_right_lifter.py", "LitLifter", "training_step")
+        ns["config"] = cfg
+        left, right = ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)
+        s = base_self(2)
+        s.full_inn2d, s.left_inn2d, s.right_inn2d = Flow(full), Flow(OF.init_flow_params(22, 43, perturb=0.3)), \
+            Flow(OF.init_flow_params(22, 44, perturb=0.3))
+        s.left_lifter, s.right_lifter = module("Left_Right_Lifter", 11, left), module("Left_Right_Lifter", 11, right)
+        s.bone_relations_mean = torch.tensor(OG.BONE_REL_H36M, dtype=torch.float32)
+        torch.manual_seed(1002)
+        ns["training_step"](s, {"p2d_gt": x.clone()}, 0)
+        for k, v in s.losses.__dict__.items():
+            out["lr_" + k] = np.float64(v.item())
+        out["lr_dW_left_upscale"] = t(s.left_lifter.upscale.weight.grad)
+        out["lr_dW_right_downscale"] = t(s.right_lifter.downscale.weight.grad)
+        # ---- occlusion step (train_occlusion_models.py:144-314)
+        ns = method("train_occlusion_models.py", "Limb_Predictor", "training_step")
+        ns["config"] = cfg
+        s = base_self(8)
+        s.leg_lifter, s.torso_lifter = module("Leg_Lifter", 7, leg), module("Torso_Lifter", 10, torso)
+        s.left_lifter, s.right_lifter = module("Left_Right_Lifter", 11, left), module("Left_Right_Lifter", 11, right)
+        attr = {"left_arm": "left_arm_predictor", "right_arm": "right_arm_predictor", "left_leg": "left_leg_predictor",
+                "right_leg": "right_leg_predictor", "left_side": "left_predictor", "right_side": "right_predictor",
+                "both_legs": "both_legs_predictor", "torso": "torso_predictor"}
+        cls = {"left_arm": "Occluded_Limb_Predictor", "right_arm": "Occluded_Limb_Predictor", "left_leg": "Occluded_Limb_Predictor",
+               "right_leg": "Occluded_Limb_Predictor", "left_side": "Occluded_Left_Right_Predictor",
+               "right_side": "Occluded_Left_Right_Predictor", "both_legs": "Occluded_Legs_Predictor", "torso": "Occluded_Torso_Predictor"}
+        nin = {"left_arm": 14, "right_arm": 14, "left_leg": 14, "right_leg": 14, "left_side": 11, "right_side": 11,
+               "both_legs": 11, "torso": 7}
+        nout = {"left_arm": 9, "right_arm": 9, "left_leg": 9, "right_leg": 9, "left_side": 18, "right_side": 18,
+                "both_legs": 18, "torso": 30}
+        for i, n in enumerate(OS.OCC_NAMES):
+            m = getattr(M, cls[n])(use_batchnorm=False, num_joints=nin[n])
+            m.load_state_dict(ON.init_predictor_params(nin[n], nout[n], 100 + i), strict=False)
+            setattr(s, attr[n], m)
+        torch.manual_seed(1003)
+        ns["training_step"](s, {"p2d_gt": x.clone()}, 0)
+        for k, v in s.losses.__dict__.items():
+            out["occ_" + k] = np.float64(v.item())
+        out["occ_dW_torso_downscale"] = t(s.torso_predictor.downscale.weight.grad)
+        out["occ_dW_left_upscale"] = t(s.left_predictor.upscale.weight.grad)
+        # ---- validation steps (train_leg_torso_lifter.py:286-337, train_occlusion_models.py:317-509): per-pose numpy
+        #      PA-MPJPE loops + metrics_batch, exactly as the scripts run them
+        xv2d, gtv = synth_poses(12, seed=92)
+        out["val_x"], out["val_gt"] = xv2d, gtv
+        val_batch = {"p2d_gt": torch.from_numpy(xv2d), "poses_3d": torch.from_numpy(gtv)}
+        wandb_stub = SimpleNamespace(log=lambda *a, **k: None)
+        cfg.use_gt = True
+        ns = method("train_leg_torso_lifter.py", "LitLifter", "validation_step")
+        ns.update(config=cfg, wandb=wandb_stub, mb=ref["metrics_batch"].Metrics)
+        s = base_self(2)
+        s.legs_lifter, s.torso_lifter = module("Leg_Lifter", 7, leg), module("Torso_Lifter", 10, torso)
+        s.metrics, s.current_epoch = ref["metrics"].Metrics(), 0
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns["validation_step"](s, val_batch, 0)
+        for k in ("pa", "mpjpe_scaled", "auc", "pck"):
+            out["ltval_" + k] = np.float64(getattr(s.losses, k))
+        ns = method("train_occlusion_models.py", "Limb_Predictor", "validation_step")
+        tree = ast.parse(open(os.path.join(REF, "train_occlusion_models.py")).read())
+        fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "combine_pose_and_limb"][0]
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "train_occlusion_models.py", "exec"), ns)
+        ns.update(config=cfg, wandb=wandb_stub, mb=ref["metrics_batch"].Metrics)
+        s = base_self(8)
+        s.leg_lifter, s.torso_lifter = module("Leg_Lifter", 7, leg), module("Torso_Lifter", 10, torso)
+        s.left_lifter, s.right_lifter = module("Left_Right_Lifter", 11, left), module("Left_Right_Lifter", 11, right)
+        for i, n in enumerate(OS.OCC_NAMES):
+            m = getattr(M, cls[n])(use_batchnorm=False, num_joints=nin[n])
+            m.load_state_dict(ON.init_predictor_params(nin[n], nout[n], 100 + i), strict=False)
+            setattr(s, attr[n], m)
+        s.metrics, s.current_epoch = ref["metrics"].Metrics(), 0
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns["validation_step"](s, val_batch, 0)
+        for k, v in s.losses.__dict__.items():
+            if k.startswith("pa_") or k.startswith("mpjpe_scaled_"):
+                out["occval_" + k] = np.float64(v)
+    finally:
+        torch.Tensor.cuda = cuda_orig
+    np.savez_compressed(os.path.join(OUT, "ref_steps.npz"), **out)
+    print("ref_steps.npz written:", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
+
+
 def main():
+    if "--only-reference-steps" in sys.argv:
+        reference_training_steps(import_reference())
+        return
     if "--only-metrics-np-extra" in sys.argv:
         metrics_np_extra(import_reference())
         return
@@ -406,6 +565,7 @@ def main():
     cli_contract()
     script_functions()
     metrics_np_extra(ref)
+    reference_training_steps(ref)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  %-20s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
