@@ -316,6 +316,16 @@ def reference_training_steps(ref):
             ns["validation_step"](s, val_batch, 0)
         for k in ("pa", "mpjpe_scaled", "auc", "pck"):
             out["ltval_" + k] = np.float64(getattr(s.losses, k))
+        ns = method("train_left_right_lifter.py", "LitLifter", "validation_step")      # :437-511, both combine choices
+        ns.update(config=cfg, wandb=wandb_stub, mb=ref["metrics_batch"].Metrics)
+        s = base_self(2)
+        s.left_lifter, s.right_lifter = module("Left_Right_Lifter", 11, left), module("Left_Right_Lifter", 11, right)
+        s.metrics, s.current_epoch = ref["metrics"].Metrics(), 0
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns["validation_step"](s, val_batch, 0)
+        for k in ("pa_left", "pa_right", "mpjpe_scaled_left", "mpjpe_scaled_right"):
+            out["lrval_" + k] = np.float64(getattr(s.losses, k))
         ns = method("train_occlusion_models.py", "Limb_Predictor", "validation_step")
         tree = ast.parse(open(os.path.join(REF, "train_occlusion_models.py")).read())
         fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "combine_pose_and_limb"][0]

@@ -123,3 +123,15 @@ def test_occlusion_validator_equals_reference_validation_step(G):
     for c in OA.CASES:
         _close(got["pa_" + c], float(G["occval_pa_" + c]), rtol=2e-5)
         _close(got["mpjpe_scaled_" + c], float(G["occval_mpjpe_scaled_" + c]), rtol=2e-5)
+
+
+def test_left_right_validation_equals_reference_validation_step(G):
+    """train_left_right_lifter.py:437-511 (the lift eval_h36m.py:50-97 also performs): both combine choices."""
+    from oracle import metrics as OM
+    x, gt = torch.from_numpy(G["val_x"]), torch.from_numpy(G["val_gt"])
+    left, right = ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)
+    for choice in ("left", "right"):
+        poses = OS.eval_lr_predict(x, left, right, choice=choice, depth=10.0)
+        _close(float(OM.pmpjpe_best_batch(gt.numpy(), poses.numpy()).mean()), float(G["lrval_pa_" + choice]), rtol=1e-5)
+        _close(OM.mpjpe(gt, poses, num_joints=17, root_joint=0).mean().item(), float(G["lrval_mpjpe_scaled_" + choice]),
+               rtol=1e-5)
