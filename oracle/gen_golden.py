@@ -326,6 +326,18 @@ def reference_training_steps(ref):
             ns["validation_step"](s, val_batch, 0)
         for k in ("pa_left", "pa_right", "mpjpe_scaled_left", "mpjpe_scaled_right"):
             out["lrval_" + k] = np.float64(getattr(s.losses, k))
+        # ---- eval_h36m.py:46-97: the script's own top-level statements from `metrics = Metrics()` to the prints
+        tree_e = ast.parse(open(os.path.join(REF, "eval_h36m.py")).read())
+        first = [n.lineno for n in tree_e.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "metrics"][0]
+        body = [n for n in tree_e.body if n.lineno >= first]
+        ns_e = {k: getattr(H, k) for k in dir(H) if not k.startswith("_")}
+        ns_e.update(torch=torch, np=np, Metrics=ref["metrics"].Metrics, mb=ref["metrics_batch"].Metrics,
+                    left_lifter=module("Left_Right_Lifter", 11, left), right_lifter=module("Left_Right_Lifter", 11, right),
+                    poses_2d=torch.from_numpy(xv2d), poses_3d=torch.from_numpy(gtv), print=lambda *a, **k: None)
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            exec(compile(ast.Module(body=body, type_ignores=[]), "eval_h36m.py", "exec"), ns_e)
+        out["evalh36m_pa"], out["evalh36m_mpjpe_scaled"] = np.float64(ns_e["pa"]), np.float64(ns_e["mpjpe_scaled"])
         ns = method("train_occlusion_models.py", "Limb_Predictor", "validation_step")
         tree = ast.parse(open(os.path.join(REF, "train_occlusion_models.py")).read())
         fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "combine_pose_and_limb"][0]

@@ -135,3 +135,15 @@ def test_left_right_validation_equals_reference_validation_step(G):
         _close(float(OM.pmpjpe_best_batch(gt.numpy(), poses.numpy()).mean()), float(G["lrval_pa_" + choice]), rtol=1e-5)
         _close(OM.mpjpe(gt, poses, num_joints=17, root_joint=0).mean().item(), float(G["lrval_mpjpe_scaled_" + choice]),
                rtol=1e-5)
+
+
+def test_eval_restatement_equals_reference_eval_script(G):
+    """eval_h36m.py:46-97 (the script's own top-level statements, executed by gen_golden.py) vs
+    oracle.steps.eval_lr_predict + eval_metrics -- the pair every GPU eval parity test is checked against."""
+    x, gt = torch.from_numpy(G["val_x"]), torch.from_numpy(G["val_gt"])
+    left, right = ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)
+    poses = OS.eval_lr_predict(x, left, right, choice="right", depth=10.0)
+    for loop in (False, True):
+        out = OS.eval_metrics(gt, poses, loop=loop)
+        _close(out["pa_mpjpe"], float(G["evalh36m_pa"]), rtol=1e-5)
+        _close(out["n_mpjpe"], float(G["evalh36m_mpjpe_scaled"]), rtol=1e-5)
