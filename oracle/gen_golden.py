@@ -338,6 +338,38 @@ def reference_training_steps(ref):
             warnings.simplefilter("ignore")
             exec(compile(ast.Module(body=body, type_ignores=[]), "eval_h36m.py", "exec"), ns_e)
         out["evalh36m_pa"], out["evalh36m_mpjpe_scaled"] = np.float64(ns_e["pa"]), np.float64(ns_e["mpjpe_scaled"])
+        # ---- flow trainers: the body of the scripts' inner batch loop, up to the last optimizer.step()
+        def loop_body(script):
+            tr = ast.parse(open(os.path.join(REF, script)).read())
+            outer = [n for n in tr.body if isinstance(n, ast.For) and getattr(n.target, "id", "") == "epoch"][0]
+            inner = [n for n in outer.body if isinstance(n, ast.For)][0]
+            last = max(i for i, n in enumerate(inner.body) if isinstance(n, ast.Expr) and isinstance(n.value, ast.Call)
+                       and getattr(n.value.func, "attr", "") == "step")
+            return compile(ast.Module(body=inner.body[:last + 1], type_ignores=[]), script, "exec")
+
+        def flow_ns(extra):
+            d = {k: getattr(H, k) for k in dir(H) if not k.startswith("_")}
+            d.update(torch=torch, np=np, losses=SimpleNamespace(), sample={"p2d_gt": x.clone()})
+            d.update(extra)
+            return d
+        fp = OS.params_require_grad(OF.init_flow_params(34, 45, perturb=0.3))
+        ns_f = flow_ns(dict(inn_2d=Flow(fp), optimizer=Opt()))
+        torch.manual_seed(1004)
+        exec(loop_body("train_full_pose_norm_flow.py"), ns_f)
+        for k, v in ns_f["losses"].__dict__.items():
+            out["flowtrain_" + k] = np.float64(v.item())
+        out["flowtrain_dW"] = t(fp["module_list.2.subnet.2.weight"].grad)
+        parts = {n: OS.params_require_grad(OF.init_flow_params(w, 60 + i, perturb=0.3))
+                 for i, (n, w) in enumerate((("legs", 14), ("torso", 20), ("left", 22), ("right", 22)))}
+        ns_p = flow_ns(dict(inn_2d_legs_split=Flow(parts["legs"]), inn_2d_torso_split=Flow(parts["torso"]),
+                            inn_2d_left_split=Flow(parts["left"]), inn_2d_right_split=Flow(parts["right"]),
+                            full_pose_inn2d=Flow(full), left_split_opt=Opt(), right_split_opt=Opt(), leg_optimizer=Opt(),
+                            torso_optimizer=Opt()))
+        torch.manual_seed(1005)
+        exec(loop_body("train_leg_torso_left_right_norm_flow.py"), ns_p)
+        for k, v in ns_p["losses"].__dict__.items():
+            out["partflow_" + k] = np.float64(v.item())
+        out["partflow_dW_left"] = t(parts["left"]["module_list.1.subnet.0.weight"].grad)
         ns = method("train_occlusion_models.py", "Limb_Predictor", "validation_step")
         tree = ast.parse(open(os.path.join(REF, "train_occlusion_models.py")).read())
         fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "combine_pose_and_limb"][0]

@@ -147,3 +147,26 @@ def test_eval_restatement_equals_reference_eval_script(G):
         out = OS.eval_metrics(gt, poses, loop=loop)
         _close(out["pa_mpjpe"], float(G["evalh36m_pa"]), rtol=1e-5)
         _close(out["n_mpjpe"], float(G["evalh36m_mpjpe_scaled"]), rtol=1e-5)
+
+
+def test_flow_trainers_equal_reference_loop_bodies(G):
+    """train_full_pose_norm_flow.py:67-98 and train_leg_torso_left_right_norm_flow.py:100-174: the bodies of the scripts'
+    batch loops (executed by gen_golden.py with the oracle flow standing in for FrEIA) vs oracle.steps.flow_step /
+    part_flow_step -- the references of the GPU FlowTrainStep / PartFlowTrainer tests."""
+    x = torch.from_numpy(G["x"])
+    fp = OS.params_require_grad(OF.init_flow_params(34, 45, perturb=0.3))
+    torch.manual_seed(1004)
+    out = OS.flow_step(x, fp, torch.randn(B, 34))
+    for k in ("dist_2d", "dist_2d_sample", "loss"):
+        _close(out[k].item(), float(G["flowtrain_" + k]))
+    out["loss"].backward()
+    _grad_close(fp["module_list.2.subnet.2.weight"].grad, G["flowtrain_dW"])
+    full = OF.init_flow_params(34, 40, perturb=0.3)
+    parts = {n: OS.params_require_grad(OF.init_flow_params(w, 60 + i, perturb=0.3))
+             for i, (n, w) in enumerate((("legs", 14), ("torso", 20), ("left", 22), ("right", 22)))}
+    torch.manual_seed(1005)
+    out = OS.part_flow_step(x, full, parts, torch.randn(B, 34))
+    for k in out:
+        _close(out[k].item(), float(G["partflow_" + k]), rtol=5e-5)
+    out["loss"].backward()
+    _grad_close(parts["left"]["module_list.1.subnet.0.weight"].grad, G["partflow_dW_left"])
