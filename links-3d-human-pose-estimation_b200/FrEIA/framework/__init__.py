@@ -40,6 +40,8 @@ class SequenceINN(nn.Module):
     (frozen flows, as in the lifter trainers); training the flow's own parameters goes through
     ``links_b200.flowtrain.FlowTrainStep`` (train_full_pose_norm_flow.py drop-in)."""
 
+    _warned = False
+
     def __init__(self, *dims, force_tuple_output=False):
         super().__init__()
         self.shapes = [tuple(dims)]
@@ -83,7 +85,20 @@ class SequenceINN(nn.Module):
         if not x_or_z.is_cuda:
             raise _cabi.LinksError("links_b200 SequenceINN runs on a B200 only (no CPU fallback)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("parameter gradients of the flow are provided by links_b200.flowtrain.FlowTrainStep; "
-                                      "freeze the flow (requires_grad=False) or wrap the call in torch.no_grad()")
+            # Every lifter trainer of the reference calls its flows with requires_grad=True parameters that NO optimiser
+            # owns (train_leg_torso_lifter.py:109-121,203-216): autograd computes their gradients and nobody reads them.
+            # The shim therefore propagates the INPUT gradient only and leaves .grad of the flow parameters None.  Code
+            # that trains the flow through this call (train_full_pose_norm_flow.py:75) must use
+            # links_b200.flowtrain.FlowTrainStep (what the drop-in train_full_pose_norm_flow.py does); strict=True turns
+            # this case into an error instead of a warning.
+            if getattr(self, "strict_param_grads", False):
+                raise NotImplementedError("parameter gradients of the flow are provided by links_b200.flowtrain."
+                                          "FlowTrainStep; freeze the flow or wrap the call in torch.no_grad()")
+            if not SequenceINN._warned:
+                SequenceINN._warned = True
+                import warnings
+                warnings.warn("links_b200 FrEIA shim: flow parameters require grad, but this call only propagates "
+                              "gradients to its INPUT (flow parameters keep .grad = None).  Train flows with "
+                              "links_b200.flowtrain.FlowTrainStep.", stacklevel=2)
         out, ld = _FlowFn.apply(self, x_or_z, bool(rev))
         return ((out,), ld) if (self.force_tuple_output or force_tuple_output) else (out, ld)

@@ -14,6 +14,7 @@ g.add_argument("--datafile", default=None, help="dataset pickle in the reference
 g.add_argument("--chunk", type=int, default=65536)
 g.add_argument("--seed", type=int, default=0)
 g.add_argument("--weights-dir", default="models")
+g.add_argument("--random-init", action="store_true", help="seeded random lifters when the checkpoints are missing")
 
 if __name__ == "__main__":
     evaluate(parser.parse_args())

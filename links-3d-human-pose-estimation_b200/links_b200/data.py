@@ -12,7 +12,9 @@ class ArrayLoader:
 
     def __init__(self, x2d, gt, batch_global, rank=0, world=1, seed=0, shuffle=True, pin=True):
         n = x2d.shape[0]
-        b, e = shard_bounds(n, rank, world)
+        # equal shards: every rank runs the same number of steps per epoch, so the per-step gradient all-reduces of
+        # all ranks pair up (an extra step on one rank would meet another rank's validation collective and hang)
+        b, e = shard_bounds(n, rank, world, equal=True)
         self.x = torch.as_tensor(x2d[b:e], dtype=torch.float32)
         self.gt = torch.as_tensor(gt[b:e], dtype=torch.float32) if gt is not None else None
         self.batch = batch_global // world

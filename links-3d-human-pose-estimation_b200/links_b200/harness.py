@@ -34,6 +34,10 @@ def add_common_args(p, batch=256, epochs=100):
     g.add_argument("--datafile", default=None, help="dataset pickle in the reference's format ({subject: {poses_2d, poses_3d}})")
     g.add_argument("--dataset", default="h36m", choices=["h36m", "mpi"], help="which dataset class reads --datafile")
     g.add_argument("--val", type=int, default=0, help="synthetic validation poses scored at every epoch end (0 = off)")
+    g.add_argument("--random-init", action="store_true",
+                   help="use seeded random weights for pretrained networks whose checkpoint is missing (benchmarks / "
+                        "smoke runs); without it a missing checkpoint raises FileNotFoundError like the reference's torch.load")
+    g.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     return p
 
 
@@ -50,12 +54,43 @@ def dist_setup():
     return rank, world, pg
 
 
-def load_state(path, fallback):
-    """Reference checkpoints are plain state dicts (torch.save(module.state_dict())).  Without one, seeded random init."""
-    if os.path.exists(path):
-        return {k: v.float() for k, v in torch.load(path, map_location="cpu").items()}
-    print("[links_b200] %s not found: using seeded random initialisation" % path, file=sys.stderr)
-    return fallback()
+# Checkpoint names.  The reference's readers and writers do not agree with each other (e.g. train_full_pose_norm_flow.py:115
+# writes models/norm_flow_sampling.pt, train_leg_torso_lifter.py:367 reads models/norm_flow_full_pose_with_sampling.pt), so
+# every reader here accepts, in this order: the name the reference script READS, the name the producing reference script
+# WRITES (so the shipped pipeline chains end to end), and the round-1 name of this repo.
+CKPT = {
+    "full_flow": ("norm_flow_full_pose_with_sampling.pt", "norm_flow_sampling.pt", "mpi_norm_flow_sampling.pt",
+                  "full_pose_norm_flow.pt"),
+    "full_flow_parts": ("mpi_norm_flow_sampling.pt", "norm_flow_sampling.pt", "norm_flow_full_pose_with_sampling.pt"),
+    "leg_flow": ("best_lifting_models/no_sched_norm_flow_leg_weights_h36m_v5.pt", "mpi_norm_flow_legs_2.pt", "leg_norm_flow.pt"),
+    "torso_flow": ("best_lifting_models/no_sched_norm_flow_torso_weights_h36m_v5.pt", "mpi_norm_flow_torso_2.pt",
+                   "torso_norm_flow.pt"),
+    "left_flow": ("no_sched_norm_flow_left_side_weights_h36m_v3_sampling.pt", "mpi_norm_flow_left_2.pt", "left_norm_flow.pt"),
+    "right_flow": ("no_sched_norm_flow_right_side_weights_h36m_v3_sampling.pt", "mpi_norm_flow_right_2.pt", "right_norm_flow.pt"),
+    "leg_lifter": ("legs_lifter.pt", "leg_lifter.pt"),                       # train_occlusion_models.py:530 / train_leg_torso_lifter.py:397
+    "torso_lifter": ("torso_lifter.pt",),
+    "left_lifter": ("left_lifter.pt", "final_best_left_lifter.pt", "left_side_lifter_final.pt"),    # eval_h36m.py:33, occlusion :532, LR trainer :560
+    "right_lifter": ("right_lifter.pt", "final_best_right_lifter.pt", "right_side_lifter_final.pt"),
+}
+
+
+def load_state(path, fallback=None, allow_random=False):
+    """Reference checkpoints are plain state dicts (torch.save(module.state_dict())).  `path`: one path or a list of
+    candidates (first existing wins).  A missing checkpoint raises FileNotFoundError -- what the reference's torch.load
+    does -- unless allow_random (--random-init) asks for seeded random weights."""
+    paths = [path] if isinstance(path, str) else list(path)
+    for q in paths:
+        if os.path.exists(q):
+            return {k: v.float() for k, v in torch.load(q, map_location="cpu").items()}
+    if allow_random and fallback is not None:
+        print("[links_b200] none of %s found: --random-init -> seeded random initialisation" % paths, file=sys.stderr)
+        return fallback()
+    raise FileNotFoundError("pretrained checkpoint not found (tried %s); train it with the producing script first, or "
+                            "pass --random-init for seeded random weights" % ", ".join(paths))
+
+
+def ckpt_paths(weights_dir, key):
+    return [os.path.join(weights_dir, n) for n in CKPT[key]]
 
 
 def save_module_state(module_cls, kwargs, params, path):
@@ -112,11 +147,15 @@ class Validator:
                  for i in range(0, self.x.shape[0], self.chunk)]
         pred = torch.cat(preds, dim=0)
         out = self.ev.result()
-        extra = torch.stack((mb().PCK(self.gt, pred, num_joints=17, root_joint=0).float(),
-                             mb().AUC(self.gt, pred, num_joints=17, root_joint=0).float()))
-        if self.world > 1:                       # equal shards: the mean of the per-rank ratios is the global ratio
+        # PCK / AUC are means over poses of per-pose hit ratios: reduce (ratio * count, count) pairs over the ranks
+        # (validation shards need not be equal)
+        n_loc = float(self.gt.shape[0])
+        extra = torch.stack((mb().PCK(self.gt, pred, num_joints=17, root_joint=0).double() * n_loc,
+                             mb().AUC(self.gt, pred, num_joints=17, root_joint=0).double() * n_loc,
+                             torch.tensor(n_loc, dtype=torch.float64, device=pred.device)))
+        if self.world > 1:
             torch.distributed.all_reduce(extra, group=self.pg)
-            extra /= self.world
+        extra = extra[:2] / extra[2]
         return {"pa": out["pa_mpjpe"], "mpjpe_scaled": out["n_mpjpe"], "pck": extra[0].item(), "auc": extra[1].item()}
 
 
@@ -166,14 +205,15 @@ def train_lifters(kind, args):
     wd = args.weights_dir
     if kind == "lt":
         nj, names = (7, 10), ("leg_lifter.pt", "torso_lifter.pt")
-        flow_files = ("leg_norm_flow.pt", "torso_norm_flow.pt")
+        flow_keys = ("leg_flow", "torso_flow")
     else:
         nj, names = (11, 11), ("left_side_lifter_final.pt", "right_side_lifter_final.pt")
-        flow_files = ("left_norm_flow.pt", "right_norm_flow.pt")
+        flow_keys = ("left_flow", "right_flow")
     nets = [INIT.init_lifter_params(n, 11 + i + args.seed) for i, n in enumerate(nj)]
-    flows = [load_state(os.path.join(wd, f), lambda C=2 * n, s=41 + i: INIT.init_flow_params(C, s))
-             for i, (f, n) in enumerate(zip(flow_files, nj))]
-    full = load_state(os.path.join(wd, "full_pose_norm_flow.pt"), lambda: INIT.init_flow_params(34, 40))
+    rnd = getattr(args, "random_init", False)
+    flows = [load_state(ckpt_paths(wd, f), lambda C=2 * n, s=41 + i: INIT.init_flow_params(C, s), rnd)
+             for i, (f, n) in enumerate(zip(flow_keys, nj))]
+    full = load_state(ckpt_paths(wd, "full_flow"), lambda: INIT.init_flow_params(34, 40), rnd)
     loader = make_loader(args, rank, world)
     step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
@@ -196,8 +236,9 @@ OCC_FILES = {"left_arm": "left_arm_estimator.pt", "right_arm": "right_arm_estima
 def train_occlusion(args):
     rank, world, pg = dist_setup()
     wd = args.weights_dir
-    lifters = [load_state(os.path.join(wd, "leg_lifter.pt"), lambda: INIT.init_lifter_params(7, 11)),
-               load_state(os.path.join(wd, "torso_lifter.pt"), lambda: INIT.init_lifter_params(10, 12))]
+    rnd = getattr(args, "random_init", False)
+    lifters = [load_state(ckpt_paths(wd, "leg_lifter"), lambda: INIT.init_lifter_params(7, 11), rnd),
+               load_state(ckpt_paths(wd, "torso_lifter"), lambda: INIT.init_lifter_params(10, 12), rnd)]
     preds = {n: INIT.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i + args.seed) for i, n in enumerate(OCC_NAMES)}
     loader = make_loader(args, rank, world)
     step = OcclusionStep(loader.batch, lifters, preds, cfg=dict(depth=args.translation), process_group=pg)
@@ -210,8 +251,8 @@ def train_occlusion(args):
     validator = None
     if args.val:                                # validation_step of the occlusion script (:316-509), on the device
         from .occ_assembly import OcclusionValidator
-        lr = [load_state(os.path.join(wd, "left_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 13)),
-              load_state(os.path.join(wd, "right_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 14))]
+        lr = [load_state(ckpt_paths(wd, "left_lifter")[1:], lambda: INIT.init_lifter_params(11, 13), rnd),
+              load_state(ckpt_paths(wd, "right_lifter")[1:], lambda: INIT.init_lifter_params(11, 14), rnd)]
         ov = OcclusionValidator.from_params({"legs": lifters[0], "torso": lifters[1], "left": lr[0], "right": lr[1]},
                                             {n: step.mlp.state_dict(s) for s, n in enumerate(OCC_NAMES)},
                                             depth=args.translation, device=step.device)
@@ -223,10 +264,11 @@ def train_occlusion(args):
             def run(self_inner):
                 ov.load_predictors({n: step.mlp.state_dict(s) for s, n in enumerate(OCC_NAMES)})
                 out = ov.run(vx, vg)
-                if world > 1:                   # equal shards: mean of the per-rank means
-                    t = torch.tensor(list(out.values()), dtype=torch.float64, device=step.device)
+                if world > 1:                   # per-pose means: reduce (mean * count, count) over the ranks
+                    n_loc = float(vx.shape[0])
+                    t = torch.tensor([v * n_loc for v in out.values()] + [n_loc], dtype=torch.float64, device=step.device)
                     torch.distributed.all_reduce(t, group=pg)
-                    out = dict(zip(out, (t / world).tolist()))
+                    out = dict(zip(out, (t[:-1] / t[-1]).tolist()))
                 return out
         validator = _V()
     n = run_training(step, loader, args, rank, feed, validator)
@@ -247,8 +289,9 @@ def evaluate(args):
     """eval_h36m.py:27-99 on a (sharded) synthetic test set: prints PA-MPJPE ('best') and N-MPJPE."""
     rank, world, pg = dist_setup()
     wd = args.weights_dir
-    lifters = [load_state(os.path.join(wd, "left_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 13)),
-               load_state(os.path.join(wd, "right_side_lifter_final.pt"), lambda: INIT.init_lifter_params(11, 14))]
+    rnd = getattr(args, "random_init", False)
+    lifters = [load_state(ckpt_paths(wd, "left_lifter"), lambda: INIT.init_lifter_params(11, 13), rnd),
+               load_state(ckpt_paths(wd, "right_lifter"), lambda: INIT.init_lifter_params(11, 14), rnd)]
     if getattr(args, "datafile", None):          # eval_h36m.py:41: test subjects, fixed-scale normalisation
         from utils.h36m_dataset_class import H36M_Data
         from utils.helpers import normalize_head_test

@@ -44,10 +44,13 @@ class _Net:
 
 class MlpSet:
     def __init__(self, kind, in_dims, head_dims, max_rows, n_passes=1, device="cuda", train=True,
-                 pass_branches=None, max_buckets=None):
+                 pass_branches=None, max_buckets=None, share_from=None):
         """in_dims[s]: input width of net s; head_dims[s]: dict head name -> width.
         max_rows: rows per pass; n_passes: forward passes per step sharing weights (1 or 2).
-        pass_branches[p]: branches evaluated in pass p (default: all)."""
+        pass_branches[p]: branches evaluated in pass p (default: all).
+        share_from: another MlpSet of the same topology whose parameter / gradient / shadow buffers this set aliases
+        (only the activation and gradient workspaces are private) -- several forward passes of one module can then be
+        alive at once, each keeping its own activations for its own backward (utils/models_def.py)."""
         self.kind = kind
         self.trunk, self.branches = TOPOLOGY[kind]
         self.S = len(in_dims)
@@ -113,15 +116,23 @@ class MlpSet:
         total = sum(_rup(K * N, 64) + _rup(N, 64) for K, N in (dims[k] for k in order))
         self.n_params = total      # padded length of the flat buffers (padding stays zero through Adam)
         self.n_params_real = sum(K * N + N for K, N in dims.values())
-        self.master = torch.zeros(total, dtype=torch.float32, device=dev)
-        if train:
-            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
-            self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
-            self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        if share_from is not None:
+            o = share_from
+            assert (o.kind, o.S, o.n_params, o.buckets) == (kind, self.S, total, buckets) and (o.train or not train)
+            self.master, self.nets, self.bucket_ranges, self.step_dev = o.master, o.nets, o.bucket_ranges, o.step_dev
+            if train:
+                self.grad, self.exp_avg, self.exp_avg_sq = o.grad, o.exp_avg, o.exp_avg_sq
+        else:
+            self.master = torch.zeros(total, dtype=torch.float32, device=dev)
+            if train:
+                self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+                self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+                self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         layers = [dict() for _ in range(self.S)]
-        self.bucket_ranges = []
+        if share_from is None:
+            self.bucket_ranges = []
         off = 0
-        for b in buckets:
+        for b in (buckets if share_from is None else []):
             start = off
             for s in range(self.S):
                 for n in b:
@@ -139,8 +150,9 @@ class MlpSet:
                     L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
                     layers[s][n] = L
             self.bucket_ranges.append((start, off))
-        self.nets = [_Net({n: layers[s][n] for n in self.layer_names}) for s in range(self.S)]
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
+        if share_from is None:
+            self.nets = [_Net({n: layers[s][n] for n in self.layer_names}) for s in range(self.S)]
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
         # ---- activation / gradient workspaces
         M = self.M
         P_ = n_passes

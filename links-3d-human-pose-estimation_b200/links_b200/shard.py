@@ -7,16 +7,18 @@ never straddle ranks.  Evaluation keeps per-rank double sums and does one final 
 import torch
 
 
-def shard_bounds(n_items, rank, world, multiple=2):
+def shard_bounds(n_items, rank, world, multiple=2, equal=False):
     """[begin, end) of rank's contiguous slice of n_items; every slice length is a multiple of `multiple` except that
-    the last rank also takes the remainder.  Raises if n_items cannot give every rank at least `multiple` items."""
+    the last rank also takes the remainder -- unless equal=True, which drops the remainder so that every rank owns
+    exactly the same number of items (training: every rank must issue the same number of steps / collectives).
+    Raises if n_items cannot give every rank at least `multiple` items."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank %r / world %r" % (rank, world))
     per = (n_items // world) // multiple * multiple
     if per < multiple and world > 1:
         raise ValueError("%d items cannot be sharded over %d ranks in multiples of %d" % (n_items, world, multiple))
     begin = rank * per
-    end = n_items if rank == world - 1 else begin + per
+    end = n_items if (rank == world - 1 and not equal) else begin + per
     return begin, end
 
 

@@ -48,7 +48,7 @@ class LifterStep:
         self.nj = nj
         self.mlp = MlpSet("lifter", [2 * n for n in nj], [{"downscale": n, "angles": 1} for n in nj], self.N,
                           n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]],
-                          max_buckets=self.cfg.get("dp_buckets") if self.world > 1 else None)
+                          max_buckets=self.cfg.get("dp_buckets") if (self.world > 1 or self.cfg.get("dp_layout")) else None)
         self.mlp.load_state_dicts(lifter_params)
         self.part_flows = [FlowPacked(2 * nj[s], part_flow_params[s], device=dev) for s in range(2)]
         self.full_flow = FlowPacked(34, full_flow_params, device=dev)

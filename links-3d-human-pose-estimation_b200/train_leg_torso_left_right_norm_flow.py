@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch  # noqa: E402
 from links_b200 import init as INIT  # noqa: E402
 from links_b200.flowtrain import PartFlowTrainer  # noqa: E402
-from links_b200.harness import GAMMA, LR0, add_common_args, dist_setup, load_state, make_loader  # noqa: E402
+from links_b200.harness import GAMMA, LR0, add_common_args, ckpt_paths, dist_setup, load_state, make_loader  # noqa: E402
 
 parser = argparse.ArgumentParser(description='Train 2D INN')
 parser.add_argument("-l", "--left_right_side_keypoints", help="number of key-points in each split", type=int, default=22)
@@ -26,7 +26,7 @@ if __name__ == "__main__":
     if args.left_right_side_keypoints != 22:
         raise NotImplementedError("split_data_left_right (utils/helpers.py:55-65) yields 11 joints = 22 values per side")
     rank, world, pg = dist_setup()
-    full = load_state(os.path.join(args.weights_dir, "mpi_norm_flow_sampling.pt"), lambda: INIT.init_flow_params(34, 40))
+    full = load_state(ckpt_paths(args.weights_dir, "full_flow_parts"), lambda: INIT.init_flow_params(34, 40), args.random_init)
     parts = {n: INIT.init_flow_params(WIDTH[n], 50 + i + args.seed, perturb=0.0) for i, n in enumerate(PartFlowTrainer.NAMES)}
     loader = make_loader(args, rank, world)
     trainer = PartFlowTrainer(full, parts, loader.batch, lr=LR0, weight_decay=1e-5, process_group=pg)

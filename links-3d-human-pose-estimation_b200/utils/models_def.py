@@ -46,6 +46,13 @@ class _EngineFn(torch.autograd.Function):
         # grad mode is always off inside Function.forward: the caller decides whether activations are kept
         eng = module._engine(x.shape[0], train=train)
         module._sync_params(eng)
+        if train:
+            # this autograd node owns the workspace's activations until its backward has run (the reference calls
+            # every lifter twice, every predictor three times per step before one backward:
+            # train_leg_torso_lifter.py:150-151,227-228; train_occlusion_models.py:196-300)
+            eng._gen += 1
+            eng._busy = True
+        ctx.gen = eng._gen
         M, K = x.shape
         lib = eng.lib
         st = torch.cuda.current_stream().cuda_stream
@@ -66,6 +73,10 @@ class _EngineFn(torch.autograd.Function):
         module, eng, M, K = ctx.module, ctx.eng, ctx.M, ctx.K
         if not eng.train:
             raise _cabi.LinksError("forward ran under no_grad; no activations were kept for backward")
+        if ctx.gen != eng._gen:
+            raise _cabi.LinksError("the activations of this forward call were recycled: more than %d forward calls of one "
+                                   "module (same batch size) were alive without a backward; raise "
+                                   "utils.models_def.MAX_LIVE_FORWARDS" % MAX_LIVE_FORWARDS)
         for (head, width), g in zip(module._heads, gouts):
             G = eng.G[0][0][head]
             G.zero_()
@@ -79,11 +90,16 @@ class _EngineFn(torch.autograd.Function):
             layer, kind = name.rsplit(".", 1)
             L = eng.nets[0].layers[layer]
             grads.append((L.gW if kind == "weight" else L.gb).clone())
+        eng._busy = False
         return (None, None, gx) + tuple(grads)
 
 
+MAX_LIVE_FORWARDS = 8     # activation workspaces kept per (module, batch size): forward calls alive before a backward
+
+
 class _EngineModule(nn.Module):
-    """Shared machinery: lazily built engines (one per batch size), parameter sync by version counter."""
+    """Shared machinery: lazily built engines (a small pool of activation workspaces per batch size that share ONE set
+    of parameter / gradient / shadow buffers), parameter sync by version counter."""
     _kind = "lifter"
 
     def _post_init(self, in_dim, heads, use_batchnorm, use_dropout):
@@ -115,19 +131,32 @@ class _EngineModule(nn.Module):
         return self._idx[K]
 
     def _engine(self, rows, train):
+        """A workspace whose activations no pending backward needs.  Workspaces of one (rows, train) key alias the
+        parameter buffers of the first one; at most MAX_LIVE_FORWARDS exist, after that the one whose forward is oldest
+        is recycled (its generation counter moves on, so a late backward of the evicted call raises instead of silently
+        using the wrong activations)."""
         key = (rows, bool(train))
-        if key not in self._engines:
-            self._engines[key] = MlpSet(self._kind, [self._in_dim], [dict(self._heads)], rows, n_passes=1,
-                                        device=next(self.parameters()).device, train=bool(train))
-            self._versions[key] = None
-        return self._engines[key]
+        pool = self._engines.setdefault(key, [])
+        for eng in pool:
+            if not eng._busy:
+                return eng
+        if len(pool) < MAX_LIVE_FORWARDS:
+            eng = MlpSet(self._kind, [self._in_dim], [dict(self._heads)], rows, n_passes=1,
+                         device=next(self.parameters()).device, train=bool(train), share_from=pool[0] if pool else None)
+            eng._gen, eng._busy, eng._key = 0, False, key
+            pool.append(eng)
+            if len(pool) == 1:
+                self._versions[key] = None
+            return eng
+        eng = min(pool, key=lambda e: e._gen)
+        return eng
 
     def _sync_params(self, eng):
         sd = dict(self.named_parameters())
         ver = tuple(sd[n]._version for n in self._param_order) + tuple(sd[n].data_ptr() for n in self._param_order)
-        key = [k for k, v in self._engines.items() if v is eng][0]
+        key = eng._key
         if self._versions.get(key) != ver:
-            eng.load_state_dicts([{n: sd[n].detach() for n in self._param_order}])
+            eng.load_state_dicts([{n: sd[n].detach() for n in self._param_order}])     # buffers shared by the pool
             self._versions[key] = ver
 
     def _run(self, x):

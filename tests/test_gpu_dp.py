@@ -1,0 +1,25 @@
+"""Data-parallel parity on hardware (SURVEY 4 "distributed": per-rank gradients after the all-reduce == single-GPU
+gradients; VERDICT r1 missing #2): spawns 2 ranks under torch.distributed.run and runs tests/dp_worker.py, which checks
+the product path LifterStep._on_bucket (fp32 and bf16-compressed buckets over NCCL, overlapped with backward) against
+the un-communicated engine and against the CPU oracle on every shard.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (gpurun --gpus 2)")
+@pytest.mark.parametrize("kind,grad_comm", [("lt", "bf16"), ("lt", "fp32"), ("lr", "bf16")])
+def test_two_rank_lifter_step(kind, grad_comm, tmp_path):
+    port = 29700 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dp_worker.py"), kind, grad_comm, "256", str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    for rank in range(2):
+        assert os.path.exists(os.path.join(str(tmp_path), "ok_%s_%s_%d" % (kind, grad_comm, rank)))

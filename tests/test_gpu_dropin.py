@@ -80,6 +80,15 @@ def test_freia_shim_matches_oracle_and_fixture(golden):
     np.testing.assert_allclose(xr.cpu().numpy(), G["x"], rtol=1e-3, atol=2e-5)
     for q in inn.parameters():
         q.requires_grad = True
+    # un-frozen flow (the state at every reference call site): input gradients still flow, parameters get none
+    x2 = torch.from_numpy(G["x"]).cuda().requires_grad_(True)
+    Ff.SequenceINN._warned = False
+    with pytest.warns(UserWarning):
+        z2, ld2 = inn(x2)
+    (0.5 * torch.sum(z2 ** 2, 1) - ld2).mean().backward()
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), xo.grad.numpy(), rtol=2e-3, atol=1e-5)
+    assert all(q.grad is None for q in inn.parameters())
+    inn.strict_param_grads = True
     with pytest.raises(NotImplementedError):
         inn(x.detach())
 
@@ -107,3 +116,53 @@ def test_metrics_batch_dropin_vs_reference_golden(golden):
     # views that do not start on a 16-byte boundary (row 1 of a [M,51] tensor) are accepted like any other tensor
     assert torch.equal(mb().mpjpe(gt[1:], pred[1:], num_joints=17, root_joint=0), mb().mpjpe(gt, pred, num_joints=17, root_joint=0)[1:])
     assert torch.allclose(mb().pmpjpe_best(gt[1:], pred[1:]), mb().pmpjpe_best(gt, pred)[1:], atol=1e-4)
+
+
+def test_module_called_twice_before_backward():
+    """The reference training_step calls each lifter twice (train_leg_torso_lifter.py:150-151 and :227-228) and each
+    occlusion predictor three times (train_occlusion_models.py:196-300) before ONE backward: every call must keep its
+    own activations.  Gradients vs the oracle networks on the same inputs."""
+    from oracle import nets as ON, steps as OS
+    from utils.models_def import Leg_Lifter, Occluded_Limb_Predictor
+    g = torch.Generator().manual_seed(5)
+    # ---- lifter: two calls, same batch size
+    p = ON.init_lifter_params(7, 21)
+    m = Leg_Lifter(use_batchnorm=False, num_joints=7, use_dropout=False, d_rate=0.25).cuda()
+    m.load_state_dict(p, strict=False)
+    xs = [(torch.randn(96, 14, generator=g) * 0.2) for _ in range(2)]
+    xg = [x.cuda().requires_grad_(True) for x in xs]
+    outs = [m(x) for x in xg]
+    loss = sum((xd.square().sum() + (i + 1) * xa.sum()) for i, (xd, xa) in enumerate(outs))
+    loss.backward()
+    pr = OS.params_require_grad(p)
+    xo = [x.clone().requires_grad_(True) for x in xs]
+    ro = [ON.lifter_forward(x, pr) for x in xo]
+    sum((xd.square().sum() + (i + 1) * xa.sum()) for i, (xd, xa) in enumerate(ro)).backward()
+    for i in range(2):
+        assert (outs[i][0].detach().cpu() - ro[i][0].detach()).abs().max() < 5e-3
+        assert rel_fro(xg[i].grad.cpu(), xo[i].grad) < 0.1, i
+    for name in ("upscale", "res_common.l1", "res_pose2.l2", "res_angle1.l1", "downscale", "angles"):
+        mod = m
+        for part in name.split("."):
+            mod = getattr(mod, part)
+        assert rel_fro(mod.weight.grad.cpu(), pr[name + ".weight"].grad) < 8e-2, name
+    # the single-call gradient is different (the second call really contributed)
+    m.zero_grad()
+    xd, xa = m(xg[0].detach())
+    (xd.square().sum() + xa.sum()).backward()
+    assert rel_fro(m.res_pose2.l2.weight.grad.cpu(), pr["res_pose2.l2.weight"].grad) > 0.2
+    # ---- predictor: three calls
+    pp = ON.init_predictor_params(14, 9, 33)
+    q = Occluded_Limb_Predictor(use_batchnorm=False, num_joints=14).cuda()
+    q.load_state_dict(pp, strict=False)
+    zs = [torch.randn(64, 42, generator=g) for _ in range(3)]
+    ys = [q(z.cuda()) for z in zs]
+    sum(((k + 1) * y.square().sum(dim=1).mean()) for k, y in enumerate(ys)).backward()
+    pq = OS.params_require_grad(pp)
+    sum(((k + 1) * ON.predictor_forward(z, pq).square().sum(dim=1).mean()) for k, z in enumerate(zs)).backward()
+    for name in ("upscale", "res_pose1.l1", "res_pose3.l2", "downscale"):
+        mod = q
+        for part in name.split("."):
+            mod = getattr(mod, part)
+        assert rel_fro(mod.weight.grad.cpu(), pq[name + ".weight"].grad) < 8e-2, name
+    assert q.res_common.l1.weight.grad is None
