@@ -79,6 +79,22 @@ struct alignas(64) GemmProblemDev {
   uint32_t stage_tx;    // bytes the boxes of one stage deliver (small M / N problems load smaller boxes)
   int vec_ok;           // every present epilogue operand is 16-byte aligned with a vector-friendly leading dimension
   int epi_mode;         // index into kEpiMask (0 = run-time flags)
+  // ---- chain launches only (links_gemm_chain_*): tile-level dependencies through completion counters in global memory
+  int cnt_base;         // first completion counter of this problem (one per PAIR of M tiles); -1: nobody waits on it
+  int dep_base[3];      // [A operand, add0, add1]: first counter of the producing problem of the chain, -1: none
+  int dep_blocks[3];    // 0: wait for the counter of the tile's own row block (base + pair index);
+                        // n > 0: wait for all n counters of the producer (operand contracted over rows: wgrad)
+  int dep_need[3];      // arrivals that complete a counter = 2 CTAs * kEpiWarps * tiles_n of the producer
+};
+
+// Kernel argument of a chain launch: everything lives in the caller's workspace (global memory).
+struct ChainDev {
+  const GemmProblemDev* probs;
+  const uint32_t* sched;     // [n_cl][sched_ld] tiles of every cluster in execution order: pi << 22 | pair_m << 11 | tn
+  const int* sched_cnt;      // [n_cl]
+  int* counters;             // [n_counters] completion counters, zero between launches (the last cluster to exit resets them)
+  int* exit_cnt;
+  int n_counters, sched_ld;
 };
 
 struct GemmGroupDev {
@@ -261,16 +277,37 @@ struct PrimaryOp {
   int ld, M, m0, n0;
   int ok;             // present, 16-byte aligned and the warp's 64-column slab lies fully inside N (the vector path)
   int pad;
+  const int* dep;     // chain launches: completion counter of the tiles that PRODUCE this operand (null: none)
+  int dep_need, pad2;
 };
-static_assert(sizeof(PrimaryOp) == 32, "PrimaryOp slot");
-__device__ __forceinline__ void prefetch_primary(const PrimaryOp* slot, uint32_t S, int h, int lane) {
+static_assert(sizeof(PrimaryOp) == 48, "PrimaryOp slot");
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Returns true when the fetch was SKIPPED because the operand's producer tiles have not completed yet (chain launches
+// only).  The prefetch runs a tile ahead of the producer warp's own dependency wait and must never block: the warp
+// still owes the completion signal of its CURRENT tile, which the missing producer may (transitively) be waiting for.
+// A skipped fetch is repeated at the top of the next tile, behind the accumulator barrier (all dependencies done).
+template <bool kChain>
+__device__ __forceinline__ bool prefetch_primary(const PrimaryOp* slot, uint32_t S, int h, int lane) {
   const uint4 a = *reinterpret_cast<const uint4*>(slot);              // p, ld, M
   const uint4 b = *(reinterpret_cast<const uint4*>(slot) + 1);        // m0, n0, ok
+  bool missed = false;
   if (b.z != 0u) {
-    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32));
-    block_fetch_async(S, p, static_cast<int>(a.z), static_cast<int>(b.x), static_cast<int>(b.y) + h * 32, static_cast<int>(a.w), lane);
+    if (kChain) {
+      const uint4 c = *(reinterpret_cast<const uint4*>(slot) + 2);    // dep, dep_need
+      const int* dp = reinterpret_cast<const int*>(static_cast<uint64_t>(c.x) | (static_cast<uint64_t>(c.y) << 32));
+      if (dp != nullptr) missed = __any_sync(0xffffffffu, ld_acquire_gpu(dp) < static_cast<int>(c.z));
+    }
+    if (!missed) {
+      const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32));
+      block_fetch_async(S, p, static_cast<int>(a.z), static_cast<int>(b.x), static_cast<int>(b.y) + h * 32, static_cast<int>(a.w), lane);
+    }
   }
   cp_async_commit();                      // one group per pass, empty or not: keeps the wait_group arithmetic uniform
+  return missed;
 }
 
 // One [32 rows x 64 columns] block of an accumulator tile per warp (this thread: row m0 + lane), in two passes of
@@ -278,10 +315,11 @@ __device__ __forceinline__ void prefetch_primary(const PrimaryOp* slot, uint32_t
 // earlier, i.e. a full pass of work ahead), then any secondary operand, then stages the pass's outputs for the
 // coalesced stores, and is finally refilled with the primary operand of the same pass of the warp's NEXT tile.
 //   t_addr : TMEM address of (lane group, first column of the block);  sbias : bias of the block's 64 columns (smem)
-template <uint32_t F>
-__device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
+template <uint32_t F, bool kChain>
+__device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
                                                const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
   constexpr bool kDyn = F == 0u;
+  bool missed = false;
   const int m = m0 + lane;
   const bool row_ok = m < E.M;
   const bool has_bias = kDyn ? E.bias != nullptr : (F & F_BIAS) != 0;
@@ -311,9 +349,9 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(acc_empty_bar, 0);
-    prefetch_primary(nxt, S0, 0, lane);
-    prefetch_primary(nxt, S0 + 2048u, 1, lane);
-    return;
+    missed |= prefetch_primary<kChain>(nxt, S0, 0, lane);
+    missed |= prefetch_primary<kChain>(nxt, S0 + 2048u, 1, lane);
+    return missed;
   }
 
   const bool y_primary = has_y && !has_add0;     // ymask is the operand fetched ahead when there is no add0
@@ -458,16 +496,18 @@ __device__ __forceinline__ void epilogue_block(const EpiParams& E, uint32_t t_ad
       }
     }
     // this pass's scratch is free again: refill it with the primary operand of the same pass of the next tile
-    prefetch_primary(nxt, SA, h, lane);
+    missed |= prefetch_primary<kChain>(nxt, SA, h, lane);
   }
+  return missed;
 }
 
 // Run-time-flag variant (rare combinations, e.g. the flow-training GEMMs) kept OUT of line: inlined next to the
 // specialised modes its register demand made the compiler spill state that is live across the mode switch in every
 // mode.  The caller passes copies, so only those copies are pinned in local memory.
-__device__ __noinline__ void epilogue_block_dyn(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
+template <bool kChain>
+__device__ __noinline__ bool epilogue_block_dyn(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
                                                 const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
-  epilogue_block<0u>(E, t_addr, sbias, S0, nxt, m0, n_blk, lane, acc_empty_bar);
+  return epilogue_block<0u, kChain>(E, t_addr, sbias, S0, nxt, m0, n_blk, lane, acc_empty_bar);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -540,10 +580,69 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmGroupDev& G, int tile)
   return t;
 }
 
+// The two launch flavours share one kernel body:
+//   grouped (links_gemm_grouped): <= 8 independent problems, descriptors in the kernel parameters, static round-robin
+//     of the pair-tiles over the clusters;
+//   chain (links_gemm_chain_run): a whole dependent sequence of layers in ONE launch -- descriptors, a host-built
+//     per-cluster tile schedule and tile-completion counters live in global memory; a tile of layer l+1 starts as soon
+//     as the tiles of layer l that produce its operand rows have signalled, so setup / TMEM allocation / pipeline fill
+//     are paid once per chain instead of once per layer and the epilogue of layer l overlaps the main loop of layer l+1.
+template <bool kChain> struct KernelArgs { typedef GemmGroupDev type; };
+template <> struct KernelArgs<true> { typedef ChainDev type; };
+
+template <bool kChain>
+__device__ __forceinline__ const GemmProblemDev& problem_of(const typename KernelArgs<kChain>::type& A, int pi);
+template <> __device__ __forceinline__ const GemmProblemDev& problem_of<false>(const GemmGroupDev& A, int pi) { return A.p[pi]; }
+template <> __device__ __forceinline__ const GemmProblemDev& problem_of<true>(const ChainDev& A, int pi) { return A.probs[pi]; }
+
+// i-th tile of cluster cl_id (false: no more tiles).  tc.tm is the PAIR index along M.
+template <bool kChain>
+__device__ __forceinline__ bool tile_at(const typename KernelArgs<kChain>::type& A, int cl_id, int n_cl, int n_mine, int i, TileCoord& tc);
+template <> __device__ __forceinline__ bool tile_at<false>(const GemmGroupDev& A, int cl_id, int n_cl, int, int i, TileCoord& tc) {
+  const int tile = cl_id + i * n_cl;
+  if (tile >= A.total_tiles) return false;
+  tc = tile_coord(A, tile);
+  return true;
+}
+template <> __device__ __forceinline__ bool tile_at<true>(const ChainDev& A, int cl_id, int, int n_mine, int i, TileCoord& tc) {
+  if (i >= n_mine) return false;
+  const uint32_t e = __ldg(A.sched + static_cast<size_t>(cl_id) * A.sched_ld + i);
+  tc.pi = static_cast<int>(e >> 22);
+  tc.tm = static_cast<int>((e >> 11) & 0x7FFu);
+  tc.tn = static_cast<int>(e & 0x7FFu);
+  return true;
+}
+
+// Block until every dependency of a tile of problem P (pair index pair_m) has completed: spin on the producers'
+// completion counters (bounded: a protocol bug traps instead of hanging the GPU), then order the TMA (async proxy)
+// reads that follow behind the acquire.
+__device__ __forceinline__ void chain_wait_deps(const GemmProblemDev& P, const int* counters, int pair_m) {
+#pragma unroll 1
+  for (int d = 0; d < 3; ++d) {
+    const int base = P.dep_base[d];
+    if (base < 0) continue;
+    const int nb = P.dep_blocks[d], need = P.dep_need[d];
+    const int* c = counters + base + (nb == 0 ? pair_m : 0);
+    const int n = nb == 0 ? 1 : nb;
+#pragma unroll 1
+    for (int b = 0; b < n; ++b) {
+      if (ld_acquire_gpu(c + b) >= need) continue;
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(c + b) < need) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+  }
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // Kernel
 // ----------------------------------------------------------------------------------------------
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_grouped_kernel(const __grid_constant__ GemmGroupDev G) {
+template <bool kChain>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;          // 1024-B aligned (128B swizzle atoms)
@@ -578,6 +677,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
   // scheduled as soon as SMs free up -- it will wait at the same point for this grid to finish.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int n_mine = 0;                                         // chain: number of tiles in this cluster's schedule
+  if (kChain) n_mine = __ldg(reinterpret_cast<const ChainDev&>(G).sched_cnt + cl_id);
 
   if (warp < kFirstEpiWarp) {
     // the control warpgroup hands registers to the epilogue warpgroups (whose 32-column accumulator slice, operand
@@ -588,32 +689,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;   // running k-block index over all tiles of this CTA
-      for (int tile = cl_id; tile < G.total_tiles; tile += n_cl) {
-        TileCoord tc = tile_coord(G, tile);
+      TileCoord tc;
+      for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti) {
+        const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
+        if (kChain) chain_wait_deps(P, reinterpret_cast<const ChainDev&>(G).counters, tc.tm);
         tc.tm = 2 * tc.tm + cta_rank;
-        const GemmProblemDev& P = G.p[tc.pi];
         const int num_kb = (P.K + BK - 1) / BK;
         const bool a_mn = (P.flags & LINKS_GEMM_A_MN) != 0, b_mn = (P.flags & LINKS_GEMM_B_MN) != 0;
         const int b_half = P.b_rows >> 1;                 // this CTA's rows (K-major) / columns (MN-major) of the pair's B tile
+        const uint32_t stage_tx = P.stage_tx;
+        const int a_boxes = P.a_boxes, b_boxes = P.b_boxes;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % kStages, use = it / kStages;
           mbar_wait(bars + (GB_EMPTY + s) * 8, (use & 1u) ^ 1u);        // own slot free (leader's commit reaches both CTAs)
           const uint32_t full = bars + (GB_FULL + s) * 8;
-          if (cta_rank == 0) mbar_expect_tx(full, 2u * P.stage_tx);     // the leader's barrier collects both CTAs' bytes
+          if (cta_rank == 0) mbar_expect_tx(full, 2u * stage_tx);       // the leader's barrier collects both CTAs' bytes
           const uint32_t sA = base + kOffStage + s * kStageBytes, sB = sA + kStageBytesA;
           if (!a_mn) {
             tma_load_2d_pair(sA, &P.tmA, full, kb * BK, tc.tm * BM);
           } else {
 #pragma unroll
             for (int q = 0; q < BM / 64; ++q)
-              if (q < P.a_boxes) tma_load_2d_pair(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
+              if (q < a_boxes) tma_load_2d_pair(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
           }
           if (!b_mn) {
             tma_load_2d_pair(sB, &P.tmB, full, kb * BK, tc.tn * BN + cta_rank * b_half);
           } else {
 #pragma unroll
             for (int q = 0; q < BN / 128; ++q)
-              if (q < P.b_boxes) tma_load_2d_pair(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK);
+              if (q < b_boxes) tma_load_2d_pair(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK);
           }
         }
       }
@@ -625,9 +729,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
     const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t bb = sb + kOffBar;
     uint32_t it = 0, lt = 0;   // k-block counter, local tile counter
-    for (int tile = cl_id; tile < G.total_tiles && cta_rank == 0; tile += n_cl, ++lt) {   // leader CTA only
-      const TileCoord tc = tile_coord(G, tile);
-      const GemmProblemDev& P = G.p[tc.pi];
+    TileCoord tc;
+    for (int ti = 0; cta_rank == 0 && tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti, ++lt) {   // leader CTA only
+      const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
       const int num_kb = (P.K + BK - 1) / BK;
       const bool a_mn = (P.flags & LINKS_GEMM_A_MN) != 0, b_mn = (P.flags & LINKS_GEMM_B_MN) != 0;
       // N actually needed by this tile (multiple of 16): the MMA cost scales with it
@@ -671,51 +775,59 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
     // bias of this warp's 64 columns: two floats per lane, loaded one tile ahead, published through the warp's own
     // scratch (no CTA-wide barrier in the epilogue: the 16 warps run fully decoupled)
     float* sbias = reinterpret_cast<float*>(smem_raw + (S + 4096u - raw));
-    auto load_bias = [&](int tile_idx, float& b0, float& b1) {
+    auto load_bias = [&](int ti, float& b0, float& b1) {
       b0 = 0.f; b1 = 0.f;
-      if (tile_idx < G.total_tiles) {
-        const TileCoord t0 = tile_coord(G, tile_idx);
-        const float* bp = G.p[t0.pi].bias;
+      TileCoord t0;
+      if (tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, t0)) {
+        const GemmProblemDev& P0 = problem_of<kChain>(G, t0.pi);
+        const float* bp = P0.bias;
         const int nb = t0.tn * BN + slab * kSlab + lane;
         if (bp != nullptr) {
-          if (nb < G.p[t0.pi].N) b0 = __ldg(bp + nb);
-          if (nb + 32 < G.p[t0.pi].N) b1 = __ldg(bp + nb + 32);
+          const int N0 = P0.N;
+          if (nb < N0) b0 = __ldg(bp + nb);
+          if (nb + 32 < N0) b1 = __ldg(bp + nb + 32);
         }
       }
     };
     float bias_n0, bias_n1;
-    load_bias(cl_id, bias_n0, bias_n1);
+    load_bias(0, bias_n0, bias_n1);
     // primary operand (add0, else ymask) of a tile's two passes for this warp -> the warp's descriptor slot
     PrimaryOp* const nxt = reinterpret_cast<PrimaryOp*>(smem_raw + (S + 4096u + 256u - raw));
-    auto publish_primary = [&](int tile_idx) {
+    auto publish_primary = [&](int ti) {
       if (lane == 0) {
         PrimaryOp o;
-        o.p = nullptr; o.ld = 0; o.M = 0; o.m0 = 0; o.n0 = 0; o.ok = 0; o.pad = 0;
-        if (tile_idx < G.total_tiles) {
-          TileCoord t0 = tile_coord(G, tile_idx);
-          const GemmProblemDev& P = G.p[t0.pi];
+        o.p = nullptr; o.ld = 0; o.M = 0; o.m0 = 0; o.n0 = 0; o.ok = 0; o.pad = 0; o.dep = nullptr; o.dep_need = 0; o.pad2 = 0;
+        TileCoord t0;
+        if (tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, t0)) {
+          const GemmProblemDev& P = problem_of<kChain>(G, t0.pi);
           o.p = P.add0 != nullptr ? P.add0 : P.ymask;
           o.ld = P.add0 != nullptr ? P.ld_add0 : P.ld_ymask;
           o.M = P.M;
           o.m0 = (2 * t0.tm + cta_rank) * BM + lane_grp * 32;
           o.n0 = t0.tn * BN + slab * kSlab;
           o.ok = (o.p != nullptr && P.vec_ok && o.n0 + kSlab <= P.N) ? 1 : 0;
+          if (kChain && P.add0 != nullptr && P.dep_base[1] >= 0) {
+            // (the contracted-over-rows flavour never applies to an element-wise operand)
+            o.dep = reinterpret_cast<const ChainDev&>(G).counters + P.dep_base[1] + t0.tm;
+            o.dep_need = P.dep_need[1];
+          }
         }
         *nxt = o;
       }
       __syncwarp();
     };
-    publish_primary(cl_id);                                  // in flight while the first main loop runs
-    prefetch_primary(nxt, S, 0, lane);
-    prefetch_primary(nxt, S + 2048u, 1, lane);
-    for (int tile = cl_id; tile < G.total_tiles; tile += n_cl, ++lt) {
-      TileCoord tc = tile_coord(G, tile);
+    publish_primary(0);                                      // in flight while the first main loop runs
+    bool missed = prefetch_primary<kChain>(nxt, S, 0, lane);
+    missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane);
+    TileCoord tc;
+    for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti, ++lt) {
+      const int pair_m = tc.tm;
       tc.tm = 2 * tc.tm + cta_rank;
       // register copy of the problem's epilogue parameters (an indexed constant-bank load per use otherwise)
       EpiParams E;
       int mode;
       {
-        const GemmProblemDev& P = G.p[tc.pi];
+        const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
         E.M = P.M; E.N = P.N; E.flags = P.flags; E.vec_ok = P.vec_ok;
         E.ld_add0 = P.ld_add0; E.ld_add1 = P.ld_add1; E.ld_ymask = P.ld_ymask; E.ld_bits = P.ld_bits; E.ld_sign = P.ld_sign;
         E.ld_f32 = P.ld_f32; E.ld_out = P.ld_out; E.ld_mid = P.ld_mid;
@@ -726,13 +838,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
       const int m0 = tc.tm * BM + lane_grp * 32, n0 = tc.tn * BN + slab * kSlab;
       __syncwarp();                                  // every lane is done with the previous tile's bias and descriptor
-      publish_primary(tile + n_cl);
+      publish_primary(ti + 1);
       sbias[lane] = bias_n0;
       sbias[lane + 32] = bias_n1;
       __syncwarp();
-      load_bias(tile + n_cl, bias_n0, bias_n1);      // next tile's bias: in flight during this tile's epilogue
+      load_bias(ti + 1, bias_n0, bias_n1);           // next tile's bias: in flight during this tile's epilogue
       mbar_wait(bars + (GB_ACCFULL + slot) * 8, acc_use & 1u);
       tc_fence_after();
+      if (kChain && missed) {
+        // The operand prefetch of THIS tile was skipped (its producer had not signalled yet).  The accumulator barrier
+        // implies the producer warp has seen every dependency of the tile complete: fetch both passes now.
+        const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
+        if (P.dep_base[1] >= 0) (void)ld_acquire_gpu(reinterpret_cast<const ChainDev&>(G).counters + P.dep_base[1] + pair_m);
+        const __nv_bfloat16* pp = E.add0 != nullptr ? E.add0 : E.ymask;
+        const int pld = E.add0 != nullptr ? E.ld_add0 : E.ld_ymask;
+        if (pp != nullptr && E.vec_ok && n0 + kSlab <= E.N) {
+          block_fetch_async(S, pp, pld, m0, n0, E.M, lane);
+          block_fetch_async(S + 2048u, pp, pld, m0, n0 + 32, E.M, lane);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+      }
+      missed = false;
       if (store_thread && lt < 3) TRACE(3 + 3 * lt);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lane_grp * 32) << 16) + slot * kAccCols + slab * kSlab;
       const uint32_t ae = bars + (GB_ACCEMPTY + slot) * 8;
@@ -741,25 +869,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ae, 0);
-        prefetch_primary(nxt, S, 0, lane);
-        prefetch_primary(nxt, S + 2048u, 1, lane);
+        missed |= prefetch_primary<kChain>(nxt, S, 0, lane);
+        missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane);
       } else {
         const float* sb = sbias;
         switch (mode) {
-          case 1: epilogue_block<kEpiMask[1]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 2: epilogue_block<kEpiMask[2]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 3: epilogue_block<kEpiMask[3]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 4: epilogue_block<kEpiMask[4]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 5: epilogue_block<kEpiMask[5]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 6: epilogue_block<kEpiMask[6]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 7: epilogue_block<kEpiMask[7]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 8: epilogue_block<kEpiMask[8]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 9: epilogue_block<kEpiMask[9]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 10: epilogue_block<kEpiMask[10]>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 1: missed = epilogue_block<kEpiMask[1], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 2: missed = epilogue_block<kEpiMask[2], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 3: missed = epilogue_block<kEpiMask[3], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 4: missed = epilogue_block<kEpiMask[4], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 5: missed = epilogue_block<kEpiMask[5], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 6: missed = epilogue_block<kEpiMask[6], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 7: missed = epilogue_block<kEpiMask[7], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 8: missed = epilogue_block<kEpiMask[8], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 9: missed = epilogue_block<kEpiMask[9], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 10: missed = epilogue_block<kEpiMask[10], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
           default: {
             const EpiParams Ed = E;
-            epilogue_block_dyn(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae);
+            missed = epilogue_block_dyn<kChain>(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae);
             break;
+          }
+        }
+      }
+      if (kChain) {
+        // completion signal: this warp's stores of the tile are ordered before the counter increment (warp barrier +
+        // gpu-scope fence by the signalling lane; the proxy fence covers consumers that read through TMA)
+        const int cb = problem_of<kChain>(G, tc.pi).cnt_base;
+        if (cb >= 0) {
+          __syncwarp();
+          if (lane == 0) {
+            int* c = reinterpret_cast<const ChainDev&>(G).counters + cb + pair_m;
+            asm volatile("fence.proxy.async.global;\n\tfence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(c) : "memory");
           }
         }
       }
@@ -773,6 +913,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_gr
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+  if (kChain && cta_rank == 0) {
+    // the last cluster to get here zeroes the completion counters for the next launch of this chain (every other
+    // cluster has finished all of its waits and signals)
+    __shared__ int s_last;
+    const ChainDev& CH = reinterpret_cast<const ChainDev&>(G);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(CH.exit_cnt, 1) == n_cl - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int i = threadIdx.x; i < CH.n_counters; i += kThreads) CH.counters[i] = 0;
+      if (threadIdx.x == 0) *CH.exit_cnt = 0;
+    }
   }
 }
 
@@ -812,76 +967,84 @@ static int encode_2d(EncodeTiledFn fn, CUtensorMap* map, const void* ptr, int ro
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Validate one group and build its device descriptor (tensor maps included).
+// Validate one problem and build its device descriptor (tensor maps included).
+static int build_problem(EncodeTiledFn fn, const LinksGemmProblem& s, GemmProblemDev& d) {
+  if (!s.A || !s.B || s.M < 1 || s.N < 1 || s.K < 1) return LINKS_E_ARG;
+  const bool a_mn = (s.flags & LINKS_GEMM_A_MN) != 0, b_mn = (s.flags & LINKS_GEMM_B_MN) != 0;
+  if (!aligned16(s.A) || !aligned16(s.B) || (s.lda & 7) || (s.ldb & 7)) return LINKS_E_ALIGN;
+  if (s.lda < (a_mn ? s.M : s.K) || s.ldb < (b_mn ? s.N : s.K)) return LINKS_E_ALIGN;
+  // small problems load smaller boxes: rows the MMA never needs are not fetched (or zero-filled) at all
+  const int a_rows = s.M >= BM ? BM : ((s.M + 7) & ~7), b_rows = s.N >= BN ? BN : ((s.N + 15) & ~15);
+  d.a_boxes = a_mn ? (s.M >= BM ? BM / 64 : (s.M + 63) / 64) : 1;
+  d.b_boxes = b_mn ? (b_rows / 2 + 63) / 64 : 1;       // per CTA: 64-wide slabs covering its half of the B tile
+  d.stage_tx = static_cast<uint32_t>((a_mn ? d.a_boxes * 64 : a_rows) * BK * 2 + (b_mn ? d.b_boxes * 64 : b_rows / 2) * BK * 2);
+  int rc = a_mn ? encode_2d(fn, &d.tmA, s.A, s.K, s.M, s.lda, 64, BK) : encode_2d(fn, &d.tmA, s.A, s.M, s.K, s.lda, BK, a_rows);
+  if (rc) return rc;
+  d.b_rows = b_rows;
+  rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, b_rows / 2);
+  if (rc) return rc;
+  d.M = s.M; d.N = s.N; d.K = s.K;
+  d.pairs_m = ((s.M + BM - 1) / BM + 1) / 2;
+  d.tiles_n = (s.N + BN - 1) / BN;
+  d.flags = s.flags;
+  if ((s.out && s.ld_out < s.N) || (s.mid && s.ld_mid < s.N)) return LINKS_E_ALIGN;
+  d.out = static_cast<__nv_bfloat16*>(s.out); d.ld_out = s.ld_out;
+  d.mid = static_cast<__nv_bfloat16*>(s.mid); d.ld_mid = s.ld_mid;
+  bool vec = true;
+  auto chk = [&](const void* p, int ld, int mult) {
+    if (p && (!aligned16(p) || (ld % mult) != 0)) vec = false;
+  };
+  chk(s.bias, 4, 4); chk(s.add0, s.ld_add0, 8); chk(s.add1, s.ld_add1, 8); chk(s.ymask, s.ld_ymask, 8);
+  chk(s.mid, s.ld_mid, 8); chk(s.out, s.ld_out, 8); chk(s.out_f32, s.ld_f32, 4);
+  d.vec_ok = vec ? 1 : 0;
+  {
+    uint32_t f = 0;
+    if (s.bias) f |= F_BIAS;
+    if (s.flags & LINKS_EPI_LEAKY_PRE) f |= F_LPRE;
+    if (s.flags & LINKS_EPI_RELU_PRE) f |= F_RPRE;
+    if (s.add0) f |= F_ADD0;
+    if (s.add1) f |= F_ADD1;
+    if (s.flags & LINKS_EPI_LEAKY_POST) f |= F_LPOST;
+    if (s.ymask) f |= F_YMASK;
+    if (s.mid) f |= F_MID;
+    if (s.bits) f |= F_BITS;
+    if (s.sign_out) f |= F_SIGN;
+    if (s.out) f |= F_OUT;
+    if (s.out_f32) f |= F_F32;
+    static const uint32_t host_masks[11] = {
+        0u, F_BIAS | F_OUT, F_BIAS | F_LPRE | F_OUT, F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,
+        F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT, F_YMASK | F_OUT, F_ADD0 | F_OUT,
+        F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT, F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,
+        F_YMASK | F_MID | F_BITS | F_OUT, F_F32};
+    d.epi_mode = 0;
+    for (int k = 1; k < 11; ++k) if (host_masks[k] == f) d.epi_mode = k;
+  }
+  d.ld_add0 = s.ld_add0; d.ld_add1 = s.ld_add1; d.ld_ymask = s.ld_ymask; d.ld_bits = s.ld_bits;
+  d.ld_sign = s.ld_sign; d.ld_f32 = s.ld_f32;
+  d.bias = s.bias;
+  d.add0 = static_cast<const __nv_bfloat16*>(s.add0);
+  d.add1 = static_cast<const __nv_bfloat16*>(s.add1);
+  d.ymask = static_cast<const __nv_bfloat16*>(s.ymask);
+  d.bits = s.bits;
+  d.sign_out = s.sign_out;
+  d.out_f32 = s.out_f32;
+  if (s.bits && s.ld_bits < (s.N + 31) / 32) return LINKS_E_RANGE;
+  if (s.sign_out && s.ld_sign < (s.N + 31) / 32) return LINKS_E_RANGE;
+  d.cnt_base = -1;
+  for (int k = 0; k < 3; ++k) { d.dep_base[k] = -1; d.dep_blocks[k] = 0; d.dep_need[k] = 0; }
+  return 0;
+}
+
+// Validate one group and build its device descriptor.
 static int build_group(EncodeTiledFn fn, const LinksGemmProblem* problems, int n_problems, GemmGroupDev& G) {
   memset(&G, 0, sizeof(G));
   int tiles = 0;
   for (int i = 0; i < n_problems; ++i) {
-    const LinksGemmProblem& s = problems[i];
     GemmProblemDev& d = G.p[i];
-    if (!s.A || !s.B || s.M < 1 || s.N < 1 || s.K < 1) return LINKS_E_ARG;
-    const bool a_mn = (s.flags & LINKS_GEMM_A_MN) != 0, b_mn = (s.flags & LINKS_GEMM_B_MN) != 0;
-    if (!aligned16(s.A) || !aligned16(s.B) || (s.lda & 7) || (s.ldb & 7)) return LINKS_E_ALIGN;
-    if (s.lda < (a_mn ? s.M : s.K) || s.ldb < (b_mn ? s.N : s.K)) return LINKS_E_ALIGN;
-    // small problems load smaller boxes: rows the MMA never needs are not fetched (or zero-filled) at all
-    const int a_rows = s.M >= BM ? BM : ((s.M + 7) & ~7), b_rows = s.N >= BN ? BN : ((s.N + 15) & ~15);
-    d.a_boxes = a_mn ? (s.M >= BM ? BM / 64 : (s.M + 63) / 64) : 1;
-    d.b_boxes = b_mn ? (b_rows / 2 + 63) / 64 : 1;       // per CTA: 64-wide slabs covering its half of the B tile
-    d.stage_tx = static_cast<uint32_t>((a_mn ? d.a_boxes * 64 : a_rows) * BK * 2 + (b_mn ? d.b_boxes * 64 : b_rows / 2) * BK * 2);
-    int rc = a_mn ? encode_2d(fn, &d.tmA, s.A, s.K, s.M, s.lda, 64, BK) : encode_2d(fn, &d.tmA, s.A, s.M, s.K, s.lda, BK, a_rows);
+    const int rc = build_problem(fn, problems[i], d);
     if (rc) return rc;
-    d.b_rows = b_rows;
-    rc = b_mn ? encode_2d(fn, &d.tmB, s.B, s.K, s.N, s.ldb, 64, BK) : encode_2d(fn, &d.tmB, s.B, s.N, s.K, s.ldb, BK, b_rows / 2);
-    if (rc) return rc;
-    d.M = s.M; d.N = s.N; d.K = s.K;
     d.tile_begin = tiles;
-    d.pairs_m = ((s.M + BM - 1) / BM + 1) / 2;
-    d.tiles_n = (s.N + BN - 1) / BN;
     tiles += d.pairs_m * d.tiles_n;
-    d.flags = s.flags;
-    if ((s.out && s.ld_out < s.N) || (s.mid && s.ld_mid < s.N)) return LINKS_E_ALIGN;
-    d.out = static_cast<__nv_bfloat16*>(s.out); d.ld_out = s.ld_out;
-    d.mid = static_cast<__nv_bfloat16*>(s.mid); d.ld_mid = s.ld_mid;
-    bool vec = true;
-    auto chk = [&](const void* p, int ld, int mult) {
-      if (p && (!aligned16(p) || (ld % mult) != 0)) vec = false;
-    };
-    chk(s.bias, 4, 4); chk(s.add0, s.ld_add0, 8); chk(s.add1, s.ld_add1, 8); chk(s.ymask, s.ld_ymask, 8);
-    chk(s.mid, s.ld_mid, 8); chk(s.out, s.ld_out, 8); chk(s.out_f32, s.ld_f32, 4);
-    d.vec_ok = vec ? 1 : 0;
-    {
-      uint32_t f = 0;
-      if (s.bias) f |= F_BIAS;
-      if (s.flags & LINKS_EPI_LEAKY_PRE) f |= F_LPRE;
-      if (s.flags & LINKS_EPI_RELU_PRE) f |= F_RPRE;
-      if (s.add0) f |= F_ADD0;
-      if (s.add1) f |= F_ADD1;
-      if (s.flags & LINKS_EPI_LEAKY_POST) f |= F_LPOST;
-      if (s.ymask) f |= F_YMASK;
-      if (s.mid) f |= F_MID;
-      if (s.bits) f |= F_BITS;
-      if (s.sign_out) f |= F_SIGN;
-      if (s.out) f |= F_OUT;
-      if (s.out_f32) f |= F_F32;
-      static const uint32_t host_masks[11] = {
-          0u, F_BIAS | F_OUT, F_BIAS | F_LPRE | F_OUT, F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,
-          F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT, F_YMASK | F_OUT, F_ADD0 | F_OUT,
-          F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT, F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,
-          F_YMASK | F_MID | F_BITS | F_OUT, F_F32};
-      d.epi_mode = 0;
-      for (int k = 1; k < 11; ++k) if (host_masks[k] == f) d.epi_mode = k;
-    }
-    d.ld_add0 = s.ld_add0; d.ld_add1 = s.ld_add1; d.ld_ymask = s.ld_ymask; d.ld_bits = s.ld_bits;
-    d.ld_sign = s.ld_sign; d.ld_f32 = s.ld_f32;
-    d.bias = s.bias;
-    d.add0 = static_cast<const __nv_bfloat16*>(s.add0);
-    d.add1 = static_cast<const __nv_bfloat16*>(s.add1);
-    d.ymask = static_cast<const __nv_bfloat16*>(s.ymask);
-    d.bits = s.bits;
-    d.sign_out = s.sign_out;
-    d.out_f32 = s.out_f32;
-    if (s.bits && s.ld_bits < (s.N + 31) / 32) return LINKS_E_RANGE;
-    if (s.sign_out && s.ld_sign < (s.N + 31) / 32) return LINKS_E_RANGE;
   }
   G.n_problems = n_problems;
   G.total_tiles = tiles;
@@ -898,9 +1061,36 @@ struct CacheEntry {
 constexpr int kCacheSize = 1024;
 static CacheEntry* g_cache = nullptr;
 static std::mutex g_cache_mu;
-static int g_num_sms = 0;
 static int g_gemm_max_ctas = 0;  // 0 = all SMs; data-parallel runs leave a few SMs to the NCCL kernels (links_gemm_set_max_ctas)
 static bool g_gemm_pdl = true;   // programmatic dependent launch between consecutive GEMM launches (env LINKS_GEMM_PDL=0 disables)
+// Per-device host state (one process may drive several devices): SM count + the kernels' shared-memory opt-in.
+constexpr int kMaxDevices = 64;
+static int g_dev_sms[kMaxDevices] = {0};
+
+// Caller holds g_cache_mu.  Returns the SM count of the current device (> 0) or a negative / CUDA error via *err.
+static int device_sms(int* err) {
+  *err = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { *err = static_cast<int>(e); return 0; }
+  if (dev < 0 || dev >= kMaxDevices) { *err = LINKS_E_RANGE; return 0; }
+  if (g_dev_sms[dev] == 0) {
+    if ((e = cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)) != cudaSuccess) {
+      *err = static_cast<int>(e);
+      return 0;
+    }
+    int sms = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) { *err = static_cast<int>(e); return 0; }
+    g_dev_sms[dev] = sms;
+    const char* pdl = getenv("LINKS_GEMM_PDL");
+    if (pdl != nullptr && pdl[0] == '0') g_gemm_pdl = false;
+  }
+  return g_dev_sms[dev];
+}
+static int max_clusters(int sms) { return (g_gemm_max_ctas > 0 && g_gemm_max_ctas < sms ? g_gemm_max_ctas : sms) / 2; }
+
+static unsigned long long g_gemm_launches = 0;   // launches of either flavour since load (links_gemm_launch_count)
 
 static uint64_t hash_bytes(const void* p, size_t n) {
   const unsigned char* b = static_cast<const unsigned char*>(p);
@@ -928,16 +1118,9 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return LINKS_E_DRIVER;
   std::lock_guard<std::mutex> lock(g_cache_mu);
-  if (g_num_sms == 0) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    int dev = 0, sms = 0;
-    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return static_cast<int>(e);
-    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return static_cast<int>(e);
-    g_num_sms = sms;
-    const char* pdl = getenv("LINKS_GEMM_PDL");
-    if (pdl != nullptr && pdl[0] == '0') g_gemm_pdl = false;
-  }
+  int derr = 0;
+  const int sms = device_sms(&derr);
+  if (derr) return derr;
   const size_t key_bytes = sizeof(LinksGemmProblem) * static_cast<size_t>(n_problems);
   const uint64_t h = hash_bytes(problems, key_bytes);
   if (g_cache == nullptr) g_cache = static_cast<CacheEntry*>(calloc(kCacheSize, sizeof(CacheEntry)));
@@ -950,8 +1133,9 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
     memcpy(ce.key, problems, key_bytes);
     ce.n = n_problems;
   }
-  const int max_cl = (g_gemm_max_ctas > 0 && g_gemm_max_ctas < g_num_sms ? g_gemm_max_ctas : g_num_sms) / 2;
+  const int max_cl = max_clusters(sms);
   const int grid = 2 * (ce.G.total_tiles < max_cl ? ce.G.total_tiles : max_cl);   // clusters of 2 CTAs
+  g_gemm_launches++;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -963,7 +1147,7 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
   attr[0].val.programmaticStreamSerializationAllowed = g_gemm_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_grouped_kernel, ce.G);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_kernel<false>, ce.G);
   if (le != cudaSuccess) return static_cast<int>(le);
   return links_launch_status();
 }

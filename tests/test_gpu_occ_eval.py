@@ -87,8 +87,6 @@ def test_eval_runner_vs_oracle(kind):
     assert abs(out["pa_mpjpe_batch"] - ref_batch) < 1.0, (out, ref_batch)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("LINKS_UNVALIDATED") != "1",
-                    reason="written after this round's GPU budget was spent: first GPU run pending (set LINKS_UNVALIDATED=1)")
 def test_occlusion_validator_vs_oracle():
     """Occlusion inference / validation (train_occlusion_models.py:316-509): drop-in modules + device metrics vs the same
     validator wired to the oracle networks and oracle metrics (tests/test_occ_assembly_cpu.py pins that one against the
