@@ -8,10 +8,15 @@ flow-sampling concat).  Weak scaling: every rank owns B poses; lifter gradients 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
 
-Prints ONE JSON line on rank 0 (see the task contract): value = poses/s with inputs resident in HBM (CUDA-graph
-replay), e2e = same through the public step API with pinned-host inputs copied H2D and losses read back D2H every
-step, roofline = the tcgen05 GEMM (dominant kernel) timed in isolation with CUDA events, cpu_baseline = the CPU
-oracle port on this box's host cores.
+Prints ONE JSON line on rank 0 (see the task contract):
+  value        poses/s with inputs resident in HBM (CUDA-graph replay of the merged LT+LR step)
+  e2e          same through the public step API with pinned-host inputs copied H2D and losses read back D2H every step
+  roofline     the tcgen05 GEMM (dominant kernel): every GEMM launch of one step timed alone with CUDA events
+  parity       first-step losses at THIS batch size vs the CPU oracle (tolerance 1e-3 relative)
+  cpu_baseline the CPU oracle port of the same step at the SAME batch on this box's host cores
+  configs      short driver-visible timings of BASELINE configs #1 (flow step B=256), #4 (occlusion step, 4096 poses
+               global) and #5 (sharded eval, 1.25 M poses per GPU, H2D included), each with its own roofline fraction
+  strong_scaling  the same lifter step at a FIXED global batch of 8192 (config #3 read as strong scaling)
 """
 import argparse
 import json
@@ -30,8 +35,7 @@ os.environ.setdefault("WANDB_MODE", "disabled")
 
 METRIC = "lifter_train_step_poses_per_sec"
 UNIT = "poses/s"
-# algorithmic FLOPs per DataLoader pose (SURVEY 8d / BASELINE.md 5): necessary work only
-FLOP_PER_POSE = {"lt": 0.560e9, "lr": 0.561e9}
+BODY = 1024 * 1024
 
 
 def gemm_flops_per_pose(kind):
@@ -41,14 +45,18 @@ def gemm_flops_per_pose(kind):
     tot = 0
     for n in nj:
         k = 2 * n
-        body = 1024 * 1024
-        full = k * 1024 + 14 * body + 1024 * n + 1024          # pass 1
-        pose = k * 1024 + 8 * body + 1024 * n                   # pass 2
+        full = k * 1024 + 14 * BODY + 1024 * n + 1024          # pass 1
+        pose = k * 1024 + 8 * BODY + 1024 * n                   # pass 2
         fwd = full + pose
-        dgrad = (14 * body + 1024 * n + 1024) + (8 * body + 1024 * n + k * 1024)
+        dgrad = (14 * BODY + 1024 * n + 1024) + (8 * BODY + 1024 * n + k * 1024)
         wgrad = full + pose
         tot += fwd + dgrad + wgrad
     return 2 * 2 * tot   # 2 rows per pose, 2 FLOP per MAC
+
+
+def lifter_pose_macs(n):
+    """MACs per row of the pose branch only (eval / occlusion use the lifters without the angle branch)."""
+    return 2 * n * 1024 + 8 * BODY + 1024 * n
 
 
 def load_peaks():
@@ -71,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -102,62 +110,75 @@ class ClockSampler:
 
 def make_weights():
     from links_b200.init import init_flow_params, init_lifter_params
-    nets = {"lt": [init_lifter_params(7, 11), init_lifter_params(10, 12)],
-            "lr": [init_lifter_params(11, 13), init_lifter_params(11, 14)]}
-    flows = {"lt": [init_flow_params(14, 41), init_flow_params(20, 42)],
-             "lr": [init_flow_params(22, 43), init_flow_params(22, 44)]}
+    nets = [init_lifter_params(7, 11), init_lifter_params(10, 12), init_lifter_params(11, 13), init_lifter_params(11, 14)]
+    flows = [init_flow_params(14, 41), init_flow_params(20, 42), init_flow_params(22, 43), init_flow_params(22, 44)]
     full = init_flow_params(34, 40)
     return nets, flows, full
+
+
+def make_inputs(B, rank, n_batches=2):
+    """Per-rank batches of synthetic poses + the step's random draws (host tensors)."""
+    import torch
+    from links_b200.synth import synth_poses
+    out = []
+    for i in range(n_batches):
+        x2d, _ = synth_poses(B, seed=1234 + 97 * i + rank)
+        gen = torch.Generator().manual_seed(1000 + 31 * i + rank)
+        out.append({"x": torch.from_numpy(x2d), "noise": torch.randn(B, 34, generator=gen),
+                    "eps_x": torch.randn(2 * B, generator=gen), "u_y": torch.rand(2 * B, generator=gen)})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle port of the same step on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def cpu_steps(batch, steps, warmup, seed=0):
+def cpu_steps(batch, steps, warmup, first_losses=False):
+    """LT + LR step of the CPU oracle (PyTorch fp32, all host cores) on `batch` poses: seconds per step, core count and
+    (optionally) the first step's losses on bench.py's own first batch (the `parity` check)."""
     import torch
-    from links_b200.synth import synth_poses
     from oracle import steps as OS
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nets, flows, full = make_weights()
-    pn = {k: [OS.params_require_grad(p) for p in v] for k, v in nets.items()}
-    opts = {k: OS.make_adam(v) for k, v in pn.items()}
-    x2d, _ = synth_poses(batch, seed=1234 + seed)
-    x = torch.from_numpy(x2d)
-    g = torch.Generator().manual_seed(seed)
-    times = []
+    pn = [OS.params_require_grad(p) for p in nets]
+    opts = OS.make_adam(pn)
+    data = make_inputs(batch, 0)
+    times, first = [], None
     for it in range(warmup + steps):
-        noise = torch.randn(batch, 34, generator=g)
-        eps_x, u_y = torch.randn(2 * batch, generator=g), torch.rand(2 * batch, generator=g)
+        d = data[0] if it == 0 else data[1]
         t0 = time.perf_counter()
-        u = OS.sample_poses(x, full, noise)
-        for kind, fn in (("lt", OS.lt_step), ("lr", OS.lr_step)):
-            for o in opts[kind]:
+        u = OS.sample_poses(d["x"], full, d["noise"])
+        losses = {}
+        for kind, fn, s0 in (("lt", OS.lt_step, 0), ("lr", OS.lr_step, 2)):
+            for o in opts[s0:s0 + 2]:
                 o.zero_grad()
-            out = fn(u, pn[kind][0], pn[kind][1], flows[kind][0], flows[kind][1], eps_x, u_y)
+            out = fn(u, pn[s0], pn[s0 + 1], flows[s0], flows[s0 + 1], d["eps_x"], d["u_y"])
             out["loss"].backward()
-            for o in opts[kind]:
+            for o in opts[s0:s0 + 2]:
                 o.step()
-            _ = out["loss"].item()
+            losses[kind] = {k: v.item() for k, v in out.items()}
         dt = time.perf_counter() - t0
+        if it == 0:
+            first = losses
         if it >= warmup:
             times.append(dt)
-    return sum(times) / len(times), cores
+    return sum(times) / max(len(times), 1), cores, (first if first_losses else None)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = args.cpu_batch
-    sec, cores = cpu_steps(batch, args.steps, args.warmup)
+    batch = args.batch
+    sec, cores, _ = cpu_steps(batch, args.steps, args.warmup)
     val = batch / sec
     sample = "oracle port (PyTorch CPU fp32), %d-pose batches (LT+LR step each), %d timed steps" % (batch, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "LT+LR lifter training step, B=%d poses/step (bounded CPU sample of the B=1024 "
-                                   "config)" % batch, "batch_per_step": batch},
+            "config": {"workload": "configs[1]: leg/torso + left/right lifter self-supervised training step, "
+                                   "B=%d poses per step (N=%d rows), 17 joints" % (batch, 2 * batch),
+                       "batch_per_gpu": batch, "global_batch": batch, "parallelism": "cpu"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -165,6 +186,132 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, world):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.world = torch, dist, world
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def __call__(self, fn, n):
+        """n calls of fn bracketed by barrier + synchronize, CUDA events on the launching stream, MAX over ranks (ms)."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+
+def rel_err(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+def extra_configs(args, timed, world, rank, pg, peaks):
+    """Driver-visible numbers for BASELINE configs #1, #4, #5 (short runs; each with its own roofline fraction)."""
+    import torch
+    from links_b200 import init as INIT
+    from links_b200.flowtrain import FlowTrainStep
+    from links_b200.occlusion import OCC_IN, OCC_NAMES, OCC_OUT, EvalRunner, OcclusionStep
+    from links_b200.synth import synth_poses
+    out = []
+    burst = peaks["bf16_burst"]
+    # ---- config #1: full-pose GLOW flow NLL fwd/bwd + Adam, batch 256 (train_full_pose_norm_flow.py:67-98); replicas
+    B1 = 256
+    ft = FlowTrainStep(34, INIT.init_flow_params(34, 40), B1, lr=2e-4)
+    x2d, _ = synth_poses(B1, seed=77 + rank)
+    ft.x.copy_(torch.from_numpy(x2d)); ft.noise.normal_()
+    for _ in range(3):
+        ft.step()
+    n1 = 20
+    ms = timed(ft.step, n1) / n1
+    # per data pose: sampling (fwd + rev = 2 subnet passes) on 1 row, NLL fwd + reversible bwd (3 passes) on 2 rows,
+    # parameter-gradient GEMMs (hidden recompute K=64 padded, dgrad, 2 wgrads) on 2 rows
+    macs_pass = 427040
+    flops1 = 2.0 * (2 * macs_pass + 2 * 3 * macs_pass + 2 * 8 * (64 * 1024 + 3 * 34 * 1024))
+    out.append({"config": "configs[0]: full-pose GLOW flow training step (sample, NLL fwd/bwd on [x ; s], Adam), B=256 per GPU, "
+                          "independent replicas",
+                "value": world * B1 / (ms * 1e-3), "unit": "poses/s", "ms_per_step": ms, "n_gpus": world,
+                "roofline": {"bound": "tensor", "achieved": flops1 * B1 / (ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                             "frac": flops1 * B1 / (ms * 1e-3) / 1e12 / burst,
+                             "note": "whole step; 512 rows = 4 row tiles of the flow kernel: latency-bound by construction "
+                                     "(8 coupling blocks x 3 passes run back to back per tile)"}})
+    del ft
+    # ---- config #4: occlusion-model training step, 4096 poses global (train_occlusion_models.py:144-314)
+    B4 = max(2, (4096 // world) // 2 * 2)
+    lifters = [INIT.init_lifter_params(7, 11), INIT.init_lifter_params(10, 12)]
+    preds = {n: INIT.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i) for i, n in enumerate(OCC_NAMES)}
+    oc = OcclusionStep(B4, lifters, preds, cfg={"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets}, process_group=pg)
+    x2d, _ = synth_poses(B4, seed=55 + rank)
+    oc.x.copy_(torch.from_numpy(x2d)); oc.u_y[0].uniform_(); oc.u_y[1].uniform_()
+    for _ in range(3):
+        oc.step()
+    n4 = 10
+    ms = timed(oc.step, n4) / n4
+    pred_macs = sum(OCC_IN[n] * 1024 + 6 * BODY + 1024 * OCC_OUT[n] for n in OCC_NAMES)
+    flops4 = 2.0 * (lifter_pose_macs(7) + lifter_pose_macs(10) + 3 * 3 * pred_macs)      # 3 rounds x (fwd, dgrad, wgrad)
+    out.append({"config": "configs[3]: occlusion-model training step (8 predictors, 3 rounds, Adam), global batch %d = %d per "
+                          "GPU, bf16 gradient all-reduce" % (B4 * world, B4),
+                "value": world * B4 / (ms * 1e-3), "unit": "poses/s", "ms_per_step": ms, "n_gpus": world,
+                "roofline": {"bound": "tensor", "achieved": flops4 * B4 / (ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
+                             "frac": flops4 * B4 / (ms * 1e-3) / 1e12 / burst, "note": "whole step incl. Adam / all-reduce"}})
+    del oc
+    # ---- config #5: sharded eval, 1.25 M poses per GPU (10 M over 8), pinned host -> H2D -> lift -> N-MPJPE / PA-MPJPE
+    n5, chunk = args.eval_poses, 65536
+    x2d, gt = synth_poses(chunk, seed=99 + rank)
+    reps = (n5 + chunk - 1) // chunk
+    hx, hg = torch.from_numpy(x2d).pin_memory(), torch.from_numpy(gt).pin_memory()       # one pinned chunk, re-sent
+    ev = EvalRunner("lr", [INIT.init_lifter_params(11, 13), INIT.init_lifter_params(11, 14)], chunk=chunk, process_group=pg)
+    dx = [torch.empty(chunk, 34, device="cuda") for _ in range(2)]
+    dg = [torch.empty(chunk, 51, device="cuda") for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    cp_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def eval_pass():
+        ev.reset()
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)
+        for i in range(reps):
+            b = i & 1
+            with torch.cuda.stream(copy_stream):
+                if i >= 2:
+                    copy_stream.wait_event(ev_done[b])
+                dx[b].copy_(hx, non_blocking=True); dg[b].copy_(hg, non_blocking=True)
+                cp_done[b].record(copy_stream)
+            main.wait_event(cp_done[b])
+            ev.run_chunk(dx[b], dg[b])
+            ev_done[b].record(main)
+    eval_pass()
+    ms = timed(eval_pass, 1)
+    res = ev.result()
+    n_done = reps * chunk
+    flops5 = 2.0 * 2 * lifter_pose_macs(11)
+    out.append({"config": "configs[4]: batched eval (lift + N-MPJPE + PA-MPJPE), %d poses per GPU in %d-pose chunks from pinned "
+                          "host memory (H2D inside the timed region, double-buffered), one final reduction" % (n_done, chunk),
+                "value": world * n_done / (ms * 1e-3), "unit": "poses/s", "ms_total": ms, "n_gpus": world,
+                "h2d_bytes": n_done * 85 * 4, "pa_mpjpe_mm": res["pa_mpjpe"], "n_mpjpe_mm": res["n_mpjpe"],
+                "roofline": {"bound": "tensor", "achieved": flops5 * n_done / (ms * 1e-3) / 1e12, "peak": burst,
+                             "unit": "TFLOP/s", "frac": flops5 * n_done / (ms * 1e-3) / 1e12 / burst,
+                             "note": "lifter GEMMs dominate (33.7 MFLOP per pose); the fused lift+score kernel moves "
+                                     "408 B per pose"}})
+    del ev
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     # Libraries (NCCL prints its version banner) write to stdout; the contract is ONE JSON line there.  Point fd 1 at
     # stderr for the whole run and keep the real stdout for the final line.
@@ -178,8 +325,8 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from links_b200 import _cabi
-    from links_b200.steps import LifterStep, StepGroup
-    from links_b200.synth import synth_poses
+    from links_b200 import mlp as MLP
+    from links_b200.steps import LifterStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,98 +340,62 @@ def run_gpu(args):
             os.environ.setdefault("NCCL_MIN_CTAS", str(args.nccl_ctas))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
-        if args.gemm_ctas > 0:
-            _cabi.lib().links_gemm_set_max_ctas(args.gemm_ctas)
+    timed = Timer(world)
     B = args.batch
     nets, flows, full = make_weights()
-    # one communicator per branch: the LT and LR all-reduces are independent and may run concurrently
-    pgs = {"lt": pg, "lr": pg}
-    if world > 1 and not args.shared_comm:
-        pgs["lr"] = dist.new_group(ranks=list(range(world)), backend="nccl")
-    cfg = {"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets}
-    steps = {k: LifterStep(k, B, nets[k], flows[k], full, cfg=cfg, process_group=pgs[k]) for k in ("lt", "lr")}
-    lt, lr = steps["lt"], steps["lr"]
-
-    # ---- inputs: per-rank shard of the global batch, pinned on the host for the e2e arm
-    x2d, _ = synth_poses(B, seed=1234 + rank)
-    gen = torch.Generator().manual_seed(1000 + rank)
-    host = {"x": torch.from_numpy(x2d).pin_memory(), "noise": torch.randn(B, 34, generator=gen).pin_memory(),
-            "eps_x": torch.randn(2 * B, generator=gen).pin_memory(), "u_y": torch.rand(2 * B, generator=gen).pin_memory()}
-    host_losses = torch.zeros(2, 8).pin_memory()
-    h2d_bytes = sum(t.numel() * 4 for t in host.values())
-    d2h_bytes = host_losses.numel() * 4
-
-    def upload():
-        for s in (lt, lr):
-            s.x.copy_(host["x"], non_blocking=True); s.noise.copy_(host["noise"], non_blocking=True)
-            s.eps_x.copy_(host["eps_x"], non_blocking=True); s.u_y.copy_(host["u_y"], non_blocking=True)
-
-    def download():
-        host_losses[0].copy_(lt.losses, non_blocking=True)
-        host_losses[1].copy_(lr.losses, non_blocking=True)
-
-    group = StepGroup([lt, lr])      # the two independent lifter steps run as parallel branches of one graph
-
-    def one_step():
-        if args.serial:
-            lt.step()
-            lr.step()
-        else:
-            group.step()
+    cfg = {"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets, "prefetch_sample": not args.no_prefetch,
+           "nccl_ctas": args.nccl_ctas}
 
     def stage(msg):
         if args.verbose:
             print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
-    # ---- count launches of one eager step (also serves as warm-up / lazy init)
-    stage("built steps")
-    upload()
+    step = LifterStep("both", B, nets, flows, full, cfg=cfg, process_group=pg)
+    data = make_inputs(B, rank)
+    host = [{k: v.pin_memory() for k, v in d.items()} for d in data]
+    host_losses = torch.zeros(2, 8).pin_memory()
+    h2d_bytes = sum(t.numel() * 4 for t in host[0].values())
+    d2h_bytes = host_losses.numel() * 4
+
+    def upload(i):
+        """Sampling inputs of the NEXT step + rotation draws of THIS step (sampling runs one step ahead)."""
+        nxt = host[1]
+        cur = host[0] if i == 0 else host[1]
+        src_s = nxt if step.prefetch else cur
+        step.x.copy_(src_s["x"], non_blocking=True); step.noise.copy_(src_s["noise"], non_blocking=True)
+        step.eps_x.copy_(cur["eps_x"], non_blocking=True); step.u_y.copy_(cur["u_y"], non_blocking=True)
+
+    def download():
+        for i, k in enumerate(step.K):
+            host_losses[i].copy_(k.losses, non_blocking=True)
+
+    # ---- first step from fresh weights, eager: parity sample + launch count (also builds every plan)
+    stage("built step")
+    if step.prefetch:
+        step.x.copy_(host[0]["x"]); step.noise.copy_(host[0]["noise"])
+        step.prime()
+    upload(0)
     counter = _cabi.install_launch_counter()
-    one_step()
+    step.step()
     launches_per_step = counter.stop()
+    gemm_launches_per_step = counter.gemm
     torch.cuda.synchronize()
+    first_losses = step.loss_dict()
     stage("first eager step done")
 
-    # ---- capture the whole step in a CUDA graph (falls back to eager launches if capture is unavailable)
-    side = torch.cuda.Stream()
+    # ---- capture the whole step in a CUDA graph
     graph = None
+    upload(1)
     if not args.no_graph:
         try:
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                one_step()
-                side.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    one_step()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = g
+            step.capture(warmup=1)
+            graph = step.graph
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print("[bench] CUDA graph capture failed (%s); timing eager launches" % e, file=sys.stderr)
             graph = None
-    run = (lambda: graph.replay()) if graph is not None else one_step
+    run = (lambda: graph.replay()) if graph is not None else step.step
     stage("graph captured: %s" % (graph is not None))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms
 
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W):
@@ -299,30 +410,40 @@ def run_gpu(args):
 
     # ---- end-to-end: pinned host inputs -> H2D, step, losses -> D2H, every step
     def e2e_step():
-        upload()
+        upload(1)
         run()
         download()
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, K)
-    final_losses = {"lt": lt.loss_dict(), "lr": lr.loss_dict()}
+    final_losses = step.loss_dict()
 
-    # ---- roofline of the dominant kernel (tcgen05 grouped GEMM): all GEMM launches of one step, timed alone
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): every GEMM launch of one step, timed alone
+    m = step.mlp
+    plans = [m.forward_ops(0), m.forward_ops(1), m.backward_ops(1, need_input_grad=True),
+             m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=world > 1)]
+    if MLP.USE_CHAIN:
+        gemm_ops = [op for plan in plans for op in plan if hasattr(op, "plan")]
+        sim = {"chain_sim_units": [float(op.plan.sim_units) for op in gemm_ops],
+               "chain_ideal_units": [float(op.plan.ideal_units) for op in gemm_ops],
+               "chain_tiles": [int(op.plan.total_tiles) for op in gemm_ops]}
+    else:
+        plans[3] = m.backward_plan(0, False) + m.wgrad_plan()[0::2]
+        gemm_ops, sim = [op for plan in plans for op in plan if not isinstance(op, tuple)], {}
+
     def gemm_only():
-        for s in (lt, lr):
-            m = s.mlp
-            for plan in (m.forward_plan(0), m.forward_plan(1), m.backward_plan(1, True), m.backward_plan(0, False)):
-                m.run(plan)
-            m.run(m.wgrad_plan()[0::2])          # the GEMM launches of every bucket (odd entries: bias column sums)
+        for op in gemm_ops:
+            op()
     counter = _cabi.install_launch_counter()
     gemm_only()
-    n_gemm_launches = counter.stop()
+    counter.stop()
+    n_gemm_launches = counter.gemm
     for _ in range(3):
         gemm_only()
     ms_gemm = timed(gemm_only, K) / K
     peaks = load_peaks()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
     gemm_flops = (gemm_flops_per_pose("lt") + gemm_flops_per_pose("lr")) * B
@@ -331,8 +452,49 @@ def run_gpu(args):
     ms_step = ms_total / K
     value = world * B / (ms_step * 1e-3)
     e2e_value = world * B / (ms_e2e / K * 1e-3)
+
+    # ---- the other BASELINE configs and the strong-scaling reading of config #3 (short runs)
+    del graph
+    step.graph = None
+    extras, strong = [], None
+    if not args.skip_extra:
+        stage("extra configs")
+        del step, m, plans, gemm_ops
+        torch.cuda.empty_cache()
+        Bs = max(2, (8192 // world) // 2 * 2)
+        st2 = LifterStep("both", Bs, nets, flows, full, cfg=cfg, process_group=pg)
+        d2 = make_inputs(Bs, rank, n_batches=1)[0]
+        st2.x.copy_(d2["x"]); st2.noise.copy_(d2["noise"]); st2.eps_x.copy_(d2["eps_x"]); st2.u_y.copy_(d2["u_y"])
+        if st2.prefetch:
+            st2.prime()
+        st2.capture(warmup=2)
+        for _ in range(3):
+            st2.replay()
+        ks = 10
+        ms_s = timed(st2.replay, ks) / ks
+        strong = {"global_batch": Bs * world, "batch_per_gpu": Bs, "n_gpus": world, "ms_per_step": ms_s,
+                  "value": Bs * world / (ms_s * 1e-3), "unit": UNIT,
+                  "gemm_tflops_in_step": (gemm_flops_per_pose("lt") + gemm_flops_per_pose("lr")) * Bs / (ms_s * 1e-3) / 1e12}
+        st2.graph = None
+        del st2
+        torch.cuda.empty_cache()
+        extras = extra_configs(args, timed, world, rank, pg, peaks)
+
     if rank == 0:
-        cpu_sec, cores = cpu_steps(args.cpu_batch, 3, 1) if not args.skip_cpu else (None, os.cpu_count())
+        parity, cpu_base = None, None
+        if not args.skip_cpu:
+            cpu_sec, cores, ref_first = cpu_steps(B, 3, 1, first_losses=True)
+            worst, per = 0.0, {}
+            for kind in ("lt", "lr"):
+                for k, v in first_losses[kind].items():
+                    e = rel_err(v, ref_first[kind][k])
+                    per["%s.%s" % (kind, k)] = {"gpu": v, "oracle": ref_first[kind][k], "rel_err": e}
+                    worst = max(worst, e)
+            parity = {"what": "first-step losses (fresh weights) of the LT and LR steps at B=%d vs the CPU oracle (fp32)" % B,
+                      "tolerance_rel": 1e-3, "max_rel_err": worst, "ok": bool(worst <= 1e-3), "losses": per}
+            cpu_base = {"value": B / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), 3 timed "
+                                  "steps after 1 warm-up" % B}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -340,9 +502,12 @@ def run_gpu(args):
             "config": {"workload": "configs[1]: leg/torso + left/right lifter self-supervised training step, "
                                    "B=%d poses per GPU (N=%d rows), 17 joints" % (B, 2 * B),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "cuda_graph": graph is not None,
-                       "branches": "LT and LR steps serial on one stream" if args.serial else
-                                   "LT and LR steps as parallel branches (2 streams) of one CUDA graph",
+                       "cuda_graph": not args.no_graph,
+                       "step": "LT and LR steps merged: one 4-network engine (every layer of both in the same GEMM launches), "
+                               "%s GEMM launches per step, sampling flow evaluated once and %s" % (
+                                   gemm_launches_per_step, "prefetched one step ahead" if not args.no_prefetch else "inline"),
+                       "gemm_mode": "chain (one persistent kernel per pass, tile-level dependencies)" if MLP.USE_CHAIN
+                                    else "layer-by-layer grouped launches",
                        "l2_policy": "no explicit flush: each step streams ~%.1f GB of activations/weights/gradients, "
                                     "far above the 126 MB L2" % (2 * 2048 * 1024 * 2 * 2 * 60 * (B / 1024) / 1e9),
                        "operands": "bf16 operands + bf16-stored activations, fp32 accumulate / master weights / losses",
@@ -351,26 +516,31 @@ def run_gpu(args):
                        "final_losses": final_losses},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
-                         "traffic_note": "mean dram read+write bytes per GEMM launch from the ncu --set full capture in "
-                                         "profiles/ (B=1024 config); algorithmic operand bytes of a 4-problem launch: 24 MB",
-                         "flops_per_launch": gemm_flops / n_gemm_launches,
-                         "us_per_launch": ms_gemm * 1e3 / n_gemm_launches,
-                         "kernel": "links::gemm_grouped_kernel (tcgen05/TMEM/TMA), %d launches per step timed in "
-                                   "isolation" % n_gemm_launches,
-                         "ms_per_step_gemm_only": ms_gemm, "flops_per_step": gemm_flops,
-                         "peak_source": "%s cuBLAS bf16 burst (kernel timed alone)" % peaks["source"]},
-            "cpu_baseline": None if cpu_sec is None else {
-                "value": args.cpu_batch / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches, 3 timed steps" % args.cpu_batch},
+            "roofline": dict({"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                              "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
+                              "traffic_note": "traffic = mean dram read+write bytes per GEMM launch from this round's ncu "
+                                              "--set full capture (profiles/r02_gemm_traffic.json; null until captured); "
+                                              "algorithmic operand bytes: %.1f MB per (2048 x 1024 x 1024) layer problem "
+                                              "(A, W, out in bf16)" % ((2048 * 1024 * 2 * 2 + 1024 * 1024 * 2) / 1e6),
+                              "flops_per_launch": gemm_flops / n_gemm_launches,
+                              "us_per_launch": ms_gemm * 1e3 / n_gemm_launches,
+                              "launches_per_step": n_gemm_launches,
+                              "kernel": "links::gemm_kernel<%s> (tcgen05 cta_group::2 / TMEM / TMA), all %d GEMM launches of "
+                                        "one step timed in isolation" % ("true" if MLP.USE_CHAIN else "false", n_gemm_launches),
+                              "ms_per_step_gemm_only": ms_gemm, "flops_per_step": gemm_flops,
+                              "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
+                              "peak_source": "%s cuBLAS bf16 burst (kernel timed alone)" % peaks["source"]}, **sim),
+            "parity": parity,
+            "cpu_baseline": cpu_base,
+            "strong_scaling": strong,
+            "configs": extras,
         }
         emit(json.dumps(line))
     if world > 1:
         # captured graphs hold NCCL work; drop them before the communicator goes away.  Tearing the process group down
         # with captured collectives alive was observed to hang on exit, so leave without running destructors.
-        graph = None
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
@@ -384,18 +554,18 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1024, help="poses per GPU per step")
-    ap.add_argument("--cpu-batch", type=int, default=256, help="poses per step of the bounded CPU sample")
     ap.add_argument("--impl", default="links_b200", choices=["links_b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="evaluate the sampling flow inside the step instead of one step ahead")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--dp-buckets", type=int, default=2, help="gradient buckets per network set under data parallelism")
-    ap.add_argument("--shared-comm", action="store_true", help="one NCCL communicator for both branches")
     ap.add_argument("--nccl-ctas", type=int, default=0, help="CTAs (SMs) the NCCL all-reduce kernels may use (0: NCCL default)")
     ap.add_argument("--gemm-ctas", type=int, default=-1, help="GEMM grid cap under data parallelism (<= 0: no cap)")
     ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"],
                     help="dtype of the data-parallel gradient all-reduce (bf16 = compressed buckets)")
-    ap.add_argument("--serial", action="store_true", help="run the LT and LR steps back to back on one stream")
+    ap.add_argument("--eval-poses", type=int, default=1_250_000, help="poses per GPU of the config #5 eval run")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-extra", action="store_true", help="only the headline config (no configs[] / strong_scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

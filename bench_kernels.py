@@ -105,7 +105,7 @@ def main():
     m2.abs_()
     step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
     t = timed(lambda: L.links_adam_step(p.data_ptr(), g.data_ptr(), m1.data_ptr(), m2.data_ptr(), n, 2e-4, 0.9, 0.999, 1e-8,
-                                        1e-5, 0, step_dev.data_ptr(), 1.0, st))
+                                        1e-5, 0, step_dev.data_ptr(), 1.0, None, st))
     rec("adam_kernel", 28, n, t, "16 B read + 12 B written per parameter (the bf16 shadow refresh is a separate launch)")
     del p, g, m1, m2
     torch.cuda.empty_cache()

@@ -42,6 +42,8 @@ extern "C" {
 int links_abi_version(void);
 /* 1 if the library was built for sm_100a and the current device is CC 10.x, else 0. */
 int links_device_ok(void);
+/* Kernels launched through this library since it was loaded (every entry point counts its own launches). */
+size_t links_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Grouped GEMM with fused epilogue (tcgen05 / TMEM / TMA).   D = epi(A[M,K] * B[N,K]^T)
@@ -89,6 +91,42 @@ typedef struct LinksGemmProblem {
 } LinksGemmProblem;
 
 int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream);
+
+/* Chain launch: a whole DEPENDENT sequence of grouped GEMMs -- all layers of a lifter forward pass (reference
+ * utils/models_def.py:133-152: upscale -> res_common -> res_pose1..3 / res_angle1..3 -> heads, for several networks at
+ * once) or of its autograd backward (dgrad chain + weight gradients) -- as ONE persistent kernel.  Tiles of layer l+1
+ * start as soon as the tiles of layer l that produce their operand rows have completed (completion counters in global
+ * memory), so kernel setup / TMEM allocation / pipeline fill are paid once per pass and the epilogue of one layer
+ * overlaps the main loop of the next.  Same arithmetic as links_gemm_grouped, problem by problem.
+ *   level        problems with equal level are independent of each other; their tiles are interleaved row block by
+ *                row block.  Levels must ascend along every dependency.
+ *   dep[0..2]    index of the EARLIER problem of the chain that writes this problem's [A operand, add0, add1] (out /
+ *                mid / out_f32 of that problem), or -1 when the operand comes from outside the chain.  A dependency is
+ *                row-block-wise: rows [256 i, 256 i + 256) of the consumer need the same rows of the producer (equal
+ *                M required) -- unless bit d of dep_all_rows is set: the operand is contracted over ALL rows of the
+ *                producer (an A_MN operand: weight gradients).
+ * The workspace (links_gemm_chain_ws_bytes, 256-byte aligned device memory owned by the caller) holds descriptors,
+ * schedule and counters; links_gemm_chain_build fills it (host work + one synchronous copy: call it outside stream
+ * capture), links_gemm_chain_run launches (capturable).  One plan must not run concurrently with itself. */
+#define LINKS_MAX_CHAIN_PROBLEMS 512
+typedef struct LinksChainProblem {
+  LinksGemmProblem g;
+  int level;
+  int dep[3];
+  int dep_all_rows;
+} LinksChainProblem;
+typedef struct LinksGemmChainPlan {
+  void* ws; void* probs; void* sched; void* sched_cnt; void* counters;
+  int grid, n_counters, sched_ld, n_problems, total_tiles;
+  float sim_units;     /* makespan of the host's schedule simulation, in 64-deep k-block units (~0.44 us) */
+  float ideal_units;   /* sum of the main loops / clusters: the dependency- and epilogue-free bound */
+} LinksGemmChainPlan;
+size_t links_gemm_chain_ws_bytes(const LinksChainProblem* problems, int n_problems);
+int links_gemm_chain_build(const LinksChainProblem* problems, int n_problems, void* ws_dev, size_t ws_bytes,
+                           LinksGemmChainPlan* plan, void* stream);
+int links_gemm_chain_run(const LinksGemmChainPlan* plan, void* stream);
+/* Number of GEMM kernel launches (grouped + chain) issued through this library since it was loaded. */
+size_t links_gemm_launch_count(void);
 /* Cap the persistent grid of links_gemm_grouped at n CTAs (0 = one per SM).  Data-parallel runs leave a few SMs free so
  * that the concurrently running NCCL all-reduce kernels never push GEMM CTAs into a second wave.  Returns the old cap. */
 int links_gemm_set_max_ctas(int n);
@@ -136,17 +174,19 @@ int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* str
  * The step number t (bias correction) is `step` (>= 1), or, when step_dev != NULL, *step_dev + 1 read on the
  * device; *step_dev is then incremented after the update (unless step == -1: used when one optimiser step is issued as
  * several per-bucket launches), so a captured CUDA graph replays correctly.
- * Gradients are multiplied by grad_scale first (1/world_size after a SUM all-reduce). */
+ * Gradients are multiplied by grad_scale first (1/world_size after a SUM all-reduce).
+ * lr_dev (may be NULL): when given, the learning rate is read from *lr_dev on the device instead of `lr`, so that a
+ * captured CUDA graph follows the ExponentialLR schedule (train_leg_torso_lifter.py:116-121) without re-capture. */
 int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                    int* step_dev, float grad_scale, void* stream);
+                    int* step_dev, float grad_scale, const float* lr_dev, void* stream);
 
 /* Data-parallel gradient compression: grad_bf16[i] = bf16(grad[i]) before the NCCL all-reduce (half the NVLink
  * bytes), and the Adam step that consumes the reduced bf16 gradients directly (same arithmetic otherwise). */
 int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream);
 int links_adam_step_g16(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, size_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                        int* step_dev, float grad_scale, void* stream);
+                        int* step_dev, float grad_scale, const float* lr_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Geometry + losses (train_leg_torso_lifter.py:153-272, train_left_right_lifter.py:150-423)

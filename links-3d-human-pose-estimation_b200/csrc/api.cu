@@ -10,7 +10,10 @@
 
 using namespace links;
 
+unsigned long long g_links_kernel_launches = 0;
+
 extern "C" __attribute__((visibility("default"))) int links_abi_version(void) { return LINKS_ABI_VERSION; }
+extern "C" __attribute__((visibility("default"))) size_t links_launch_count(void) { return static_cast<size_t>(g_links_kernel_launches); }
 
 extern "C" __attribute__((visibility("default"))) int links_device_ok(void) {
   int dev = 0;
@@ -66,7 +69,7 @@ extern "C" __attribute__((visibility("default"))) int links_colsum_bf16_batched(
   const int rows_per_block = 256;
   dim3 grid((maxN + 31) / 32, n_items, (maxM + rows_per_block - 1) / rows_per_block);
   colsum_batched_kernel<<<grid, dim3(32, 8), 0, s>>>(B, rows_per_block);
-  return links_launch_status();
+  return links_launch_status(2);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_cast_weight(const float* W, int N, int K, void* W_bf16, int ldw, void* WT_bf16, int ldwt,
@@ -98,30 +101,31 @@ extern "C" __attribute__((visibility("default"))) int links_cast_weight_batched(
 
 template <typename GradT>
 static int adam_launch(float* param, const GradT* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
-                       float beta2, float eps, float weight_decay, int step, int* step_dev, float grad_scale, void* stream) {
+                       float beta2, float eps, float weight_decay, int step, int* step_dev, float grad_scale, const float* lr_dev,
+                       void* stream) {
   LINKS_CHECK_PTR(param); LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(exp_avg); LINKS_CHECK_PTR(exp_avg_sq);
   if (n == 0 || (step_dev == nullptr && step < 1)) return LINKS_E_RANGE;
   const int threads = 256;
   size_t blocks = (n + threads - 1) / threads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<GradT><<<static_cast<int>(blocks), threads, 0, links_stream(stream)>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev, step, grad_scale);
+      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step_dev, step, grad_scale, lr_dev);
   if (step_dev != nullptr && step >= 0) adam_incr_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev);
-  return links_launch_status();
+  return links_launch_status(step_dev != nullptr && step >= 0 ? 2 : 1);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step, int* step_dev,
-                               float grad_scale, void* stream) {
+                               float grad_scale, const float* lr_dev, void* stream) {
   return adam_launch<float>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, step_dev,
-                            grad_scale, stream);
+                            grad_scale, lr_dev, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_adam_step_g16(float* param, const void* grad_bf16, float* exp_avg, float* exp_avg_sq, size_t n,
                                    float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                                   int* step_dev, float grad_scale, void* stream) {
+                                   int* step_dev, float grad_scale, const float* lr_dev, void* stream) {
   return adam_launch<__nv_bfloat16>(param, static_cast<const __nv_bfloat16*>(grad_bf16), exp_avg, exp_avg_sq, n, lr, beta1,
-                                    beta2, eps, weight_decay, step, step_dev, grad_scale, stream);
+                                    beta2, eps, weight_decay, step, step_dev, grad_scale, lr_dev, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream) {

@@ -162,7 +162,9 @@ __global__ void grad_compress_bf16_kernel(const float* __restrict__ g, __nv_bflo
 template <typename GradT>
 __global__ void adam_kernel(float* __restrict__ p, const GradT* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            const int* __restrict__ step_dev, int step_host, float grad_scale) {
+                            const int* __restrict__ step_dev, int step_host, float grad_scale,
+                            const float* __restrict__ lr_dev) {
+  if (lr_dev != nullptr) lr = *lr_dev;      // device-side learning rate: graph replays follow the scheduler
   // step number t: host value, or (completed steps on device) + 1 so that a captured CUDA graph replays correctly
   const int t = step_dev != nullptr ? (*step_dev + 1) : step_host;
   const float bc1 = 1.f - powf(b1, static_cast<float>(t));

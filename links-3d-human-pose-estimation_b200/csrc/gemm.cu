@@ -23,7 +23,9 @@
 // strided): dgrad reads W itself as an MN-major B operand and wgrad reads the row-major activations / gradients as
 // MN-major A and B, so no transposed copies of weights or activations are ever written.
 #include <cuda.h>
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -1151,3 +1153,254 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_grouped(const L
   if (le != cudaSuccess) return static_cast<int>(le);
   return links_launch_status();
 }
+
+// ----------------------------------------------------------------------------------------------
+// Chain launches (host side): descriptors + dependency counters + a per-cluster tile schedule in the caller's workspace
+// ----------------------------------------------------------------------------------------------
+namespace links {
+
+struct ChainLayout {
+  size_t off_probs, off_sched, off_cnt, off_counters, total;
+  int n_cl, sched_ld, n_counters, total_tiles;
+};
+
+static size_t rup256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+struct ChainTile { int pi, tm, tn; };
+
+// Tiles in execution order: levels ascending; inside a level row block by row block, the problems of the level side
+// by side, then the N tiles -- the producers of a row block finish together and a consumer of level l+1 finds the same
+// distance (one level's worth of tiles) to its producers wherever it sits.
+static void chain_tile_order(const LinksChainProblem* problems, const GemmProblemDev* d, int n, std::vector<ChainTile>& tiles) {
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return problems[a].level < problems[b].level; });
+  size_t i0 = 0;
+  while (i0 < order.size()) {
+    size_t i1 = i0;
+    int max_pairs = 0;
+    while (i1 < order.size() && problems[order[i1]].level == problems[order[i0]].level) {
+      max_pairs = std::max(max_pairs, d[order[i1]].pairs_m);
+      ++i1;
+    }
+    for (int tm = 0; tm < max_pairs; ++tm)
+      for (size_t j = i0; j < i1; ++j) {
+        const int pi = order[j];
+        if (tm >= d[pi].pairs_m) continue;
+        for (int tn = 0; tn < d[pi].tiles_n; ++tn) tiles.push_back({pi, tm, tn});
+      }
+    i0 = i1;
+  }
+}
+
+static int chain_prepare(const LinksChainProblem* problems, int n, std::vector<GemmProblemDev>& d, bool encode) {
+  if (problems == nullptr || n < 1 || n > LINKS_MAX_CHAIN_PROBLEMS) return LINKS_E_ARG;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return LINKS_E_DRIVER;
+  d.assign(n, GemmProblemDev());
+  for (int i = 0; i < n; ++i) {
+    memset(&d[i], 0, sizeof(GemmProblemDev));
+    if (encode) {
+      const int rc = build_problem(fn, problems[i].g, d[i]);
+      if (rc) return rc;
+    } else {
+      const LinksGemmProblem& g = problems[i].g;
+      if (g.M < 1 || g.N < 1 || g.K < 1) return LINKS_E_ARG;
+      d[i].pairs_m = ((g.M + BM - 1) / BM + 1) / 2;
+      d[i].tiles_n = (g.N + BN - 1) / BN;
+      d[i].K = g.K;
+    }
+    if (d[i].pairs_m > 2047 || d[i].tiles_n > 2047) return LINKS_E_RANGE;
+    for (int k = 0; k < 3; ++k) {
+      const int dp = problems[i].dep[k];
+      if (dp >= i) return LINKS_E_RANGE;                       // producers come first: the chain is topologically ordered
+      if (dp >= 0 && problems[dp].level >= problems[i].level) return LINKS_E_RANGE;
+    }
+  }
+  return 0;
+}
+
+static int chain_layout(const LinksChainProblem* problems, const std::vector<GemmProblemDev>& d, int n, int sms, ChainLayout& L) {
+  std::vector<char> is_dep(n, 0);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) if (problems[i].dep[k] >= 0) is_dep[problems[i].dep[k]] = 1;
+  int counters = 0, tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    if (is_dep[i]) counters += d[i].pairs_m;
+    tiles += d[i].pairs_m * d[i].tiles_n;
+  }
+  const int max_cl = max_clusters(sms);
+  L.n_cl = tiles < max_cl ? tiles : max_cl;
+  L.total_tiles = tiles;
+  L.n_counters = counters + 1;                                  // + the exit counter (last word)
+  L.sched_ld = tiles;                                           // upper bound; the real maximum is known after scheduling
+  L.off_probs = 0;
+  L.off_sched = rup256(sizeof(GemmProblemDev) * static_cast<size_t>(n));
+  // worst-case schedule length per cluster is bounded below once the schedule exists; reserve 2x the mean + slack
+  const size_t per = static_cast<size_t>((tiles + L.n_cl - 1) / L.n_cl) * 2 + 8;
+  L.sched_ld = static_cast<int>(per);
+  L.off_cnt = L.off_sched + rup256(per * L.n_cl * 4);
+  L.off_counters = L.off_cnt + rup256(static_cast<size_t>(L.n_cl) * 4);
+  L.total = L.off_counters + rup256(static_cast<size_t>(L.n_counters) * 4);
+  return 0;
+}
+
+}  // namespace links
+
+extern "C" __attribute__((visibility("default"))) size_t links_gemm_chain_ws_bytes(const LinksChainProblem* problems, int n_problems) {
+  using namespace links;
+  std::vector<GemmProblemDev> d;
+  if (chain_prepare(problems, n_problems, d, false)) return 0;
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  int derr = 0;
+  const int sms = device_sms(&derr);
+  if (derr) return 0;
+  ChainLayout L;
+  chain_layout(problems, d, n_problems, sms, L);
+  return L.total;
+}
+
+extern "C" __attribute__((visibility("default"))) int links_gemm_chain_build(const LinksChainProblem* problems, int n_problems, void* ws_dev,
+                                                                            size_t ws_bytes, LinksGemmChainPlan* plan, void* stream) {
+  using namespace links;
+  if (ws_dev == nullptr || plan == nullptr) return LINKS_E_ARG;
+  if (reinterpret_cast<uintptr_t>(ws_dev) & 255u) return LINKS_E_ALIGN;
+  std::vector<GemmProblemDev> d;
+  int rc = chain_prepare(problems, n_problems, d, true);
+  if (rc) return rc;
+  const int n = n_problems;
+  int sms;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int derr = 0;
+    sms = device_sms(&derr);
+    if (derr) return derr;
+  }
+  ChainLayout L;
+  chain_layout(problems, d, n, sms, L);
+  if (ws_bytes < L.total) return LINKS_E_RANGE;
+  // ---- completion counters and dependencies
+  {
+    std::vector<char> is_dep(n, 0);
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) if (problems[i].dep[k] >= 0) is_dep[problems[i].dep[k]] = 1;
+    int c = 0;
+    for (int i = 0; i < n; ++i) if (is_dep[i]) { d[i].cnt_base = c; c += d[i].pairs_m; }
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        const int dp = problems[i].dep[k];
+        if (dp < 0) continue;
+        const bool all_rows = ((problems[i].dep_all_rows >> k) & 1) != 0;
+        if (!all_rows && d[dp].pairs_m != d[i].pairs_m) return LINKS_E_RANGE;     // row-block dependencies need equal M tiling
+        if (all_rows && k != 0) return LINKS_E_RANGE;                             // only the A operand is ever contracted over rows
+        d[i].dep_base[k] = d[dp].cnt_base;
+        d[i].dep_blocks[k] = all_rows ? d[dp].pairs_m : 0;
+        d[i].dep_need[k] = 2 * kEpiWarps * d[dp].tiles_n;
+      }
+  }
+  // ---- tile order and the per-cluster schedule (list scheduling on a simple cost model; 1 unit = one 64-deep k-block
+  //      of a 256x256 pair tile ~ 0.44 us): every cluster's list ascends in the global tile order, so the lowest
+  //      unfinished tile is always at the head of some cluster's list and its producers (lower tiles) are done or running
+  std::vector<ChainTile> tiles;
+  chain_tile_order(problems, d.data(), n, tiles);
+  const int T = static_cast<int>(tiles.size()), n_cl = L.n_cl;
+  std::vector<std::vector<uint32_t>> lists(n_cl);
+  {
+    const double kEpi = 11.0, kSignal = 3.0, kMinMain = 2.0;
+    std::vector<double> mma_free(n_cl, 0.0), epi_free(n_cl, 0.0), epi_prev(n_cl, 0.0), epi_prev2(n_cl, 0.0);
+    std::vector<std::vector<double>> done(n);                   // per problem, per pair row: completion time of the LAST N tile
+    for (int i = 0; i < n; ++i) done[i].assign(d[i].pairs_m, 0.0);
+    double makespan = 0.0;
+    for (int t = 0; t < T; ++t) {
+      const ChainTile& ct = tiles[t];
+      double ready = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        const int dp = problems[ct.pi].dep[k];
+        if (dp < 0) continue;
+        if ((problems[ct.pi].dep_all_rows >> k) & 1) { for (double v : done[dp]) ready = std::max(ready, v + kSignal); }
+        else ready = std::max(ready, done[dp][ct.tm] + kSignal);
+      }
+      int best = 0;
+      double best_start = 1e300;
+      for (int c = 0; c < n_cl; ++c) {
+        const double st = std::max(std::max(mma_free[c], epi_prev2[c]), ready);
+        if (st < best_start - 1e-9) { best_start = st; best = c; }
+      }
+      const double main_units = std::max(kMinMain, static_cast<double>((d[ct.pi].K + BK - 1) / BK));
+      const double main_end = best_start + main_units;
+      const double epi_end = std::max(main_end, epi_free[best]) + kEpi;
+      mma_free[best] = main_end;
+      epi_free[best] = epi_end;
+      epi_prev2[best] = epi_prev[best];                          // two accumulator buffers: tile i+2 waits for epilogue i
+      epi_prev[best] = epi_end;
+      done[ct.pi][ct.tm] = std::max(done[ct.pi][ct.tm], epi_end);
+      makespan = std::max(makespan, epi_end);
+      lists[best].push_back((static_cast<uint32_t>(ct.pi) << 22) | (static_cast<uint32_t>(ct.tm) << 11) | static_cast<uint32_t>(ct.tn));
+    }
+    plan->sim_units = static_cast<float>(makespan);
+  }
+  int max_len = 0;
+  for (int c = 0; c < n_cl; ++c) max_len = std::max(max_len, static_cast<int>(lists[c].size()));
+  if (max_len > L.sched_ld) return LINKS_E_RANGE;
+  // ---- workspace image
+  std::vector<unsigned char> img(L.total, 0);
+  memcpy(img.data() + L.off_probs, d.data(), sizeof(GemmProblemDev) * static_cast<size_t>(n));
+  uint32_t* sched = reinterpret_cast<uint32_t*>(img.data() + L.off_sched);
+  int* cnt = reinterpret_cast<int*>(img.data() + L.off_cnt);
+  for (int c = 0; c < n_cl; ++c) {
+    cnt[c] = static_cast<int>(lists[c].size());
+    for (size_t i = 0; i < lists[c].size(); ++i) sched[static_cast<size_t>(c) * L.sched_ld + i] = lists[c][i];
+  }
+  cudaError_t e = cudaMemcpyAsync(ws_dev, img.data(), L.total, cudaMemcpyHostToDevice, links_stream(stream));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if ((e = cudaStreamSynchronize(links_stream(stream))) != cudaSuccess) return static_cast<int>(e);   // img dies with this frame
+  memset(plan, 0, sizeof(*plan));
+  unsigned char* w = static_cast<unsigned char*>(ws_dev);
+  plan->ws = ws_dev;
+  plan->probs = w + L.off_probs;
+  plan->sched = w + L.off_sched;
+  plan->sched_cnt = w + L.off_cnt;
+  plan->counters = w + L.off_counters;
+  plan->grid = 2 * n_cl;
+  plan->n_counters = L.n_counters - 1;
+  plan->sched_ld = L.sched_ld;
+  plan->n_problems = n;
+  plan->total_tiles = T;
+  {
+    double units = 0.0;
+    for (int t = 0; t < T; ++t) units += std::max(2.0, static_cast<double>((d[tiles[t].pi].K + BK - 1) / BK));
+    plan->ideal_units = static_cast<float>(units / n_cl);
+  }
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int links_gemm_chain_run(const LinksGemmChainPlan* plan, void* stream) {
+  using namespace links;
+  if (plan == nullptr || plan->ws == nullptr || plan->grid < 2) return LINKS_E_ARG;
+  ChainDev C;
+  C.probs = static_cast<const GemmProblemDev*>(plan->probs);
+  C.sched = static_cast<const uint32_t*>(plan->sched);
+  C.sched_cnt = static_cast<const int*>(plan->sched_cnt);
+  C.counters = static_cast<int*>(plan->counters);
+  C.exit_cnt = C.counters + plan->n_counters;
+  C.n_counters = plan->n_counters;
+  C.sched_ld = plan->sched_ld;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(plan->grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = links_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_gemm_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  g_gemm_launches++;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_kernel<true>, C);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return links_launch_status();
+}
+
+/* GEMM kernel launches (grouped + chain) issued through this library since it was loaded. */
+extern "C" __attribute__((visibility("default"))) size_t links_gemm_launch_count(void) { return static_cast<size_t>(links::g_gemm_launches); }

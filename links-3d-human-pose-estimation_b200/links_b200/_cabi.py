@@ -32,6 +32,21 @@ class GemmProblem(C.Structure):
                 ("out", vp), ("ld_out", ci), ("out_f32", vp), ("ld_f32", ci)]
 
 
+class ChainProblem(C.Structure):
+    """LinksChainProblem: one GEMM of a chain launch + its level and producer indices [A operand, add0, add1]."""
+    _fields_ = [("g", GemmProblem), ("level", ci), ("dep", ci * 3), ("dep_all_rows", ci)]
+
+
+class ChainPlan(C.Structure):
+    """LinksGemmChainPlan (filled by links_gemm_chain_build, consumed by links_gemm_chain_run)."""
+    _fields_ = [("ws", vp), ("probs", vp), ("sched", vp), ("sched_cnt", vp), ("counters", vp),
+                ("grid", ci), ("n_counters", ci), ("sched_ld", ci), ("n_problems", ci), ("total_tiles", ci),
+                ("sim_units", cf), ("ideal_units", cf)]
+
+
+MAX_CHAIN_PROBLEMS = 512
+
+
 class ColsumItem(C.Structure):
     _fields_ = [("G", vp), ("out", vp), ("ldg", ci), ("M", ci), ("N", ci), ("accumulate", ci)]
 
@@ -60,8 +75,8 @@ SIGNATURES = {
     "links_colsum_bf16_batched": (ci, [C.POINTER(ColsumItem), ci]),
     "links_cast_weight": (ci, [vp, ci, ci, vp, ci, vp, ci]),
     "links_cast_weight_batched": (ci, [C.POINTER(CastItem), ci]),
-    "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
-    "links_adam_step_g16": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf]),
+    "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf, vp]),
+    "links_adam_step_g16": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf, vp]),
     "links_grad_compress_bf16": (ci, [vp, vp, sz]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
@@ -89,8 +104,13 @@ PLAIN = {
     "links_flow_packed_floats": (sz, [ci, ci]),
     "links_flow_set_simt_only": (ci, [ci]),
     "links_gemm_set_max_ctas": (ci, [ci]),
+    "links_gemm_launch_count": (sz, []),
+    "links_launch_count": (sz, []),
+    "links_gemm_chain_ws_bytes": (sz, [C.POINTER(ChainProblem), ci]),
 }
-GEMM = {"links_gemm_grouped": (ci, [C.POINTER(GemmProblem), ci, vp])}
+GEMM = {"links_gemm_grouped": (ci, [C.POINTER(GemmProblem), ci, vp]),
+        "links_gemm_chain_build": (ci, [C.POINTER(ChainProblem), ci, vp, sz, C.POINTER(ChainPlan), vp]),
+        "links_gemm_chain_run": (ci, [C.POINTER(ChainPlan), vp])}
 
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(PLAIN) + list(GEMM))
 
@@ -143,31 +163,18 @@ def check(rc, what):
 
 
 class _LaunchCounter:
-    """Counts kernel launches issued through the C ABI (bench.py `gpu_launches`)."""
-    KERNELS_PER_CALL = {"links_adam_step": 2}
+    """Kernel launches issued through the C ABI between construction and stop() (bench.py `gpu_launches`): counted
+    inside the library (links_launch_count / links_gemm_launch_count), so cached plans and captured function pointers
+    cannot hide launches from it."""
 
     def __init__(self, L):
-        self.L, self.count, self.active = L, 0, True
-        self._orig = {}
-        for name in list(SIGNATURES) + list(GEMM):
-            fn = getattr(L, name)
-            self._orig[name] = fn
-            setattr(L, name, self._wrap(name, fn))
-
-    def _wrap(self, name, fn):
-        k = self.KERNELS_PER_CALL.get(name, 1)
-
-        def call(*a):
-            if self.active:
-                self.count += k
-            return fn(*a)
-        return call
+        self.L = L
+        self.k0, self.g0 = L.links_launch_count(), L.links_gemm_launch_count()
+        self.gemm = 0
 
     def stop(self):
-        self.active = False
-        for name, fn in self._orig.items():
-            setattr(self.L, name, fn)
-        return self.count
+        self.gemm = self.L.links_gemm_launch_count() - self.g0
+        return self.L.links_launch_count() - self.k0
 
 
 def install_launch_counter():

@@ -53,6 +53,7 @@ class FlowTrainStep:
         self.exp_avg = torch.zeros(total, **f32)
         self.exp_avg_sq = torch.zeros(total, **f32)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.P, self.Gd = [], []          # per block: name -> view
         off = 0
         for k in range(nb):
@@ -172,7 +173,7 @@ class FlowTrainStep:
         st = torch.cuda.current_stream().cuda_stream
         check(self.lib.links_adam_step(self.master.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                                        self.exp_avg_sq.data_ptr(), self.master.numel(), self.lr, 0.9, 0.999, 1e-8, self.wd, 0,
-                                       self.step_dev.data_ptr(), 1.0 / self.world, st), "links_adam_step")
+                                       self.step_dev.data_ptr(), 1.0 / self.world, self.lr_dev.data_ptr(), st), "links_adam_step")
         self._refresh_shadows()
 
     def step(self):
@@ -181,6 +182,7 @@ class FlowTrainStep:
 
     def set_lr(self, lr):
         self.lr = lr
+        self.lr_dev.fill_(float(lr))          # read on the device by the Adam kernel (graph replays follow the scheduler)
 
     def loss_dict(self):
         return {"loss": self.loss.item()}

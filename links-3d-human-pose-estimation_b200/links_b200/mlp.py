@@ -16,7 +16,14 @@ Data layout (per network s, per pass p):
 import torch
 
 from . import _cabi
-from ._cabi import EPI_LEAKY_POST, EPI_LEAKY_PRE, GEMM_A_MN, GEMM_B_MN, GemmProblem, HEAD_LD, check
+import ctypes as C
+import os
+
+from ._cabi import EPI_LEAKY_POST, EPI_LEAKY_PRE, GEMM_A_MN, GEMM_B_MN, ChainPlan, ChainProblem, GemmProblem, HEAD_LD, check
+
+# Chain launches (one persistent kernel per forward pass / dgrad chain, csrc/gemm.cu) are the default; LINKS_GEMM_CHAIN=0
+# keeps the layer-by-layer grouped launches (A/B measurements).
+USE_CHAIN = os.environ.get("LINKS_GEMM_CHAIN", "1") != "0"
 
 WIDTH = 1024
 TOPOLOGY = {
@@ -254,6 +261,15 @@ class MlpSet:
               "links_grad_compress_bf16")
         return self.grad16[a:b]
 
+    def set_lr(self, lr):
+        """Learning rate of the following adam_step calls, kept in a device word: captured graphs see new values."""
+        if getattr(self, "lr_dev", None) is None:
+            self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._lr_host = None
+        if lr != self._lr_host:
+            self.lr_dev.fill_(float(lr))
+            self._lr_host = lr
+
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0, bucket=None,
                   last=True, grads_bf16=False):
         """Adam on the whole flat buffer, or on one bucket's contiguous range.  The device-side step counter is
@@ -265,14 +281,19 @@ class MlpSet:
         gptr = self.grad16.data_ptr() + 2 * a if grads_bf16 else self.grad.data_ptr() + a * es
         check(fn(self.master.data_ptr() + a * es, gptr, self.exp_avg.data_ptr() + a * es,
                  self.exp_avg_sq.data_ptr() + a * es, b - a, lr, betas[0], betas[1], eps, weight_decay,
-                 0 if last else -1, self.step_dev.data_ptr(), grad_scale, st), "links_adam_step")
+                 0 if last else -1, self.step_dev.data_ptr(), grad_scale,
+                 self.lr_dev.data_ptr() if getattr(self, "lr_dev", None) is not None else None, st), "links_adam_step")
         self.refresh_shadows(bucket)
 
     # ------------------------------------------------------------------------------------------
     # launch planning
     # ------------------------------------------------------------------------------------------
     def _launch(self, problems):
-        """Returns a callable running one grouped launch (<= 8 problems each, split if more)."""
+        """Returns a callable running one grouped launch (<= 8 problems each, split if more).  While a chain is being
+        collected (_collect is a list) the problems become one LEVEL of the chain instead."""
+        if getattr(self, "_collect", None) is not None:
+            self._collect.append(list(problems))
+            return ("level", len(self._collect) - 1)
         chunks = [problems[i:i + _cabi.MAX_GEMM_PROBLEMS] for i in range(0, len(problems), _cabi.MAX_GEMM_PROBLEMS)]
         arrs = [((GemmProblem * len(c))(*c), len(c)) for c in chunks]
         fn = self.lib.links_gemm_grouped
@@ -306,8 +327,11 @@ class MlpSet:
     def forward_plan(self, p, rows=None):
         """Launch list for pass p; inputs are self.x0[p][s] (bf16 [M,64]); outputs self.head_out[p][s]."""
         key = ("fwd", p, rows)
-        if key in self._plans:
-            return self._plans[key]
+        if key not in self._plans:
+            self._plans[key] = self._build_forward(p, rows)
+        return self._plans[key]
+
+    def _build_forward(self, p, rows=None):
         M = rows or self.M
         tr = self.train
         ops = []
@@ -355,7 +379,6 @@ class MlpSet:
                 heads.append(self._prob(act[s][xin[br]], L.Wb, M, L.N, WIDTH, WIDTH, WIDTH, bias=L.b,
                                         out_f32=self.head_out[p][s][head]))
         ops.append(self._launch(heads))
-        self._plans[key] = ops
         return ops
 
     def backward_plan(self, p, need_input_grad, rows=None, wgrad=False):
@@ -366,8 +389,11 @@ class MlpSet:
         the dgrad chain has completed its G buffers, each followed by a ("bucket", b) marker: run(plan, on_bucket)
         calls on_bucket(b) there so the step driver can start the bucket's all-reduce / Adam on another stream."""
         key = ("bwd", p, need_input_grad, rows, wgrad)
-        if key in self._plans:
-            return self._plans[key]
+        if key not in self._plans:
+            self._plans[key] = self._build_backward(p, need_input_grad, rows, wgrad)
+        return self._plans[key]
+
+    def _build_backward(self, p, need_input_grad, rows=None, wgrad=False):
         M = rows or self.M
         ops = []
 
@@ -467,7 +493,6 @@ class MlpSet:
                                         out_f32=self.din[p][s]))
             ops.append(self._launch(probs))
         bucket_done(self._n_levels - 1)
-        self._plans[key] = ops
         return ops
 
     def _layer_input(self, name):
@@ -541,11 +566,14 @@ class MlpSet:
         """All weight / bias gradients (every bucket), for callers that do not interleave them with backward."""
         key = ("wgrad", rows)
         if key not in self._plans:
-            ops = []
-            for b in range(len(self.buckets)):
-                ops.extend(self._wgrad_ops(b, rows))
-            self._plans[key] = ops
+            self._plans[key] = self._build_wgrad(rows)
         return self._plans[key]
+
+    def _build_wgrad(self, rows=None):
+        ops = []
+        for b in range(len(self.buckets)):
+            ops.extend(self._wgrad_ops(b, rows))
+        return ops
 
     @staticmethod
     def run(ops, on_bucket=None):
@@ -555,3 +583,115 @@ class MlpSet:
                     on_bucket(op[1])
             else:
                 op()
+
+    # ------------------------------------------------------------------------------------------
+    # chain launches: a whole pass as ONE persistent kernel with tile-level dependencies
+    # ------------------------------------------------------------------------------------------
+    def _chain_op(self, levels):
+        """levels: list of problem lists in dependency order -> callable running one links_gemm_chain_run.  Producers
+        are found by address: an operand (A, add0, add1) that overlaps the out / mid / out_f32 range of an earlier
+        problem of the chain depends on it -- row block by row block, or on ALL of its rows when the operand is an
+        MN-major A (weight gradients contract over the rows)."""
+        flat = [(lv, P) for lv, probs in enumerate(levels) for P in probs]
+        n = len(flat)
+        assert 0 < n <= _cabi.MAX_CHAIN_PROBLEMS, n
+        arr = (ChainProblem * n)()
+        written = []           # (begin, end, problem index)
+
+        def extent(ptr, rows, ld, esize):
+            return (ptr, ptr + rows * ld * esize)
+
+        def producer(ptr, rows, ld, esize):
+            if not ptr:
+                return -1
+            b, e = extent(ptr, rows, ld, esize)
+            hits = sorted({i for (wb, we, i) in written if wb < e and b < we})
+            assert len(hits) <= 1, "operand written by several problems of one chain"
+            return hits[0] if hits else -1
+
+        for i, (lv, P) in enumerate(flat):
+            cp = arr[i]
+            C.memmove(C.byref(cp.g), C.byref(P), C.sizeof(GemmProblem))
+            cp.level = lv
+            a_mn = bool(P.flags & GEMM_A_MN)
+            cp.dep[0] = producer(P.A, P.K if a_mn else P.M, P.lda, 2)
+            cp.dep[1] = producer(P.add0, P.M, P.ld_add0, 2)
+            cp.dep[2] = producer(P.add1, P.M, P.ld_add1, 2)
+            cp.dep_all_rows = 1 if (a_mn and cp.dep[0] >= 0) else 0
+            for ptr, ld, es in ((P.out, P.ld_out, 2), (P.mid, P.ld_mid, 2), (P.out_f32, P.ld_f32, 4)):
+                if ptr:
+                    written.append(extent(ptr, P.M, ld, es) + (i,))
+        L = self.lib
+        nbytes = L.links_gemm_chain_ws_bytes(arr, n)
+        if nbytes == 0:
+            raise _cabi.LinksError("links_gemm_chain_ws_bytes rejected the chain")
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        plan = ChainPlan()
+        st = torch.cuda.current_stream().cuda_stream
+        check(L.links_gemm_chain_build(arr, n, ws.data_ptr(), nbytes, C.byref(plan), st), "links_gemm_chain_build")
+        self._chain_keep = getattr(self, "_chain_keep", []) + [(ws, plan, arr)]
+        fn = L.links_gemm_chain_run
+        ref = C.byref(plan)
+
+        def run():
+            rc = fn(ref, torch.cuda.current_stream().cuda_stream)
+            if rc:
+                check(rc, "links_gemm_chain_run")
+        run.plan = plan
+        return run
+
+    def _chained(self, key, build, split_at_buckets=False, max_ctas=None):
+        """Re-plan `build()` (which issues self._launch calls and returns an op list) as chain launches: consecutive GEMM
+        levels become one chain; the other ops (bias column sums, bucket markers) follow the chain that feeds them.  With
+        split_at_buckets a chain ends at every bucket marker, so the bucket's all-reduce / Adam can start while the next
+        chain runs (data parallelism); otherwise the whole op list is a single chain."""
+        if key in self._plans:
+            return self._plans[key]
+        self._collect = []
+        try:
+            ops = build()
+        finally:
+            levels_all, self._collect = self._collect, None
+        out, cur, deferred = [], [], []
+        # max_ctas: the chain's persistent grid leaves (SMs - max_ctas) SMs to kernels that run NEXT to it (flows, NCCL):
+        # a persistent grid that does not fit next to them would wait for them with its dependent tiles stalled
+        prev = self.lib.links_gemm_set_max_ctas(max_ctas) if max_ctas else None
+
+        def flush():
+            if cur:
+                out.append(self._chain_op([levels_all[i] for i in cur]))
+            out.extend(deferred)
+            del cur[:], deferred[:]
+        try:
+            for op in ops:
+                if isinstance(op, tuple) and op[0] == "level":
+                    cur.append(op[1])
+                elif isinstance(op, tuple):                       # ("bucket", b)
+                    deferred.append(op)
+                    if split_at_buckets:
+                        flush()
+                else:
+                    deferred.append(op)
+            flush()
+        finally:
+            if max_ctas:
+                self.lib.links_gemm_set_max_ctas(prev)
+        self._plans[key] = out
+        return out
+
+    def forward_ops(self, p, rows=None, max_ctas=None):
+        """Launch list of forward pass p: one chain launch (default) or the layer-by-layer grouped launches."""
+        if not USE_CHAIN:
+            return self.forward_plan(p, rows)
+        return self._chained(("cfwd", p, rows), lambda: self._build_forward(p, rows), max_ctas=max_ctas)
+
+    def backward_ops(self, p, need_input_grad, rows=None, wgrad=False, split_at_buckets=False, max_ctas=None):
+        if not USE_CHAIN:
+            return self.backward_plan(p, need_input_grad, rows, wgrad)
+        return self._chained(("cbwd", p, need_input_grad, rows, wgrad, split_at_buckets),
+                             lambda: self._build_backward(p, need_input_grad, rows, wgrad), split_at_buckets, max_ctas)
+
+    def wgrad_ops(self, rows=None):
+        if not USE_CHAIN:
+            return self.wgrad_plan(rows)
+        return self._chained(("cwgrad", rows), lambda: self._build_wgrad(rows))

@@ -79,7 +79,7 @@ class OcclusionStep:
             nidx = self.idx_lift[s].numel()
             check(L.links_pack_rows(self.x.data_ptr(), 34, B, self.idx_lift[s].data_ptr(), nidx, 1,
                                     lf.x0[0][s].data_ptr(), None, 0, 0, st), "links_pack_rows")
-        lf.run(lf.forward_plan(0))
+        lf.run(lf.forward_ops(0))
         check(L.links_occ_lift(self.x.data_ptr(), lf.head_out[0][0]["downscale"].data_ptr(),
                                lf.head_out[0][1]["downscale"].data_ptr(), B, self.cfg["depth"], self.pose[0].data_ptr(), st),
               "links_occ_lift")
@@ -93,7 +93,7 @@ class OcclusionStep:
                 check(L.links_pack_rows(self.pose[r].data_ptr(), 51, B, self.idx_in[s].data_ptr(), n_idx, self.period[s],
                                         m.x0[r][s].data_ptr(), None, 0, 0, st),
                       "links_pack_rows")
-            m.run(m.forward_plan(r))
+            m.run(m.forward_ops(r))
             for s in range(8):
                 n_out = self.idx_tgt[s].numel()
                 pred = m.head_out[r][s]["downscale"]
@@ -101,8 +101,8 @@ class OcclusionStep:
                                       n_out, B, 1.0 / B, self.loss_sums[s:s + 1].data_ptr(),
                                       m.G[r][s]["downscale"].data_ptr(), None, 0, 0, st), "links_occ_mse")
         for r in range(2):
-            m.run(m.backward_plan(r, need_input_grad=False))
-        m.run(m.backward_plan(2, need_input_grad=False, wgrad=True), on_bucket=self._on_bucket if fused_optimizer else None)
+            m.run(m.backward_ops(r, need_input_grad=False))
+        m.run(m.backward_ops(2, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1), on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
             torch.cuda.current_stream().wait_stream(self.comm)
         self.losses[:8] = self.loss_sums / B
@@ -170,7 +170,7 @@ class EvalRunner:
         for s in range(2):
             check(L.links_pack_rows(poses_2d.data_ptr(), 34, n, self.idx[s].data_ptr(), 2 * self.nj[s], 1,
                                     m.x0[0][s].data_ptr(), None, 0, 0, st), "links_pack_rows")
-        m.run(m.forward_plan(0, rows=n if n != m.M else None))
+        m.run(m.forward_ops(0, rows=n if n != m.M else None))
         # assemble the 17 depth offsets (integer gather of the two heads; root joint zeroed, eval_h36m.py:55-58)
         heads = torch.cat((m.head_out[0][0]["downscale"][:n], m.head_out[0][1]["downscale"][:n]), dim=1)
         d = heads[:, self.gather]

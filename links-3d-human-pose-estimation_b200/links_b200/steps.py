@@ -27,12 +27,23 @@ DEFAULT_CFG = dict(depth=10.0, weight_bl=50.0, weight_2d=1.0, weight_3d=1.0, wei
                    lr=2e-4, weight_decay=1e-5)
 
 
+class _Kind:
+    """Per-flavour state of a LifterStep: 'lt' (Leg_Lifter + Torso_Lifter) or 'lr' (left + right Left_Right_Lifter)."""
+    pass
+
+
 class LifterStep:
-    """kind = 'lt' (Leg_Lifter + Torso_Lifter) or 'lr' (left + right Left_Right_Lifter)."""
+    """kind = 'lt' (Leg_Lifter + Torso_Lifter), 'lr' (left + right Left_Right_Lifter) or 'both'.
+
+    'both' runs the leg/torso step and the left/right step of the SAME batch as one step: the four lifters are one
+    4-network MlpSet, so every layer of both flavours sits in the same GEMM launches (twice the tiles per chain launch,
+    one gradient bucket stream), the sampling flow is evaluated once, and only the small geometry / flow kernels are
+    issued per flavour.  lifter_params / part_flow_params are then [leg, torso, left, right]."""
 
     def __init__(self, kind, batch, lifter_params, part_flow_params, full_flow_params, cfg=None, device="cuda",
                  process_group=None, comm_stream=None):
         self.kind = kind
+        self.kinds = ["lt", "lr"] if kind == "both" else [kind]
         self.cfg = dict(DEFAULT_CFG)
         self.cfg.update(cfg or {})
         self.B = batch
@@ -42,50 +53,82 @@ class LifterStep:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         dev = self.device
-        self.maps = maps.geom_maps(kind, self.cfg)
-        self.joints = maps.part_joint_lists(kind)
-        nj = [len(j) for j in self.joints]
-        self.nj = nj
-        self.mlp = MlpSet("lifter", [2 * n for n in nj], [{"downscale": n, "angles": 1} for n in nj], self.N,
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        N, B = self.N, self.B
+        c = self.cfg
+        self.K = []
+        nj_all = []
+        for ki, kd in enumerate(self.kinds):
+            k = _Kind()
+            k.kind, k.s0 = kd, 2 * ki
+            k.maps = maps.geom_maps(kd, self.cfg)
+            k.joints = maps.part_joint_lists(kd)
+            k.nj = [len(j) for j in k.joints]
+            nj_all += k.nj
+            k.part_flows = [FlowPacked(2 * k.nj[s], part_flow_params[k.s0 + s], device=dev) for s in range(2)]
+            k.stats = torch.zeros(2, **f32)
+            k.qpart = [torch.zeros(N, 2 * k.nj[s], **f32) for s in range(2)]
+            k.qfull = [torch.zeros(N, 34, **f32) for _ in range(2)]
+            k.dflow = [torch.zeros(N, 2 * k.nj[s], **f32) for s in range(2)]
+            k.scal = torch.zeros(8, **f32)     # [0:4] loss sums (L3d, rep, pair, bl), [4:6] nll sums, [6:8] red
+            k.dgamma = torch.zeros(N, **f32)
+            k.da = torch.zeros(N, **f32)
+            k.losses = torch.zeros(8, **f32)   # L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
+            k.idx_u = [torch.tensor(maps.part_index(k.joints[s]), **i32) for s in range(2)]
+            k.idx_q = [torch.arange(2 * k.nj[s], **i32) for s in range(2)]
+            # the two part-flow NLL kernels (few CTAs each) run on forked streams next to the pass-2 GEMMs; they are
+            # joined right before the geometry backward that consumes their input gradients
+            k.flow_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+            k.stream = torch.cuda.Stream(device=dev) if ki > 0 else None      # small per-flavour kernels of flavour > 0
+            self.K.append(k)
+        self.mlp = MlpSet("lifter", [2 * n for n in nj_all], [{"downscale": n, "angles": 1} for n in nj_all], self.N,
                           n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]],
                           max_buckets=self.cfg.get("dp_buckets") if (self.world > 1 or self.cfg.get("dp_layout")) else None)
         self.mlp.load_state_dicts(lifter_params)
-        self.part_flows = [FlowPacked(2 * nj[s], part_flow_params[s], device=dev) for s in range(2)]
         self.full_flow = FlowPacked(34, full_flow_params, device=dev)
-        f32 = dict(dtype=torch.float32, device=dev)
-        N, B = self.N, self.B
         # inputs (filled by the caller before step())
         self.x = torch.zeros(B, 34, **f32)
         self.noise = torch.zeros(B, 34, **f32)
         self.eps_x = torch.zeros(N, **f32)
         self.u_y = torch.zeros(N, **f32)
-        # intermediates
         self.u = torch.zeros(N, 34, **f32)
-        self.stats = torch.zeros(2, **f32)
-        self.qpart = [torch.zeros(N, 2 * nj[s], **f32) for s in range(2)]
-        self.qfull = [torch.zeros(N, 34, **f32) for _ in range(2)]
-        self.dflow = [torch.zeros(N, 2 * nj[s], **f32) for s in range(2)]
-        self.scal = torch.zeros(8, **f32)     # [0:4] loss sums (L3d, rep, pair, bl), [4:6] nll sums, [6:8] red
-        self.dgamma = torch.zeros(N, **f32)
-        self.da = torch.zeros(N, **f32)
-        self.losses = torch.zeros(8, **f32)   # L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
-        i32 = dict(dtype=torch.int32, device=dev)
-        self.idx_u = [torch.tensor(maps.part_index(self.joints[s]), **i32) for s in range(2)]
-        self.idx_q = [torch.arange(2 * nj[s], **i32) for s in range(2)]
         self._norm = torch.tensor([1.0 / N, 1.0 / N, 1.0 / max(N // 2, 1), 1.0 / N, 1.0 / N, 1.0 / N], **f32)
-        c = self.cfg
         self._w = torch.tensor([c["weight_3d"], c["weight_2d"], c["weight_velocity"], c["weight_bl"],
                                 c["weight_likeli"], c["weight_likeli"]], **f32)
         self.graph = None
-        # the two part-flow NLL kernels (few CTAs each, ~0.3 ms) run on forked streams next to the pass-2 GEMMs;
-        # they are joined right before the geometry backward that consumes their input gradients
-        self._flow_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        # Sampling prefetch (cfg prefetch_sample): the sampling block (train_leg_torso_lifter.py:133-142) depends on no
+        # trained weight, so the poses of step k+1 are drawn WHILE step k runs: step() first moves the prefetched
+        # poses u_next -> u, then issues the next sampling pass on a side stream.  Protocol: before step k the caller
+        # loads x / noise of step k+1 (and eps_x / u_y of step k); prime() draws the very first batch.
+        self.prefetch = bool(self.cfg.get("prefetch_sample", False))
+        # SM partition.  A chain launch is a persistent grid; kernels that should run NEXT to it need SMs of their own:
+        #   window chains (forward pass 2, its dgrad chain) run beside the part-flow NLL kernels (ceil(N/128) CTAs each),
+        #   the tail chain (pass-1 dgrad + weight gradients) runs beside the prefetched sampling pass (ceil(B/128) CTAs)
+        #   and, data-parallel, beside the NCCL all-reduce CTAs.
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        tiles = (N + 127) // 128
+        r_win = self.cfg.get("reserve_window")
+        if r_win is None:
+            r_win = min(2 * len(self.kinds) * tiles, n_sms // 2 - 2)
+        r_tail = self.cfg.get("reserve_tail")
+        if r_tail is None:
+            r_tail = (min((B + 127) // 128, 16) if self.prefetch else 0) + (int(self.cfg.get("nccl_ctas") or 0) if self.world > 1 else 0)
+        self._ctas_window = (n_sms - r_win) // 2 * 2 if r_win > 0 else None
+        self._ctas_tail = (n_sms - r_tail) // 2 * 2 if r_tail > 0 else None
+        self.u_next = torch.zeros(N, 34, **f32) if self.prefetch else None
+        self._sample_stream = torch.cuda.Stream(device=dev) if self.prefetch else None
         # gradient buckets are all-reduced (NCCL), Adam-updated and re-cast on this stream as soon as the backward
         # pass has produced them, overlapping the rest of backward.  Steps that run concurrently (StepGroup) must
         # share ONE comm stream so that every rank issues its collectives in the same order.
         self.comm = comm_stream if comm_stream is not None else torch.cuda.Stream(device=dev)
         # Adam + shadow refresh of a reduced bucket run on their own stream so the collectives stay back to back
         self.opt_stream = torch.cuda.Stream(device=dev)
+        if len(self.K) == 1:       # single-flavour attribute names (tests / scripts)
+            k = self.K[0]
+            self.maps, self.joints, self.nj, self.part_flows = k.maps, k.joints, k.nj, k.part_flows
+            self.stats, self.qpart, self.qfull, self.dflow, self.scal = k.stats, k.qpart, k.qfull, k.dflow, k.scal
+            self.dgamma, self.da, self.losses = k.dgamma, k.da, k.losses
 
     # ------------------------------------------------------------------------------------------
     def _st(self):
@@ -117,60 +160,115 @@ class LifterStep:
                         last=(b == len(m.buckets) - 1),
                         grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"))
 
+    class _Fork:
+        """`with step._fork(k):` -- the small kernels of flavour k > 0 go to that flavour's side stream (forked from the
+        current stream at entry); _join() makes the main stream wait for them."""
+
+        def __init__(self, k):
+            self.k = k
+            self.ctx = None
+
+        def __enter__(self):
+            if self.k.stream is not None:
+                self.k.stream.wait_stream(torch.cuda.current_stream())
+                self.ctx = torch.cuda.stream(self.k.stream)
+                self.ctx.__enter__()
+
+        def __exit__(self, *a):
+            if self.ctx is not None:
+                self.ctx.__exit__(*a)
+
+    def _fork(self, k):
+        return LifterStep._Fork(k)
+
+    def _join(self):
+        main = torch.cuda.current_stream()
+        for k in self.K:
+            if k.stream is not None:
+                main.wait_stream(k.stream)
+
+    def prime(self):
+        """Draw the first batch of sampled poses from the current x / noise (sampling prefetch only)."""
+        self.full_flow.sample(self.x, self.noise, self.u_next)
+
     def forward_backward(self, fused_optimizer=False):
         """Everything of one step up to (and including) the gradients.  fused_optimizer=True also runs the
         per-bucket all-reduce / Adam / shadow refresh overlapped with the backward pass (what step() does)."""
         L, m, N = self.lib, self.mlp, self.N
-        mp = C.byref(self.maps)
-        self.full_flow.sample(self.x, self.noise, self.u)
-        for s in range(2):
-            self._pack(self.u, self.idx_u[s], 2 * self.nj[s], 0, s)
-        m.run(m.forward_plan(0))
-        h1 = [m.head_out[0][s]["downscale"] for s in range(2)]
-        a1 = [m.head_out[0][s]["angles"] for s in range(2)]
-        h2 = [m.head_out[1][s]["downscale"] for s in range(2)]
-        check(L.links_elev_stats(a1[0].data_ptr(), a1[1].data_ptr(), N, self.stats.data_ptr(), self._st()),
-              "links_elev_stats")
-        common = [self.u.data_ptr(), h1[0].data_ptr(), h1[1].data_ptr(), a1[0].data_ptr(), a1[1].data_ptr(),
-                  self.eps_x.data_ptr(), self.u_y.data_ptr(), self.stats.data_ptr()]
-        check(L.links_geom_forward(mp, *common, N, self.qpart[0].data_ptr(), self.qpart[1].data_ptr(),
-                                   self.qfull[0].data_ptr(), self.qfull[1].data_ptr(), self._st()), "links_geom_forward")
-        self.scal.zero_()
         main = torch.cuda.current_stream()
-        for s in range(2):
-            fs = self._flow_streams[s]
-            fs.wait_stream(main)
-            with torch.cuda.stream(fs):
-                self.part_flows[s].nll_fwdbwd(self.qpart[s], self.cfg["weight_likeli"] / N, self.scal[4 + s:5 + s],
-                                              self.dflow[s])
-        for s in range(2):
-            self._pack(self.qpart[s], self.idx_q[s], 2 * self.nj[s], 1, s)
-        m.run(m.forward_plan(1))
-        g2 = [m.G[1][s]["downscale"] for s in range(2)]
-        check(L.links_geom_loss(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), N, self.scal.data_ptr(),
-                                g2[0].data_ptr(), g2[1].data_ptr(), None, None, 0, 0, self._st()), "links_geom_loss")
-        m.run(m.backward_plan(1, need_input_grad=True))
-        g1 = [m.G[0][s]["downscale"] for s in range(2)]
-        ga = [m.G[0][s]["angles"] for s in range(2)]
-        for fs in self._flow_streams:
-            main.wait_stream(fs)
-        check(L.links_geom_backward(mp, *common, h2[0].data_ptr(), h2[1].data_ptr(), self.dflow[0].data_ptr(),
-                                    self.dflow[1].data_ptr(), m.din[1][0].data_ptr(), m.din[1][1].data_ptr(), N,
-                                    g1[0].data_ptr(), g1[1].data_ptr(), None, None, 0, 0,
-                                    self.dgamma.data_ptr(), self.da.data_ptr(), self.scal[6:8].data_ptr(), self._st()),
-              "links_geom_backward")
-        check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
-                                           self.stats.data_ptr(), self.dgamma.data_ptr(), self.scal[6:8].data_ptr(), N,
-                                           ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, self._st()),
-              "links_geom_backward_angles")
-        m.run(m.backward_plan(0, need_input_grad=False, wgrad=True), on_bucket=self._on_bucket if fused_optimizer else None)
+        if self.prefetch:
+            self.u.copy_(self.u_next)
+        else:
+            self.full_flow.sample(self.x, self.noise, self.u)
+        for k in self.K:
+            for s in range(2):
+                self._pack(self.u, k.idx_u[s], 2 * k.nj[s], 0, k.s0 + s)
+        m.run(m.forward_ops(0))
+        for k in self.K:
+            with self._fork(k):
+                mp = C.byref(k.maps)
+                a1 = [m.head_out[0][k.s0 + s]["angles"] for s in range(2)]
+                check(L.links_elev_stats(a1[0].data_ptr(), a1[1].data_ptr(), N, k.stats.data_ptr(), self._st()),
+                      "links_elev_stats")
+                k.common = [self.u.data_ptr()] + [m.head_out[0][k.s0 + s]["downscale"].data_ptr() for s in range(2)] + \
+                           [a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(), self.u_y.data_ptr(), k.stats.data_ptr()]
+                check(L.links_geom_forward(mp, *k.common, N, k.qpart[0].data_ptr(), k.qpart[1].data_ptr(),
+                                           k.qfull[0].data_ptr(), k.qfull[1].data_ptr(), self._st()), "links_geom_forward")
+                k.scal.zero_()
+                here = torch.cuda.current_stream()
+                for s in range(2):
+                    fs = k.flow_streams[s]
+                    fs.wait_stream(here)
+                    with torch.cuda.stream(fs):
+                        k.part_flows[s].nll_fwdbwd(k.qpart[s], self.cfg["weight_likeli"] / N, k.scal[4 + s:5 + s], k.dflow[s])
+                for s in range(2):
+                    self._pack(k.qpart[s], k.idx_q[s], 2 * k.nj[s], 1, k.s0 + s)
+        self._join()
+        m.run(m.forward_ops(1, max_ctas=self._ctas_window))
+        for k in self.K:
+            with self._fork(k):
+                h2 = [m.head_out[1][k.s0 + s]["downscale"] for s in range(2)]
+                g2 = [m.G[1][k.s0 + s]["downscale"] for s in range(2)]
+                check(L.links_geom_loss(C.byref(k.maps), *k.common, h2[0].data_ptr(), h2[1].data_ptr(), N, k.scal.data_ptr(),
+                                        g2[0].data_ptr(), g2[1].data_ptr(), None, None, 0, 0, self._st()), "links_geom_loss")
+        self._join()
+        m.run(m.backward_ops(1, need_input_grad=True, max_ctas=self._ctas_window))
+        for k in self.K:
+            with self._fork(k):
+                here = torch.cuda.current_stream()
+                for fs in k.flow_streams:
+                    here.wait_stream(fs)
+                h2 = [m.head_out[1][k.s0 + s]["downscale"] for s in range(2)]
+                g1 = [m.G[0][k.s0 + s]["downscale"] for s in range(2)]
+                ga = [m.G[0][k.s0 + s]["angles"] for s in range(2)]
+                a1 = [m.head_out[0][k.s0 + s]["angles"] for s in range(2)]
+                check(L.links_geom_backward(C.byref(k.maps), *k.common, h2[0].data_ptr(), h2[1].data_ptr(),
+                                            k.dflow[0].data_ptr(), k.dflow[1].data_ptr(), m.din[1][k.s0].data_ptr(),
+                                            m.din[1][k.s0 + 1].data_ptr(), N, g1[0].data_ptr(), g1[1].data_ptr(), None, None,
+                                            0, 0, k.dgamma.data_ptr(), k.da.data_ptr(), k.scal[6:8].data_ptr(), self._st()),
+                      "links_geom_backward")
+                check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
+                                                   k.stats.data_ptr(), k.dgamma.data_ptr(), k.scal[6:8].data_ptr(), N,
+                                                   ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, self._st()),
+                      "links_geom_backward_angles")
+        self._join()
+        if self.prefetch:
+            # poses of the NEXT step, drawn beside the longest GEMM chain of this one (which leaves it the SMs it needs)
+            self._sample_stream.wait_stream(main)
+            with torch.cuda.stream(self._sample_stream):
+                self.full_flow.sample(self.x, self.noise, self.u_next)
+        m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1, max_ctas=self._ctas_tail),
+              on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
             main.wait_stream(self.opt_stream)
+        if self.prefetch:
+            main.wait_stream(self._sample_stream)
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
-        t = self.scal[:6] * self._norm
-        self.losses[:6] = t
-        self.losses[6] = t[4] + t[5]
-        self.losses[7] = (t * self._w).sum()
+        for k in self.K:
+            t = k.scal[:6] * self._norm
+            k.losses[:6] = t
+            k.losses[6] = t[4] + t[5]
+            k.losses[7] = (t * self._w).sum()
 
     def optimizer_step(self):
         if self.world > 1:
@@ -180,19 +278,44 @@ class LifterStep:
     def step(self):
         self.forward_backward(fused_optimizer=True)
 
-    def loss_dict(self):
-        v = self.losses.tolist()
+    @staticmethod
+    def _loss_dict(k):
+        v = k.losses.tolist()
         names = ("L3d", "rep_rot", "re_rot_3d", "bl_prior")
         d = dict(zip(names, v[:4]))
-        if self.kind == "lt":
+        if k.kind == "lt":
             d["leg_likeli"], d["torso_likeli"] = v[4], v[5]
         else:
             d["likeli_right"], d["likeli_left"] = v[4], v[5]   # the reference swaps the names (:334-342)
         d["likeli"], d["loss"] = v[6], v[7]
         return d
 
+    def loss_dict(self):
+        """Loss names of the reference's step; for kind='both' a dict {'lt': {...}, 'lr': {...}}."""
+        if len(self.K) == 1:
+            return self._loss_dict(self.K[0])
+        return {k.kind: self._loss_dict(k) for k in self.K}
+
     def set_lr(self, lr):
         self.cfg["lr"] = lr
+
+    def capture(self, warmup=2):
+        """Capture step() into one CUDA graph (replay with .replay()); eager warm-up runs first (lazy plan builds)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
 
 
 class StepGroup:
@@ -218,6 +341,13 @@ class StepGroup:
                 by_pg[key] = st
 
     def step(self):
+        from . import mlp as _mlp
+        if _mlp.USE_CHAIN:
+            # Chain launches are persistent kernels that spin on each other's tiles: two of them must never share the
+            # machine (each could hold SMs the other's unscheduled clusters need).  Run the branches back to back.
+            for step in self.steps:
+                step.step()
+            return
         main = torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(main)

@@ -60,7 +60,7 @@ class _EngineFn(torch.autograd.Function):
         idx = module._identity_index(K, x.device)
         _cabi.check(lib.links_pack_rows(xc.data_ptr(), K, M, idx.data_ptr(), K, 1, eng.x0[0][0].data_ptr(), None, 0, 0, st),
                     "links_pack_rows")
-        eng.run(eng.forward_plan(0))
+        eng.run(eng.forward_ops(0))
         outs = []
         for head, width in module._heads:
             outs.append(eng.head_out[0][0][head][:, :width].clone())
@@ -82,8 +82,7 @@ class _EngineFn(torch.autograd.Function):
             G.zero_()
             if g is not None:
                 G[:, :width] = g.to(torch.bfloat16)
-        eng.run(eng.backward_plan(0, need_input_grad=ctx.need_x))
-        eng.run(eng.wgrad_plan())
+        eng.run(eng.backward_ops(0, need_input_grad=ctx.need_x, wgrad=True))     # dgrad chain + weight / bias gradients
         gx = eng.din[0][0][:, :K].clone() if ctx.need_x else None
         grads = []
         for name in module._param_order:

@@ -57,15 +57,15 @@ SIM int sim_cast_weight_batched(const LinksCastItem* items, int n_items) {
   return 0;
 }
 SIM int sim_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
-                      float wd, int step, int* step_dev, float grad_scale) {
-  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel<float>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale); });
+                      float wd, int step, int* step_dev, float grad_scale, const float* lr_dev) {
+  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel<float>(p, g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale, lr_dev); });
   if (step_dev && step >= 0) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
   return 0;
 }
 
 SIM int sim_adam_step_g16(float* p, const void* g, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
-                          float wd, int step, int* step_dev, float grad_scale) {
-  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel<bf16>(p, (const bf16*)g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale); });
+                          float wd, int step, int* step_dev, float grad_scale, const float* lr_dev) {
+  hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel<bf16>(p, (const bf16*)g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale, lr_dev); });
   if (step_dev && step >= 0) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
   return 0;
 }

@@ -51,7 +51,7 @@ def test_plain_gemm_f32_out(M, N, K):
     A = (torch.randn(M, lda, device="cuda", generator=g) * 0.5).bfloat16()
     B = (torch.randn(N, ldb, device="cuda", generator=g) * 0.5).bfloat16()
     bias = torch.randn(N, device="cuda", generator=g)
-    out = torch.full((M, N), float("nan"), device="cuda")
+    out = torch.full((M, N), 777.0, device="cuda")
     P = _prob(cabi, A, B, M, N, K, bias=bias, out_f32=out)
     _run(cabi, L, [P])
     ref = A[:, :K].float() @ B[:, :K].float().t() + bias
@@ -124,7 +124,7 @@ def test_dgrad_mn_major_b(M, N, K):
     G[:, :K] = (torch.randn(M, K, device="cuda", generator=g) * 0.3).bfloat16()
     W = torch.zeros(K, ldw, device="cuda", dtype=torch.bfloat16)
     W[:, :N] = (torch.randn(K, N, device="cuda", generator=g) * 0.1).bfloat16()
-    out = torch.full((M, (N + 3) // 4 * 4), float("nan"), device="cuda")
+    out = torch.full((M, (N + 3) // 4 * 4), 777.0, device="cuda")
     P = _prob(cabi, G, W, M, N, K, flags=cabi.GEMM_B_MN, out_f32=out)
     P.ldb = ldw
     _run(cabi, L, [P])
@@ -142,7 +142,7 @@ def test_wgrad_mn_major_ab(rows, N, K):
     G[:, :N] = (torch.randn(rows, N, device="cuda", generator=g) * 0.1).bfloat16()
     X = torch.zeros(rows, ldx, device="cuda", dtype=torch.bfloat16)
     X[:, :K] = (torch.randn(rows, K, device="cuda", generator=g) * 0.3).bfloat16()
-    out = torch.full((N, K), float("nan"), device="cuda")
+    out = torch.full((N, K), 777.0, device="cuda")
     P = _prob(cabi, G, X, N, K, rows, flags=cabi.GEMM_A_MN | cabi.GEMM_B_MN, out_f32=out)
     P.lda, P.ldb = ldg, ldx
     _run(cabi, L, [P])
@@ -179,3 +179,88 @@ def test_argument_errors():
     assert L.links_gemm_grouped(arr, 0, None) == -1
     with pytest.raises(ValueError):
         cabi.check(-2, "x")
+
+
+@pytest.mark.parametrize("M,passes", [(200, 1), (640, 1), (2048, 2)])
+def test_chain_launch_equals_layer_by_layer(M, passes):
+    """links_gemm_chain_run (one persistent kernel per pass, tile-level dependencies through completion counters) must
+    reproduce the layer-by-layer grouped launches BIT FOR BIT: same tiles, same MMA order, same epilogues -- forward
+    (heads, activations, sign masks), dgrad chain (all G buffers, input gradient) and the weight gradients.  Repeated
+    launches of one plan exercise the counter reset by the last cluster to exit."""
+    from links_b200.mlp import MlpSet
+    from oracle import nets as ON
+    nj = (7, 10)
+    params = [ON.init_lifter_params(nj[0], 11), ON.init_lifter_params(nj[1], 12)]
+    mlp = MlpSet("lifter", [14, 20], [{"downscale": 7, "angles": 1}, {"downscale": 10, "angles": 1}], M, n_passes=passes,
+                 pass_branches=[["pose", "angle"], ["pose"]][:passes])
+    mlp.load_state_dicts(params)
+    g = torch.Generator().manual_seed(M)
+    for p in range(passes):
+        for s in range(2):
+            mlp.x0[p][s].zero_()
+            mlp.x0[p][s][:, :2 * nj[s]] = (torch.randn(M, 2 * nj[s], generator=g) * 0.2).bfloat16().cuda()
+
+    def seed_head_grads():
+        gg = torch.Generator().manual_seed(7)
+        for p in range(passes):
+            for s in range(2):
+                for head, w in (("downscale", nj[s]), ("angles", 1)):
+                    if head == "angles" and p == 1:
+                        continue
+                    G = mlp.G[p][s][head]
+                    G.zero_()
+                    G[:, :w] = (torch.randn(M, w, generator=gg) * 0.1).bfloat16().cuda()
+
+    def snapshot():
+        torch.cuda.synchronize()
+        out = {}
+        for p in range(passes):
+            for s in range(2):
+                for k, v in mlp.act[p][s].items():
+                    out[("act", p, s, k)] = v.clone()
+                for k, v in mlp.head_out[p][s].items():
+                    out[("head", p, s, k)] = v.clone()
+                for k, v in mlp.sign[p][s].items():
+                    out[("sign", p, s, k)] = v.clone()
+                for k, v in mlp.G[p][s].items():
+                    out[("G", p, s, k)] = v.clone()
+                out[("din", p, s)] = mlp.din[p][s].clone()
+        out["grad"] = mlp.grad.clone()
+        return out
+
+    def clear():
+        for p in range(passes):
+            for s in range(2):
+                for v in mlp.act[p][s].values():
+                    v.fill_(777.0)
+                for v in mlp.head_out[p][s].values():
+                    v.fill_(777.0)
+                for k, v in mlp.G[p][s].items():
+                    if k not in ("downscale", "angles"):
+                        v.fill_(777.0)
+                mlp.din[p][s].fill_(777.0)
+                mlp.E[p][s].fill_(777.0)
+                for v in mlp.dt[p][s].values():
+                    v.fill_(777.0)
+        mlp.grad.fill_(777.0)
+
+    def run_all(chain):
+        clear()
+        seed_head_grads()
+        last = passes - 1
+        for p in range(passes):
+            mlp.run(mlp._chained(("t_fwd", p), lambda p=p: mlp._build_forward(p)) if chain else mlp.forward_plan(p))
+        order = list(range(passes - 1, -1, -1))          # the step runs the LAST pass's backward first
+        for i, p in enumerate(order):
+            wg = i == len(order) - 1 and p == 0
+            ops = (mlp._chained(("t_bwd", p, wg), lambda p=p, wg=wg: mlp._build_backward(p, True, None, wg)) if chain
+                   else mlp.backward_plan(p, True, None, wg))
+            mlp.run(ops)
+        return snapshot()
+
+    ref = run_all(False)
+    for rep in range(3):
+        got = run_all(True)
+        for k, v in ref.items():
+            a, b = v, got[k]
+            assert torch.equal(a, b), (rep, k, (a.float() - b.float()).abs().max().item())

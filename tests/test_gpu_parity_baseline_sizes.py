@@ -122,3 +122,46 @@ def test_eval_at_200k_poses():
     assert cnt == n
     assert abs(out["pa_mpjpe"] - pa / n) < 0.05, (out, pa / n)
     assert abs(out["n_mpjpe"] - nm / n) < 0.05, (out, nm / n)
+
+
+def test_merged_lt_lr_step_with_sampling_prefetch():
+    """kind='both' (config #2 as bench.py runs it): the leg/torso and the left/right step of one batch share a
+    4-network engine, one sampling pass and -- with prefetch_sample -- draw the poses of step k+1 while step k runs.
+    Both flavours' losses and gradients vs the oracle, for two consecutive batches (the second one exercises the
+    prefetched poses)."""
+    from links_b200.steps import LifterStep
+    from links_b200.synth import synth_poses
+    from oracle import steps as OS
+    B = 1024
+    n_lt, f_lt, full = _weights("lt")
+    n_lr, f_lr, _ = _weights("lr")
+    step = LifterStep("both", B, n_lt + n_lr, f_lt + f_lr, full, cfg={"prefetch_sample": True})
+    batches = []
+    for i in range(2):
+        x2d, _ = synth_poses(B, seed=900 + i)
+        g = torch.Generator().manual_seed(40 + i)
+        batches.append(dict(x=torch.from_numpy(x2d), noise=torch.randn(B, 34, generator=g),
+                            eps_x=torch.randn(2 * B, generator=g), u_y=torch.rand(2 * B, generator=g)))
+    step.x.copy_(batches[0]["x"]); step.noise.copy_(batches[0]["noise"])
+    step.prime()
+    for i in range(2):
+        nxt = batches[min(i + 1, 1)]
+        step.x.copy_(nxt["x"]); step.noise.copy_(nxt["noise"])                     # sampling inputs of the NEXT step
+        step.eps_x.copy_(batches[i]["eps_x"]); step.u_y.copy_(batches[i]["u_y"])    # rotation draws of THIS step
+        step.forward_backward()
+        torch.cuda.synchronize()
+        u = OS.sample_poses(batches[i]["x"], full, batches[i]["noise"])
+        assert rel_fro(step.u.cpu(), u) < 1e-3
+        got = step.loss_dict()
+        for kind, nets, flows, fn, s0 in (("lt", n_lt, f_lt, OS.lt_step, 0), ("lr", n_lr, f_lr, OS.lr_step, 2)):
+            pn = [OS.params_require_grad(p) for p in nets]
+            ref = fn(u, pn[0], pn[1], flows[0], flows[1], batches[i]["eps_x"], batches[i]["u_y"])
+            for k, v in got[kind].items():
+                r = ref[k].item()
+                assert abs(v - r) <= 1e-3 * abs(r) + 1e-6, (i, kind, k, v, r)
+            if i == 1:
+                ref["loss"].backward()
+                for s in range(2):
+                    for name in ("upscale", "res_common.l1", "res_pose2.l2", "res_angle3.l1", "downscale", "angles"):
+                        e = rel_fro(step.mlp.nets[s0 + s].layers[name].gW.cpu(), pn[s][name + ".weight"].grad)
+                        assert e < 6e-2, (kind, s, name, e)

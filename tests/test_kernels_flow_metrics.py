@@ -274,15 +274,18 @@ def test_adam_colsum_cast(backend):
     tp = torch.from_numpy(p0.copy()).requires_grad_(True)
     opt = torch.optim.Adam([tp], lr=2e-4, weight_decay=1e-5)
     p, m, v = p0.copy(), np.zeros(n, np.float32), np.zeros(n, np.float32)
-    for step in range(1, 4):
+    for step in range(1, 5):
         g = rng.normal(size=n).astype(np.float32) * 0.1
         tp.grad = torch.from_numpy(g.copy())
         opt.step()
-        if step < 3:
-            assert L.call("adam_step", p, g, m, v, n, 2e-4, 0.9, 0.999, 1e-8, 1e-5, step, None, 1.0) == 0
+        if step == 4:   # device-side learning rate (wins over the by-value argument): graph replays follow the scheduler
+            cnt, lr_dev = np.array([step - 1], np.int32), np.array([2e-4], np.float32)
+            assert L.call("adam_step", p, g, m, v, n, 123.0, 0.9, 0.999, 1e-8, 1e-5, 0, cnt, 1.0, lr_dev) == 0
+        elif step < 3:
+            assert L.call("adam_step", p, g, m, v, n, 2e-4, 0.9, 0.999, 1e-8, 1e-5, step, None, 1.0, None) == 0
         else:   # device-side step counter (CUDA-graph friendly): holds the number of completed steps
             cnt = np.array([step - 1], np.int32)
-            assert L.call("adam_step", p, g, m, v, n, 2e-4, 0.9, 0.999, 1e-8, 1e-5, 0, cnt, 1.0) == 0
+            assert L.call("adam_step", p, g, m, v, n, 2e-4, 0.9, 0.999, 1e-8, 1e-5, 0, cnt, 1.0, None) == 0
             assert cnt[0] == step
         np.testing.assert_allclose(p, tp.detach().numpy(), rtol=0, atol=2e-7)
     Gm = rng.normal(size=(300, 40)).astype(np.float32)
