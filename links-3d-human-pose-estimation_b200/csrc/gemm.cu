@@ -58,7 +58,11 @@ constexpr uint32_t kOffBar = kOffScratch + kEpiWarps * kScratchBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024 /*align slack*/;
 
 // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2]
-enum { GB_FULL = 0, GB_EMPTY = kStages, GB_ACCFULL = 2 * kStages, GB_ACCEMPTY = 2 * kStages + 2, GB_COUNT = 2 * kStages + 4 };
+// chain launches: tile_done[4] -- the 16 epilogue warps of a CTA arrive when their stores of a tile are issued; the
+// signalling warp (warp 2) then publishes the tile's completion counter (see the kernel).  Four slots: an epilogue warp
+// can run at most two tiles ahead of the slowest one (it needs that warp's accumulator release two tiles back).
+enum { GB_FULL = 0, GB_EMPTY = kStages, GB_ACCFULL = 2 * kStages, GB_ACCEMPTY = 2 * kStages + 2, GB_TILEDONE = 2 * kStages + 4,
+       GB_COUNT = 2 * kStages + 8 };
 
 struct alignas(64) GemmProblemDev {
   CUtensorMap tmA;
@@ -279,8 +283,10 @@ struct PrimaryOp {
   int ld, M, m0, n0;
   int ok;             // present, 16-byte aligned and the warp's 64-column slab lies fully inside N (the vector path)
   int pad;
-  const int* dep;     // chain launches: completion counter of the tiles that PRODUCE this operand (null: none)
-  int dep_need, pad2;
+  int dep_tile;       // chain launches: 1 + index (in this cluster's schedule) of the tile the operand belongs to when it is
+                      // produced inside the chain -- its fetch may only start once the scout warp has seen the tile's
+                      // dependencies complete (deps_ok >= dep_tile); 0: no dependency
+  int pad2, pad3, pad4;
 };
 static_assert(sizeof(PrimaryOp) == 48, "PrimaryOp slot");
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -292,16 +298,20 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // only).  The prefetch runs a tile ahead of the producer warp's own dependency wait and must never block: the warp
 // still owes the completion signal of its CURRENT tile, which the missing producer may (transitively) be waiting for.
 // A skipped fetch is repeated at the top of the next tile, behind the accumulator barrier (all dependencies done).
+__device__ __forceinline__ int ld_acquire_cta_shared(uint32_t saddr) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
 template <bool kChain>
-__device__ __forceinline__ bool prefetch_primary(const PrimaryOp* slot, uint32_t S, int h, int lane) {
+__device__ __forceinline__ bool prefetch_primary(const PrimaryOp* slot, uint32_t S, int h, int lane, uint32_t deps_ok_addr) {
   const uint4 a = *reinterpret_cast<const uint4*>(slot);              // p, ld, M
   const uint4 b = *(reinterpret_cast<const uint4*>(slot) + 1);        // m0, n0, ok
   bool missed = false;
   if (b.z != 0u) {
     if (kChain) {
-      const uint4 c = *(reinterpret_cast<const uint4*>(slot) + 2);    // dep, dep_need
-      const int* dp = reinterpret_cast<const int*>(static_cast<uint64_t>(c.x) | (static_cast<uint64_t>(c.y) << 32));
-      if (dp != nullptr) missed = __any_sync(0xffffffffu, ld_acquire_gpu(dp) < static_cast<int>(c.z));
+      const int dep_tile = *reinterpret_cast<const int*>(reinterpret_cast<const uint4*>(slot) + 2);
+      if (dep_tile > 0) missed = __any_sync(0xffffffffu, ld_acquire_cta_shared(deps_ok_addr) < dep_tile);
     }
     if (!missed) {
       const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(static_cast<uint64_t>(a.x) | (static_cast<uint64_t>(a.y) << 32));
@@ -319,7 +329,8 @@ __device__ __forceinline__ bool prefetch_primary(const PrimaryOp* slot, uint32_t
 //   t_addr : TMEM address of (lane group, first column of the block);  sbias : bias of the block's 64 columns (smem)
 template <uint32_t F, bool kChain>
 __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
-                                               const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
+                                               const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar,
+                                               uint32_t deps_ok_addr) {
   constexpr bool kDyn = F == 0u;
   bool missed = false;
   const int m = m0 + lane;
@@ -351,8 +362,8 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive_cluster(acc_empty_bar, 0);
-    missed |= prefetch_primary<kChain>(nxt, S0, 0, lane);
-    missed |= prefetch_primary<kChain>(nxt, S0 + 2048u, 1, lane);
+    missed |= prefetch_primary<kChain>(nxt, S0, 0, lane, deps_ok_addr);
+    missed |= prefetch_primary<kChain>(nxt, S0 + 2048u, 1, lane, deps_ok_addr);
     return missed;
   }
 
@@ -498,7 +509,7 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
       }
     }
     // this pass's scratch is free again: refill it with the primary operand of the same pass of the next tile
-    missed |= prefetch_primary<kChain>(nxt, SA, h, lane);
+    missed |= prefetch_primary<kChain>(nxt, SA, h, lane, deps_ok_addr);
   }
   return missed;
 }
@@ -508,8 +519,9 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
 // mode.  The caller passes copies, so only those copies are pinned in local memory.
 template <bool kChain>
 __device__ __noinline__ bool epilogue_block_dyn(const EpiParams& E, uint32_t t_addr, const float* sbias, uint32_t S0,
-                                                const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar) {
-  return epilogue_block<0u, kChain>(E, t_addr, sbias, S0, nxt, m0, n_blk, lane, acc_empty_bar);
+                                                const PrimaryOp* nxt, int m0, int n_blk, int lane, uint32_t acc_empty_bar,
+                                                uint32_t deps_ok_addr) {
+  return epilogue_block<0u, kChain>(E, t_addr, sbias, S0, nxt, m0, n_blk, lane, acc_empty_bar, deps_ok_addr);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -656,8 +668,11 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const int cl_id = blockIdx.x >> 1, n_cl = gridDim.x >> 1;
   if (threadIdx.x == 0) TRACE(0);
+  // chain launches: number of tiles of this cluster's schedule whose dependencies the scout warp has seen complete
+  const uint32_t deps_ok_addr = bars + GB_COUNT * 8 + 16;
 
   if (warp == 0 && lane == 0) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(deps_ok_addr), "r"(0) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bars + (GB_FULL + s) * 8, 1);
       mbar_init(bars + (GB_EMPTY + s) * 8, 1);     // released by the leader's pair-MMA commit (multicast to both CTAs)
@@ -666,6 +681,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
       mbar_init(bars + (GB_ACCFULL + s) * 8, 1);
       mbar_init(bars + (GB_ACCEMPTY + s) * 8, 2 * kEpiWarps);   // leader's copy: one arrival per epilogue warp of BOTH CTAs
     }
+    for (int s = 0; s < 4; ++s) mbar_init(bars + (GB_TILEDONE + s) * 8, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc_pair(bars + GB_COUNT * 8, kTmemCols);
@@ -694,7 +710,17 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
       TileCoord tc;
       for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti) {
         const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
-        if (kChain) chain_wait_deps(P, reinterpret_cast<const ChainDev&>(G).counters, tc.tm);
+        if (kChain) {
+          // the scout warp has seen every producer tile of this tile complete (acquire at gpu scope, handed over at cta
+          // scope); order the TMA (async proxy) reads behind it
+          if (ld_acquire_cta_shared(deps_ok_addr) <= ti) {
+            const long long t0 = clock64();
+            while (ld_acquire_cta_shared(deps_ok_addr) <= ti) {
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
         tc.tm = 2 * tc.tm + cta_rank;
         const int num_kb = (P.K + BK - 1) / BK;
         const bool a_mn = (P.flags & LINKS_GEMM_A_MN) != 0, b_mn = (P.flags & LINKS_GEMM_B_MN) != 0;
@@ -765,6 +791,36 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
         __syncwarp();
       }
     }
+  } else if (kChain && warp == 3) {
+    // ================= dependency scout (chain launches) =================
+    // Walks this cluster's schedule ahead of the producer: spins on the completion counters of each tile's producer
+    // tiles (gpu-scope acquire loads: an L2 round trip each) and publishes the number of cleared tiles in shared memory,
+    // where the TMA producer and the epilogue's operand prefetch read it at shared-memory latency.
+    if (lane == 0) {
+      TileCoord tc;
+      for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti) {
+        chain_wait_deps(problem_of<kChain>(G, tc.pi), reinterpret_cast<const ChainDev&>(G).counters, tc.tm);
+        asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(deps_ok_addr), "r"(ti + 1) : "memory");
+      }
+    }
+  } else if (kChain && warp == 2) {
+    // ================= completion signaller (chain launches) =================
+    // Publishing a tile needs a gpu-scope fence behind the epilogue's stores; issued by the epilogue warps themselves it
+    // sat on their critical path (the epilogue is the longer side of the per-tile pipeline).  They only arrive on a
+    // CTA-local barrier (release.cta) and move on; this otherwise idle warp observes the barrier (acquire.cta), fences at
+    // gpu scope -- cumulative over the stores it has synchronised with -- and bumps the tile's completion counter.
+    if (lane == 0) {
+      TileCoord tc;
+      for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti) {
+        mbar_wait(bars + (GB_TILEDONE + (ti & 3)) * 8, static_cast<uint32_t>(ti >> 2) & 1u);
+        const int cb = problem_of<kChain>(G, tc.pi).cnt_base;
+        if (cb >= 0) {
+          int* c = reinterpret_cast<const ChainDev&>(G).counters + cb + tc.tm;
+          asm volatile("fence.proxy.async.global;\n\tfence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.s32 [%0], %1;"
+                       ::"l"(c), "r"(kEpiWarps) : "memory");
+        }
+      }
+    }
   }
   } else {
     // ================= epilogue warps (512 threads) =================
@@ -798,7 +854,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
     auto publish_primary = [&](int ti) {
       if (lane == 0) {
         PrimaryOp o;
-        o.p = nullptr; o.ld = 0; o.M = 0; o.m0 = 0; o.n0 = 0; o.ok = 0; o.pad = 0; o.dep = nullptr; o.dep_need = 0; o.pad2 = 0;
+        o.p = nullptr; o.ld = 0; o.M = 0; o.m0 = 0; o.n0 = 0; o.ok = 0; o.pad = 0; o.dep_tile = 0; o.pad2 = 0; o.pad3 = 0; o.pad4 = 0;
         TileCoord t0;
         if (tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, t0)) {
           const GemmProblemDev& P = problem_of<kChain>(G, t0.pi);
@@ -808,19 +864,15 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
           o.m0 = (2 * t0.tm + cta_rank) * BM + lane_grp * 32;
           o.n0 = t0.tn * BN + slab * kSlab;
           o.ok = (o.p != nullptr && P.vec_ok && o.n0 + kSlab <= P.N) ? 1 : 0;
-          if (kChain && P.add0 != nullptr && P.dep_base[1] >= 0) {
-            // (the contracted-over-rows flavour never applies to an element-wise operand)
-            o.dep = reinterpret_cast<const ChainDev&>(G).counters + P.dep_base[1] + t0.tm;
-            o.dep_need = P.dep_need[1];
-          }
+          if (kChain && P.add0 != nullptr && P.dep_base[1] >= 0) o.dep_tile = ti + 1;
         }
         *nxt = o;
       }
       __syncwarp();
     };
     publish_primary(0);                                      // in flight while the first main loop runs
-    bool missed = prefetch_primary<kChain>(nxt, S, 0, lane);
-    missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane);
+    bool missed = prefetch_primary<kChain>(nxt, S, 0, lane, deps_ok_addr);
+    missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane, deps_ok_addr);
     TileCoord tc;
     for (int ti = 0; tile_at<kChain>(G, cl_id, n_cl, n_mine, ti, tc); ++ti, ++lt) {
       const int pair_m = tc.tm;
@@ -850,8 +902,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
       if (kChain && missed) {
         // The operand prefetch of THIS tile was skipped (its producer had not signalled yet).  The accumulator barrier
         // implies the producer warp has seen every dependency of the tile complete: fetch both passes now.
-        const GemmProblemDev& P = problem_of<kChain>(G, tc.pi);
-        if (P.dep_base[1] >= 0) (void)ld_acquire_gpu(reinterpret_cast<const ChainDev&>(G).counters + P.dep_base[1] + pair_m);
+        (void)ld_acquire_cta_shared(deps_ok_addr);
         const __nv_bfloat16* pp = E.add0 != nullptr ? E.add0 : E.ymask;
         const int pld = E.add0 != nullptr ? E.ld_add0 : E.ld_ymask;
         if (pp != nullptr && E.vec_ok && n0 + kSlab <= E.N) {
@@ -871,39 +922,32 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(ae, 0);
-        missed |= prefetch_primary<kChain>(nxt, S, 0, lane);
-        missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane);
+        missed |= prefetch_primary<kChain>(nxt, S, 0, lane, deps_ok_addr);
+        missed |= prefetch_primary<kChain>(nxt, S + 2048u, 1, lane, deps_ok_addr);
       } else {
         const float* sb = sbias;
         switch (mode) {
-          case 1: missed = epilogue_block<kEpiMask[1], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 2: missed = epilogue_block<kEpiMask[2], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 3: missed = epilogue_block<kEpiMask[3], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 4: missed = epilogue_block<kEpiMask[4], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 5: missed = epilogue_block<kEpiMask[5], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 6: missed = epilogue_block<kEpiMask[6], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 7: missed = epilogue_block<kEpiMask[7], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 8: missed = epilogue_block<kEpiMask[8], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 9: missed = epilogue_block<kEpiMask[9], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
-          case 10: missed = epilogue_block<kEpiMask[10], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae); break;
+          case 1: missed = epilogue_block<kEpiMask[1], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 2: missed = epilogue_block<kEpiMask[2], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 3: missed = epilogue_block<kEpiMask[3], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 4: missed = epilogue_block<kEpiMask[4], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 5: missed = epilogue_block<kEpiMask[5], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 6: missed = epilogue_block<kEpiMask[6], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 7: missed = epilogue_block<kEpiMask[7], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 8: missed = epilogue_block<kEpiMask[8], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 9: missed = epilogue_block<kEpiMask[9], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 10: missed = epilogue_block<kEpiMask[10], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           default: {
             const EpiParams Ed = E;
-            missed = epilogue_block_dyn<kChain>(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae);
+            missed = epilogue_block_dyn<kChain>(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr);
             break;
           }
         }
       }
       if (kChain) {
-        // completion signal: this warp's stores of the tile are ordered before the counter increment (warp barrier +
-        // gpu-scope fence by the signalling lane; the proxy fence covers consumers that read through TMA)
-        const int cb = problem_of<kChain>(G, tc.pi).cnt_base;
-        if (cb >= 0) {
-          __syncwarp();
-          if (lane == 0) {
-            int* c = reinterpret_cast<const ChainDev&>(G).counters + cb + pair_m;
-            asm volatile("fence.proxy.async.global;\n\tfence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(c) : "memory");
-          }
-        }
+        // this warp's stores of the tile are issued: tell the signalling warp (release.cta orders them before the arrive)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (GB_TILEDONE + (lt & 3u)) * 8);
       }
       if (store_thread && lt < 3) TRACE(4 + 3 * lt);
     }
@@ -1305,6 +1349,7 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_chain_build(con
   chain_tile_order(problems, d.data(), n, tiles);
   const int T = static_cast<int>(tiles.size()), n_cl = L.n_cl;
   std::vector<std::vector<uint32_t>> lists(n_cl);
+  double sim_makespan = 0.0;
   {
     const double kEpi = 11.0, kSignal = 3.0, kMinMain = 2.0;
     std::vector<double> mma_free(n_cl, 0.0), epi_free(n_cl, 0.0), epi_prev(n_cl, 0.0), epi_prev2(n_cl, 0.0);
@@ -1337,7 +1382,7 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_chain_build(con
       makespan = std::max(makespan, epi_end);
       lists[best].push_back((static_cast<uint32_t>(ct.pi) << 22) | (static_cast<uint32_t>(ct.tm) << 11) | static_cast<uint32_t>(ct.tn));
     }
-    plan->sim_units = static_cast<float>(makespan);
+    sim_makespan = makespan;
   }
   int max_len = 0;
   for (int c = 0; c < n_cl; ++c) max_len = std::max(max_len, static_cast<int>(lists[c].size()));
@@ -1366,6 +1411,7 @@ extern "C" __attribute__((visibility("default"))) int links_gemm_chain_build(con
   plan->sched_ld = L.sched_ld;
   plan->n_problems = n;
   plan->total_tiles = T;
+  plan->sim_units = static_cast<float>(sim_makespan);
   {
     double units = 0.0;
     for (int t = 0; t < T; ++t) units += std::max(2.0, static_cast<double>((d[tiles[t].pi].K + BK - 1) / BK));

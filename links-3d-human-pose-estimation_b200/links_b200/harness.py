@@ -38,6 +38,8 @@ def add_common_args(p, batch=256, epochs=100):
                    help="use seeded random weights for pretrained networks whose checkpoint is missing (benchmarks / "
                         "smoke runs); without it a missing checkpoint raises FileNotFoundError like the reference's torch.load")
     g.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    g.add_argument("--no-prefetch", action="store_true",
+                   help="lifter trainers: draw the sampled poses inside the step instead of one step ahead")
     return p
 
 
@@ -160,19 +162,61 @@ class Validator:
 
 
 def run_training(step, loader, args, rank, feed, validator=None):
-    """Epoch loop: feed(step, batch) uploads inputs + draws, step.step() does the rest on the device."""
+    """Epoch loop: feed(step, batch, ...) uploads inputs + draws, then the step runs on the device.
+
+    The whole step is captured into ONE CUDA graph after the first (eager) step and replayed from then on (--no-graph
+    keeps eager launches): the static input buffers are refilled by `feed` on the same stream before every replay, the
+    learning rate lives in a device word (step.set_lr), so ExponentialLR needs no re-capture.
+    Steps with sampling prefetch (LifterStep(cfg prefetch_sample)) draw the poses of batch i+1 while batch i trains:
+    feed(..., sampling=True) loads the NEXT batch's sampling inputs, feed(..., draws=True) this step's random draws."""
     n_steps, t0 = 0, time.time()
     lr = LR0
+    use_graph = not getattr(args, "no_graph", False)
+    prefetch = bool(getattr(step, "prefetch", False))
+    graph = None
+
+    def run_step():
+        nonlocal graph
+        if graph is not None:
+            graph.replay()
+        elif use_graph and n_steps >= 1 and hasattr(step, "capture"):
+            graph = step.capture(warmup=0)          # plans exist after the first eager step
+            graph.replay()
+        else:
+            step.step()
+
     for epoch in range(args.epochs):
         step.set_lr(lr)
-        for xb in DevicePrefetcher(loader, step.device):     # batch i+1 crosses PCIe while step i runs
-            feed(step, xb)
-            step.step()
+        it = iter(DevicePrefetcher(loader, step.device))     # batch i+1 crosses PCIe while step i runs
+        pending = None
+        if prefetch:
+            first = next(it, None)
+            if first is None:
+                break
+            feed(step, first, sampling=True, draws=False)
+            step.prime()                                     # poses of the first batch
+            pending = first
+        while True:
+            xb = next(it, None)
+            if prefetch:
+                if pending is None:
+                    break
+                if xb is not None:
+                    feed(step, xb, sampling=True, draws=False)     # sampled while this step trains on `pending`
+                feed(step, pending, sampling=False, draws=True)
+                pending = xb
+            else:
+                if xb is None:
+                    break
+                feed(step, xb, sampling=True, draws=True)
+            run_step()
             n_steps += 1
             if rank == 0 and n_steps % args.log_every == 0:
                 torch.cuda.synchronize()
                 d = step.loss_dict()
-                print("epoch %d step %d  %s  (%.0f poses/s)" % (epoch, n_steps, " ".join("%s=%.5f" % kv for kv in d.items()),
+                flat = d if not isinstance(next(iter(d.values())), dict) else \
+                    {"%s.%s" % (k, kk): vv for k, v in d.items() for kk, vv in v.items()}
+                print("epoch %d step %d  %s  (%.0f poses/s)" % (epoch, n_steps, " ".join("%s=%.5f" % kv for kv in flat.items()),
                                                                 n_steps * args.batch / (time.time() - t0)), flush=True)
             if args.steps and n_steps >= args.steps:
                 break
@@ -188,13 +232,14 @@ def run_training(step, loader, args, rank, feed, validator=None):
 
 
 def lifter_feed(gen_dev):
-    def feed(step, xb):
-        B = xb.shape[0]
-        step.x.copy_(xb, non_blocking=True)
-        step.noise.normal_(generator=gen_dev)        # add_noise eps (utils/helpers.py:298-308)
-        step.eps_x.normal_(generator=gen_dev)        # elevation draw (train_leg_torso_lifter.py:169-171)
-        step.u_y.uniform_(generator=gen_dev)         # azimuth draw (:176)
-        assert B == step.B
+    def feed(step, xb, sampling=True, draws=True):
+        if sampling:
+            assert xb.shape[0] == step.B
+            step.x.copy_(xb, non_blocking=True)
+            step.noise.normal_(generator=gen_dev)        # add_noise eps (utils/helpers.py:298-308)
+        if draws:
+            step.eps_x.normal_(generator=gen_dev)        # elevation draw (train_leg_torso_lifter.py:169-171)
+            step.u_y.uniform_(generator=gen_dev)         # azimuth draw (:176)
     return feed
 
 
@@ -215,6 +260,7 @@ def train_lifters(kind, args):
              for i, (f, n) in enumerate(zip(flow_keys, nj))]
     full = load_state(ckpt_paths(wd, "full_flow"), lambda: INIT.init_flow_params(34, 40), rnd)
     loader = make_loader(args, rank, world)
+    cfg["prefetch_sample"] = not getattr(args, "no_prefetch", False)
     step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
     validator = Validator(kind, step, args.val, args.seed, args.translation, rank, world, pg) if args.val else None
@@ -244,7 +290,7 @@ def train_occlusion(args):
     step = OcclusionStep(loader.batch, lifters, preds, cfg=dict(depth=args.translation), process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
 
-    def feed(st, xb):
+    def feed(st, xb, sampling=True, draws=True):
         st.x.copy_(xb, non_blocking=True)
         st.u_y[0].uniform_(generator=gen_dev)        # Ry augmentation draws (train_occlusion_models.py:213-217,256-260)
         st.u_y[1].uniform_(generator=gen_dev)

@@ -209,6 +209,9 @@ class MlpSet:
                     for blk in all_blocks:
                         self.dt[p][s][blk] = torch.empty(M, WIDTH, **bf)
         self._plans = {}
+        # learning rate of adam_step, read on the device (a captured graph follows set_lr without re-capture)
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._lr_host = None
 
     # ------------------------------------------------------------------------------------------
     # parameters
@@ -263,9 +266,6 @@ class MlpSet:
 
     def set_lr(self, lr):
         """Learning rate of the following adam_step calls, kept in a device word: captured graphs see new values."""
-        if getattr(self, "lr_dev", None) is None:
-            self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
-            self._lr_host = None
         if lr != self._lr_host:
             self.lr_dev.fill_(float(lr))
             self._lr_host = lr
@@ -274,6 +274,7 @@ class MlpSet:
                   last=True, grads_bf16=False):
         """Adam on the whole flat buffer, or on one bucket's contiguous range.  The device-side step counter is
         advanced by the call with last=True (the other buckets of the same step pass last=False)."""
+        self.set_lr(lr)               # no-op unless the value changed (never inside a captured step: see set_lr callers)
         st = torch.cuda.current_stream().cuda_stream
         a, b = (0, self.n_params) if bucket is None else self.bucket_ranges[bucket]
         es = 4
@@ -282,7 +283,7 @@ class MlpSet:
         check(fn(self.master.data_ptr() + a * es, gptr, self.exp_avg.data_ptr() + a * es,
                  self.exp_avg_sq.data_ptr() + a * es, b - a, lr, betas[0], betas[1], eps, weight_decay,
                  0 if last else -1, self.step_dev.data_ptr(), grad_scale,
-                 self.lr_dev.data_ptr() if getattr(self, "lr_dev", None) is not None else None, st), "links_adam_step")
+                 self.lr_dev.data_ptr(), st), "links_adam_step")
         self.refresh_shadows(bucket)
 
     # ------------------------------------------------------------------------------------------

@@ -118,6 +118,22 @@ class OcclusionStep:
 
     def set_lr(self, lr):
         self.cfg["lr"] = lr
+        self.mlp.set_lr(lr)           # device word read by the Adam kernel: captured graphs follow the schedule
+
+    def capture(self, warmup=2):
+        """Capture step() into one CUDA graph (replay with the returned graph's .replay())."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+        return g
 
     def loss_dict(self):
         v = self.losses.tolist()

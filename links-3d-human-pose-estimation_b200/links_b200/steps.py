@@ -298,6 +298,7 @@ class LifterStep:
 
     def set_lr(self, lr):
         self.cfg["lr"] = lr
+        self.mlp.set_lr(lr)           # device word read by the Adam kernel: captured graphs follow the schedule
 
     def capture(self, warmup=2):
         """Capture step() into one CUDA graph (replay with .replay()); eager warm-up runs first (lazy plan builds)."""
