@@ -420,15 +420,17 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): every GEMM launch of one step, timed alone
     m = step.mlp
-    plans = [m.forward_ops(0), m.forward_ops(1), m.backward_ops(1, need_input_grad=True),
-             m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=world > 1)]
+    plans = [m.forward_ops(0), m.forward_ops(1, max_ctas=step._ctas_window),
+             m.backward_ops(1, need_input_grad=True, max_ctas=step._ctas_window),
+             m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=world > 1, max_ctas=step._ctas_tail,
+                            fuse_adam=step._fuse_adam)]
     if MLP.USE_CHAIN:
         gemm_ops = [op for plan in plans for op in plan if hasattr(op, "plan")]
         sim = {"chain_sim_units": [float(op.plan.sim_units) for op in gemm_ops],
                "chain_ideal_units": [float(op.plan.ideal_units) for op in gemm_ops],
                "chain_tiles": [int(op.plan.total_tiles) for op in gemm_ops]}
     else:
-        plans[3] = m.backward_plan(0, False) + m.wgrad_plan()[0::2]
+        plans[3] = m.backward_plan(0, False) + m.wgrad_plan()
         gemm_ops, sim = [op for plan in plans for op in plan if not isinstance(op, tuple)], {}
 
     def gemm_only():

@@ -88,6 +88,14 @@ typedef struct LinksGemmProblem {
   void* mid; int ld_mid;           /* bf16 [M, ld], ld multiple of 8 */
   void* out; int ld_out;           /* bf16 [M, ld], ld multiple of 8 */
   float* out_f32; int ld_f32;      /* fp32 [M, ld] */
+  /* Fused optimiser (weight-gradient problems of a single-GPU step; all NULL otherwise).  When adam_p is set the
+   * problem must have NO other epilogue step and no out_f32: instead of storing dW the epilogue applies
+   * torch.optim.Adam (train_leg_torso_lifter.py:111-114) to its tile -- g = acc * grad_scale + weight_decay * p, then m,
+   * v, p in place (fp32 [M, ld_f32], 16-byte aligned rows, N a multiple of 64) -- and refreshes the bf16 shadow
+   * [M, ld_shadow] that the next step's GEMMs read.  adam_hyper: 8 device floats written by links_adam_prepare. */
+  float* adam_p; float* adam_m; float* adam_v;
+  void* adam_shadow; int ld_shadow;
+  const float* adam_hyper;
 } LinksGemmProblem;
 
 int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream);
@@ -181,6 +189,12 @@ int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     int* step_dev, float grad_scale, const float* lr_dev, void* stream);
 
+/* Step constants of the fused optimiser (LinksGemmProblem.adam_*), computed on the device so that captured graphs
+ * replay correctly: hyper[0..7] = { lr / (1 - beta1^t), sqrt(1 - beta2^t), eps, beta1, beta2, weight_decay, grad_scale, t }
+ * with t = *step_dev + 1 and lr = *lr_dev when lr_dev != NULL.  Does not advance *step_dev. */
+int links_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float grad_scale, float* hyper, void* stream);
+
 /* Data-parallel gradient compression: grad_bf16[i] = bf16(grad[i]) before the NCCL all-reduce (half the NVLink
  * bytes), and the Adam step that consumes the reduced bf16 gradients directly (same arithmetic otherwise). */
 int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream);
@@ -255,9 +269,14 @@ int links_flow_set_simt_only(int on);
 /* z, log_jac_det = inn(x, rev) for x [M,C] (ld = C). */
 int links_flow_apply(const float* packed, int C, int n_blocks, const float* x, int M, int rev,
                      float* out, float* log_jac_det, void* stream);
-/* nll[m] = 0.5*|z|^2 - log_jac_det, nll_sum += sum_m nll, dx = scale * d(nll)/dx (frozen flow). */
+/* nll[m] = 0.5*|z|^2 - log_jac_det, nll_sum += sum_m nll, dx = scale * d(nll)/dx (frozen flow).
+ * stash (may be NULL): scratch of links_flow_stash_floats(C, n_blocks, M) floats, 16-byte aligned.  With it the
+ * tensor-core kernel keeps every block's input and subnet output from the forward pass instead of reconstructing them
+ * with the inverse coupling in the backward pass (2 instead of 3 subnet evaluations per block; same results up to the
+ * round-off of the inverse). */
+size_t links_flow_stash_floats(int C, int n_blocks, int M);
 int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
-                          float* nll_sum, float* dx, void* stream);
+                          float* nll_sum, float* dx, float* stash, void* stream);
 /* Training a flow (train_full_pose_norm_flow.py:75-98): NLL forward + backward as above, and in addition, per coupling
  * block k, the operands of the parameter-gradient GEMMs -- ex_x1[k] = subnet input x1 (bf16 [M,64], first c1 columns)
  * and ex_dsub[k] = d nll / d subnet output (bf16 [M,64], first 2*c2 columns; the caller keeps the padding zero) -- and
@@ -267,7 +286,7 @@ int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float*
  * which the host issues as grouped GEMMs (links_gemm_grouped).  Tensor-core kernel for every M. */
 int links_flow_nll_train(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
                          float* nll_sum, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale, float* d_goffset,
-                         void* stream);
+                         float* stash, void* stream);
 /* Vector-Jacobian product of the forward map (z, log_jac_det) = inn(x):
  * dx = (dz/dx)^T gz + (d log_jac_det/dx)^T gld  (gld may be NULL = 0).  Backs autograd of the FrEIA shim. */
 int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,

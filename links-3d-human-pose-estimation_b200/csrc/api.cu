@@ -128,6 +128,13 @@ extern "C" __attribute__((visibility("default"))) int links_adam_step_g16(float*
                                     beta2, eps, weight_decay, step, step_dev, grad_scale, lr_dev, stream);
 }
 
+extern "C" __attribute__((visibility("default"))) int links_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float beta1, float beta2,
+                                  float eps, float weight_decay, float grad_scale, float* hyper, void* stream) {
+  LINKS_CHECK_PTR(step_dev); LINKS_CHECK_PTR(hyper); LINKS_CHECK_ALIGN16(hyper);
+  adam_prepare_kernel<<<1, 32, 0, links_stream(stream)>>>(step_dev, lr_dev, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream) {
   LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(grad_bf16);
   if (n == 0) return LINKS_E_RANGE;
@@ -317,6 +324,7 @@ static int launch_flow_tc_c(const FlowArgs& A, cudaStream_t s) {
   T.x = A.x; T.noise = A.noise; T.out = A.out; T.ld = A.ld; T.nll_sum = A.nll_sum; T.scale = A.scale;
   T.gz = A.gz; T.gld = A.gld; T.M = A.M; T.n_blocks = A.n_blocks;
   T.ex_x1 = A.ex_x1; T.ex_dsub = A.ex_dsub; T.d_gscale = A.d_gscale; T.d_goffset = A.d_goffset;
+  T.stash = A.stash;
   const int blocks = (A.M + kTcRows - 1) / kTcRows;
   flow_tc_kernel<C, MODE><<<blocks, kTcThreads, kTcSmemBytes, s>>>(T);
   return links_launch_status();
@@ -356,13 +364,20 @@ extern "C" __attribute__((visibility("default"))) int links_flow_apply(const flo
   return rev ? launch_flow<FLOW_REV>(C, A, links_stream(stream)) : launch_flow<FLOW_FWD>(C, A, links_stream(stream));
 }
 
+extern "C" __attribute__((visibility("default"))) size_t links_flow_stash_floats(int C, int n_blocks, int M) {
+  if (C < 2 || n_blocks < 1 || M < 1) return 0;
+  return static_cast<size_t>(M) * static_cast<size_t>(n_blocks) * static_cast<size_t>(C + 2 * flow_c2(C));
+}
+
 extern "C" __attribute__((visibility("default"))) int links_flow_nll_fwdbwd(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
-                                     float* nll_sum, float* dx, void* stream) {
+                                     float* nll_sum, float* dx, float* stash, void* stream) {
   LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_ALIGN16(packed);
   if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  if (stash != nullptr) LINKS_CHECK_ALIGN16(stash);
   FlowArgs A;
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = n_blocks;
+  A.stash = stash;
   return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
 }
 
@@ -380,14 +395,16 @@ static int launch_flow_tc_only(int C, const FlowArgs& A, cudaStream_t s) {
 
 extern "C" __attribute__((visibility("default"))) int links_flow_nll_train(const float* packed, int C, int n_blocks, const float* x, int M, float scale,
                                     float* nll_sum, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale,
-                                    float* d_goffset, void* stream) {
+                                    float* d_goffset, float* stash, void* stream) {
   LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(ex_x1); LINKS_CHECK_PTR(ex_dsub);
   LINKS_CHECK_PTR(d_gscale); LINKS_CHECK_PTR(d_goffset); LINKS_CHECK_ALIGN16(packed);
   if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  if (stash != nullptr) LINKS_CHECK_ALIGN16(stash);
   FlowArgs A;
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = n_blocks;
   A.ex_x1 = ex_x1; A.ex_dsub = ex_dsub; A.d_gscale = d_gscale; A.d_goffset = d_goffset;
+  A.stash = stash;
   return launch_flow_tc_only<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
 }
 

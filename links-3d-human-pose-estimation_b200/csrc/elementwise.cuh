@@ -184,6 +184,17 @@ __global__ void adam_kernel(float* __restrict__ p, const GradT* __restrict__ g, 
   }
 }
 
+__global__ void adam_prepare_kernel(const int* __restrict__ step_dev, const float* __restrict__ lr_dev, float lr, float b1,
+                                    float b2, float eps, float wd, float grad_scale, float* __restrict__ hyper) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int t = *step_dev + 1;
+  if (lr_dev != nullptr) lr = *lr_dev;
+  const float bc1 = 1.f - powf(b1, static_cast<float>(t));
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, static_cast<float>(t)));
+  hyper[0] = lr / bc1; hyper[1] = bc2_sqrt; hyper[2] = eps; hyper[3] = b1;
+  hyper[4] = b2; hyper[5] = wd; hyper[6] = grad_scale; hyper[7] = static_cast<float>(t);
+}
+
 __global__ void adam_incr_kernel(int* step_dev) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
 }

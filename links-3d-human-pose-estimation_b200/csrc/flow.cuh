@@ -98,6 +98,7 @@ struct FlowArgs {
   void* ex_dsub;
   float* d_gscale;
   float* d_goffset;
+  float* stash;         // NLL_FWDBWD, tensor-core kernel only, optional: activation stash (see flow_tc.cuh)
   int M, n_blocks;
 };
 

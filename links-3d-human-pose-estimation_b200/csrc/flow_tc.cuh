@@ -211,6 +211,10 @@ struct FlowTcArgs {
   void* ex_dsub;
   float* d_gscale;
   float* d_goffset;
+  // NLL mode, optional: [M][n_blocks][C + 2*c2] floats.  When given, the forward pass stores every block's input and its
+  // scaled subnet output there and the backward pass reads them back instead of reconstructing them with the inverse
+  // coupling: 2 GEMM chains per block instead of 3 (the kernel is bound by the length of its dependent chain sequence).
+  float* stash;
   int M, n_blocks;
 };
 
@@ -231,17 +235,18 @@ constexpr uint32_t kTcColD1 = 0, kTcColD3 = 128, kTcColD2 = 256, kTcTmemCols = 5
 // The GEMM chains of one kernel, in execution order: chain i works on block k, forward (a = subnet(x1)) or
 // backward (dx1 = subnet_vjp) flavour.
 template <int MODE>
-__device__ __forceinline__ int tc_num_chains(int nb) {
-  return MODE == FLOW_FWD || MODE == FLOW_REV ? nb : (MODE == FLOW_SAMPLE ? 2 * nb : 3 * nb);
+__device__ __forceinline__ int tc_num_chains(int nb, bool stash) {
+  return MODE == FLOW_FWD || MODE == FLOW_REV ? nb : (MODE == FLOW_SAMPLE || stash ? 2 * nb : 3 * nb);
 }
 template <int MODE>
-__device__ __forceinline__ void tc_chain_info(int i, int nb, int& k, bool& bwd) {
+__device__ __forceinline__ void tc_chain_info(int i, int nb, bool stash, int& k, bool& bwd) {
   bwd = false;
   if (MODE == FLOW_FWD) { k = i; }
   else if (MODE == FLOW_REV) { k = nb - 1 - i; }
   else if (MODE == FLOW_SAMPLE) { k = i < nb ? i : 2 * nb - 1 - i; }
   else {
     if (i < nb) { k = i; }
+    else if (stash) { k = 2 * nb - 1 - i; bwd = true; }
     else { const int j = i - nb; k = nb - 1 - (j >> 1); bwd = (j & 1) != 0; }
   }
 }
@@ -376,6 +381,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb = A.n_blocks;
+  const bool stash = MODE == FLOW_NLL_FWDBWD && A.stash != nullptr;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(bars + (TCB_WFULL + s) * 8, 1); mbar_init(bars + (TCB_WEMPTY + s) * 8, 1); }
@@ -395,11 +401,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
     // ================= producer =================
     if (lane == 0) {
       uint32_t g = 0;   // running chunk index
-      const int nch = tc_num_chains<MODE>(nb);
+      const int nch = tc_num_chains<MODE>(nb, stash);
 #pragma unroll 1
       for (int ci = 0; ci < nch; ++ci) {
         int k; bool bwd;
-        tc_chain_info<MODE>(ci, nb, k, bwd);
+        tc_chain_info<MODE>(ci, nb, stash, k, bwd);
         const unsigned char* src = A.packed + static_cast<size_t>(k) * tc_block_bytes(C) +
                                    (bwd ? static_cast<size_t>(kTcChunks) * fw : 0);
         const uint32_t bytes = bwd ? bw : fw;
@@ -427,14 +433,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
     constexpr uint32_t idesc4 = make_idesc_bf16(128, 2 * n4p);
     constexpr uint32_t idesc4h = make_idesc_bf16(128, n4p);
     uint32_t g0 = 0, n_a = 0, n_h0 = 0, n_h1 = 0;
-    const int nch = tc_num_chains<MODE>(nb);
+    const int nch = tc_num_chains<MODE>(nb, stash);
     const uint64_t a_slab0 = make_smem_desc_k128(sb + kTcOffA);
     const uint64_t a_slab1 = make_smem_desc_k128(sb + kTcOffA + 16384u);
     const uint64_t a_slab2 = make_smem_desc_k128(sb + kTcOffA + 2 * 16384u);
 #pragma unroll 1
     for (int ci = 0; ci < nch; ++ci) {
       int kblk; bool bwd;
-      tc_chain_info<MODE>(ci, nb, kblk, bwd);
+      tc_chain_info<MODE>(ci, nb, stash, kblk, bwd);
       mbar_wait(bb + TCB_AFULL * 8, n_a & 1u);
       n_a++;
       tc_fence_after();
@@ -506,11 +512,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
     const int row = lane_grp * 32 + lane;
     uint32_t n_d1a = 0, n_d1b = 0;
     if (half == 1) {
-      const int nch = tc_num_chains<MODE>(nb);
+      const int nch = tc_num_chains<MODE>(nb, stash);
 #pragma unroll 1
       for (int ci = 0; ci < nch; ++ci) {
         int kblk; bool bwd;
-        tc_chain_info<MODE>(ci, nb, kblk, bwd);
+        tc_chain_info<MODE>(ci, nb, stash, kblk, bwd);
         if (bwd) tc_chain_convert<true>(sbase, bars, tmem_base, lane_grp, lane, 1, n_d1a, n_d1b);
         else tc_chain_convert<false>(sbase, bars, tmem_base, lane_grp, lane, 1, n_d1a, n_d1b);
       }
@@ -570,10 +576,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
         tc_fence_before();
       };
 
+      constexpr int kStashRow = C + 2 * c2;                      // floats per (row, block): block input, then a
+      static_assert(kStashRow % 4 == 0, "stash rows are moved as float4");
+      float* stash_row = stash ? A.stash + static_cast<size_t>(ok ? grow : 0) * nb * kStashRow : nullptr;
       auto block_fwd = [&](int k) {
         const TcTail T = tc_tail<C>(A.packed, k);
         float a[2 * c2];
         subnet_fwd(x, T, a);
+        if (MODE == FLOW_NLL_FWDBWD && stash && ok) {
+          float buf[kStashRow];
+#pragma unroll
+          for (int i = 0; i < C; ++i) buf[i] = x[i];
+#pragma unroll
+          for (int i = 0; i < 2 * c2; ++i) buf[C + i] = a[i];
+          float4* dst = reinterpret_cast<float4*>(stash_row + k * kStashRow);
+#pragma unroll
+          for (int q = 0; q < kStashRow / 4; ++q) dst[q] = make_float4(buf[4 * q], buf[4 * q + 1], buf[4 * q + 2], buf[4 * q + 3]);
+        }
         ldp += T.logg;
 #pragma unroll
         for (int c = 0; c < c2; ++c) {
@@ -667,9 +686,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowTcArgs
           }
 #pragma unroll
           for (int i = 0; i < C; ++i) dy[i] *= __ldg(T.g + i);
-          // reconstruct the block input (x <- input) and the coupling coefficients
+          // the block input (x <- input) and the coupling coefficients: read back, or reconstructed with the inverse
           float a[2 * c2];
-          block_rev(k, T, a);
+          if (stash) {
+            const float4* src = reinterpret_cast<const float4*>(stash_row + k * kStashRow);
+            float buf[kStashRow];
+#pragma unroll
+            for (int q = 0; q < kStashRow / 4; ++q) {
+              const float4 t = ok ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+              buf[4 * q] = t.x; buf[4 * q + 1] = t.y; buf[4 * q + 2] = t.z; buf[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int i = 0; i < C; ++i) x[i] = buf[i];
+#pragma unroll
+            for (int i = 0; i < 2 * c2; ++i) a[i] = buf[C + i];
+          } else {
+            block_rev(k, T, a);
+          }
           float da[2 * c2];
 #pragma unroll
           for (int c = 0; c < c2; ++c) {

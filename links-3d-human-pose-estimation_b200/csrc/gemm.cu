@@ -85,6 +85,13 @@ struct alignas(64) GemmProblemDev {
   uint32_t stage_tx;    // bytes the boxes of one stage deliver (small M / N problems load smaller boxes)
   int vec_ok;           // every present epilogue operand is 16-byte aligned with a vector-friendly leading dimension
   int epi_mode;         // index into kEpiMask (0 = run-time flags)
+  // ---- fused Adam (weight-gradient problems): the tile's gradient updates p / m / v and the bf16 shadow in place
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  __nv_bfloat16* adam_shadow;
+  const float* adam_hyper;
+  int ld_shadow;
   // ---- chain launches only (links_gemm_chain_*): tile-level dependencies through completion counters in global memory
   int cnt_base;         // first completion counter of this problem (one per PAIR of M tiles); -1: nobody waits on it
   int dep_base[3];      // [A operand, add0, add1]: first counter of the producing problem of the chain, -1: none
@@ -165,6 +172,12 @@ struct EpiParams {
   float* out_f32;
   __nv_bfloat16* out;
   __nv_bfloat16* mid;
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  __nv_bfloat16* adam_shadow;
+  const float* adam_hyper;
+  int ld_shadow;
 };
 
 // Element-wise path for one 16-column chunk of row m: N tails and operands that are not 16-byte aligned (heads,
@@ -209,8 +222,9 @@ __device__ __forceinline__ void epilogue_chunk_scalar(const EpiParams& E, const 
 // everything at run time).  The arithmetic is identical in every mode (see include/links_b200.h).
 // ----------------------------------------------------------------------------------------------
 enum : uint32_t { F_BIAS = 1, F_LPRE = 2, F_RPRE = 4, F_ADD0 = 8, F_ADD1 = 16, F_LPOST = 32, F_YMASK = 64, F_MID = 128,
-                  F_BITS = 256, F_SIGN = 512, F_OUT = 1024, F_F32 = 2048, F_ACC = 4096 };
-__device__ constexpr uint32_t kEpiMask[11] = {
+                  F_BITS = 256, F_SIGN = 512, F_OUT = 1024, F_F32 = 2048, F_ACC = 4096, F_ADAM = 8192 };
+constexpr int kEpiModes = 12;
+__device__ constexpr uint32_t kEpiMask[kEpiModes] = {
     0u,
     F_BIAS | F_OUT,                                             // 1  upscale forward
     F_BIAS | F_LPRE | F_OUT,                                    // 2  res-block l1 forward
@@ -222,6 +236,7 @@ __device__ constexpr uint32_t kEpiMask[11] = {
     F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,         // 8  l1 dgrad merging two branches
     F_YMASK | F_MID | F_BITS | F_OUT,                           // 9  head dgrad
     F_F32,                                                      // 10 wgrad
+    F_ADAM,                                                     // 11 wgrad with the optimiser step fused (no gradient is stored)
 };
 
 // arrive on the barrier at the same shared offset in CTA `rank` of the cluster.  Relaxed: the TMEM reads are ordered by
@@ -347,6 +362,7 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
   const bool has_sign = kDyn ? E.sign_out != nullptr : (F & F_SIGN) != 0;
   const bool has_out = kDyn ? E.out != nullptr : (F & F_OUT) != 0;
   const bool has_f32 = kDyn ? E.out_f32 != nullptr : (F & F_F32) != 0;
+  const bool has_adam = kDyn ? false : (F & F_ADAM) != 0;          // specialised mode only (host rejects other combinations)
   const size_t mo = static_cast<size_t>(m);
   const float yneg = (E.flags & LINKS_EPI_YMASK_ZERO) ? 0.f : 0.01f;  // slope applied where the mask activation is <= 0
   const bool fast = E.vec_ok && (n_blk + kSlab <= E.N);               // warp-uniform
@@ -503,6 +519,52 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
             float4 o = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
             if (accum) { const float4 a = *p; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
             *p = o;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if (has_adam) {
+      // torch.optim.Adam with coupled L2 decay on this [32 x 32] block of the weight matrix, in the coalesced domain
+      // (same staging as the fp32 store above): g = acc * grad_scale + wd * p; m, v, p updated in place; the bf16 shadow
+      // (the GEMM operand of the next step) is refreshed from the new p.  Arithmetic = csrc/elementwise.cuh::adam_kernel.
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(E.adam_hyper));        // lr / (1 - b1^t), sqrt(1 - b2^t), eps, b1
+      const float4 h1 = __ldg(reinterpret_cast<const float4*>(E.adam_hyper) + 1);    // b2, weight decay, grad scale, -
+#pragma unroll
+      for (int qq = 0; qq < 2; ++qq) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          sts128(scr_addr(SB, lane, j), make_uint4(__float_as_uint(v[qq * 16 + j * 4]), __float_as_uint(v[qq * 16 + j * 4 + 1]),
+                                                  __float_as_uint(v[qq * 16 + j * 4 + 2]), __float_as_uint(v[qq * 16 + j * 4 + 3])));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + (lane >> 2), j = lane & 3;
+          const uint4 q = lds128(scr_addr(SB, r, j));
+          if (m0 + r < E.M) {
+            const size_t off = static_cast<size_t>(m0 + r) * E.ld_f32 + n0 + qq * 16 + j * 4;
+            float4* pp = reinterpret_cast<float4*>(E.adam_p + off);
+            float4* pm = reinterpret_cast<float4*>(E.adam_m + off);
+            float4* pv = reinterpret_cast<float4*>(E.adam_v + off);
+            float4 P4 = *pp, M4 = *pm, V4 = *pv;
+            float gq[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+            float pa[4] = {P4.x, P4.y, P4.z, P4.w}, ma[4] = {M4.x, M4.y, M4.z, M4.w}, va[4] = {V4.x, V4.y, V4.z, V4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float gi = gq[e] * h1.z;
+              gi = gi + h1.y * pa[e];
+              const float mi = ma[e] + (gi - ma[e]) * (1.f - h0.w);
+              const float vi = va[e] * h1.x + (1.f - h1.x) * gi * gi;
+              const float denom = sqrtf(vi) / h0.y + h0.z;
+              pa[e] = pa[e] - h0.x * (mi / denom);
+              ma[e] = mi;
+              va[e] = vi;
+            }
+            *pp = make_float4(pa[0], pa[1], pa[2], pa[3]);
+            *pm = make_float4(ma[0], ma[1], ma[2], ma[3]);
+            *pv = make_float4(va[0], va[1], va[2], va[3]);
+            *reinterpret_cast<uint2*>(E.adam_shadow + static_cast<size_t>(m0 + r) * E.ld_shadow + n0 + qq * 16 + j * 4) =
+                make_uint2(pack_bf16x2(pa[0], pa[1]), pack_bf16x2(pa[2], pa[3]));
           }
         }
         __syncwarp();
@@ -887,6 +949,8 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
         E.ld_f32 = P.ld_f32; E.ld_out = P.ld_out; E.ld_mid = P.ld_mid;
         E.bias = P.bias; E.add0 = P.add0; E.add1 = P.add1; E.ymask = P.ymask; E.bits = P.bits; E.sign_out = P.sign_out;
         E.out_f32 = P.out_f32; E.out = P.out; E.mid = P.mid;
+        E.adam_p = P.adam_p; E.adam_m = P.adam_m; E.adam_v = P.adam_v; E.adam_shadow = P.adam_shadow;
+        E.adam_hyper = P.adam_hyper; E.ld_shadow = P.ld_shadow;
         mode = P.epi_mode;
       }
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
@@ -937,6 +1001,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
           case 8: missed = epilogue_block<kEpiMask[8], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           case 9: missed = epilogue_block<kEpiMask[9], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           case 10: missed = epilogue_block<kEpiMask[10], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 11: missed = epilogue_block<kEpiMask[11], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           default: {
             const EpiParams Ed = E;
             missed = epilogue_block_dyn<kChain>(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr);
@@ -1057,14 +1122,27 @@ static int build_problem(EncodeTiledFn fn, const LinksGemmProblem& s, GemmProble
     if (s.sign_out) f |= F_SIGN;
     if (s.out) f |= F_OUT;
     if (s.out_f32) f |= F_F32;
-    static const uint32_t host_masks[11] = {
+    if (s.adam_p) f |= F_ADAM;
+    static const uint32_t host_masks[kEpiModes] = {
         0u, F_BIAS | F_OUT, F_BIAS | F_LPRE | F_OUT, F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,
         F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT, F_YMASK | F_OUT, F_ADD0 | F_OUT,
         F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT, F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,
-        F_YMASK | F_MID | F_BITS | F_OUT, F_F32};
+        F_YMASK | F_MID | F_BITS | F_OUT, F_F32, F_ADAM};
     d.epi_mode = 0;
-    for (int k = 1; k < 11; ++k) if (host_masks[k] == f) d.epi_mode = k;
+    for (int k = 1; k < kEpiModes; ++k) if (host_masks[k] == f) d.epi_mode = k;
+    if (s.adam_p) {
+      // the fused optimiser exists in the vector path of its own epilogue mode only: a plain weight-gradient problem
+      // whose tiles are full 64-column slabs of 16-byte aligned fp32 / bf16 rows
+      if (f != F_ADAM || !s.adam_m || !s.adam_v || !s.adam_shadow || !s.adam_hyper) return LINKS_E_ARG;
+      if ((s.N % kSlab) != 0 || (s.ld_f32 & 3) || (s.ld_shadow & 7) || s.ld_f32 < s.N || s.ld_shadow < s.N ||
+          !aligned16(s.adam_p) || !aligned16(s.adam_m) || !aligned16(s.adam_v) || !aligned16(s.adam_shadow) ||
+          !aligned16(s.adam_hyper))
+        return LINKS_E_ALIGN;
+    }
   }
+  d.adam_p = s.adam_p; d.adam_m = s.adam_m; d.adam_v = s.adam_v;
+  d.adam_shadow = static_cast<__nv_bfloat16*>(s.adam_shadow);
+  d.adam_hyper = s.adam_hyper; d.ld_shadow = s.ld_shadow;
   d.ld_add0 = s.ld_add0; d.ld_add1 = s.ld_add1; d.ld_ymask = s.ld_ymask; d.ld_bits = s.ld_bits;
   d.ld_sign = s.ld_sign; d.ld_f32 = s.ld_f32;
   d.bias = s.bias;

@@ -29,7 +29,8 @@ class GemmProblem(C.Structure):
                 ("add0", vp), ("ld_add0", ci), ("add1", vp), ("ld_add1", ci),
                 ("ymask", vp), ("ld_ymask", ci), ("bits", vp), ("ld_bits", ci),
                 ("sign_out", vp), ("ld_sign", ci), ("mid", vp), ("ld_mid", ci),
-                ("out", vp), ("ld_out", ci), ("out_f32", vp), ("ld_f32", ci)]
+                ("out", vp), ("ld_out", ci), ("out_f32", vp), ("ld_f32", ci),
+                ("adam_p", vp), ("adam_m", vp), ("adam_v", vp), ("adam_shadow", vp), ("ld_shadow", ci), ("adam_hyper", vp)]
 
 
 class ChainProblem(C.Structure):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "links_adam_step": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf, vp]),
     "links_adam_step_g16": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf, vp]),
     "links_grad_compress_bf16": (ci, [vp, vp, sz]),
+    "links_adam_prepare": (ci, [vp, vp, cf, cf, cf, cf, cf, cf, vp]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
     "links_geom_loss": (ci, [C.POINTER(GeomMaps)] + [vp] * 10 + [ci] + [vp] * 5 + [ci, ci]),
@@ -85,10 +87,10 @@ SIGNATURES = {
     "links_geom_backward_angles": (ci, [vp] * 6 + [ci] + [vp] * 4 + [ci, ci]),
     "links_flow_pack": (ci, [ci, ci] + [PP] * 8 + [vp]),
     "links_flow_apply": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
-    "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp]),
+    "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp]),
     "links_flow_sample": (ci, [vp, ci, vp, vp, ci, vp]),
     "links_flow_vjp": (ci, [vp, ci, ci, vp, ci, vp, vp, vp]),
-    "links_flow_nll_train": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp, vp, vp, vp]),
+    "links_flow_nll_train": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp]),
     "links_mpjpe": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]),
     "links_threshold_counts": (ci, [vp, sz, vp, ci, ci, vp]),
     "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
@@ -102,6 +104,7 @@ PLAIN = {
     "links_abi_version": (ci, []),
     "links_device_ok": (ci, []),
     "links_flow_packed_floats": (sz, [ci, ci]),
+    "links_flow_stash_floats": (sz, [ci, ci, ci]),
     "links_flow_set_simt_only": (ci, [ci]),
     "links_gemm_set_max_ctas": (ci, [ci]),
     "links_gemm_launch_count": (sz, []),

@@ -42,9 +42,18 @@ class FlowPacked:
               "links_flow_apply")
         return out, ld
 
-    def nll_fwdbwd(self, x, scale, nll_sum, dx):
+    def stash_for(self, rows):
+        """Activation stash for nll_fwdbwd on `rows` rows (kept per row count; see links_flow_nll_fwdbwd)."""
+        st = getattr(self, "_stash", None)
+        if st is None or st[0] != rows:
+            n = self.lib.links_flow_stash_floats(self.C, self.n_blocks, rows)
+            self._stash = st = (rows, torch.empty(n, dtype=torch.float32, device=self.device))
+        return st[1]
+
+    def nll_fwdbwd(self, x, scale, nll_sum, dx, stash=True):
+        sp = self.stash_for(x.shape[0]).data_ptr() if stash else None
         check(self.lib.links_flow_nll_fwdbwd(self.packed.data_ptr(), self.C, self.n_blocks, x.data_ptr(), x.shape[0],
-                                             scale, nll_sum.data_ptr(), dx.data_ptr() if dx is not None else None,
+                                             scale, nll_sum.data_ptr(), dx.data_ptr() if dx is not None else None, sp,
                                              torch.cuda.current_stream().cuda_stream), "links_flow_nll_fwdbwd")
 
     def sample(self, x, noise, out):

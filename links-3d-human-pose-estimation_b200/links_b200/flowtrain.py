@@ -157,7 +157,8 @@ class FlowTrainStep:
         self._dgo.zero_()
         check(L.links_flow_nll_train(self.flow.packed.data_ptr(), self.C, self.nb, self.u.data_ptr(), self.M, 1.0 / self.B,
                                      self.nll_sum.data_ptr(), None, self.X1.data_ptr(), self.DS.data_ptr(),
-                                     self._dgs.data_ptr(), self._dgo.data_ptr(), st), "links_flow_nll_train")
+                                     self._dgs.data_ptr(), self._dgo.data_ptr(), self.flow.stash_for(self.M).data_ptr(), st),
+              "links_flow_nll_train")
         gemms, (carr, cn) = self._plans
         for arr, n in gemms:
             check(L.links_gemm_grouped(arr, n, st), "links_gemm_grouped")

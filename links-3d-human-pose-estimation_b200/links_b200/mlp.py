@@ -39,7 +39,7 @@ def _rup(x, m):
 
 
 class _Layer:
-    __slots__ = ("name", "K", "N", "Kp", "Np", "W", "b", "gW", "gb", "Wb")
+    __slots__ = ("name", "K", "N", "Kp", "Np", "W", "b", "gW", "gb", "Wb", "fused_ok", "off_W", "off_b")
 
 
 class _Net:
@@ -138,9 +138,18 @@ class MlpSet:
         layers = [dict() for _ in range(self.S)]
         if share_from is None:
             self.bucket_ranges = []
+            self.bucket_mid = []           # [start, mid): the big (1024 x 1024) weights; [mid, end): biases + small layers
         off = 0
+
+        def fusable(K, N):
+            """Weights whose gradient tiles are full 64-column slabs: their Adam step can run in the wgrad epilogue."""
+            return K % 64 == 0 and N % 64 == 0
+
         for b in (buckets if share_from is None else []):
             start = off
+            # Inside a bucket: first every big weight matrix (the wgrad GEMM may apply Adam to them in its epilogue and
+            # then nothing else touches that range), then all biases and the small layers (one contiguous "rest" range
+            # for the plain Adam kernel).  Every view starts on a 256-byte boundary.
             for s in range(self.S):
                 for n in b:
                     K, N = dims[(s, n)]
@@ -148,15 +157,32 @@ class MlpSet:
                     L.name, L.K, L.N = n, K, N
                     L.Kp = _rup(K, 64)
                     L.Np = _rup(N, 64)
-                    L.W = self.master[off:off + N * K].view(N, K)
-                    L.gW = self.grad[off:off + N * K].view(N, K) if train else None
-                    off += _rup(N * K, 64)
-                    L.b = self.master[off:off + N]
-                    L.gb = self.grad[off:off + N] if train else None
-                    off += _rup(N, 64)
+                    L.fused_ok = fusable(K, N)
                     L.Wb = torch.zeros(N, L.Kp, dtype=torch.bfloat16, device=dev)
                     layers[s][n] = L
+                    if L.fused_ok:
+                        L.off_W = off
+                        off += _rup(N * K, 64)
+            mid = off
+            for s in range(self.S):
+                for n in b:
+                    L = layers[s][n]
+                    if not L.fused_ok:
+                        L.off_W = off
+                        off += _rup(L.N * L.K, 64)
+                    L.off_b = off
+                    off += _rup(L.N, 64)
+            for s in range(self.S):
+                for n in b:
+                    L = layers[s][n]
+                    L.W = self.master[L.off_W:L.off_W + L.N * L.K].view(L.N, L.K)
+                    L.gW = self.grad[L.off_W:L.off_W + L.N * L.K].view(L.N, L.K) if train else None
+                    L.b = self.master[L.off_b:L.off_b + L.N]
+                    L.gb = self.grad[L.off_b:L.off_b + L.N] if train else None
             self.bucket_ranges.append((start, off))
+            self.bucket_mid.append(mid)
+        if share_from is not None:
+            self.bucket_mid = share_from.bucket_mid
         if share_from is None:
             self.nets = [_Net({n: layers[s][n] for n in self.layer_names}) for s in range(self.S)]
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # completed Adam steps (device counter)
@@ -212,6 +238,10 @@ class MlpSet:
         # learning rate of adam_step, read on the device (a captured graph follows set_lr without re-capture)
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self._lr_host = None
+        self.adam_hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        # B operand of the bias-gradient GEMMs: db = G^T . 1 (column 0 of a [rows, 16] matrix of ones)
+        self._ones = torch.zeros(P_ * M, 16, **bf)
+        self._ones[:, 0] = 1.0
 
     # ------------------------------------------------------------------------------------------
     # parameters
@@ -232,12 +262,13 @@ class MlpSet:
             out[n + ".bias"] = L.b.detach().clone()
         return out
 
-    def _cast_plan(self, bucket=None):
-        key = ("cast", bucket)
+    def _cast_plan(self, bucket=None, rest_only=False):
+        key = ("cast", bucket, rest_only)
         if key not in self._plans:
             names = self.layer_names if bucket is None else self.buckets[bucket]
             items = [(net.layers[n].W.data_ptr(), net.layers[n].Wb.data_ptr(), net.layers[n].N, net.layers[n].K,
-                      net.layers[n].Kp) for net in self.nets for n in names]
+                      net.layers[n].Kp) for net in self.nets for n in names
+                     if not (rest_only and net.layers[n].fused_ok)]
             batches = []
             for i in range(0, len(items), _cabi.MAX_CAST_ITEMS):
                 chunk = items[i:i + _cabi.MAX_CAST_ITEMS]
@@ -248,10 +279,11 @@ class MlpSet:
             self._plans[key] = batches
         return self._plans[key]
 
-    def refresh_shadows(self, bucket=None):
-        """fp32 master weights -> bf16 shadows (all layers, or the layers of one gradient bucket), one launch."""
+    def refresh_shadows(self, bucket=None, rest_only=False):
+        """fp32 master weights -> bf16 shadows (all layers, or the layers of one gradient bucket), one launch.
+        rest_only: skip the big layers (the fused optimiser already refreshed their shadows)."""
         st = torch.cuda.current_stream().cuda_stream
-        for arr, n in self._cast_plan(bucket):
+        for arr, n in self._cast_plan(bucket, rest_only):
             check(self.lib.links_cast_weight_batched(arr, n, st), "links_cast_weight_batched")
 
     def compress_grads(self, bucket):
@@ -270,13 +302,24 @@ class MlpSet:
             self.lr_dev.fill_(float(lr))
             self._lr_host = lr
 
+    def adam_prepare(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0):
+        """Step constants of the fused optimiser (read by the wgrad epilogues of this step) -> self.adam_hyper."""
+        self.set_lr(lr)
+        check(self.lib.links_adam_prepare(self.step_dev.data_ptr(), self.lr_dev.data_ptr(), lr, betas[0], betas[1], eps,
+                                          weight_decay, grad_scale, self.adam_hyper.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream), "links_adam_prepare")
+
     def adam_step(self, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, grad_scale=1.0, bucket=None,
-                  last=True, grads_bf16=False):
+                  last=True, grads_bf16=False, rest_only=False):
         """Adam on the whole flat buffer, or on one bucket's contiguous range.  The device-side step counter is
-        advanced by the call with last=True (the other buckets of the same step pass last=False)."""
+        advanced by the call with last=True (the other buckets of the same step pass last=False).
+        rest_only (needs a bucket): only the biases and small layers -- the big weights of the bucket were updated by the
+        fused optimiser in the wgrad epilogue (backward_ops(..., fuse_adam=True))."""
         self.set_lr(lr)               # no-op unless the value changed (never inside a captured step: see set_lr callers)
         st = torch.cuda.current_stream().cuda_stream
         a, b = (0, self.n_params) if bucket is None else self.bucket_ranges[bucket]
+        if rest_only:
+            a = self.bucket_mid[bucket]
         es = 4
         fn = self.lib.links_adam_step_g16 if grads_bf16 else self.lib.links_adam_step
         gptr = self.grad16.data_ptr() + 2 * a if grads_bf16 else self.grad.data_ptr() + a * es
@@ -284,7 +327,7 @@ class MlpSet:
                  self.exp_avg_sq.data_ptr() + a * es, b - a, lr, betas[0], betas[1], eps, weight_decay,
                  0 if last else -1, self.step_dev.data_ptr(), grad_scale,
                  self.lr_dev.data_ptr(), st), "links_adam_step")
-        self.refresh_shadows(bucket)
+        self.refresh_shadows(bucket, rest_only)
 
     # ------------------------------------------------------------------------------------------
     # launch planning
@@ -309,7 +352,7 @@ class MlpSet:
 
     @staticmethod
     def _prob(A, B, M, N, K, lda, ldb, flags=0, bias=None, add0=None, add1=None, ymask=None, bits=None,
-              sign_out=None, mid=None, out=None, out_f32=None, ld_f32=0):
+              sign_out=None, mid=None, out=None, out_f32=None, ld_f32=0, adam=None):
         P = GemmProblem()
         P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb, P.flags = A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb, flags
         P.bias = bias.data_ptr() if bias is not None else None
@@ -323,6 +366,10 @@ class MlpSet:
             P.sign_out, P.ld_sign = sign_out.data_ptr(), sign_out.stride(0)
         if out_f32 is not None:
             P.out_f32, P.ld_f32 = out_f32.data_ptr(), ld_f32 or out_f32.stride(0)
+        if adam is not None:       # (p, m, v, shadow, hyper): fused optimiser instead of a stored gradient
+            p_, m_, v_, sh, hy = adam
+            P.adam_p, P.adam_m, P.adam_v, P.ld_f32 = p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), p_.stride(0)
+            P.adam_shadow, P.ld_shadow, P.adam_hyper = sh.data_ptr(), sh.stride(0), hy.data_ptr()
         return P
 
     def forward_plan(self, p, rows=None):
@@ -382,19 +429,19 @@ class MlpSet:
         ops.append(self._launch(heads))
         return ops
 
-    def backward_plan(self, p, need_input_grad, rows=None, wgrad=False):
+    def backward_plan(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False):
         """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64], zero beyond the head width) filled by the
         loss kernels.  Outputs: G of every layer, optionally self.din[p][s] = d/d(input part) fp32.
         dX = G . W reads the forward shadow W [N, Kp] as an MN-major B operand."""
         """With wgrad=True (the LAST pass to run backward) the weight-gradient GEMMs of a bucket are issued as soon as
         the dgrad chain has completed its G buffers, each followed by a ("bucket", b) marker: run(plan, on_bucket)
         calls on_bucket(b) there so the step driver can start the bucket's all-reduce / Adam on another stream."""
-        key = ("bwd", p, need_input_grad, rows, wgrad)
+        key = ("bwd", p, need_input_grad, rows, wgrad, fuse_adam)
         if key not in self._plans:
-            self._plans[key] = self._build_backward(p, need_input_grad, rows, wgrad)
+            self._plans[key] = self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam)
         return self._plans[key]
 
-    def _build_backward(self, p, need_input_grad, rows=None, wgrad=False):
+    def _build_backward(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False):
         M = rows or self.M
         ops = []
 
@@ -409,7 +456,7 @@ class MlpSet:
             for b, members in enumerate(self._bucket_levels):
                 if b not in self._issued and all(l in done for l in members):
                     self._issued.add(b)
-                    ops.extend(self._wgrad_ops(b, rows))
+                    ops.extend(self._wgrad_ops(b, rows, fuse_adam))
                     ops.append(("bucket", b))
         self._issued = set()
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
@@ -526,12 +573,15 @@ class MlpSet:
                 return [p for p in range(self.n_passes) if br in self.pass_branches[p]]
         raise KeyError(name)
 
-    def _wgrad_ops(self, bucket, rows=None):
+    def _wgrad_ops(self, bucket, rows=None, fuse_adam=False):
         """dW = G^T . X of one bucket's layers, contracted over the rows of every pass that used the layer (G and X read
-        as MN-major operands straight from their row-major buffers); db = column sums of G."""
+        as MN-major operands straight from their row-major buffers); db = G^T . 1 as one more (N = 1) GEMM problem per
+        layer, written straight into the flat gradient buffer.  fuse_adam: the big layers' problems apply the optimiser
+        step in their epilogue instead of storing dW (adam_prepare must have run; adam_step(rest_only=True) finishes the
+        bucket)."""
         M = rows or self.M
         assert rows is None or self.n_passes == 1, "partial rows only supported for single-pass sets"
-        probs, colsums = [], []
+        probs = []
         for s in range(self.S):
             for n in self.buckets[bucket]:
                 L = self.nets[s].layers[n]
@@ -541,27 +591,18 @@ class MlpSet:
                 xin = self._layer_input(n)
                 X = self._x0buf[s] if xin == "x0" else self._actbuf[s][xin]
                 Gb = self._Gbuf[s][n]
-                probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
-                                        out_f32=L.gW, ld_f32=L.K))
-                colsums.append((Gb.data_ptr(), Gb.stride(0), Kc, L.N, L.gb.data_ptr(), 0))
-        ops = [self._launch(probs)]
-        fn = self.lib.links_colsum_bf16_batched
-        batches = []
-        for i in range(0, len(colsums), _cabi.MAX_COLSUM_ITEMS):
-            chunk = colsums[i:i + _cabi.MAX_COLSUM_ITEMS]
-            arr = (_cabi.ColsumItem * len(chunk))()
-            for j, (g, ldg, Mi, Ni, out, acc) in enumerate(chunk):
-                arr[j].G, arr[j].out, arr[j].ldg, arr[j].M, arr[j].N, arr[j].accumulate = g, out, ldg, Mi, Ni, acc
-            batches.append((arr, len(chunk)))
-
-        def run_colsums():
-            st = torch.cuda.current_stream().cuda_stream
-            for arr, n in batches:
-                rc = fn(arr, n, st)
-                if rc:
-                    check(rc, "links_colsum_bf16_batched")
-        ops.append(run_colsums)
-        return ops
+                if fuse_adam and L.fused_ok:
+                    off = L.off_W
+                    adam = (L.W, self.exp_avg[off:off + L.N * L.K].view(L.N, L.K),
+                            self.exp_avg_sq[off:off + L.N * L.K].view(L.N, L.K), L.Wb, self.adam_hyper)
+                    probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
+                                            adam=adam))
+                else:
+                    probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
+                                            out_f32=L.gW, ld_f32=L.K))
+                probs.append(self._prob(Gb, self._ones, L.N, 1, Kc, Gb.stride(0), 16, flags=GEMM_A_MN | GEMM_B_MN,
+                                        out_f32=L.gb.view(L.N, 1), ld_f32=1))
+        return [self._launch(probs)]
 
     def wgrad_plan(self, rows=None):
         """All weight / bias gradients (every bucket), for callers that do not interleave them with backward."""
@@ -686,11 +727,15 @@ class MlpSet:
             return self.forward_plan(p, rows)
         return self._chained(("cfwd", p, rows), lambda: self._build_forward(p, rows), max_ctas=max_ctas)
 
-    def backward_ops(self, p, need_input_grad, rows=None, wgrad=False, split_at_buckets=False, max_ctas=None):
+    def backward_ops(self, p, need_input_grad, rows=None, wgrad=False, split_at_buckets=False, max_ctas=None,
+                     fuse_adam=False):
+        """dgrad chain of pass p (+ weight / bias gradients with wgrad=True; + the optimiser step of the big layers
+        inside the wgrad epilogues with fuse_adam=True -- single-GPU steps only, gradients are then never stored)."""
         if not USE_CHAIN:
-            return self.backward_plan(p, need_input_grad, rows, wgrad)
-        return self._chained(("cbwd", p, need_input_grad, rows, wgrad, split_at_buckets),
-                             lambda: self._build_backward(p, need_input_grad, rows, wgrad), split_at_buckets, max_ctas)
+            return self.backward_plan(p, need_input_grad, rows, wgrad, fuse_adam)
+        return self._chained(("cbwd", p, need_input_grad, rows, wgrad, split_at_buckets, fuse_adam),
+                             lambda: self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam), split_at_buckets,
+                             max_ctas)
 
     def wgrad_ops(self, rows=None):
         if not USE_CHAIN:

@@ -67,7 +67,8 @@ class OcclusionStep:
                     torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
             m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
                         last=(b == len(m.buckets) - 1),
-                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"))
+                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"),
+                        rest_only=self._fuse_adam)
 
     def _st(self):
         return torch.cuda.current_stream().cuda_stream
@@ -75,6 +76,9 @@ class OcclusionStep:
     def forward_backward(self, fused_optimizer=False):
         L, B, m, lf = self.lib, self.B, self.mlp, self.lifters
         st = self._st()
+        self._fuse_adam = bool(fused_optimizer and self.world == 1 and self.cfg.get("fuse_adam", True))
+        if self._fuse_adam:
+            m.adam_prepare(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0)
         for s in range(2):
             nidx = self.idx_lift[s].numel()
             check(L.links_pack_rows(self.x.data_ptr(), 34, B, self.idx_lift[s].data_ptr(), nidx, 1,
@@ -102,7 +106,8 @@ class OcclusionStep:
                                       m.G[r][s]["downscale"].data_ptr(), None, 0, 0, st), "links_occ_mse")
         for r in range(2):
             m.run(m.backward_ops(r, need_input_grad=False))
-        m.run(m.backward_ops(2, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1), on_bucket=self._on_bucket if fused_optimizer else None)
+        m.run(m.backward_ops(2, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1, fuse_adam=self._fuse_adam),
+              on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
             torch.cuda.current_stream().wait_stream(self.comm)
         self.losses[:8] = self.loss_sums / B

@@ -158,7 +158,8 @@ class LifterStep:
         with torch.cuda.stream(self.opt_stream):
             m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
                         last=(b == len(m.buckets) - 1),
-                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"))
+                        grads_bf16=(self.world > 1 and self.cfg.get("grad_comm", "bf16") == "bf16"),
+                        rest_only=self._fuse_adam)     # fused: the big layers were updated in the wgrad epilogues
 
     class _Fork:
         """`with step._fork(k):` -- the small kernels of flavour k > 0 go to that flavour's side stream (forked from the
@@ -196,6 +197,11 @@ class LifterStep:
         per-bucket all-reduce / Adam / shadow refresh overlapped with the backward pass (what step() does)."""
         L, m, N = self.lib, self.mlp, self.N
         main = torch.cuda.current_stream()
+        # single GPU: no gradient leaves the device, so the optimiser step of the big layers runs inside the weight-gradient
+        # epilogues (no stored gradients, no separate Adam / shadow-cast pass over 59 M parameters)
+        self._fuse_adam = bool(fused_optimizer and self.world == 1 and self.cfg.get("fuse_adam", True))
+        if self._fuse_adam:
+            m.adam_prepare(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0)
         if self.prefetch:
             self.u.copy_(self.u_next)
         else:
@@ -257,7 +263,8 @@ class LifterStep:
             self._sample_stream.wait_stream(main)
             with torch.cuda.stream(self._sample_stream):
                 self.full_flow.sample(self.x, self.noise, self.u_next)
-        m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1, max_ctas=self._ctas_tail),
+        m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1, max_ctas=self._ctas_tail,
+                             fuse_adam=self._fuse_adam),
               on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
             main.wait_stream(self.opt_stream)

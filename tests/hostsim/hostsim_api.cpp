@@ -69,6 +69,11 @@ SIM int sim_adam_step_g16(float* p, const void* g, float* m, float* v, size_t n,
   if (step_dev && step >= 0) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
   return 0;
 }
+SIM int sim_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float b1, float b2, float eps, float wd,
+                         float grad_scale, float* hyper) {
+  hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_prepare_kernel(step_dev, lr_dev, lr, b1, b2, eps, wd, grad_scale, hyper); });
+  return 0;
+}
 SIM int sim_grad_compress_bf16(const float* g, void* out, size_t n) {
   hostsim::launch(dim3(2), dim3(64), 0, [&] { grad_compress_bf16_kernel(g, (bf16*)out, n); });
   return 0;
@@ -193,7 +198,8 @@ SIM int sim_flow_apply(const float* packed, int C, int nb, const float* x, int M
   A.packed = packed; A.x = x; A.out = out; A.ld = ld; A.M = M; A.n_blocks = nb;
   return rev ? sim_flow_dispatch<FLOW_REV>(C, A) : sim_flow_dispatch<FLOW_FWD>(C, A);
 }
-SIM int sim_flow_nll_fwdbwd(const float* packed, int C, int nb, const float* x, int M, float scale, float* nll_sum, float* dx) {
+SIM int sim_flow_nll_fwdbwd(const float* packed, int C, int nb, const float* x, int M, float scale, float* nll_sum, float* dx,
+                            float* /*stash: tensor-core kernel only*/) {
   FlowArgs A;
   memset(&A, 0, sizeof(A));
   A.packed = packed; A.x = x; A.out = dx; A.nll_sum = nll_sum; A.scale = scale; A.M = M; A.n_blocks = nb;

@@ -65,10 +65,14 @@ def test_flow_tc_nll_and_vjp(Cdim, M):
     xd = x.cuda()
     nll_sum = torch.zeros(1, device="cuda")
     dx = torch.zeros(M, Cdim, device="cuda")
-    fp.nll_fwdbwd(xd, scale, nll_sum, dx)
-    torch.cuda.synchronize()
-    np.testing.assert_allclose(nll_sum.item(), nll.sum().item(), rtol=1e-4)
-    _assert_grad_close(dx.cpu().numpy(), xg.grad.numpy())
+    # both backward flavours: activations stashed by the forward pass (2 subnet evaluations per block), and the
+    # reversible one that reconstructs them with the inverse coupling (3 per block, no scratch memory)
+    for stash in (True, False):
+        nll_sum.zero_(); dx.zero_()
+        fp.nll_fwdbwd(xd, scale, nll_sum, dx, stash=stash)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(nll_sum.item(), nll.sum().item(), rtol=1e-4)
+        _assert_grad_close(dx.cpu().numpy(), xg.grad.numpy())
     # general VJP
     gz = torch.randn(M, Cdim, generator=g) * 0.3
     gld = torch.randn(M, generator=g)

@@ -184,3 +184,45 @@ def test_step_vs_oracle_with_optimizer(kind):
         d_ref = pn[s]["res_pose1.l1.weight"].detach() - W0
         cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
         assert cos.item() > 0.9, cos.item()
+
+
+@pytest.mark.parametrize("kind", ["lt", "both"])
+def test_fused_adam_equals_separate_adam(kind):
+    """Single-GPU steps apply Adam to the big layers inside the weight-gradient epilogues (no stored gradients, no separate
+    optimiser pass).  Two steps from identical state must leave master weights, both moments and the bf16 shadows where
+    the separate links_adam_step + shadow cast path leaves them (same arithmetic; fp32 contraction may differ by an ulp)."""
+    from links_b200.steps import LifterStep
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, nets as ON
+    B = 192
+    nets = [ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12), ON.init_lifter_params(11, 13), ON.init_lifter_params(11, 14)]
+    flows = [OF.init_flow_params(14, 41, perturb=0.3), OF.init_flow_params(20, 42, perturb=0.3),
+             OF.init_flow_params(22, 43, perturb=0.3), OF.init_flow_params(22, 44, perturb=0.3)]
+    full = OF.init_flow_params(34, 40, perturb=0.3)
+    if kind == "lt":
+        nets, flows = nets[:2], flows[:2]
+    x2d, _ = synth_poses(B, seed=3)
+    g = torch.Generator().manual_seed(8)
+    d = dict(x=torch.from_numpy(x2d), noise=torch.randn(B, 34, generator=g), eps_x=torch.randn(2 * B, generator=g),
+             u_y=torch.rand(2 * B, generator=g))
+    steps = [LifterStep(kind, B, nets, flows, full, cfg={"fuse_adam": f}) for f in (True, False)]
+    for st in steps:
+        for _ in range(2):
+            _load(st, d)
+            st.step()
+    torch.cuda.synchronize()
+    a, b = steps[0].mlp, steps[1].mlp
+    assert steps[0]._fuse_adam and not steps[1]._fuse_adam
+    assert int(a.step_dev.item()) == int(b.step_dev.item()) == 2
+    for name, x, y in (("master", a.master, b.master), ("exp_avg", a.exp_avg, b.exp_avg), ("exp_avg_sq", a.exp_avg_sq, b.exp_avg_sq)):
+        err = (x - y).abs().max().item()
+        assert err <= 1e-6 * max(y.abs().max().item(), 1e-12) + 1e-12, (name, err)
+    moved = (a.master - torch.cat([torch.zeros(0, device="cuda")])).abs().sum().item()
+    assert moved > 0
+    for s in range(a.S):
+        for n in a.layer_names:
+            wa, wb = a.nets[s].layers[n].Wb.float(), b.nets[s].layers[n].Wb.float()
+            # a 1-ulp fp32 difference can flip a bf16 rounding: allow isolated single-ulp shadow differences
+            bad = (wa != wb).float().mean().item()
+            assert bad < 1e-4, (s, n, bad)
+            assert (wa - wb).abs().max().item() <= 2.0 ** -7 * wb.abs().max().item()

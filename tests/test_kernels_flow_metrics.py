@@ -46,7 +46,7 @@ def test_flow_forward_reverse_nll(Cdim, M, backend):
     (nll.sum() * scale).backward()
     nll_sum = np.zeros(1, np.float32)
     dx = np.zeros((M, Cdim), np.float32)
-    assert L.call("flow_nll_fwdbwd", packed, Cdim, 8, xn, M, scale, nll_sum, dx) == 0
+    assert L.call("flow_nll_fwdbwd", packed, Cdim, 8, xn, M, scale, nll_sum, dx, None) == 0
     np.testing.assert_allclose(nll_sum[0], nll.sum().item(), rtol=1e-4)
     gref = xg.grad.numpy()
     np.testing.assert_allclose(dx, gref, rtol=2e-3, atol=2e-5 * np.abs(gref).max())
