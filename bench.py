@@ -418,31 +418,44 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, K)
     final_losses = step.loss_dict()
 
-    # ---- roofline of the dominant kernel (tcgen05 GEMM): every GEMM launch of one step, timed alone
+    # ---- roofline of the dominant kernel (tcgen05 GEMM chain kernel), timed alone with CUDA events:
+    #   (a) `roofline`: the step's four chain launches as pure GEMM work on the whole machine -- the unfused plans (the
+    #       weight-gradient tiles store dW instead of running Adam's 26 B/parameter read-modify-write in their epilogue)
+    #       with no SMs set aside for the flow kernels;
+    #   (b) `roofline.in_step`: the very launches the captured step issues (SM reservation next to the flows, optimiser
+    #       fused into the weight-gradient epilogues), same FLOP count.
     m = step.mlp
-    plans = [m.forward_ops(0), m.forward_ops(1, max_ctas=step._ctas_window),
-             m.backward_ops(1, need_input_grad=True, max_ctas=step._ctas_window),
-             m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=world > 1, max_ctas=step._ctas_tail,
-                            fuse_adam=step._fuse_adam)]
+    split = world > 1
+    step_plans = [m.forward_ops(0), m.forward_ops(1, max_ctas=step._ctas_window),
+                  m.backward_ops(1, need_input_grad=True, max_ctas=step._ctas_window),
+                  m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=split, max_ctas=step._ctas_tail,
+                                 fuse_adam=step._fuse_adam)]
     if MLP.USE_CHAIN:
-        gemm_ops = [op for plan in plans for op in plan if hasattr(op, "plan")]
-        sim = {"chain_sim_units": [float(op.plan.sim_units) for op in gemm_ops],
-               "chain_ideal_units": [float(op.plan.ideal_units) for op in gemm_ops],
+        pure_plans = [m._chained(("roof", 0), lambda: m._build_forward(0)), m._chained(("roof", 1), lambda: m._build_forward(1)),
+                      m._chained(("roof", 2), lambda: m._build_backward(1, True)),
+                      m._chained(("roof", 3), lambda: m._build_backward(0, False, None, True, False))]
+        sel = lambda plans: [op for plan in plans for op in plan if hasattr(op, "plan")]
+        gemm_ops, step_ops = sel(pure_plans), sel(step_plans)
+        sim = {"chain_sim_us": [float(op.plan.sim_units) * 0.44 for op in gemm_ops],
+               "chain_ideal_us": [float(op.plan.ideal_units) * 0.44 for op in gemm_ops],
                "chain_tiles": [int(op.plan.total_tiles) for op in gemm_ops]}
     else:
-        plans[3] = m.backward_plan(0, False) + m.wgrad_plan()
-        gemm_ops, sim = [op for plan in plans for op in plan if not isinstance(op, tuple)], {}
+        pure_plans = [m.forward_plan(0), m.forward_plan(1), m.backward_plan(1, True), m.backward_plan(0, False, None, True, False)]
+        sel = lambda plans: [op for plan in plans for op in plan if not isinstance(op, tuple)]
+        gemm_ops, step_ops, sim = sel(pure_plans), sel(step_plans), {}
 
-    def gemm_only():
-        for op in gemm_ops:
-            op()
-    counter = _cabi.install_launch_counter()
-    gemm_only()
-    counter.stop()
-    n_gemm_launches = counter.gemm
-    for _ in range(3):
-        gemm_only()
-    ms_gemm = timed(gemm_only, K) / K
+    def time_ops(ops):
+        def run_ops():
+            for op in ops:
+                op()
+        counter = _cabi.install_launch_counter()
+        run_ops()
+        counter.stop()
+        for _ in range(3):
+            run_ops()
+        return timed(run_ops, K) / K, counter.gemm
+    ms_gemm, n_gemm_launches = time_ops(gemm_ops)
+    ms_gemm_step, n_step_launches = time_ops(step_ops)
     peaks = load_peaks()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
@@ -450,6 +463,12 @@ def run_gpu(args):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch_mean")
     gemm_flops = (gemm_flops_per_pose("lt") + gemm_flops_per_pose("lr")) * B
     achieved = gemm_flops / (ms_gemm * 1e-3) / 1e12
+    in_step = {"ms_per_step_gemm_launches": ms_gemm_step, "launches_per_step": n_step_launches,
+               "achieved": gemm_flops / (ms_gemm_step * 1e-3) / 1e12,
+               "frac": gemm_flops / (ms_gemm_step * 1e-3) / 1e12 / peaks["bf16_burst"],
+               "note": "the launches of the captured step, timed alone: forward pass 2 and its dgrad chain run on %s SMs (the "
+                       "rest is left to the concurrent part-flow NLL kernels), the tail chain on %s SMs with Adam fused into "
+                       "the weight-gradient epilogues (HBM-bound: +26 B per parameter)" % (step._ctas_window, step._ctas_tail)}
 
     ms_step = ms_total / K
     value = world * B / (ms_step * 1e-3)
@@ -461,7 +480,7 @@ def run_gpu(args):
     extras, strong = [], None
     if not args.skip_extra:
         stage("extra configs")
-        del step, m, plans, gemm_ops
+        del step, m, step_plans, pure_plans, gemm_ops, step_ops
         torch.cuda.empty_cache()
         Bs = max(2, (8192 // world) // 2 * 2)
         st2 = LifterStep("both", Bs, nets, flows, full, cfg=cfg, process_group=pg)
@@ -529,9 +548,10 @@ def run_gpu(args):
                               "flops_per_launch": gemm_flops / n_gemm_launches,
                               "us_per_launch": ms_gemm * 1e3 / n_gemm_launches,
                               "launches_per_step": n_gemm_launches,
-                              "kernel": "links::gemm_kernel<%s> (tcgen05 cta_group::2 / TMEM / TMA), all %d GEMM launches of "
-                                        "one step timed in isolation" % ("true" if MLP.USE_CHAIN else "false", n_gemm_launches),
-                              "ms_per_step_gemm_only": ms_gemm, "flops_per_step": gemm_flops,
+                              "kernel": "links::gemm_kernel<%s> (tcgen05 cta_group::2 / TMEM / TMA): the %d GEMM launches of one "
+                                        "step as pure GEMM work on all SMs, timed in isolation" % (
+                                            "true" if MLP.USE_CHAIN else "false", n_gemm_launches),
+                              "ms_per_step_gemm_only": ms_gemm, "flops_per_step": gemm_flops, "in_step": in_step,
                               "frac_of_sustained_peak": achieved / peaks["bf16_sustained"],
                               "peak_source": "%s cuBLAS bf16 burst (kernel timed alone)" % peaks["source"]}, **sim),
             "parity": parity,

@@ -111,8 +111,10 @@ int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* s
  *   dep[0..2]    index of the EARLIER problem of the chain that writes this problem's [A operand, add0, add1] (out /
  *                mid / out_f32 of that problem), or -1 when the operand comes from outside the chain.  A dependency is
  *                row-block-wise: rows [256 i, 256 i + 256) of the consumer need the same rows of the producer (equal
- *                M required) -- unless bit d of dep_all_rows is set: the operand is contracted over ALL rows of the
- *                producer (an A_MN operand: weight gradients).
+ *                M required) -- unless bit d of dep_all_rows is set: the consumer waits for ALL tiles of the producer
+ *                (an A_MN operand contracted over the rows: weight gradients; or a write-after-read hazard: the fused
+ *                optimiser may only overwrite a layer's bf16 shadow once the dgrad problem that reads it has finished --
+ *                such ordering-only dependencies use a slot whose operand pointer is NULL).
  * The workspace (links_gemm_chain_ws_bytes, 256-byte aligned device memory owned by the caller) holds descriptors,
  * schedule and counters; links_gemm_chain_build fills it (host work + one synchronous copy: call it outside stream
  * capture), links_gemm_chain_run launches (capturable).  One plan must not run concurrently with itself. */
@@ -188,6 +190,10 @@ int links_cast_weight_batched(const LinksCastItem* items, int n_items, void* str
 int links_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                     float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     int* step_dev, float grad_scale, const float* lr_dev, void* stream);
+
+/* out[n_out] = mat[n_out, n_in] . in[n_in] (fp32, tiny sizes): the loss summary of a step (train_leg_torso_lifter.py:
+ * 266-284 -- means, weights and the total of the device-side loss sums) as one launch. */
+int links_small_matvec(const float* mat, const float* in, int n_in, int n_out, float* out, void* stream);
 
 /* Step constants of the fused optimiser (LinksGemmProblem.adam_*), computed on the device so that captured graphs
  * replay correctly: hyper[0..7] = { lr / (1 - beta1^t), sqrt(1 - beta2^t), eps, beta1, beta2, weight_decay, grad_scale, t }

@@ -128,6 +128,13 @@ extern "C" __attribute__((visibility("default"))) int links_adam_step_g16(float*
                                     beta2, eps, weight_decay, step, step_dev, grad_scale, lr_dev, stream);
 }
 
+extern "C" __attribute__((visibility("default"))) int links_small_matvec(const float* mat, const float* in, int n_in, int n_out, float* out, void* stream) {
+  LINKS_CHECK_PTR(mat); LINKS_CHECK_PTR(in); LINKS_CHECK_PTR(out);
+  if (n_in < 1 || n_out < 1 || n_in > 4096 || n_out > 4096) return LINKS_E_RANGE;
+  small_matvec_kernel<<<(n_out + 63) / 64, 64, 0, links_stream(stream)>>>(mat, in, n_in, n_out, out);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float beta1, float beta2,
                                   float eps, float weight_decay, float grad_scale, float* hyper, void* stream) {
   LINKS_CHECK_PTR(step_dev); LINKS_CHECK_PTR(hyper); LINKS_CHECK_ALIGN16(hyper);

@@ -184,6 +184,17 @@ __global__ void adam_kernel(float* __restrict__ p, const GradT* __restrict__ g, 
   }
 }
 
+// out[i] = sum_j mat[i * n_in + j] * in[j]  (tiny: the step's loss summary -- normalisation, weighting and totals of the
+// device-side loss sums in one launch instead of a handful of framework element-wise kernels)
+__global__ void small_matvec_kernel(const float* __restrict__ mat, const float* __restrict__ in, int n_in, int n_out,
+                                    float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  float acc = 0.f;
+  for (int j = 0; j < n_in; ++j) acc = fmaf(mat[i * n_in + j], in[j], acc);
+  out[i] = acc;
+}
+
 __global__ void adam_prepare_kernel(const int* __restrict__ step_dev, const float* __restrict__ lr_dev, float lr, float b1,
                                     float b2, float eps, float wd, float grad_scale, float* __restrict__ hyper) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;

@@ -651,6 +651,7 @@ class MlpSet:
             assert len(hits) <= 1, "operand written by several problems of one chain"
             return hits[0] if hits else -1
 
+        b_reads = []           # (begin, end, problem index) of every B operand (weights)
         for i, (lv, P) in enumerate(flat):
             cp = arr[i]
             C.memmove(C.byref(cp.g), C.byref(P), C.sizeof(GemmProblem))
@@ -660,6 +661,17 @@ class MlpSet:
             cp.dep[1] = producer(P.add0, P.M, P.ld_add0, 2)
             cp.dep[2] = producer(P.add1, P.M, P.ld_add1, 2)
             cp.dep_all_rows = 1 if (a_mn and cp.dep[0] >= 0) else 0
+            if P.adam_shadow:
+                # write-after-read: the fused optimiser overwrites the layer's bf16 shadow, which earlier problems of the
+                # chain (the dgrad of that layer) read as their B operand -- wait for all of their tiles
+                sb, se = extent(P.adam_shadow, P.M, P.ld_shadow, 2)
+                readers = sorted({j for (rb, re, j) in b_reads if rb < se and sb < re})
+                assert len(readers) <= 2 and not P.add0 and not P.add1, "too many readers of a shadow inside one chain"
+                for slot, j in zip((1, 2), readers):
+                    cp.dep[slot] = j
+                    cp.dep_all_rows |= 1 << slot
+            b_mn = bool(P.flags & GEMM_B_MN)
+            b_reads.append(extent(P.B, P.K if b_mn else P.N, P.ldb, 2) + (i,))
             for ptr, ld, es in ((P.out, P.ld_out, 2), (P.mid, P.ld_mid, 2), (P.out_f32, P.ld_f32, 4)):
                 if ptr:
                     written.append(extent(ptr, P.M, ld, es) + (i,))

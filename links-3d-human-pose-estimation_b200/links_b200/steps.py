@@ -93,9 +93,16 @@ class LifterStep:
         self.eps_x = torch.zeros(N, **f32)
         self.u_y = torch.zeros(N, **f32)
         self.u = torch.zeros(N, 34, **f32)
-        self._norm = torch.tensor([1.0 / N, 1.0 / N, 1.0 / max(N // 2, 1), 1.0 / N, 1.0 / N, 1.0 / N], **f32)
-        self._w = torch.tensor([c["weight_3d"], c["weight_2d"], c["weight_velocity"], c["weight_bl"],
-                                c["weight_likeli"], c["weight_likeli"]], **f32)
+        # loss summary as one [8 x 8] mat-vec on the device-side sums scal[0:8] = (L3d, rep, pair, bl, nll_0, nll_1, -, -):
+        # rows 0-5 the means, row 6 likeli = nll_0 + nll_1, row 7 the weighted total (train_leg_torso_lifter.py:266-272)
+        norm = [1.0 / N, 1.0 / N, 1.0 / max(N // 2, 1), 1.0 / N, 1.0 / N, 1.0 / N]
+        w = [c["weight_3d"], c["weight_2d"], c["weight_velocity"], c["weight_bl"], c["weight_likeli"], c["weight_likeli"]]
+        lm = torch.zeros(8, 8, dtype=torch.float32)
+        for i in range(6):
+            lm[i, i] = norm[i]
+            lm[7, i] = w[i] * norm[i]
+        lm[6, 4], lm[6, 5] = norm[4], norm[5]
+        self._loss_mat = lm.to(dev)
         self.graph = None
         # Sampling prefetch (cfg prefetch_sample): the sampling block (train_leg_torso_lifter.py:133-142) depends on no
         # trained weight, so the poses of step k+1 are drawn WHILE step k runs: step() first moves the prefetched
@@ -272,10 +279,8 @@ class LifterStep:
             main.wait_stream(self._sample_stream)
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
         for k in self.K:
-            t = k.scal[:6] * self._norm
-            k.losses[:6] = t
-            k.losses[6] = t[4] + t[5]
-            k.losses[7] = (t * self._w).sum()
+            check(L.links_small_matvec(self._loss_mat.data_ptr(), k.scal.data_ptr(), 8, 8, k.losses.data_ptr(), self._st()),
+                  "links_small_matvec")
 
     def optimizer_step(self):
         if self.world > 1:

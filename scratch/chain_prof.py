@@ -40,7 +40,13 @@ cases = [("fwd0", lambda: m._chained(("c", 0), lambda: m._build_forward(0), max_
          ("bwd0", lambda: m._chained(("c", 3), lambda: m._build_backward(0, False), max_ctas=mc), lambda: m.backward_plan(0, False)),
          ("bwd0+wgrad", lambda: m._chained(("c", 4), lambda: m._build_backward(0, False, None, True), max_ctas=mc),
           lambda: m.backward_plan(0, False, None, True)),
-         ("wgrad", lambda: m._chained(("c", 5), lambda: m._build_wgrad(), max_ctas=mc), lambda: m.wgrad_plan())]
+         ("wgrad", lambda: m._chained(("c", 5), lambda: m._build_wgrad(), max_ctas=mc), lambda: m.wgrad_plan()),
+         ("bwd0+wgrad+adam", lambda: m._chained(("c", 6), lambda: m._build_backward(0, False, None, True, True), max_ctas=mc),
+          lambda: m.backward_plan(0, False, None, True, True))]
+m.adam_prepare()
+only = os.environ.get("CHAIN_PROF_ONLY")
+if only:
+    cases = [c for c in cases if c[0] in only.split(",")]
 out = {}
 for name, chain, grouped in cases:
     cops = [op for op in chain() if hasattr(op, "plan")]

