@@ -344,6 +344,7 @@ def run_gpu(args):
     B = args.batch
     nets, flows, full = make_weights()
     cfg = {"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets, "prefetch_sample": not args.no_prefetch,
+           "store_rot_2d": False,      # the full projected poses are a debugging output; the step consumes the part gathers
            "nccl_ctas": args.nccl_ctas}
 
     def stage(msg):

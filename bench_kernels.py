@@ -52,9 +52,12 @@ def main():
     f32 = dict(dtype=torch.float32, device="cuda")
     m = maps.geom_maps("lt")
     u = torch.randn(N, 34, **f32) * 0.1
-    heads = [torch.randn(N, 32, **f32) * 0.1 for _ in range(2)]
-    angs = [torch.randn(N, 32, **f32) * 0.1 for _ in range(2)]
-    heads2 = [torch.randn(N, 32, **f32) * 0.1 for _ in range(2)]
+    # all depth / angle heads of a pass side by side in ONE [N, 32] row (what LifterStep allocates: MlpSet head_groups):
+    # leg depths cols 0-6, torso depths 7-16, the two angle heads 17 and 18
+    pack1, pack2 = torch.randn(N, 32, **f32) * 0.1, torch.randn(N, 32, **f32) * 0.1
+    heads = [pack1[:, 0:], pack1[:, 7:]]
+    angs = [pack1[:, 17:], pack1[:, 18:]]
+    heads2 = [pack2[:, 0:], pack2[:, 7:]]
     eps, uy = torch.randn(N, **f32), torch.rand(N, **f32)
     stats = torch.zeros(2, **f32)
     qp = [torch.zeros(N, 14, **f32), torch.zeros(N, 20, **f32)]
@@ -62,8 +65,8 @@ def main():
     common = [u.data_ptr(), heads[0].data_ptr(), heads[1].data_ptr(), angs[0].data_ptr(), angs[1].data_ptr(), eps.data_ptr(),
               uy.data_ptr(), stats.data_ptr()]
     _cabi.check(L.links_elev_stats(angs[0].data_ptr(), angs[1].data_ptr(), N, stats.data_ptr(), st), "stats")
-    t = timed(lambda: L.links_geom_forward(C.byref(m), *common, N, qp[0].data_ptr(), qp[1].data_ptr(), qf[0].data_ptr(), None, st))
-    rec("geom_forward", 352, N, t, "u 34 + depth heads 17 + angles 2 + draws 2 read, rot_2d 34 written (fp32)")
+    t = timed(lambda: L.links_geom_forward(C.byref(m), *common, N, qp[0].data_ptr(), qp[1].data_ptr(), None, None, st))
+    rec("geom_forward", 352, N, t, "u 34 + depth heads 17 + angles 2 + draws 2 read, projected part inputs 34 written (fp32)")
     sums = torch.zeros(4, **f32)
     g2 = [torch.zeros(N, 64, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
     t = timed(lambda: L.links_geom_loss(C.byref(m), *common, heads2[0].data_ptr(), heads2[1].data_ptr(), N, sums.data_ptr(),
@@ -77,7 +80,7 @@ def main():
                                             dfl[1].data_ptr(), dli[0].data_ptr(), dli[1].data_ptr(), N, g1[0].data_ptr(),
                                             g1[1].data_ptr(), None, None, 0, 0, dgam.data_ptr(), da.data_ptr(), red.data_ptr(), st))
     rec("geom_lossgrad<1> (backward)", 492, N, t, "inputs 54+34+17 floats (+recompute), outputs 17+1 (SURVEY 8d)")
-    del u, heads, angs, heads2, qp, qf, g2, g1, dfl, dli
+    del u, heads, angs, heads2, pack1, pack2, qp, qf, g2, g1, dfl, dli
     torch.cuda.empty_cache()
 
     # ---------------- metrics, M poses

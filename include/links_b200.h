@@ -303,6 +303,16 @@ int links_flow_sample(const float* packed, int n_blocks, const float* x, const f
                       float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input pipeline: normalize_head / normalize_head_test (utils/helpers.py:198-207, 222-230) fused with the dataset
+ * classes' transpose-flatten (utils/h36m_dataset_class.py:25-27).
+ *   raw  [n, 17, 2] key-points (transposed_input = 0) or already flattened [n, 34] = (17 x, 17 y) rows (= 1), fp32
+ *   out  [n, 34]: root-centred, divided by the mean over ALL n poses of |joint 0 - joint 10| (fixed_scale <= 0; the mean
+ *        is accumulated in *dist_sum, a device double) or by fixed_scale (> 0), times 1/10.
+ * ------------------------------------------------------------------------------------------ */
+int links_normalize_head(const float* raw, int n, int root_joint, int transposed_input, float fixed_scale, float* out,
+                         double* dist_sum, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Metrics (utils/metrics_batch.py:8-159, utils/metrics.py:35-171)
  * per_pose / per_pose_max [M] and dist [M, num_joints] (each may be null) receive per-pose mean / max joint
  * distance and all joint distances; sum (may be null) accumulates sum_m per_pose[m] in double.

@@ -6,6 +6,7 @@
 #include "flow.cuh"
 #include "flow_tc.cuh"
 #include "occ.cuh"
+#include "dataprep.cuh"
 #include <math.h>
 
 using namespace links;
@@ -126,6 +127,24 @@ extern "C" __attribute__((visibility("default"))) int links_adam_step_g16(float*
                                    int* step_dev, float grad_scale, const float* lr_dev, void* stream) {
   return adam_launch<__nv_bfloat16>(param, static_cast<const __nv_bfloat16*>(grad_bf16), exp_avg, exp_avg_sq, n, lr, beta1,
                                     beta2, eps, weight_decay, step, step_dev, grad_scale, lr_dev, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int links_normalize_head(const float* raw, int n, int root_joint, int transposed_input, float fixed_scale,
+                                    float* out, double* dist_sum, void* stream) {
+  LINKS_CHECK_PTR(raw); LINKS_CHECK_PTR(out);
+  if (n < 1 || root_joint < 0 || root_joint > 16) return LINKS_E_RANGE;
+  if (fixed_scale <= 0.f && dist_sum == nullptr) return LINKS_E_ARG;
+  cudaStream_t s = links_stream(stream);
+  if (dist_sum != nullptr) {
+    cudaError_t e = cudaMemsetAsync(dist_sum, 0, sizeof(double), s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  normalize_head_center_kernel<<<(n + 255) / 256, 256, 0, s>>>(raw, n, root_joint, transposed_input, out, dist_sum);
+  const size_t total = static_cast<size_t>(n) * 34;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  normalize_head_scale_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(out, total, n, fixed_scale, dist_sum);
+  return links_launch_status(2);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_small_matvec(const float* mat, const float* in, int n_in, int n_out, float* out, void* stream) {

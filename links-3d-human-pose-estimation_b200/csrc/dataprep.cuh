@@ -7,7 +7,7 @@
 // Two passes over HBM for the data-dependent scale (the mean must be known before anything can be scaled), one for the fixed
 // one.  One thread per pose; rows are 136 B in, 136 B out.
 #pragma once
-#include "common.cuh"
+#include "devdefs.cuh"
 
 namespace links {
 

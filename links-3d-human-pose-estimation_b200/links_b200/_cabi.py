@@ -80,6 +80,7 @@ SIGNATURES = {
     "links_adam_step_g16": (ci, [vp, vp, vp, vp, sz, cf, cf, cf, cf, cf, ci, vp, cf, vp]),
     "links_grad_compress_bf16": (ci, [vp, vp, sz]),
     "links_small_matvec": (ci, [vp, vp, ci, ci, vp]),
+    "links_normalize_head": (ci, [vp, ci, ci, ci, cf, vp, vp]),
     "links_adam_prepare": (ci, [vp, vp, cf, cf, cf, cf, cf, cf, vp]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),

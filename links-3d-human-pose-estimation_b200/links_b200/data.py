@@ -81,3 +81,25 @@ class DevicePrefetcher:
             yield self._dev[i & 1]
             i += 1
             more = more_next
+
+
+def normalize_head_device(raw, fixed_scale=None, root_joint=0, out=None):
+    """normalize_head / normalize_head_test (reference utils/helpers.py:198-207, 222-230) on the device, fused with the
+    dataset classes' transpose-flatten (utils/h36m_dataset_class.py:25-27).
+
+    raw: CUDA fp32 tensor, [n, 17, 2] key-points (as stored in the reference's pickles) or [n, 34] = (17 x, 17 y) rows.
+    fixed_scale=None divides by the mean root-to-head distance over all n poses (normalize_head); a number divides by that
+    number (normalize_head_test's 145.40964, ...).  Returns [n, 34] fp32 (root-centred, scaled, * 1/10)."""
+    from . import _cabi
+    if not raw.is_cuda:
+        raise _cabi.LinksError("normalize_head_device runs on a B200 only (utils.helpers.normalize_head is the host version)")
+    raw = raw.contiguous().float()
+    transposed = 0 if raw.dim() == 3 else 1
+    n = raw.shape[0]
+    assert raw.numel() == n * 34
+    out = torch.empty(n, 34, dtype=torch.float32, device=raw.device) if out is None else out
+    acc = torch.zeros(1, dtype=torch.float64, device=raw.device)
+    _cabi.check(_cabi.lib().links_normalize_head(raw.data_ptr(), n, root_joint, transposed,
+                                                 float(fixed_scale) if fixed_scale else 0.0, out.data_ptr(), acc.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream), "links_normalize_head")
+    return out

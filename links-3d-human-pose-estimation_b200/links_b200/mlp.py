@@ -51,10 +51,13 @@ class _Net:
 
 class MlpSet:
     def __init__(self, kind, in_dims, head_dims, max_rows, n_passes=1, device="cuda", train=True,
-                 pass_branches=None, max_buckets=None, share_from=None):
+                 pass_branches=None, max_buckets=None, share_from=None, head_groups=None):
         """in_dims[s]: input width of net s; head_dims[s]: dict head name -> width.
         max_rows: rows per pass; n_passes: forward passes per step sharing weights (1 or 2).
         pass_branches[p]: branches evaluated in pass p (default: all).
+        head_groups: lists of (net, head) whose fp32 outputs share ONE [M, 32] buffer side by side (column offsets in list
+        order): the geometry kernels read all depth / angle heads of a row from a single 128-byte line instead of one line
+        per head (they index rows with the common leading dimension HEAD_LD, so a column-offset pointer is all they need).
         share_from: another MlpSet of the same topology whose parameter / gradient / shadow buffers this set aliases
         (only the activation and gradient workspaces are private) -- several forward passes of one module can then be
         alive at once, each keeping its own activations for its own backward (utils/models_def.py)."""
@@ -214,6 +217,13 @@ class MlpSet:
                               if train else {})
                 head_p.append({head: torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev)
                                for _, head in self.branches.values()})
+            for grp in (head_groups or []):
+                width = sum(head_dims[s][h] for s, h in grp)
+                assert width <= HEAD_LD, "packed heads do not fit one HEAD_LD-wide row"
+                buf, col = torch.zeros(M, HEAD_LD, dtype=torch.float32, device=dev), 0
+                for s, h in grp:
+                    head_p[s][h] = buf[:, col:]           # row stride stays HEAD_LD
+                    col += head_dims[s][h]
             self.sign.append(sign_p)
             self.head_out.append(head_p)
         if train:

@@ -84,6 +84,8 @@ class LifterStep:
             self.K.append(k)
         self.mlp = MlpSet("lifter", [2 * n for n in nj_all], [{"downscale": n, "angles": 1} for n in nj_all], self.N,
                           n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]],
+                          head_groups=[[(k.s0, "downscale"), (k.s0 + 1, "downscale"), (k.s0, "angles"), (k.s0 + 1, "angles")]
+                                       for k in self.K],
                           max_buckets=self.cfg.get("dp_buckets") if (self.world > 1 or self.cfg.get("dp_layout")) else None)
         self.mlp.load_state_dicts(lifter_params)
         self.full_flow = FlowPacked(34, full_flow_params, device=dev)
@@ -225,8 +227,9 @@ class LifterStep:
                       "links_elev_stats")
                 k.common = [self.u.data_ptr()] + [m.head_out[0][k.s0 + s]["downscale"].data_ptr() for s in range(2)] + \
                            [a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(), self.u_y.data_ptr(), k.stats.data_ptr()]
-                check(L.links_geom_forward(mp, *k.common, N, k.qpart[0].data_ptr(), k.qpart[1].data_ptr(),
-                                           k.qfull[0].data_ptr(), k.qfull[1].data_ptr(), self._st()), "links_geom_forward")
+                qf = [q.data_ptr() for q in k.qfull] if self.cfg.get("store_rot_2d", True) else [None, None]
+                check(L.links_geom_forward(mp, *k.common, N, k.qpart[0].data_ptr(), k.qpart[1].data_ptr(), qf[0], qf[1],
+                                           self._st()), "links_geom_forward")
                 k.scal.zero_()
                 here = torch.cuda.current_stream()
                 for s in range(2):

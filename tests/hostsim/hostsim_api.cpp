@@ -11,6 +11,7 @@ using std::max;
 #include "../../links-3d-human-pose-estimation_b200/csrc/geom.cuh"
 #include "../../links-3d-human-pose-estimation_b200/csrc/flow.cuh"
 #include "../../links-3d-human-pose-estimation_b200/csrc/occ.cuh"
+#include "../../links-3d-human-pose-estimation_b200/csrc/dataprep.cuh"
 
 using namespace links;
 typedef __nv_bfloat16 bf16;
@@ -67,6 +68,12 @@ SIM int sim_adam_step_g16(float* p, const void* g, float* m, float* v, size_t n,
                           float wd, int step, int* step_dev, float grad_scale, const float* lr_dev) {
   hostsim::launch(dim3(2), dim3(64), 0, [&] { adam_kernel<bf16>(p, (const bf16*)g, m, v, n, lr, b1, b2, eps, wd, step_dev, step, grad_scale, lr_dev); });
   if (step_dev && step >= 0) hostsim::launch(dim3(1), dim3(32), 0, [&] { adam_incr_kernel(step_dev); });
+  return 0;
+}
+SIM int sim_normalize_head(const float* raw, int n, int root, int transposed, float fixed_scale, float* out, double* dist_sum) {
+  if (dist_sum) *dist_sum = 0.0;
+  hostsim::launch(dim3((n + 255) / 256), dim3(256), 0, [&] { normalize_head_center_kernel(raw, n, root, transposed, out, dist_sum); });
+  hostsim::launch(dim3(2), dim3(256), 0, [&] { normalize_head_scale_kernel(out, (size_t)n * 34, n, fixed_scale, dist_sum); });
   return 0;
 }
 SIM int sim_small_matvec(const float* mat, const float* in, int n_in, int n_out, float* out) {

@@ -301,3 +301,26 @@ def test_adam_colsum_cast(backend):
     assert np.all(Wb[:, 22:] == 0)
     np.testing.assert_array_equal(WT[:, :70], f32_to_bf16(W).T)
     assert np.all(WT[:, 70:] == 0)
+
+
+@backend_params
+def test_normalize_head_kernel(backend):
+    """Device normalize_head / normalize_head_test (+ transpose-flatten) vs the drop-in utils.helpers functions, which
+    tests/test_dropin_cpu.py pins against the reference's outputs (golden/helpers_extra.npz)."""
+    from utils import helpers as H
+    L = backend
+    rng = np.random.RandomState(4)
+    n = 1000
+    raw = (rng.normal(size=(n, 17, 2)) * 200 + 500).astype(np.float32)
+    flat = np.ascontiguousarray(raw.transpose(0, 2, 1).reshape(n, 34))
+    ref = H.normalize_head(flat.astype(np.float64).copy())
+    out = np.zeros((n, 34), np.float32)
+    acc = np.zeros(1, np.float64)
+    assert L.call("normalize_head", raw, n, 0, 0, 0.0, out, acc) == 0
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-7)
+    out2 = np.zeros((n, 34), np.float32)
+    assert L.call("normalize_head", flat, n, 0, 1, 0.0, out2, acc) == 0           # already flattened rows
+    np.testing.assert_allclose(out2, ref, rtol=2e-5, atol=1e-7)
+    ref_t = H.normalize_head_test(flat.astype(np.float64).copy())
+    assert L.call("normalize_head", raw, n, 0, 0, 145.40964, out, None) == 0
+    np.testing.assert_allclose(out, ref_t, rtol=2e-5, atol=1e-7)
