@@ -253,7 +253,8 @@ def extra_configs(args, timed, world, rank, pg, peaks):
     B4 = max(2, (4096 // world) // 2 * 2)
     lifters = [INIT.init_lifter_params(7, 11), INIT.init_lifter_params(10, 12)]
     preds = {n: INIT.init_predictor_params(OCC_IN[n] // 3, OCC_OUT[n], 100 + i) for i, n in enumerate(OCC_NAMES)}
-    oc = OcclusionStep(B4, lifters, preds, cfg={"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets}, process_group=pg)
+    oc = OcclusionStep(B4, lifters, preds, cfg={"grad_comm": "bf16" if args.grad_comm == "push" else args.grad_comm,
+                                                "dp_buckets": args.dp_buckets}, process_group=pg)
     x2d, _ = synth_poses(B4, seed=55 + rank)
     oc.x.copy_(torch.from_numpy(x2d)); oc.u_y[0].uniform_(); oc.u_y[1].uniform_()
     for _ in range(3):
@@ -534,7 +535,10 @@ def run_gpu(args):
                                     "far above the 126 MB L2" % (2 * 2048 * 1024 * 2 * 2 * 60 * (B / 1024) / 1e9),
                        "operands": "bf16 operands + bf16-stored activations, fp32 accumulate / master weights / losses",
                        "elevation_stats": "local shard" if world > 1 else "global",
-                       "grad_allreduce": ("%s buckets over NCCL, overlapped with backward" % args.grad_comm) if world > 1 else "none",
+                       "grad_allreduce": ("none" if world == 1 else
+                                          "push: wgrad epilogues store bf16 tiles into the owner rank's staging buffer over "
+                                          "NVLink, sharded Adam, bf16 shadows stored into every rank" if args.grad_comm == "push"
+                                          else "%s buckets over NCCL, overlapped with backward" % args.grad_comm),
                        "final_losses": final_losses},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": launches_per_step * K,
@@ -584,8 +588,10 @@ def main():
     ap.add_argument("--dp-buckets", type=int, default=2, help="gradient buckets per network set under data parallelism")
     ap.add_argument("--nccl-ctas", type=int, default=0, help="CTAs (SMs) the NCCL all-reduce kernels may use (0: NCCL default)")
     ap.add_argument("--gemm-ctas", type=int, default=-1, help="GEMM grid cap under data parallelism (<= 0: no cap)")
-    ap.add_argument("--grad-comm", default="bf16", choices=["bf16", "fp32"],
-                    help="dtype of the data-parallel gradient all-reduce (bf16 = compressed buckets)")
+    ap.add_argument("--grad-comm", default="push", choices=["push", "bf16", "fp32"],
+                    help="data-parallel gradient exchange: push = reduce-scatter by peer stores fused into the weight-gradient "
+                         "GEMM epilogues + sharded Adam + shadow all-gather by peer stores (NVLink, symmetric memory); "
+                         "bf16 / fp32 = bucketed NCCL all-reduce of compressed / fp32 gradients")
     ap.add_argument("--eval-poses", type=int, default=1_250_000, help="poses per GPU of the config #5 eval run")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="only the headline config (no configs[] / strong_scaling)")

@@ -35,6 +35,7 @@ extern "C" {
 #define LINKS_E_DRIVER (-4)   /* cuTensorMapEncodeTiled unavailable / failed */
 
 #define LINKS_MAX_GEMM_PROBLEMS 8
+#define LINKS_MAX_PUSH_RANKS 8
 #define LINKS_HEAD_LD 32      /* leading dimension of fp32 head outputs / part-gradient buffers */
 #define LINKS_KPAD 64         /* bf16 operand rows are padded to a multiple of 64 in K */
 #define LINKS_J 17
@@ -96,6 +97,12 @@ typedef struct LinksGemmProblem {
   float* adam_p; float* adam_m; float* adam_v;
   void* adam_shadow; int ld_shadow;
   const float* adam_hyper;
+  /* Data-parallel reduce-scatter fused into the weight-gradient GEMM (push_rows > 0; no other epilogue step, no out_f32):
+   * rows [r * push_rows, (r + 1) * push_rows) of the result are stored as bf16 to push[r] ([push_rows, ld_push] row-major) --
+   * rank r's staging buffer, mapped into this process over NVLink (torch symmetric memory / CUDA IPC).  push_rows is a
+   * multiple of 128 that divides M, M / push_rows <= LINKS_MAX_PUSH_RANKS, N a multiple of 64.  The owner then reduces
+   * the ranks' slots and updates its rows with links_adam_zero. */
+  void* push[LINKS_MAX_PUSH_RANKS]; int push_rows; int ld_push;
 } LinksGemmProblem;
 
 int links_gemm_grouped(const LinksGemmProblem* problems, int n_problems, void* stream);
@@ -200,6 +207,21 @@ int links_small_matvec(const float* mat, const float* in, int n_in, int n_out, f
  * with t = *step_dev + 1 and lr = *lr_dev when lr_dev != NULL.  Does not advance *step_dev. */
 int links_adam_prepare(const int* step_dev, const float* lr_dev, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float grad_scale, float* hyper, void* stream);
+
+/* Sharded optimiser step behind the push reduce-scatter (ZeRO-1 style; one launch for all big layers of a network set).
+ * For layer l (rows x cols weights, row-major, at offset master_off in the flat fp32 buffers p / m / v) this rank owns rows
+ * [rank * rows_per_owner, +rows_per_owner).  The gradient of an owned element is the fp32 sum over the `world` slots of
+ * `stage` (bf16, slot s at stage + s * stage_slot_elems, the layer's owned block at stage_off inside a slot, written by
+ * rank s's GEMM epilogue); Adam with the constants of links_adam_prepare (grad_scale = 1 / world) updates p, m, v in place
+ * and the new bf16 value is stored into EVERY rank's shadow of the layer (shadow[r]: peer-mapped [rows, cols] bf16) --
+ * the all-gather of the updated weights, also by peer stores. */
+typedef struct LinksAdamZeroLayer {
+  unsigned long long master_off;    /* element offset of the layer's [rows, cols] block in p / m / v */
+  unsigned long long stage_off;     /* element offset of the layer's owned block inside one staging slot */
+  void* shadow[LINKS_MAX_PUSH_RANKS];
+} LinksAdamZeroLayer;
+int links_adam_zero(float* p, float* m, float* v, const void* stage, size_t stage_slot_elems, const LinksAdamZeroLayer* layers_dev,
+                    int n_layers, int rows_per_owner, int cols, int world, int rank, const float* hyper, void* stream);
 
 /* Data-parallel gradient compression: grad_bf16[i] = bf16(grad[i]) before the NCCL all-reduce (half the NVLink
  * bytes), and the Adam step that consumes the reduced bf16 gradients directly (same arithmetic otherwise). */

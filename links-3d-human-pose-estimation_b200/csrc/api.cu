@@ -161,6 +161,22 @@ extern "C" __attribute__((visibility("default"))) int links_adam_prepare(const i
   return links_launch_status();
 }
 
+extern "C" __attribute__((visibility("default"))) int links_adam_zero(float* p, float* m, float* v, const void* stage, size_t stage_slot_elems,
+                               const LinksAdamZeroLayer* layers_dev, int n_layers, int rows_per_owner, int cols, int world, int rank,
+                               const float* hyper, void* stream) {
+  LINKS_CHECK_PTR(p); LINKS_CHECK_PTR(m); LINKS_CHECK_PTR(v); LINKS_CHECK_PTR(stage); LINKS_CHECK_PTR(layers_dev); LINKS_CHECK_PTR(hyper);
+  LINKS_CHECK_ALIGN16(stage);
+  if (n_layers < 1 || rows_per_owner < 1 || cols < 8 || (cols & 7) || world < 1 || world > LINKS_MAX_PUSH_RANKS || rank < 0 ||
+      rank >= world || (stage_slot_elems & 7))
+    return LINKS_E_RANGE;
+  const size_t n = static_cast<size_t>(rows_per_owner) * cols;
+  size_t bx = (n / 8 + 255) / 256;
+  if (bx > 64) bx = 64;
+  adam_zero_kernel<<<dim3(static_cast<unsigned>(bx), n_layers), 256, 0, links_stream(stream)>>>(
+      p, m, v, static_cast<const __nv_bfloat16*>(stage), stage_slot_elems, layers_dev, rows_per_owner, cols, world, rank, hyper);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream) {
   LINKS_CHECK_PTR(grad); LINKS_CHECK_PTR(grad_bf16);
   if (n == 0) return LINKS_E_RANGE;

@@ -206,6 +206,71 @@ __global__ void adam_prepare_kernel(const int* __restrict__ step_dev, const floa
   hyper[4] = b2; hyper[5] = wd; hyper[6] = grad_scale; hyper[7] = static_cast<float>(t);
 }
 
+// Sharded Adam behind the push reduce-scatter (include/links_b200.h::links_adam_zero).  grid = (blocks, n_layers); a thread
+// owns 8 consecutive elements of the layer's owned block (16 bytes of bf16 per staging slot / shadow).
+__global__ void adam_zero_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                 const __nv_bfloat16* __restrict__ stage, size_t slot_elems,
+                                 const LinksAdamZeroLayer* __restrict__ layers, int rows_per_owner, int cols, int world, int rank,
+                                 const float* __restrict__ hyper) {
+  const LinksAdamZeroLayer L = layers[blockIdx.y];
+  const size_t n = static_cast<size_t>(rows_per_owner) * cols;         // owned elements of this layer
+  const float step_size = hyper[0], bc2_sqrt = hyper[1], eps = hyper[2], b1 = hyper[3], b2 = hyper[4], wd = hyper[5],
+              gs = hyper[6];
+  const size_t own0 = static_cast<size_t>(rank) * n;                   // first owned element inside the layer
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 8;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < world; ++s) {
+      const uint4 q = *reinterpret_cast<const uint4*>(stage + static_cast<size_t>(s) * slot_elems + L.stage_off + i);
+      const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        g[2 * e] += __uint_as_float(w[e] << 16);
+        g[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+      }
+    }
+    const size_t mo = L.master_off + own0 + i;
+    float pa[8], ma[8], va[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 P4 = *reinterpret_cast<const float4*>(p + mo + 4 * h), M4 = *reinterpret_cast<const float4*>(m + mo + 4 * h),
+                   V4 = *reinterpret_cast<const float4*>(v + mo + 4 * h);
+      pa[4 * h] = P4.x; pa[4 * h + 1] = P4.y; pa[4 * h + 2] = P4.z; pa[4 * h + 3] = P4.w;
+      ma[4 * h] = M4.x; ma[4 * h + 1] = M4.y; ma[4 * h + 2] = M4.z; ma[4 * h + 3] = M4.w;
+      va[4 * h] = V4.x; va[4 * h + 1] = V4.y; va[4 * h + 2] = V4.z; va[4 * h + 3] = V4.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float gi = g[e] * gs;
+      gi = gi + wd * pa[e];
+      const float mi = ma[e] + (gi - ma[e]) * (1.f - b1);
+      const float vi = va[e] * b2 + (1.f - b2) * gi * gi;
+      const float denom = sqrtf(vi) / bc2_sqrt + eps;
+      pa[e] = pa[e] - step_size * (mi / denom);
+      ma[e] = mi;
+      va[e] = vi;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      *reinterpret_cast<float4*>(p + mo + 4 * h) = make_float4(pa[4 * h], pa[4 * h + 1], pa[4 * h + 2], pa[4 * h + 3]);
+      *reinterpret_cast<float4*>(m + mo + 4 * h) = make_float4(ma[4 * h], ma[4 * h + 1], ma[4 * h + 2], ma[4 * h + 3]);
+      *reinterpret_cast<float4*>(v + mo + 4 * h) = make_float4(va[4 * h], va[4 * h + 1], va[4 * h + 2], va[4 * h + 3]);
+    }
+    uint4 sh;
+    {
+      unsigned int hw[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const __nv_bfloat16 b = __float2bfloat16_rn(pa[e]);
+        hw[e] = *reinterpret_cast<const unsigned short*>(&b);
+      }
+      sh.x = hw[0] | (hw[1] << 16); sh.y = hw[2] | (hw[3] << 16); sh.z = hw[4] | (hw[5] << 16); sh.w = hw[6] | (hw[7] << 16);
+    }
+    for (int r = 0; r < world; ++r)
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(L.shadow[r]) + own0 + i) = sh;
+  }
+}
+
 __global__ void adam_incr_kernel(int* step_dev) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
 }

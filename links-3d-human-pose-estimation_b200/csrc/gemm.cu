@@ -100,6 +100,9 @@ struct alignas(64) GemmProblemDev {
   __nv_bfloat16* adam_shadow;
   const float* adam_hyper;
   int ld_shadow;
+  // ---- reduce-scatter by peer stores (weight-gradient problems under data parallelism)
+  __nv_bfloat16* push[LINKS_MAX_PUSH_RANKS];
+  int push_rows, ld_push;
   // ---- chain launches only (links_gemm_chain_*): tile-level dependencies through completion counters in global memory
   int cnt_base;         // first completion counter of this problem (one per PAIR of M tiles); -1: nobody waits on it
   int dep_base[3];      // [A operand, add0, add1]: first counter of the producing problem of the chain, -1: none
@@ -186,6 +189,8 @@ struct EpiParams {
   __nv_bfloat16* adam_shadow;
   const float* adam_hyper;
   int ld_shadow;
+  __nv_bfloat16* const* push;      // -> the problem descriptor's push[] (global / parameter memory)
+  int push_rows, ld_push;
 };
 
 // Element-wise path for one 16-column chunk of row m: N tails and operands that are not 16-byte aligned (heads,
@@ -230,8 +235,8 @@ __device__ __forceinline__ void epilogue_chunk_scalar(const EpiParams& E, const 
 // everything at run time).  The arithmetic is identical in every mode (see include/links_b200.h).
 // ----------------------------------------------------------------------------------------------
 enum : uint32_t { F_BIAS = 1, F_LPRE = 2, F_RPRE = 4, F_ADD0 = 8, F_ADD1 = 16, F_LPOST = 32, F_YMASK = 64, F_MID = 128,
-                  F_BITS = 256, F_SIGN = 512, F_OUT = 1024, F_F32 = 2048, F_ACC = 4096, F_ADAM = 8192 };
-constexpr int kEpiModes = 12;
+                  F_BITS = 256, F_SIGN = 512, F_OUT = 1024, F_F32 = 2048, F_ACC = 4096, F_ADAM = 8192, F_PUSH = 16384 };
+constexpr int kEpiModes = 13;
 __device__ constexpr uint32_t kEpiMask[kEpiModes] = {
     0u,
     F_BIAS | F_OUT,                                             // 1  upscale forward
@@ -245,6 +250,7 @@ __device__ constexpr uint32_t kEpiMask[kEpiModes] = {
     F_YMASK | F_MID | F_BITS | F_OUT,                           // 9  head dgrad
     F_F32,                                                      // 10 wgrad
     F_ADAM,                                                     // 11 wgrad with the optimiser step fused (no gradient is stored)
+    F_PUSH,                                                     // 12 wgrad stored as bf16 into the OWNER rank's staging buffer (P2P)
 };
 
 // arrive on the barrier at the same shared offset in CTA `rank` of the cluster.  Relaxed: the TMEM reads are ordered by
@@ -371,6 +377,7 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
   const bool has_out = kDyn ? E.out != nullptr : (F & F_OUT) != 0;
   const bool has_f32 = kDyn ? E.out_f32 != nullptr : (F & F_F32) != 0;
   const bool has_adam = kDyn ? false : (F & F_ADAM) != 0;          // specialised mode only (host rejects other combinations)
+  const bool has_push = kDyn ? false : (F & F_PUSH) != 0;
   const size_t mo = static_cast<size_t>(m);
   const float yneg = (E.flags & LINKS_EPI_YMASK_ZERO) ? 0.f : 0.01f;  // slope applied where the mask activation is <= 0
   const bool fast = E.vec_ok && (n_blk + kSlab <= E.N);               // warp-uniform
@@ -507,6 +514,21 @@ __device__ __forceinline__ bool epilogue_block(const EpiParams& E, uint32_t t_ad
         block_store(SB, E.out, E.ld_out, m0, n0, E.M, lane);
         __syncwarp();
       }
+    }
+    if (has_push) {
+      // Data-parallel reduce-scatter fused into the weight-gradient GEMM: rows [r * push_rows, (r+1) * push_rows) of dW
+      // belong to rank r, whose staging buffer (peer-mapped over NVLink) receives this block as bf16 -- plain coalesced
+      // stores, overlapped with the main loops of the following tiles; the owner sums the ranks' slots in its Adam kernel.
+      const int owner = m0 / E.push_rows;                              // warp-uniform (push_rows is a multiple of 128)
+      __nv_bfloat16* pbase = E.push[owner];
+      const int lrow = m0 - owner * E.push_rows;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(scr_addr(SB, lane, j), make_uint4(pack_bf16x2(v[j * 8], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                                                pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7])));
+      __syncwarp();
+      block_store(SB, pbase, E.ld_push, lrow, n0, E.push_rows, lane);
+      __syncwarp();
     }
     if (has_f32) {
       // fp32 [32 x 32] block in two quarters of 16 columns (one scratch row = 16 floats); coalesced read-modify-write
@@ -993,6 +1015,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
         E.out_f32 = P.out_f32; E.out = P.out; E.mid = P.mid;
         E.adam_p = P.adam_p; E.adam_m = P.adam_m; E.adam_v = P.adam_v; E.adam_shadow = P.adam_shadow;
         E.adam_hyper = P.adam_hyper; E.ld_shadow = P.ld_shadow;
+        E.push = P.push; E.push_rows = P.push_rows; E.ld_push = P.ld_push;
         mode = P.epi_mode;
       }
       const uint32_t slot = lt & 1u, acc_use = lt >> 1;
@@ -1057,6 +1080,7 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
           case 9: missed = epilogue_block<kEpiMask[9], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           case 10: missed = epilogue_block<kEpiMask[10], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           case 11: missed = epilogue_block<kEpiMask[11], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
+          case 12: missed = epilogue_block<kEpiMask[12], kChain>(E, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr); break;
           default: {
             const EpiParams Ed = E;
             missed = epilogue_block_dyn<kChain>(Ed, t_addr, sb, S, nxt, m0, n0, lane, ae, deps_ok_addr);
@@ -1179,11 +1203,12 @@ static int build_problem(EncodeTiledFn fn, const LinksGemmProblem& s, GemmProble
     if (s.out) f |= F_OUT;
     if (s.out_f32) f |= F_F32;
     if (s.adam_p) f |= F_ADAM;
+    if (s.push_rows > 0) f |= F_PUSH;
     static const uint32_t host_masks[kEpiModes] = {
         0u, F_BIAS | F_OUT, F_BIAS | F_LPRE | F_OUT, F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_SIGN | F_OUT,
         F_BIAS | F_LPRE | F_ADD0 | F_LPOST | F_OUT, F_YMASK | F_OUT, F_ADD0 | F_OUT,
         F_ADD0 | F_YMASK | F_MID | F_BITS | F_OUT, F_ADD0 | F_ADD1 | F_YMASK | F_MID | F_BITS | F_OUT,
-        F_YMASK | F_MID | F_BITS | F_OUT, F_F32, F_ADAM};
+        F_YMASK | F_MID | F_BITS | F_OUT, F_F32, F_ADAM, F_PUSH};
     d.epi_mode = 0;
     for (int k = 1; k < kEpiModes; ++k) if (host_masks[k] == f) d.epi_mode = k;
     if (s.adam_p) {
@@ -1195,7 +1220,16 @@ static int build_problem(EncodeTiledFn fn, const LinksGemmProblem& s, GemmProble
           !aligned16(s.adam_hyper))
         return LINKS_E_ALIGN;
     }
+    if (s.push_rows > 0) {
+      if (f != F_PUSH) return LINKS_E_ARG;
+      if ((s.push_rows % BM) != 0 || (s.M % s.push_rows) != 0 || s.M / s.push_rows > LINKS_MAX_PUSH_RANKS) return LINKS_E_RANGE;
+      if ((s.N % kSlab) != 0 || (s.ld_push & 7) || s.ld_push < s.N) return LINKS_E_ALIGN;
+      for (int r = 0; r < s.M / s.push_rows; ++r)
+        if (!s.push[r] || !aligned16(s.push[r])) return LINKS_E_ALIGN;
+    }
   }
+  for (int r = 0; r < LINKS_MAX_PUSH_RANKS; ++r) d.push[r] = static_cast<__nv_bfloat16*>(s.push[r]);
+  d.push_rows = s.push_rows; d.ld_push = s.ld_push;
   d.adam_p = s.adam_p; d.adam_m = s.adam_m; d.adam_v = s.adam_v;
   d.adam_shadow = static_cast<__nv_bfloat16*>(s.adam_shadow);
   d.adam_hyper = s.adam_hyper; d.ld_shadow = s.ld_shadow;

@@ -30,7 +30,8 @@ class GemmProblem(C.Structure):
                 ("ymask", vp), ("ld_ymask", ci), ("bits", vp), ("ld_bits", ci),
                 ("sign_out", vp), ("ld_sign", ci), ("mid", vp), ("ld_mid", ci),
                 ("out", vp), ("ld_out", ci), ("out_f32", vp), ("ld_f32", ci),
-                ("adam_p", vp), ("adam_m", vp), ("adam_v", vp), ("adam_shadow", vp), ("ld_shadow", ci), ("adam_hyper", vp)]
+                ("adam_p", vp), ("adam_m", vp), ("adam_v", vp), ("adam_shadow", vp), ("ld_shadow", ci), ("adam_hyper", vp),
+                ("push", vp * 8), ("push_rows", ci), ("ld_push", ci)]
 
 
 class ChainProblem(C.Structure):
@@ -46,6 +47,11 @@ class ChainPlan(C.Structure):
 
 
 MAX_CHAIN_PROBLEMS = 512
+
+
+class AdamZeroLayer(C.Structure):
+    """LinksAdamZeroLayer (links_adam_zero)."""
+    _fields_ = [("master_off", C.c_ulonglong), ("stage_off", C.c_ulonglong), ("shadow", vp * 8)]
 
 
 class ColsumItem(C.Structure):
@@ -81,6 +87,7 @@ SIGNATURES = {
     "links_grad_compress_bf16": (ci, [vp, vp, sz]),
     "links_small_matvec": (ci, [vp, vp, ci, ci, vp]),
     "links_normalize_head": (ci, [vp, ci, ci, ci, cf, vp, vp]),
+    "links_adam_zero": (ci, [vp, vp, vp, vp, sz, vp, ci, ci, ci, ci, ci, vp]),
     "links_adam_prepare": (ci, [vp, vp, cf, cf, cf, cf, cf, cf, vp]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),

@@ -51,13 +51,18 @@ class _Net:
 
 class MlpSet:
     def __init__(self, kind, in_dims, head_dims, max_rows, n_passes=1, device="cuda", train=True,
-                 pass_branches=None, max_buckets=None, share_from=None, head_groups=None):
+                 pass_branches=None, max_buckets=None, share_from=None, head_groups=None, zero_group=None):
         """in_dims[s]: input width of net s; head_dims[s]: dict head name -> width.
         max_rows: rows per pass; n_passes: forward passes per step sharing weights (1 or 2).
         pass_branches[p]: branches evaluated in pass p (default: all).
         head_groups: lists of (net, head) whose fp32 outputs share ONE [M, 32] buffer side by side (column offsets in list
         order): the geometry kernels read all depth / angle heads of a row from a single 128-byte line instead of one line
         per head (they index rows with the common leading dimension HEAD_LD, so a column-offset pointer is all they need).
+        zero_group: a process group (one rank per GPU of ONE node) -> data parallelism WITHOUT gradient all-reduce of the big
+        layers: rank r owns rows [r * 1024 / W, (r + 1) * 1024 / W) of every 1024 x 1024 weight matrix; the weight-gradient
+        GEMM epilogues store their tiles as bf16 straight into the owner's staging buffer over NVLink (symmetric memory),
+        the owner sums the W slots, runs Adam on its rows only and stores the new bf16 weights into every rank's shadow
+        (push_*/zero_* methods; ZeRO-1 with both collectives fused into the producing kernels).
         share_from: another MlpSet of the same topology whose parameter / gradient / shadow buffers this set aliases
         (only the activation and gradient workspaces are private) -- several forward passes of one module can then be
         alive at once, each keeping its own activations for its own backward (utils/models_def.py)."""
@@ -249,9 +254,80 @@ class MlpSet:
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self._lr_host = None
         self.adam_hyper = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.zero = None
+        if zero_group is not None:
+            assert train and share_from is None
+            self._enable_zero(zero_group)
         # B operand of the bias-gradient GEMMs: db = G^T . 1 (column 0 of a [rows, 16] matrix of ones)
         self._ones = torch.zeros(P_ * M, 16, **bf)
         self._ones[:, 0] = 1.0
+
+    # ------------------------------------------------------------------------------------------
+    # data parallelism by peer stores (reduce-scatter in the wgrad epilogue, sharded Adam, all-gather of the shadows)
+    # ------------------------------------------------------------------------------------------
+    def _enable_zero(self, pg):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        W, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        big = [(s, n) for b in self.buckets for s in range(self.S) for n in b if self.nets[s].layers[n].fused_ok]
+        rows = cols = WIDTH
+        assert all(self.nets[s].layers[n].N == rows and self.nets[s].layers[n].K == cols for s, n in big)
+        assert 1 < W <= 8 and rows % (128 * W) == 0, "rows per owner must be a multiple of the 128-row CTA tile"
+        rpo = rows // W
+        owned = len(big) * rpo * cols                                   # elements of one staging slot
+        dev = self.device
+        stage = symm.empty(W * owned, dtype=torch.bfloat16, device=dev)
+        stage.zero_()
+        h_stage = symm.rendezvous(stage, pg)
+        shadow = symm.empty(len(big) * rows * cols, dtype=torch.bfloat16, device=dev)
+        shadow.zero_()
+        h_shadow = symm.rendezvous(shadow, pg)
+        table = (_cabi.AdamZeroLayer * len(big))()
+        for li, (s, n) in enumerate(big):
+            L = self.nets[s].layers[n]
+            L.Wb = shadow[li * rows * cols:(li + 1) * rows * cols].view(rows, cols)      # shadows of the big layers: symmetric
+            table[li].master_off = L.off_W
+            table[li].stage_off = li * rpo * cols
+            for r in range(W):
+                table[li].shadow[r] = h_shadow.buffer_ptrs[r] + li * rows * cols * 2
+        tbytes = bytes(table)
+        tdev = torch.frombuffer(bytearray(tbytes), dtype=torch.uint8).to(dev)
+        self.zero = dict(pg=pg, W=W, rank=rank, big=big, index={k: i for i, k in enumerate(big)}, rpo=rpo, rows=rows, cols=cols,
+                         owned=owned, stage=stage, h_stage=h_stage, shadow=shadow, h_shadow=h_shadow, table=tdev, n=len(big))
+        torch.cuda.synchronize()
+        h_stage.barrier(channel=0)
+
+    def zero_barrier(self):
+        """Device-side barrier over the ranks (symmetric-memory signal pads): everything the ranks stored into each
+        other's buffers before it is visible after it."""
+        self.zero["h_stage"].barrier(channel=0)
+
+    def zero_adam(self):
+        """Sharded optimiser step of the big layers: sum of the W staging slots -> Adam on the owned rows -> new bf16
+        weights stored into every rank's shadow.  adam_prepare(grad_scale = 1 / W) must have run this step."""
+        z = self.zero
+        check(self.lib.links_adam_zero(self.master.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                       z["stage"].data_ptr(), z["owned"], z["table"].data_ptr(), z["n"], z["rpo"], z["cols"],
+                                       z["W"], z["rank"], self.adam_hyper.data_ptr(), torch.cuda.current_stream().cuda_stream),
+              "links_adam_zero")
+
+    def zero_sync_master(self):
+        """Collective: make the fp32 master copies of the big layers complete on every rank (each rank only keeps its own
+        rows up to date during training) -- call on ALL ranks before reading state_dict() for a checkpoint / validation."""
+        import torch.distributed as dist
+        z = self.zero
+        if z is None:
+            return
+        W, rank, rpo, cols = z["W"], z["rank"], z["rpo"], z["cols"]
+        mine = torch.cat([self.nets[s].layers[n].W[rank * rpo:(rank + 1) * rpo].reshape(-1) for s, n in z["big"]])
+        full = torch.empty(W, mine.numel(), dtype=mine.dtype, device=mine.device)
+        dist.all_gather_into_tensor(full, mine, group=z["pg"])
+        blk = rpo * cols
+        for li, (s, n) in enumerate(z["big"]):
+            Wt = self.nets[s].layers[n].W
+            for r in range(W):
+                if r != rank:
+                    Wt[r * rpo:(r + 1) * rpo].copy_(full[r, li * blk:(li + 1) * blk].view(rpo, cols))
 
     # ------------------------------------------------------------------------------------------
     # parameters
@@ -362,7 +438,7 @@ class MlpSet:
 
     @staticmethod
     def _prob(A, B, M, N, K, lda, ldb, flags=0, bias=None, add0=None, add1=None, ymask=None, bits=None,
-              sign_out=None, mid=None, out=None, out_f32=None, ld_f32=0, adam=None):
+              sign_out=None, mid=None, out=None, out_f32=None, ld_f32=0, adam=None, push=None):
         P = GemmProblem()
         P.A, P.B, P.M, P.N, P.K, P.lda, P.ldb, P.flags = A.data_ptr(), B.data_ptr(), M, N, K, lda, ldb, flags
         P.bias = bias.data_ptr() if bias is not None else None
@@ -380,6 +456,11 @@ class MlpSet:
             p_, m_, v_, sh, hy = adam
             P.adam_p, P.adam_m, P.adam_v, P.ld_f32 = p_.data_ptr(), m_.data_ptr(), v_.data_ptr(), p_.stride(0)
             P.adam_shadow, P.ld_shadow, P.adam_hyper = sh.data_ptr(), sh.stride(0), hy.data_ptr()
+        if push is not None:       # (peer pointers, rows per owner, ld): reduce-scatter by peer stores
+            ptrs, rpo, ld = push
+            for r, q in enumerate(ptrs):
+                P.push[r] = q
+            P.push_rows, P.ld_push = rpo, ld
         return P
 
     def forward_plan(self, p, rows=None):
@@ -439,19 +520,19 @@ class MlpSet:
         ops.append(self._launch(heads))
         return ops
 
-    def backward_plan(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False):
+    def backward_plan(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False, push=False):
         """dgrad chain of pass p.  Inputs: self.G[p][s][head] (bf16 [M,64], zero beyond the head width) filled by the
         loss kernels.  Outputs: G of every layer, optionally self.din[p][s] = d/d(input part) fp32.
         dX = G . W reads the forward shadow W [N, Kp] as an MN-major B operand."""
         """With wgrad=True (the LAST pass to run backward) the weight-gradient GEMMs of a bucket are issued as soon as
         the dgrad chain has completed its G buffers, each followed by a ("bucket", b) marker: run(plan, on_bucket)
         calls on_bucket(b) there so the step driver can start the bucket's all-reduce / Adam on another stream."""
-        key = ("bwd", p, need_input_grad, rows, wgrad, fuse_adam)
+        key = ("bwd", p, need_input_grad, rows, wgrad, fuse_adam, push)
         if key not in self._plans:
-            self._plans[key] = self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam)
+            self._plans[key] = self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam, push)
         return self._plans[key]
 
-    def _build_backward(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False):
+    def _build_backward(self, p, need_input_grad, rows=None, wgrad=False, fuse_adam=False, push=False):
         M = rows or self.M
         ops = []
 
@@ -466,7 +547,7 @@ class MlpSet:
             for b, members in enumerate(self._bucket_levels):
                 if b not in self._issued and all(l in done for l in members):
                     self._issued.add(b)
-                    ops.extend(self._wgrad_ops(b, rows, fuse_adam))
+                    ops.extend(self._wgrad_ops(b, rows, fuse_adam, push))
                     ops.append(("bucket", b))
         self._issued = set()
         act, G, dt, sign, nets = self.act[p], self.G[p], self.dt[p], self.sign[p], self.nets
@@ -583,7 +664,7 @@ class MlpSet:
                 return [p for p in range(self.n_passes) if br in self.pass_branches[p]]
         raise KeyError(name)
 
-    def _wgrad_ops(self, bucket, rows=None, fuse_adam=False):
+    def _wgrad_ops(self, bucket, rows=None, fuse_adam=False, push=False):
         """dW = G^T . X of one bucket's layers, contracted over the rows of every pass that used the layer (G and X read
         as MN-major operands straight from their row-major buffers); db = G^T . 1 as one more (N = 1) GEMM problem per
         layer, written straight into the flat gradient buffer.  fuse_adam: the big layers' problems apply the optimiser
@@ -601,7 +682,14 @@ class MlpSet:
                 xin = self._layer_input(n)
                 X = self._x0buf[s] if xin == "x0" else self._actbuf[s][xin]
                 Gb = self._Gbuf[s][n]
-                if fuse_adam and L.fused_ok:
+                if push and L.fused_ok:
+                    z = self.zero
+                    li = z["index"][(s, n)]
+                    base = (z["rank"] * z["owned"] + li * z["rpo"] * z["cols"]) * 2
+                    ptrs = [z["h_stage"].buffer_ptrs[r] + base for r in range(z["W"])]
+                    probs.append(self._prob(Gb, X, L.N, L.K, Kc, Gb.stride(0), X.stride(0), flags=GEMM_A_MN | GEMM_B_MN,
+                                            push=(ptrs, z["rpo"], z["cols"])))
+                elif fuse_adam and L.fused_ok:
                     off = L.off_W
                     adam = (L.W, self.exp_avg[off:off + L.N * L.K].view(L.N, L.K),
                             self.exp_avg_sq[off:off + L.N * L.K].view(L.N, L.K), L.Wb, self.adam_hyper)
@@ -750,13 +838,13 @@ class MlpSet:
         return self._chained(("cfwd", p, rows), lambda: self._build_forward(p, rows), max_ctas=max_ctas)
 
     def backward_ops(self, p, need_input_grad, rows=None, wgrad=False, split_at_buckets=False, max_ctas=None,
-                     fuse_adam=False):
+                     fuse_adam=False, push=False):
         """dgrad chain of pass p (+ weight / bias gradients with wgrad=True; + the optimiser step of the big layers
         inside the wgrad epilogues with fuse_adam=True -- single-GPU steps only, gradients are then never stored)."""
         if not USE_CHAIN:
-            return self.backward_plan(p, need_input_grad, rows, wgrad, fuse_adam)
-        return self._chained(("cbwd", p, need_input_grad, rows, wgrad, split_at_buckets, fuse_adam),
-                             lambda: self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam), split_at_buckets,
+            return self.backward_plan(p, need_input_grad, rows, wgrad, fuse_adam, push)
+        return self._chained(("cbwd", p, need_input_grad, rows, wgrad, split_at_buckets, fuse_adam, push),
+                             lambda: self._build_backward(p, need_input_grad, rows, wgrad, fuse_adam, push), split_at_buckets,
                              max_ctas)
 
     def wgrad_ops(self, rows=None):

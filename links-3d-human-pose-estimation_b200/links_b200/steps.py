@@ -82,8 +82,14 @@ class LifterStep:
             k.flow_streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
             k.stream = torch.cuda.Stream(device=dev) if ki > 0 else None      # small per-flavour kernels of flavour > 0
             self.K.append(k)
+        # data-parallel gradient exchange: "push" = reduce-scatter by peer stores fused into the wgrad epilogues + sharded
+        # Adam + shadow all-gather by peer stores (mlp.MlpSet zero_group); "bf16" / "fp32" = bucketed NCCL all-reduce
+        self.push = self.world > 1 and self.cfg.get("grad_comm", "bf16") == "push"
+        if self.push:
+            self.cfg["dp_buckets"] = 1            # no bucketed all-reduce: one contiguous "rest" range for the small layers
         self.mlp = MlpSet("lifter", [2 * n for n in nj_all], [{"downscale": n, "angles": 1} for n in nj_all], self.N,
                           n_passes=2, device=dev, train=True, pass_branches=[["pose", "angle"], ["pose"]],
+                          zero_group=process_group if self.push else None,
                           head_groups=[[(k.s0, "downscale"), (k.s0 + 1, "downscale"), (k.s0, "angles"), (k.s0 + 1, "angles")]
                                        for k in self.K],
                           max_buckets=self.cfg.get("dp_buckets") if (self.world > 1 or self.cfg.get("dp_layout")) else None)
@@ -149,8 +155,27 @@ class LifterStep:
                                        m.x0[p][s].data_ptr(), None, 0, 0, self._st()),
               "links_pack_rows")
 
+    def _on_bucket_push(self, b):
+        """Push mode: the chain has stored every big weight gradient into its owner's staging buffer.  All-reduce the
+        small rest (biases, upscale, heads: ~100 K values) over NCCL, then barrier -> sharded Adam (+ shadow stores into
+        every rank) -> Adam of the rest -> barrier."""
+        main = torch.cuda.current_stream()
+        m = self.mlp
+        a, e = m.bucket_mid[b], m.bucket_ranges[b][1]
+        self.comm.wait_stream(main)
+        with torch.cuda.stream(self.comm):
+            torch.distributed.all_reduce(m.grad[a:e], group=self.pg)
+        m.zero_barrier()                      # every rank's pushes have landed
+        m.zero_adam()
+        main.wait_stream(self.comm)
+        m.adam_step(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world, bucket=b,
+                    last=(b == len(m.buckets) - 1), rest_only=True)
+        m.zero_barrier()                      # every rank's new shadows have landed (and the staging slots are free again)
+
     def _on_bucket(self, b):
         """Bucket b of the flat gradient buffer is final: all-reduce + Adam + shadow refresh on the comm stream."""
+        if self.push:
+            return self._on_bucket_push(b)
         main = torch.cuda.current_stream()
         m = self.mlp
         src = main
@@ -211,6 +236,9 @@ class LifterStep:
         self._fuse_adam = bool(fused_optimizer and self.world == 1 and self.cfg.get("fuse_adam", True))
         if self._fuse_adam:
             m.adam_prepare(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0)
+        push = self.push and fused_optimizer
+        if push:
+            m.adam_prepare(lr=self.cfg["lr"], weight_decay=self.cfg["weight_decay"], grad_scale=1.0 / self.world)
         if self.prefetch:
             self.u.copy_(self.u_next)
         else:
@@ -273,8 +301,8 @@ class LifterStep:
             self._sample_stream.wait_stream(main)
             with torch.cuda.stream(self._sample_stream):
                 self.full_flow.sample(self.x, self.noise, self.u_next)
-        m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1, max_ctas=self._ctas_tail,
-                             fuse_adam=self._fuse_adam),
+        m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1 and not push,
+                             max_ctas=self._ctas_tail, fuse_adam=self._fuse_adam, push=push),
               on_bucket=self._on_bucket if fused_optimizer else None)
         if fused_optimizer:
             main.wait_stream(self.opt_stream)

@@ -54,7 +54,7 @@ def main():
         step.eps_x.copy_(EPS[r]); step.u_y.copy_(UY[r])
 
     # ---- (1) local gradients of this rank's shard, no communication
-    solo = LifterStep(kind, B, nets, flows, full, cfg={"dp_buckets": 2, "dp_layout": True})   # same flat layout
+    solo = LifterStep(kind, B, nets, flows, full, cfg={"dp_buckets": 1 if grad_comm == "push" else 2, "dp_layout": True})   # same flat layout
     load(solo, rank)
     solo.forward_backward()
     torch.cuda.synchronize()
@@ -72,6 +72,8 @@ def main():
     step.step()
     torch.cuda.synchronize()
     m = step.mlp
+    if grad_comm == "push":
+        return check_push(step, solo, nets, flows, full, X, NOISE, EPS, UY, g_sum, abs_sum, w0, rank, world, kind, out_dir)
     reduced = m.grad16.float() if grad_comm == "bf16" else m.grad
     err = (reduced - g_sum).abs()
     if grad_comm == "bf16":
@@ -128,6 +130,72 @@ def main():
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0)      # captured/in-flight NCCL state: leave without running destructors (see bench.py)
+
+
+def check_push(step, solo, nets, flows, full, X, NOISE, EPS, UY, g_sum, abs_sum, w0, rank, world, kind, out_dir):
+    """grad_comm = "push": reduce-scatter by peer stores out of the wgrad epilogues, sharded Adam, shadows stored into every
+    rank.  (1) the W staging slots of this rank hold every rank's bf16 gradient of the rows it owns: their fp32 sum equals
+    the sum of the ranks' local gradients to bf16 rounding of each addend; (2) every rank ends the step with identical
+    bf16 shadows, equal to bf16(master) on the owner; (3) the owned master rows moved the way the oracle's Adam moves them."""
+    from links_b200.shard import shard_rows
+    from oracle import steps as OS
+    m, ms = step.mlp, solo.mlp
+    z = m.zero
+    rpo, cols, owned, W = z["rpo"], z["cols"], z["owned"], z["W"]
+    stage = z["stage"].view(W, owned).float()
+    worst = 0.0
+    for li, (s, n) in enumerate(z["big"]):
+        Ls = ms.nets[s].layers[n]                       # same layer in the un-communicated engine (its own flat layout)
+        blk = slice(li * rpo * cols, (li + 1) * rpo * cols)
+        got = stage[:, blk].sum(0).view(rpo, cols)
+        off = Ls.off_W + rank * rpo * cols
+        ref = g_sum[off:off + rpo * cols].view(rpo, cols)
+        bound = abs_sum[off:off + rpo * cols].view(rpo, cols) * 2.0 ** -8 + 1e-30
+        worst = max(worst, ((got - ref).abs() / bound).max().item())
+    assert worst <= 1.0, "push reduce-scatter outside bf16 rounding: %g" % worst
+    # rest (small layers, biases): plain NCCL sum in fp32
+    a, e = m.bucket_mid[0], m.bucket_ranges[0][1]
+    a_s, e_s = ms.bucket_mid[0], ms.bucket_ranges[0][1]
+    assert (e - a) == (e_s - a_s)
+    assert rel_fro(m.grad[a:e], g_sum[a_s:e_s]) < 1e-6
+    # identical shadows everywhere, = bf16(master) on the owner's rows
+    chk = torch.stack((z["shadow"].double().sum(), z["shadow"].double().abs().sum()))
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "ranks hold different shadows after a push step"
+    for s, n in z["big"][:6]:
+        L = m.nets[s].layers[n]
+        own = slice(rank * rpo, (rank + 1) * rpo)
+        assert torch.equal(L.Wb[own], L.W[own].bfloat16()), (s, n)
+    assert (m.master - w0).abs().max().item() > 0
+    # complete masters after the explicit gather; then the direction of the first Adam update vs the oracle
+    m.zero_sync_master()
+    chk = torch.stack((m.master.double().sum(), m.master.double().abs().sum()))
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    assert torch.equal(lo, hi), "masters differ after zero_sync_master"
+    if rank == 0:
+        pn = [OS.params_require_grad(p) for p in nets]
+        fn = OS.lt_step if kind == "lt" else OS.lr_step
+        for r in range(world):
+            u = OS.sample_poses(shard_rows(X, r, world), full, shard_rows(NOISE, r, world))
+            out = fn(u, pn[0], pn[1], flows[0], flows[1], EPS[r], UY[r])
+            (out["loss"] / world).backward()
+        opts = OS.make_adam(pn)
+        for o in opts:
+            o.step()
+        for s in range(2):
+            for name in ("res_pose1.l1", "res_angle2.l2", "downscale", "upscale"):
+                L = m.nets[s].layers[name]
+                d_gpu = L.W.cpu() - nets[s][name + ".weight"]
+                d_ref = pn[s][name + ".weight"].detach() - nets[s][name + ".weight"]
+                cos = ((d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())).item()
+                assert cos > 0.9, (s, name, cos)
+    dist.barrier()
+    open(os.path.join(out_dir, "ok_%s_%s_%d" % (kind, "push", rank)), "w").write("ok")
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
