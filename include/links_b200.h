@@ -223,6 +223,12 @@ typedef struct LinksAdamZeroLayer {
 int links_adam_zero(float* p, float* m, float* v, const void* stage, size_t stage_slot_elems, const LinksAdamZeroLayer* layers_dev,
                     int n_layers, int rows_per_owner, int cols, int world, int rank, const float* hyper, void* stream);
 
+/* Device-side barrier over the ranks of one node (one process per GPU): flag_ptrs[r] (HOST array of `world` device
+ * pointers) is rank r's zero-initialised flag array (>= 64 uint32), mapped into this process (symmetric memory).  Peer
+ * stores issued by earlier work of the stream are visible to every rank behind the barrier.  slot 0..7: independent
+ * barriers.  A plain kernel launch (CUDA-graph capturable); traps after ~10 s if a rank never arrives. */
+int links_peer_barrier(void* const* flag_ptrs, int world, int rank, int slot, void* stream);
+
 /* Data-parallel gradient compression: grad_bf16[i] = bf16(grad[i]) before the NCCL all-reduce (half the NVLink
  * bytes), and the Adam step that consumes the reduced bf16 gradients directly (same arithmetic otherwise). */
 int links_grad_compress_bf16(const float* grad, void* grad_bf16, size_t n, void* stream);

@@ -161,6 +161,41 @@ extern "C" __attribute__((visibility("default"))) int links_adam_prepare(const i
   return links_launch_status();
 }
 
+// Device-side barrier over the ranks of one node through peer-mapped flag words (flags[r]: rank r's flag array, >= world
+// uint32 zero-initialised words per slot): rank `rank` sets word [slot * 8 + rank] in every rank's array and consumes the
+// words [slot * 8 + r] of its own.  System-scope fences on both sides: peer stores issued before the barrier (by earlier
+// kernels of the stream) are visible to every rank after it.  A plain kernel launch: CUDA-graph capturable.
+struct PeerFlags { unsigned int* f[LINKS_MAX_PUSH_RANKS]; };
+__global__ void peer_barrier_kernel(PeerFlags P, int world, int rank, int slot) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  __threadfence_system();
+  unsigned int* remote = P.f[t] + slot * LINKS_MAX_PUSH_RANKS + rank;
+  long long t0 = clock64();
+  while (atomicCAS_system(remote, 0u, 1u) != 0u) {
+    if (clock64() - t0 > 20000000000LL) __trap();       // ~10 s: a rank never arrived
+  }
+  unsigned int* local = P.f[rank] + slot * LINKS_MAX_PUSH_RANKS + t;
+  t0 = clock64();
+  while (atomicCAS_system(local, 1u, 0u) != 1u) {
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+  __threadfence_system();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_peer_barrier(void* const* flag_ptrs, int world, int rank, int slot, void* stream) {
+  LINKS_CHECK_PTR(flag_ptrs);
+  if (world < 1 || world > LINKS_MAX_PUSH_RANKS || rank < 0 || rank >= world || slot < 0 || slot > 7) return LINKS_E_RANGE;
+  PeerFlags P;
+  memset(&P, 0, sizeof(P));
+  for (int r = 0; r < world; ++r) {
+    if (flag_ptrs[r] == nullptr) return LINKS_E_ARG;
+    P.f[r] = static_cast<unsigned int*>(flag_ptrs[r]);
+  }
+  peer_barrier_kernel<<<1, 32, 0, links_stream(stream)>>>(P, world, rank, slot);
+  return links_launch_status();
+}
+
 extern "C" __attribute__((visibility("default"))) int links_adam_zero(float* p, float* m, float* v, const void* stage, size_t stage_slot_elems,
                                const LinksAdamZeroLayer* layers_dev, int n_layers, int rows_per_owner, int cols, int world, int rank,
                                const float* hyper, void* stream) {

@@ -87,6 +87,7 @@ SIGNATURES = {
     "links_grad_compress_bf16": (ci, [vp, vp, sz]),
     "links_small_matvec": (ci, [vp, vp, ci, ci, vp]),
     "links_normalize_head": (ci, [vp, ci, ci, ci, cf, vp, vp]),
+    "links_peer_barrier": (ci, [vp, ci, ci, ci]),
     "links_adam_zero": (ci, [vp, vp, vp, vp, sz, vp, ci, ci, ci, ci, ci, vp]),
     "links_adam_prepare": (ci, [vp, vp, cf, cf, cf, cf, cf, cf, vp]),
     "links_elev_stats": (ci, [vp, vp, ci, vp]),

@@ -290,17 +290,24 @@ class MlpSet:
             table[li].stage_off = li * rpo * cols
             for r in range(W):
                 table[li].shadow[r] = h_shadow.buffer_ptrs[r] + li * rows * cols * 2
+        flags = symm.empty(64, dtype=torch.int32, device=dev)
+        flags.zero_()
+        h_flags = symm.rendezvous(flags, pg)
+        flag_ptrs = (C.c_void_p * W)(*[h_flags.buffer_ptrs[r] for r in range(W)])
         tbytes = bytes(table)
         tdev = torch.frombuffer(bytearray(tbytes), dtype=torch.uint8).to(dev)
         self.zero = dict(pg=pg, W=W, rank=rank, big=big, index={k: i for i, k in enumerate(big)}, rpo=rpo, rows=rows, cols=cols,
-                         owned=owned, stage=stage, h_stage=h_stage, shadow=shadow, h_shadow=h_shadow, table=tdev, n=len(big))
+                         owned=owned, stage=stage, h_stage=h_stage, shadow=shadow, h_shadow=h_shadow, table=tdev, n=len(big),
+                         flags=flags, h_flags=h_flags, flag_ptrs=flag_ptrs)
         torch.cuda.synchronize()
-        h_stage.barrier(channel=0)
+        dist.barrier(group=pg)                 # every rank has zeroed its buffers before anybody stores into them
 
     def zero_barrier(self):
         """Device-side barrier over the ranks (symmetric-memory signal pads): everything the ranks stored into each
         other's buffers before it is visible after it."""
-        self.zero["h_stage"].barrier(channel=0)
+        z = self.zero
+        check(self.lib.links_peer_barrier(z["flag_ptrs"], z["W"], z["rank"], 0, torch.cuda.current_stream().cuda_stream),
+              "links_peer_barrier")
 
     def zero_adam(self):
         """Sharded optimiser step of the big layers: sum of the W staging slots -> Adam on the owned rows -> new bf16
