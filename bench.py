@@ -352,7 +352,17 @@ def run_gpu(args):
         if args.verbose:
             print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
-    step = LifterStep("both", B, nets, flows, full, cfg=cfg, process_group=pg)
+    try:
+        step = LifterStep("both", B, nets, flows, full, cfg=cfg, process_group=pg)
+    except Exception as e:  # noqa: BLE001
+        if not (world > 1 and cfg["grad_comm"] == "push"):
+            raise
+        # symmetric memory (peer mapping over NVLink) unavailable on this box: fall back to the bucketed NCCL all-reduce
+        print("[bench rank %d] push mode unavailable (%s: %s); falling back to bf16 NCCL buckets" % (rank, type(e).__name__, e),
+              file=sys.stderr, flush=True)
+        args.grad_comm = cfg["grad_comm"] = "bf16"
+        cfg["dp_buckets"] = args.dp_buckets
+        step = LifterStep("both", B, nets, flows, full, cfg=cfg, process_group=pg)
     data = make_inputs(B, rank)
     host = [{k: v.pin_memory() for k, v in d.items()} for d in data]
     host_losses = torch.zeros(2, 8).pin_memory()

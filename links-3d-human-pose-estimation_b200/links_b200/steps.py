@@ -304,8 +304,8 @@ class LifterStep:
         m.run(m.backward_ops(0, need_input_grad=False, wgrad=True, split_at_buckets=self.world > 1 and not push,
                              max_ctas=self._ctas_tail, fuse_adam=self._fuse_adam, push=push),
               on_bucket=self._on_bucket if fused_optimizer else None)
-        if fused_optimizer:
-            main.wait_stream(self.opt_stream)
+        if fused_optimizer and not push:
+            main.wait_stream(self.opt_stream)       # (push mode runs its optimiser on the main stream)
         if self.prefetch:
             main.wait_stream(self._sample_stream)
         # loss scalars (device side, no sync): L3d, rep_rot, re_rot_3d, bl_prior, likeli_0, likeli_1, likeli, loss
