@@ -345,6 +345,7 @@ def run_gpu(args):
     B = args.batch
     nets, flows, full = make_weights()
     cfg = {"grad_comm": args.grad_comm, "dp_buckets": args.dp_buckets, "prefetch_sample": not args.no_prefetch,
+           "global_elevation_stats": args.global_elevation_stats,
            "store_rot_2d": False,      # the full projected poses are a debugging output; the step consumes the part gathers
            "nccl_ctas": args.nccl_ctas}
 
@@ -544,7 +545,7 @@ def run_gpu(args):
                        "l2_policy": "no explicit flush: each step streams ~%.1f GB of activations/weights/gradients, "
                                     "far above the 126 MB L2" % (2 * 2048 * 1024 * 2 * 2 * 60 * (B / 1024) / 1e9),
                        "operands": "bf16 operands + bf16-stored activations, fp32 accumulate / master weights / losses",
-                       "elevation_stats": "local shard" if world > 1 else "global",
+                       "elevation_stats": "global" if (world == 1 or args.global_elevation_stats) else "local shard",
                        "grad_allreduce": ("none" if world == 1 else
                                           "push: wgrad epilogues store bf16 tiles into the owner rank's staging buffer over "
                                           "NVLink, sharded Adam, bf16 shadows stored into every rank" if args.grad_comm == "push"
@@ -602,6 +603,8 @@ def main():
                     help="data-parallel gradient exchange: push = reduce-scatter by peer stores fused into the weight-gradient "
                          "GEMM epilogues + sharded Adam + shadow all-gather by peer stores (NVLink, symmetric memory); "
                          "bf16 / fp32 = bucketed NCCL all-reduce of compressed / fp32 gradients")
+    ap.add_argument("--global-elevation-stats", action="store_true",
+                    help="elevation statistic (props.mean()/std()) over the global batch instead of each rank's shard")
     ap.add_argument("--eval-poses", type=int, default=1_250_000, help="poses per GPU of the config #5 eval run")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-extra", action="store_true", help="only the headline config (no configs[] / strong_scaling)")

@@ -284,7 +284,13 @@ int links_geom_backward(const LinksGeomMaps* maps, const float* u, const float* 
                         void* stream);
 int links_geom_backward_angles(const float* ang0, const float* ang1, const float* eps_x, const float* stats,
                                const float* dgamma_direct, const float* red, int N, void* g_ang0,
-                               void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0, void* stream);
+                               void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0, int n_stat, void* stream);
+/* Global elevation statistics under data parallelism (the reference's props.mean() / props.std() over the WHOLE batch,
+ * train_leg_torso_lifter.py:168): links_elev_sums writes this rank's (sum gamma, sum gamma^2) as doubles; after a SUM
+ * all-reduce links_elev_finalize turns them into stats = (mean, unbiased std) over n_total rows.  In backward, red[2] of
+ * links_geom_backward is all-reduced as well and links_geom_backward_angles gets n_stat = n_total (<= 0: N). */
+int links_elev_sums(const float* ang0, const float* ang1, int N, double* sums, void* stream);
+int links_elev_finalize(const double* sums, int n_total, float* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Normalising flow (FrEIA SequenceINN of 8 AllInOneBlock, permute_soft=True; call sites

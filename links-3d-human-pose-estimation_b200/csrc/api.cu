@@ -329,16 +329,31 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
 
 extern "C" __attribute__((visibility("default"))) int links_geom_backward_angles(const float* ang0, const float* ang1, const float* eps_x, const float* stats,
                                           const float* dgamma_direct, const float* red, int N, void* g_ang0,
-                                          void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0,
+                                          void* g_ang1, void* gT_ang0, void* gT_ang1, int ldT, int colT0, int n_stat,
                                           void* stream) {
   (void)eps_x;
+  if (n_stat <= 0) n_stat = N;
   LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(dgamma_direct);
   LINKS_CHECK_PTR(red); LINKS_CHECK_PTR(g_ang0); LINKS_CHECK_PTR(g_ang1);
   if (N < 2) return LINKS_E_RANGE;
   geom_backward_angles_kernel<<<(N + 255) / 256, 256, 0, links_stream(stream)>>>(
       ang0, ang1, stats, dgamma_direct, red, N, static_cast<__nv_bfloat16*>(g_ang0),
       static_cast<__nv_bfloat16*>(g_ang1), static_cast<__nv_bfloat16*>(gT_ang0), static_cast<__nv_bfloat16*>(gT_ang1),
-      ldT, colT0);
+      ldT, colT0, n_stat);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_elev_sums(const float* ang0, const float* ang1, int N, double* sums, void* stream) {
+  LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1); LINKS_CHECK_PTR(sums);
+  if (N < 1) return LINKS_E_RANGE;
+  elev_sums_kernel<<<1, 1024, 0, links_stream(stream)>>>(ang0, ang1, N, sums);
+  return links_launch_status();
+}
+
+extern "C" __attribute__((visibility("default"))) int links_elev_finalize(const double* sums, int n_total, float* stats, void* stream) {
+  LINKS_CHECK_PTR(sums); LINKS_CHECK_PTR(stats);
+  if (n_total < 2) return LINKS_E_RANGE;
+  elev_finalize_kernel<<<1, 32, 0, links_stream(stream)>>>(sums, static_cast<double>(n_total), stats);
   return links_launch_status();
 }
 

@@ -554,6 +554,42 @@ __global__ void __launch_bounds__(1024) elev_stats_kernel(const float* __restric
   }
 }
 
+// Data-parallel "global elevation statistics" (train_leg_torso_lifter.py:168 evaluated over the GLOBAL batch instead of the
+// rank's shard): per-rank sums (sum gamma, sum gamma^2) in double -> all-reduce -> finalize.
+__global__ void __launch_bounds__(1024) elev_sums_kernel(const float* __restrict__ ang0, const float* __restrict__ ang1,
+                                                         int N, double* __restrict__ sums) {
+  __shared__ double sh[2][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double g = 0.5 * (static_cast<double>(ang0[static_cast<size_t>(i) * LINKS_HEAD_LD]) +
+                            static_cast<double>(ang1[static_cast<size_t>(i) * LINKS_HEAD_LD]));
+    a += g;
+    b += g * g;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(LINKS_FULL_MASK, a, o);
+    b += __shfl_xor_sync(LINKS_FULL_MASK, b, o);
+  }
+  if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < nwarps; ++w) { ta += sh[0][w]; tb += sh[1][w]; }
+    sums[0] = ta;
+    sums[1] = tb;
+  }
+}
+__global__ void elev_finalize_kernel(const double* __restrict__ sums, double n_total, float* __restrict__ stats) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const double mean = sums[0] / n_total;
+  double var = (sums[1] - n_total * mean * mean) / (n_total - 1.0);
+  if (var < 0.0) var = 0.0;
+  stats[0] = static_cast<float>(mean);
+  stats[1] = static_cast<float>(sqrt(var));
+}
+
 // Phase B of the backward: batch-statistic terms of d gamma, angle-head gradients (props = (a0+a1)/2).
 //   a_n = -mu + sigma*eps_n  =>  dL/dmu = -sum da, dL/dsigma = sum eps*da,
 //   dmu/dgamma_m = 1/N, dsigma/dgamma_m = (gamma_m - mu)/((N-1) sigma)
@@ -561,14 +597,15 @@ __global__ void geom_backward_angles_kernel(const float* __restrict__ ang0, cons
                                             const float* __restrict__ stats, const float* __restrict__ dgamma,
                                             const float* __restrict__ red, int N, __nv_bfloat16* __restrict__ g0,
                                             __nv_bfloat16* __restrict__ g1, __nv_bfloat16* __restrict__ gT0,
-                                            __nv_bfloat16* __restrict__ gT1, int ldT, int colT0) {
+                                            __nv_bfloat16* __restrict__ gT1, int ldT, int colT0, int n_stat) {
+  // n_stat: rows behind the statistic (= N, or the global row count when stats / red were reduced over the ranks)
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const float mu = stats[0], sigma = stats[1];
   const float gam = 0.5f * (ang0[static_cast<size_t>(n) * LINKS_HEAD_LD] + ang1[static_cast<size_t>(n) * LINKS_HEAD_LD]);
   const float dmu = -red[0], dsig = red[1];
-  float dg = dgamma[n] + dmu / static_cast<float>(N);
-  if (sigma > 0.f) dg += dsig * (gam - mu) / (static_cast<float>(N - 1) * sigma);
+  float dg = dgamma[n] + dmu / static_cast<float>(n_stat);
+  if (sigma > 0.f) dg += dsig * (gam - mu) / (static_cast<float>(n_stat - 1) * sigma);
   const __nv_bfloat16 h = __float2bfloat16_rn(0.5f * dg);
   g0[static_cast<size_t>(n) * 64] = h;
   g1[static_cast<size_t>(n) * 64] = h;

@@ -94,7 +94,9 @@ SIGNATURES = {
     "links_geom_forward": (ci, [C.POINTER(GeomMaps)] + [vp] * 8 + [ci] + [vp] * 4),
     "links_geom_loss": (ci, [C.POINTER(GeomMaps)] + [vp] * 10 + [ci] + [vp] * 5 + [ci, ci]),
     "links_geom_backward": (ci, [C.POINTER(GeomMaps)] + [vp] * 14 + [ci] + [vp] * 4 + [ci, ci] + [vp] * 3),
-    "links_geom_backward_angles": (ci, [vp] * 6 + [ci] + [vp] * 4 + [ci, ci]),
+    "links_geom_backward_angles": (ci, [vp] * 6 + [ci] + [vp] * 4 + [ci, ci, ci]),
+    "links_elev_sums": (ci, [vp, vp, ci, vp]),
+    "links_elev_finalize": (ci, [vp, ci, vp]),
     "links_flow_pack": (ci, [ci, ci] + [PP] * 8 + [vp]),
     "links_flow_apply": (ci, [vp, ci, ci, vp, ci, ci, vp, vp]),
     "links_flow_nll_fwdbwd": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp]),

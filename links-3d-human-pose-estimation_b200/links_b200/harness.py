@@ -38,6 +38,11 @@ def add_common_args(p, batch=256, epochs=100):
                    help="use seeded random weights for pretrained networks whose checkpoint is missing (benchmarks / "
                         "smoke runs); without it a missing checkpoint raises FileNotFoundError like the reference's torch.load")
     g.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    g.add_argument("--grad-comm", default="push", choices=["push", "bf16", "fp32"],
+                   help="data-parallel gradient exchange of the lifter trainers: push = reduce-scatter by peer stores out of the "
+                        "weight-gradient GEMM epilogues + sharded Adam (NVLink, symmetric memory); bf16 / fp32 = NCCL all-reduce")
+    g.add_argument("--global-elevation-stats", action="store_true",
+                   help="data parallel: props.mean() / props.std() over the global batch instead of each rank's shard")
     g.add_argument("--no-prefetch", action="store_true",
                    help="lifter trainers: draw the sampled poses inside the step instead of one step ahead")
     return p
@@ -138,11 +143,13 @@ class Validator:
         self.x, self.gt = torch.from_numpy(x2d[b:e]).to(dev), torch.from_numpy(gt[b:e]).to(dev)
         self.step, self.pg, self.world = step, pg, world
         self.chunk = min(chunk, max(e - b, 1))
+        step.mlp.zero_sync_master()            # push mode: each rank only keeps its own rows of the big layers current
         self.ev = EvalRunner(kind, [step.mlp.state_dict(s) for s in range(2)], chunk=self.chunk, depth=depth,
                              choice="right", process_group=pg)
 
     def run(self):
         from utils.metrics_batch import Metrics as mb
+        self.step.mlp.zero_sync_master()
         self.ev.load_lifters([self.step.mlp.state_dict(s) for s in range(2)])
         self.ev.reset()
         preds = [self.ev.run_chunk(self.x[i:i + self.chunk], self.gt[i:i + self.chunk], want_pred=True)
@@ -261,10 +268,20 @@ def train_lifters(kind, args):
     full = load_state(ckpt_paths(wd, "full_flow"), lambda: INIT.init_flow_params(34, 40), rnd)
     loader = make_loader(args, rank, world)
     cfg["prefetch_sample"] = not getattr(args, "no_prefetch", False)
-    step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
+    cfg["grad_comm"] = getattr(args, "grad_comm", "push")
+    cfg["global_elevation_stats"] = getattr(args, "global_elevation_stats", False)
+    try:
+        step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
+    except Exception as e:  # noqa: BLE001
+        if not (world > 1 and cfg["grad_comm"] == "push"):
+            raise
+        print("[links_b200] push mode unavailable (%s); using bf16 NCCL gradient buckets" % e, file=sys.stderr)
+        cfg["grad_comm"] = "bf16"
+        step = LifterStep(kind, loader.batch, nets, flows, full, cfg=cfg, process_group=pg)
     gen_dev = torch.Generator(device="cuda").manual_seed(args.seed * 7919 + rank)
     validator = Validator(kind, step, args.val, args.seed, args.translation, rank, world, pg) if args.val else None
     n = run_training(step, loader, args, rank, lifter_feed(gen_dev), validator)
+    step.mlp.zero_sync_master()                # collective: complete fp32 masters on every rank before rank 0 saves them
     if rank == 0 and not args.no_save:
         from utils import models_def as MD
         cls = (MD.Leg_Lifter, MD.Torso_Lifter) if kind == "lt" else (MD.Left_Right_Lifter, MD.Left_Right_Lifter)

@@ -95,6 +95,15 @@ class LifterStep:
                           max_buckets=self.cfg.get("dp_buckets") if (self.world > 1 or self.cfg.get("dp_layout")) else None)
         self.mlp.load_state_dicts(lifter_params)
         self.full_flow = FlowPacked(34, full_flow_params, device=dev)
+        # cfg global_elevation_stats: props.mean() / props.std() (train_leg_torso_lifter.py:168) over the GLOBAL batch -- two
+        # tiny all-reduces per step (sums of gamma / gamma^2 forward, the two statistic cotangents backward) make the
+        # data-parallel step equal to the reference's step on the concatenated batch; default: the rank's shard (DDP)
+        self.gstats = bool(self.cfg.get("global_elevation_stats")) and self.world > 1
+        self._esums = torch.zeros(2 * len(self.K), dtype=torch.float64, device=dev)
+        self._red_all = torch.zeros(2 * len(self.K), **f32)
+        for i, k in enumerate(self.K):
+            k.esum = self._esums[2 * i:2 * i + 2]
+            k.red = self._red_all[2 * i:2 * i + 2] if self.gstats else k.scal[6:8]
         # inputs (filled by the caller before step())
         self.x = torch.zeros(B, 34, **f32)
         self.noise = torch.zeros(B, 34, **f32)
@@ -247,12 +256,22 @@ class LifterStep:
             for s in range(2):
                 self._pack(self.u, k.idx_u[s], 2 * k.nj[s], 0, k.s0 + s)
         m.run(m.forward_ops(0))
+        if self.gstats:
+            for k in self.K:
+                a1 = [m.head_out[0][k.s0 + s]["angles"] for s in range(2)]
+                check(L.links_elev_sums(a1[0].data_ptr(), a1[1].data_ptr(), N, k.esum.data_ptr(), self._st()), "links_elev_sums")
+            torch.distributed.all_reduce(self._esums, group=self.pg)
+            self._red_all.zero_()
         for k in self.K:
             with self._fork(k):
                 mp = C.byref(k.maps)
                 a1 = [m.head_out[0][k.s0 + s]["angles"] for s in range(2)]
-                check(L.links_elev_stats(a1[0].data_ptr(), a1[1].data_ptr(), N, k.stats.data_ptr(), self._st()),
-                      "links_elev_stats")
+                if self.gstats:
+                    check(L.links_elev_finalize(k.esum.data_ptr(), N * self.world, k.stats.data_ptr(), self._st()),
+                          "links_elev_finalize")
+                else:
+                    check(L.links_elev_stats(a1[0].data_ptr(), a1[1].data_ptr(), N, k.stats.data_ptr(), self._st()),
+                          "links_elev_stats")
                 k.common = [self.u.data_ptr()] + [m.head_out[0][k.s0 + s]["downscale"].data_ptr() for s in range(2)] + \
                            [a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(), self.u_y.data_ptr(), k.stats.data_ptr()]
                 qf = [q.data_ptr() for q in k.qfull] if self.cfg.get("store_rot_2d", True) else [None, None]
@@ -289,13 +308,24 @@ class LifterStep:
                 check(L.links_geom_backward(C.byref(k.maps), *k.common, h2[0].data_ptr(), h2[1].data_ptr(),
                                             k.dflow[0].data_ptr(), k.dflow[1].data_ptr(), m.din[1][k.s0].data_ptr(),
                                             m.din[1][k.s0 + 1].data_ptr(), N, g1[0].data_ptr(), g1[1].data_ptr(), None, None,
-                                            0, 0, k.dgamma.data_ptr(), k.da.data_ptr(), k.scal[6:8].data_ptr(), self._st()),
+                                            0, 0, k.dgamma.data_ptr(), k.da.data_ptr(), k.red.data_ptr(), self._st()),
                       "links_geom_backward")
-                check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
-                                                   k.stats.data_ptr(), k.dgamma.data_ptr(), k.scal[6:8].data_ptr(), N,
-                                                   ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, self._st()),
-                      "links_geom_backward_angles")
+                if not self.gstats:
+                    check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
+                                                       k.stats.data_ptr(), k.dgamma.data_ptr(), k.red.data_ptr(), N,
+                                                       ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, 0, self._st()),
+                          "links_geom_backward_angles")
         self._join()
+        if self.gstats:
+            # the statistic's cotangents (sum da, sum eps * da) over ALL ranks' rows, then the angle-head gradients
+            torch.distributed.all_reduce(self._red_all, group=self.pg)
+            for k in self.K:
+                a1 = [m.head_out[0][k.s0 + s]["angles"] for s in range(2)]
+                ga = [m.G[0][k.s0 + s]["angles"] for s in range(2)]
+                check(L.links_geom_backward_angles(a1[0].data_ptr(), a1[1].data_ptr(), self.eps_x.data_ptr(),
+                                                   k.stats.data_ptr(), k.dgamma.data_ptr(), k.red.data_ptr(), N,
+                                                   ga[0].data_ptr(), ga[1].data_ptr(), None, None, 0, 0, N * self.world, self._st()),
+                      "links_geom_backward_angles")
         if self.prefetch:
             # poses of the NEXT step, drawn beside the longest GEMM chain of this one (which leaves it the SMs it needs)
             self._sample_stream.wait_stream(main)

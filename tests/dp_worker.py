@@ -54,7 +54,7 @@ def main():
         step.eps_x.copy_(EPS[r]); step.u_y.copy_(UY[r])
 
     # ---- (1) local gradients of this rank's shard, no communication
-    solo = LifterStep(kind, B, nets, flows, full, cfg={"dp_buckets": 1 if grad_comm == "push" else 2, "dp_layout": True})   # same flat layout
+    solo = LifterStep(kind, B, nets, flows, full, cfg={"dp_buckets": 1 if grad_comm.startswith("push") else 2, "dp_layout": True})   # same flat layout
     load(solo, rank)
     solo.forward_backward()
     torch.cuda.synchronize()
@@ -65,13 +65,18 @@ def main():
     dist.all_reduce(abs_sum)
 
     # ---- the product path
-    cfg = {"grad_comm": grad_comm, "dp_buckets": 2}
+    gstats = grad_comm == "push_global"
+    if gstats:
+        grad_comm = "push"
+    cfg = {"grad_comm": grad_comm, "dp_buckets": 2, "global_elevation_stats": gstats}
     step = LifterStep(kind, B, nets, flows, full, cfg=cfg, process_group=dist.group.WORLD)
     load(step, rank)
     w0 = step.mlp.master.clone()
     step.step()
     torch.cuda.synchronize()
     m = step.mlp
+    if gstats:
+        return check_global(step, nets, flows, full, X, NOISE, EPS, UY, rank, world, kind, out_dir)
     if grad_comm == "push":
         return check_push(step, solo, nets, flows, full, X, NOISE, EPS, UY, g_sum, abs_sum, w0, rank, world, kind, out_dir)
     reduced = m.grad16.float() if grad_comm == "bf16" else m.grad
@@ -193,6 +198,53 @@ def check_push(step, solo, nets, flows, full, X, NOISE, EPS, UY, g_sum, abs_sum,
                 assert cos > 0.9, (s, name, cos)
     dist.barrier()
     open(os.path.join(out_dir, "ok_%s_%s_%d" % (kind, "push", rank)), "w").write("ok")
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)
+
+
+def check_global(step, nets, flows, full, X, NOISE, EPS, UY, rank, world, kind, out_dir):
+    """global_elevation_stats: the data-parallel step must equal the reference step on the CONCATENATED batch (the only
+    term of the step that couples rows across ranks is props.mean() / props.std(), train_leg_torso_lifter.py:168):
+    rank-averaged losses, the reduced gradients of the owned rows and the first Adam update vs ONE oracle step on all rows."""
+    from links_b200.shard import shard_rows
+    from oracle import steps as OS
+    m = step.mlp
+    z = m.zero
+    losses = torch.tensor(list(step.loss_dict().values()), dtype=torch.float64, device="cuda")
+    dist.all_reduce(losses)
+    losses = (losses / world).tolist()
+    m.zero_sync_master()
+    if rank == 0:
+        pn = [OS.params_require_grad(p) for p in nets]
+        fn = OS.lt_step if kind == "lt" else OS.lr_step
+        us = [OS.sample_poses(shard_rows(X, r, world), full, shard_rows(NOISE, r, world)) for r in range(world)]
+        u = torch.cat(us, dim=0)                     # every shard = [real ; sampled]: row pairs stay inside a shard
+        out = fn(u, pn[0], pn[1], flows[0], flows[1], EPS.reshape(-1), UY.reshape(-1))
+        out["loss"].backward()
+        for (k, v), got in zip(step.loss_dict().items(), losses):
+            r_ = out[k].item()
+            assert abs(got - r_) <= 1e-3 * abs(r_) + 1e-6, (k, got, r_)
+        rpo, cols, owned, W = z["rpo"], z["cols"], z["owned"], z["W"]
+        stage = z["stage"].view(W, owned).float()
+        for li, (s, n) in enumerate(z["big"]):
+            if n not in ("res_common.l1", "res_pose2.l2", "res_angle1.l1", "res_angle3.l2"):
+                continue
+            got = stage[:, li * rpo * cols:(li + 1) * rpo * cols].sum(0).view(rpo, cols).cpu() / world
+            ref = pn[s][n + ".weight"].grad[rank * rpo:(rank + 1) * rpo]
+            assert rel_fro(got, ref) < 6e-2, (s, n, rel_fro(got, ref))
+        opts = OS.make_adam(pn)
+        for o in opts:
+            o.step()
+        for s in range(2):
+            for name in ("res_pose1.l1", "res_angle2.l2", "angles", "upscale"):
+                L = m.nets[s].layers[name]
+                d_gpu = L.W.cpu() - nets[s][name + ".weight"]
+                d_ref = pn[s][name + ".weight"].detach() - nets[s][name + ".weight"]
+                cos = ((d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())).item()
+                assert cos > 0.9, (s, name, cos)
+    dist.barrier()
+    open(os.path.join(out_dir, "ok_%s_%s_%d" % (kind, "push_global", rank)), "w").write("ok")
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0)

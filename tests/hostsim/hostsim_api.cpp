@@ -167,11 +167,21 @@ SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float
   return 0;
 }
 SIM int sim_geom_backward_angles(const float* a0, const float* a1, const float* eps, const float* stats, const float* dgamma,
-                                 const float* red, int N, void* g0, void* g1, void* gT0, void* gT1, int ldT, int colT0) {
+                                 const float* red, int N, void* g0, void* g1, void* gT0, void* gT1, int ldT, int colT0,
+                                 int n_stat) {
   (void)eps;
+  if (n_stat <= 0) n_stat = N;
   hostsim::launch(dim3((N + 255) / 256), dim3(256), 0, [&] {
-    geom_backward_angles_kernel(a0, a1, stats, dgamma, red, N, (bf16*)g0, (bf16*)g1, (bf16*)gT0, (bf16*)gT1, ldT, colT0);
+    geom_backward_angles_kernel(a0, a1, stats, dgamma, red, N, (bf16*)g0, (bf16*)g1, (bf16*)gT0, (bf16*)gT1, ldT, colT0, n_stat);
   });
+  return 0;
+}
+SIM int sim_elev_sums(const float* a0, const float* a1, int N, double* sums) {
+  hostsim::launch(dim3(1), dim3(1024), 0, [&] { elev_sums_kernel(a0, a1, N, sums); });
+  return 0;
+}
+SIM int sim_elev_finalize(const double* sums, int n_total, float* stats) {
+  hostsim::launch(dim3(1), dim3(32), 0, [&] { elev_finalize_kernel(sums, (double)n_total, stats); });
   return 0;
 }
 

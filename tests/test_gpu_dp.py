@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs on one box (gpurun --gpus 2)")
-@pytest.mark.parametrize("kind,grad_comm", [("lt", "push"), ("lt", "bf16"), ("lt", "fp32"), ("lr", "push")])
+@pytest.mark.parametrize("kind,grad_comm", [("lt", "push"), ("lt", "bf16"), ("lt", "fp32"), ("lr", "push"), ("lt", "push_global"),
+                                            ("lr", "push_global")])
 def test_two_rank_lifter_step(kind, grad_comm, tmp_path):
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",

@@ -153,7 +153,7 @@ def test_geometry_kernels_match_oracle(kind, N, clamp, root_zero, backend):
     ga = [np.zeros((N, 64), np.uint16) for _ in range(2)]
     gaT = [np.zeros((1, ldT), np.uint16) for _ in range(2)]
     assert L.call("geom_backward_angles", inp["angs"][0], inp["angs"][1], inp["eps"], stats, dgam,
-                                      red, N, ga[0], ga[1], gaT[0], gaT[1], ldT, 0) == 0
+                                      red, N, ga[0], ga[1], gaT[0], gaT[1], ldT, 0, 0) == 0
     for p in range(2):
         got = bf16_to_f32(ga[p])[:, 0]
         scale = np.abs(ref["dA"][p]).max()
