@@ -223,7 +223,7 @@ extern "C" __attribute__((visibility("default"))) int links_grad_compress_bf16(c
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid of the row-walking geometry kernels (one warp per row / row pair, kGeomWarps warps per block)
+// grid of the row-walking geometry kernels (kGeomRows rows per warp iteration, kGeomWarps warps per block)
 static int geom_grid(int warps_needed) {
   const int blocks = (warps_needed + kGeomWarps - 1) / kGeomWarps;
   return blocks < 148 * 16 ? blocks : 148 * 16;
@@ -257,15 +257,15 @@ extern "C" __attribute__((visibility("default"))) int links_geom_forward(const L
   if (rc) return rc;
   LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(head0); LINKS_CHECK_PTR(head1); LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1);
   LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(qpart0); LINKS_CHECK_PTR(qpart1);
-  if (N < 1) return LINKS_E_RANGE;
+  if (N < 1 || N > kGeomMaxRows) return LINKS_E_RANGE;
   GeomArgs A;
   memset(&A, 0, sizeof(A));
   A.maps = *maps;
   A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
   A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
   A.qpart[0] = qpart0; A.qpart[1] = qpart1; A.qfull[0] = q_full0; A.qfull[1] = q_full1;
-  if (maps->V == 1) geom_forward_kernel<1><<<geom_grid((N + 1) / 2), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
-  else geom_forward_kernel<2><<<geom_grid((N + 1) / 2), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  if (maps->V == 1) geom_forward_kernel<1><<<geom_grid((N + kGeomRows - 1) / kGeomRows), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  else geom_forward_kernel<2><<<geom_grid((N + kGeomRows - 1) / kGeomRows), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
   return links_launch_status();
 }
 
@@ -279,7 +279,7 @@ extern "C" __attribute__((visibility("default"))) int links_geom_loss(const Link
   LINKS_CHECK_PTR(u); LINKS_CHECK_PTR(head0); LINKS_CHECK_PTR(head1); LINKS_CHECK_PTR(ang0); LINKS_CHECK_PTR(ang1);
   LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(head2_0); LINKS_CHECK_PTR(head2_1);
   LINKS_CHECK_PTR(loss_sums); LINKS_CHECK_PTR(g2_head0); LINKS_CHECK_PTR(g2_head1);
-  if (N < 1) return LINKS_E_RANGE;
+  if (N < 1 || N > kGeomMaxRows) return LINKS_E_RANGE;
   GeomArgs A;
   memset(&A, 0, sizeof(A));
   A.maps = *maps;
@@ -290,9 +290,16 @@ extern "C" __attribute__((visibility("default"))) int links_geom_loss(const Link
   A.g2[0] = static_cast<__nv_bfloat16*>(g2_head0); A.g2[1] = static_cast<__nv_bfloat16*>(g2_head1);
   A.g2T[0] = static_cast<__nv_bfloat16*>(g2T_head0); A.g2T[1] = static_cast<__nv_bfloat16*>(g2T_head1);
   A.ldT = ldT; A.colT0 = colT0;
-  const int pairs = (N + 1) / 2;
-  if (maps->V == 1) geom_lossgrad_kernel<false, 1><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
-  else geom_lossgrad_kernel<false, 2><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  const int pairs = (N + kGeomRows - 1) / kGeomRows;   // warp iterations: kGeomRows rows each
+  const bool tr = g2T_head0 != nullptr || g2T_head1 != nullptr;
+  const dim3 grid(geom_grid(pairs)), block(kGeomWarps * 32);
+  if (maps->V == 1) {
+    if (tr) geom_lossgrad_kernel<false, 1, true><<<grid, block, 0, links_stream(stream)>>>(A);
+    else geom_lossgrad_kernel<false, 1, false><<<grid, block, 0, links_stream(stream)>>>(A);
+  } else {
+    if (tr) geom_lossgrad_kernel<false, 2, true><<<grid, block, 0, links_stream(stream)>>>(A);
+    else geom_lossgrad_kernel<false, 2, false><<<grid, block, 0, links_stream(stream)>>>(A);
+  }
   return links_launch_status();
 }
 
@@ -309,7 +316,7 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
   LINKS_CHECK_PTR(eps_x); LINKS_CHECK_PTR(u_y); LINKS_CHECK_PTR(stats); LINKS_CHECK_PTR(head2_0); LINKS_CHECK_PTR(head2_1);
   LINKS_CHECK_PTR(dpart_flow0); LINKS_CHECK_PTR(dpart_flow1); LINKS_CHECK_PTR(dpart_lift0); LINKS_CHECK_PTR(dpart_lift1);
   LINKS_CHECK_PTR(g1_head0); LINKS_CHECK_PTR(g1_head1); LINKS_CHECK_PTR(dgamma_direct); LINKS_CHECK_PTR(da); LINKS_CHECK_PTR(red);
-  if (N < 1) return LINKS_E_RANGE;
+  if (N < 1 || N > kGeomMaxRows) return LINKS_E_RANGE;
   GeomArgs A;
   memset(&A, 0, sizeof(A));
   A.maps = *maps;
@@ -321,9 +328,16 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
   A.g1T[0] = static_cast<__nv_bfloat16*>(g1T_head0); A.g1T[1] = static_cast<__nv_bfloat16*>(g1T_head1);
   A.ldT = ldT; A.colT0 = colT0;
   A.dgamma = dgamma_direct; A.da = da; A.red = red;
-  const int pairs = (N + 1) / 2;
-  if (maps->V == 1) geom_lossgrad_kernel<true, 1><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
-  else geom_lossgrad_kernel<true, 2><<<geom_grid(pairs), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
+  const int pairs = (N + kGeomRows - 1) / kGeomRows;   // warp iterations: kGeomRows rows each
+  const bool tr = g1T_head0 != nullptr || g1T_head1 != nullptr;
+  const dim3 grid(geom_grid(pairs)), block(kGeomWarps * 32);
+  if (maps->V == 1) {
+    if (tr) geom_lossgrad_kernel<true, 1, true><<<grid, block, 0, links_stream(stream)>>>(A);
+    else geom_lossgrad_kernel<true, 1, false><<<grid, block, 0, links_stream(stream)>>>(A);
+  } else {
+    if (tr) geom_lossgrad_kernel<true, 2, true><<<grid, block, 0, links_stream(stream)>>>(A);
+    else geom_lossgrad_kernel<true, 2, false><<<grid, block, 0, links_stream(stream)>>>(A);
+  }
   return links_launch_status();
 }
 

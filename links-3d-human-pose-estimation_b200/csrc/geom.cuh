@@ -2,20 +2,22 @@
 // Reference: train_leg_torso_lifter.py:153-272 (V = 1 pose variant) and train_left_right_lifter.py:150-423
 // (V = 2 variants: 'left' / 'right' choice of combine_left_right_pred_1d, utils/helpers.py:40-53).
 //
-// Mapping: one warp per consecutive row pair (2k, 2k+1) -- the pairwise deformation loss (:250-254) couples exactly
-// those rows.  Lanes 0-15 own row 2k, lanes 16-31 row 2k+1; lane s of a half owns joint s+1 AND bone s (whose child is
-// joint s+1).  The root joint needs no lane: after root-centring (:188-192) its lifted, rotated, re-lifted and
-// back-rotated positions are identically zero, its depth offset is forced to 0 (:183) so it receives no gradient, and
-// its only loss contribution is the constant |u_root| of the reprojection term.  Per-row reductions are 4-step
-// half-warp shuffles, the pair exchange is one xor-16 shuffle, the three sin/cos pairs of a row are evaluated by three
-// different lanes in one call.  Nothing but the network outputs is read: P, R, Q, q are recomputed from
-// (u, depth heads, angle heads, eps_x, u_y, stats).
+// Mapping: four lanes per row, eight consecutive rows (four row pairs) per warp.  Lane q of a row's quad owns joints
+// 4q+1 .. 4q+4 and the bones whose children they are ("slots" 0-3): the per-joint math of a slot is straight-line code over
+// registers, the row-uniform work (rotation, reductions) is shared by 4 lanes instead of being replicated in 16, per-row
+// reductions are two xor-shuffles, the pairwise deformation loss (:250-254) couples rows 2k and 2k+1 = lanes l and l^4.
+// The root joint needs no slot: after root-centring (:188-192) its lifted, rotated, re-lifted and back-rotated positions
+// are identically zero, its depth offset is forced to 0 (:183) so it receives no gradient, and its only loss contribution
+// is the constant |u_root| of the reprojection term.  Nothing but the network outputs is read: P, R, Q, q are recomputed
+// from (u, depth heads, angle heads, eps_x, u_y, stats).
 #pragma once
 #include "devdefs.cuh"
 
 namespace links {
 
 constexpr int kGeomWarps = 4;
+constexpr int kGeomRows = 8;    // rows per warp and grid-stride iteration
+constexpr int kGeomMaxRows = (1 << 25) - 8;   // element offsets (row * 64 + column) are formed in 32 bits
 constexpr int kJ = 17;
 
 struct GeomArgs {
@@ -65,8 +67,26 @@ __device__ __forceinline__ float half_sum(float v) {
   return v;
 }
 
-// 1/x by the hardware approximation (<= 2 ulp): the projections divide by depths ~ 10, far from its range limits
-__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.f, x); }
+// 1/x and sqrt(x) by the hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp, one instruction each, no denormal or
+// range fix-up code): the projections divide by depths ~ 10, the roots are of sums of squares -- far from the range limits
+__device__ __forceinline__ float fast_rcp(float x) {
+#ifndef LINKS_HOSTSIM
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.f / x;
+#endif
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+#ifndef LINKS_HOSTSIM
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
 
 struct Vec3 { float x, y, z; };
 __device__ __forceinline__ Vec3 shfl3(Vec3 v, int src) {
@@ -91,182 +111,140 @@ __device__ __forceinline__ Vec3 matT_vec(const float (&R)[9], Vec3 p) {  // R^T 
   return q;
 }
 
-// bone table (utils/helpers.py:140-141): bone b joins parent kBoneParent[b] and child b+1 (4 bits per entry);
-// bit j of kHasNextBone: joint j is the parent of bone j; joint 8 is also the parent of bones 10 and 13, the root
-// of bones 0, 3 and 6.
-constexpr unsigned long long kBoneParent = 0xfe8cb89870540210ull;
-constexpr unsigned kHasNextBone = 0xdbb6u;
-
-// Lane-constant indexing state (one joint, one bone).
-struct LaneMaps {
-  int lane, sub, hbase, j;     // j = sub + 1
-  int net[2], col;             // depth-head source of joint j per variant
-  int pnet[2], pidx[2];        // which part (flow / pass-2 lifter input) receives joint j per variant, and where
-  int parent_src;              // lane holding the parent joint of bone `sub`
-  bool parent_is_root, has_next;
-  float crel;                  // bone_rel[sub]
+// Per-block lookup tables (shared memory, built once per block): for every (variant, joint) the ELEMENT of row 0 that
+// a lane reads or writes, so that the row loop forms an address with one 32 x 32 + 64 bit multiply-add from one 8-byte
+// table entry instead of chasing net / column / part indices through the maps.  Entries without a source point at a zero
+// word with pitch 0 (loads stay unconditional); entries without a destination are null (stores are predicated).
+__device__ float g_geom_zero[4];
+struct GeomTabs {
+  const float* hp[2][kJ];     // pass-1 depth-head output of joint j in variant v
+  const float* h2p[2][kJ];    // pass-2 depth-head output
+  const float* dfx[2][kJ];    // d/d(projected x) from the part flow; y sits njy floats further
+  const float* dlx[2][kJ];    // ... from the pass-2 lifter input gradient
+  float* qp[2][kJ];           // projected x in the part's flow / pass-2 input row; y sits njy floats further
+  __nv_bfloat16* gp[2][kJ];   // [net][j]: head-gradient element, null when net never feeds joint j
+  int pitch_f[2][kJ], pitch_l[2][kJ], njy[2][kJ];
 };
-__device__ __forceinline__ void lane_maps(const GeomArgs& A, LaneMaps& m) {
-  m.lane = threadIdx.x & 31;
-  m.sub = m.lane & 15;
-  m.hbase = m.lane & 16;
-  m.j = m.sub + 1;
+template <int V>
+__device__ __forceinline__ void build_tabs(const GeomArgs& A, GeomTabs& T, bool full) {
+  for (int i = threadIdx.x; i < 2 * kJ; i += blockDim.x) {
+    const int v = i / kJ, j = i - v * kJ;
+    // gradient destinations are per NET (first index), everything else per VARIANT
+    {
+      bool fed = false;
 #pragma unroll
-  for (int v = 0; v < 2; ++v) {
-    m.net[v] = A.maps.src_net[v][m.j];
-    m.pnet[v] = A.maps.part_net[v][m.j];
-    m.pidx[v] = A.maps.part_idx[v][m.j];
+      for (int w = 0; w < V; ++w) fed = fed || A.maps.src_net[w][j] == v;
+      __nv_bfloat16* g = full ? A.g1[v] : A.g2[v];
+      T.gp[v][j] = (fed && g) ? g + A.maps.col[j] : nullptr;
+    }
+    if (v >= V) continue;
+    const int net = A.maps.src_net[v][j], col = A.maps.col[j];
+    T.hp[v][j] = A.head[net] + col;
+    T.h2p[v][j] = A.head2[net] ? A.head2[net] + col : g_geom_zero;
+    const int pn = A.maps.part_net[v][j];
+    const bool has = pn >= 0;
+    const int pi = has ? pn : 0;
+    const int nj = A.maps.n_joints[pi], idx = A.maps.part_idx[v][j];
+    const bool ext = has && A.dflow[pi] && A.dlift[pi];
+    T.dfx[v][j] = ext ? A.dflow[pi] + idx : g_geom_zero;
+    T.dlx[v][j] = ext ? A.dlift[pi] + idx : g_geom_zero;
+    T.pitch_f[v][j] = ext ? 2 * nj : 0;
+    T.pitch_l[v][j] = ext ? LINKS_HEAD_LD : 0;
+    T.njy[v][j] = has ? nj : 0;
+    T.qp[v][j] = (has && A.qpart[pi]) ? A.qpart[pi] + idx : nullptr;
   }
-  m.col = A.maps.col[m.j];
-  const int parent = static_cast<int>((kBoneParent >> (4 * m.sub)) & 15ull);
-  m.parent_is_root = parent == 0;
-  m.parent_src = m.hbase | (parent > 0 ? parent - 1 : 0);
-  m.has_next = (kHasNextBone >> m.j) & 1u;
-  m.crel = A.maps.bone_rel[m.sub];
+  __syncthreads();
+}
+
+// bone table (utils/helpers.py:140-141): bone b joins parent kBoneParent[b] and child b+1 (4 bits per entry)
+constexpr unsigned long long kBoneParent = 0xfe8cb89870540210ull;
+__host__ __device__ constexpr int bone_parent(int child) { return static_cast<int>((kBoneParent >> (4 * (child - 1))) & 15ull); }
+// The quad mapping below hard-wires where a slot finds the parent joint of its bone; tie it to the table.
+//   slot 0 (joints 1, 5, 9, 13): root for quad lane 0, else slot 3 of the previous lane (joints 4, 8, 12)
+//   slot 1 (2, 6, 10, 14): own slot 0, except joint 14 <- joint 8 (lane 1, slot 3)
+//   slot 2 (3, 7, 11, 15): own slot 1, except joint 7 <- root and joint 11 <- joint 8
+//   slot 3 (4, 8, 12, 16): own slot 2, except joint 4 <- root
+static_assert(bone_parent(1) == 0 && bone_parent(5) == 4 && bone_parent(9) == 8 && bone_parent(13) == 12, "slot 0 parents");
+static_assert(bone_parent(2) == 1 && bone_parent(6) == 5 && bone_parent(10) == 9 && bone_parent(14) == 8, "slot 1 parents");
+static_assert(bone_parent(3) == 2 && bone_parent(7) == 0 && bone_parent(11) == 8 && bone_parent(15) == 14, "slot 2 parents");
+static_assert(bone_parent(4) == 0 && bone_parent(8) == 7 && bone_parent(12) == 11 && bone_parent(16) == 15, "slot 3 parents");
+
+// Lane-constant indexing state.
+struct Quad {
+  int lane, q, gb, j0;   // q = lane & 3; gb = first lane of this row's quad; j0 = 4 q + 1 = joint of slot 0
+};
+__device__ __forceinline__ void quad_init(Quad& m) {
+  m.lane = threadIdx.x & 31;
+  m.q = m.lane & 3;
+  m.gb = m.lane & ~3;
+  m.j0 = 4 * m.q + 1;
+}
+__device__ __forceinline__ float quad_sum(float v) {          // sum over the 4 lanes of a row (every lane receives it)
+  v += __shfl_xor_sync(LINKS_FULL_MASK, v, 1);
+  v += __shfl_xor_sync(LINKS_FULL_MASK, v, 2);
+  return v;
 }
 
 // R = Rx(a) @ (Ry(b) @ Rx(g))   (utils/rotation_conversions.py:11-36; train_leg_torso_lifter.py:159-181).
-// Lanes 0, 1, 2 of each half evaluate sincos(a), sincos(b), sincos(g) in one call; the results are broadcast.
-__device__ __forceinline__ void make_rotation(const LaneMaps& m, float a, float b, float g, float (&R)[9]) {
-  const int k = m.sub % 3;
-  const float arg = k == 0 ? a : (k == 1 ? b : g);
+// Lanes 0, 1, 2 of a row's quad evaluate sincos(a), sincos(b), sincos(g) in one call; the results are broadcast.
+__device__ __forceinline__ void make_rotation(const Quad& m, float a, float b, float g, float (&R)[9]) {
+  const float arg = m.q == 0 ? a : (m.q == 1 ? b : g);
   float s, c;
   sincosf(arg, &s, &c);
-  const float sa = __shfl_sync(LINKS_FULL_MASK, s, m.hbase), ca = __shfl_sync(LINKS_FULL_MASK, c, m.hbase);
-  const float sb = __shfl_sync(LINKS_FULL_MASK, s, m.hbase | 1), cb = __shfl_sync(LINKS_FULL_MASK, c, m.hbase | 1);
-  const float sg = __shfl_sync(LINKS_FULL_MASK, s, m.hbase | 2), cg = __shfl_sync(LINKS_FULL_MASK, c, m.hbase | 2);
+  const float sa = __shfl_sync(LINKS_FULL_MASK, s, m.gb), ca = __shfl_sync(LINKS_FULL_MASK, c, m.gb);
+  const float sb = __shfl_sync(LINKS_FULL_MASK, s, m.gb | 1), cb = __shfl_sync(LINKS_FULL_MASK, c, m.gb | 1);
+  const float sg = __shfl_sync(LINKS_FULL_MASK, s, m.gb | 2), cg = __shfl_sync(LINKS_FULL_MASK, c, m.gb | 2);
   R[0] = cb;       R[1] = sb * sg;                 R[2] = sb * cg;
   R[3] = sa * sb;  R[4] = ca * cg - sa * cb * sg;  R[5] = -ca * sg - sa * cb * cg;
   R[6] = -ca * sb; R[7] = sa * cg + ca * cb * sg;  R[8] = -sa * sg + ca * cb * cg;
 }
 
-// Everything a lane reads from global memory for one row: loaded one grid-stride iteration AHEAD of its use so that
-// the load latency hides behind the math of the current row pair (these kernels run a few hundred dependent
-// instructions per pair on few resident warps).  kLevel: 0 forward, 1 + pass-2 heads, 2 + external d/dq.
-template <int V, int kLevel>
-struct RawRow {
-  int n;
-  float ux, uy, u0x, u0y;      // this lane's 2D joint, root joint
-  float ang0, ang1, eps, uyaw;
-  float delta[V];              // pass-1 depth-head output of this lane's joint, per variant
-  float delta2[V];             // pass-2 depth-head output
-  float xqx[V], xqy[V];        // external d/d(projected joint): flow + pass-2 lifter input gradients
-};
-template <int V, int kLevel>
-__device__ __forceinline__ void load_raw(const GeomArgs& A, const LaneMaps& m, int n, RawRow<V, kLevel>& w) {
-  w.n = n;
-  const size_t nn = static_cast<size_t>(n);
-  const float* u = A.u + nn * 34;
-  w.ux = u[m.j];
-  w.uy = u[kJ + m.j];
-  w.u0x = u[0];
-  w.u0y = u[kJ];
-  w.ang0 = A.ang[0][nn * LINKS_HEAD_LD];
-  w.ang1 = A.ang[1][nn * LINKS_HEAD_LD];
-  w.eps = A.eps_x[n];
-  w.uyaw = A.u_y[n];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    w.delta[v] = A.head[m.net[v]][nn * LINKS_HEAD_LD + m.col];
-    w.delta2[v] = 0.f; w.xqx[v] = 0.f; w.xqy[v] = 0.f;
-    if (kLevel >= 1) w.delta2[v] = A.head2[m.net[v]][nn * LINKS_HEAD_LD + m.col];
-    if (kLevel >= 2) {
-      const int p = m.pnet[v];
-      if (p >= 0) {
-        const int nj = A.maps.n_joints[p];
-        const int idx = m.pidx[v];
-        w.xqx[v] = A.dflow[p][nn * (2 * nj) + idx] + A.dlift[p][nn * LINKS_HEAD_LD + idx];
-        w.xqy[v] = A.dflow[p][nn * (2 * nj) + nj + idx] + A.dlift[p][nn * LINKS_HEAD_LD + nj + idx];
-      }
-    }
-  }
-}
-
-// Per-row inputs shared by all variants.
+// Per-row inputs shared by all variants: this lane's four 2D joints, the root joint, the rotation.
 struct RowIn {
-  size_t n;
-  float ux, uy;        // this lane's 2D joint
-  float u0x, u0y;      // root joint
-  float gamma, eps;
+  int n;               // row (element offsets are formed in 32 bits: the host checks N * 64 < 2^31)
+  float ux[4], uy[4];
+  float u0x, u0y;
+  float eps;
   float R[9];
 };
-template <int V, int kLevel>
-__device__ __forceinline__ void derive_row(const GeomArgs& A, const LaneMaps& m, const RawRow<V, kLevel>& w, RowIn& r) {
-  r.n = static_cast<size_t>(w.n);
-  r.ux = w.ux; r.uy = w.uy; r.u0x = w.u0x; r.u0y = w.u0y;
-  r.gamma = 0.5f * (w.ang0 + w.ang1);
-  r.eps = w.eps;
+__device__ __forceinline__ void load_row(const GeomArgs& A, const Quad& m, int n, RowIn& r) {
+  r.n = n;
+  const float* u = A.u + n * 34;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    r.ux[k] = __ldg(u + m.j0 + k);
+    r.uy[k] = __ldg(u + kJ + m.j0 + k);
+  }
+  r.u0x = __ldg(u);
+  r.u0y = __ldg(u + kJ);
+  const float ang0 = __ldg(A.ang[0] + n * LINKS_HEAD_LD), ang1 = __ldg(A.ang[1] + n * LINKS_HEAD_LD);
+  r.eps = __ldg(A.eps_x + n);
+  const float uyaw = __ldg(A.u_y + n);
+  const float gamma = 0.5f * (ang0 + ang1);
   const float a = -A.stats[0] + A.stats[1] * r.eps;
-  const float b = (w.uyaw - 0.5f) * (1.99f * 3.14159265358979323846f);
-  make_rotation(m, a, b, r.gamma, r.R);
+  const float b = (uyaw - 0.5f) * (1.99f * 3.14159265358979323846f);
+  make_rotation(m, a, b, gamma, r.R);
 }
 
-// Per-lane state of one (row, variant).
-struct RowVar {
-  float mask;        // 1 where depth not clamped (:186)
-  float d;           // clamped depth
-  Vec3 P;            // root-centred lifted joint (:188-192)
-  Vec3 Q;            // rotated joint (:195)
-  float izq, qx, qy; // projection (:198-199); izq = 1 / (Q.z + depth)
-  // pass-2 side
-  float mask2, d2;
-  Vec3 P2;           // re-lifted joint (:235-238)
-  Vec3 F;            // Q - P2
-  float L3d;
-  Vec3 S;            // R^T P2 (:242)
-  float izs, rx, ry; // izs = 1 / (S.z + depth)
-  // bones
-  Vec3 e;            // P_parent - P_child of this lane's bone
-  float bl_len, bl_imean, bl_rho;   // bone length, 1 / mean bone length, their ratio
+// lift (:183-192), rotate (:195), project (:198-199) one joint
+struct JointFwd {
+  float mask;        // 1 where the depth is not clamped (:186)
+  Vec3 P;            // root-centred lifted joint
+  Vec3 Q;            // rotated joint
+  float izq, qx, qy; // izq = 1 / (Q.z + depth)
 };
-
-__device__ __forceinline__ void row_forward(const GeomArgs& A, float delta, const RowIn& r, RowVar& s) {
-  const float D = A.maps.depth;
-  const float d0 = D < 1.0f ? 1.0f : D;                   // root depth: offset forced to 0 (:183), then clamped
+__device__ __forceinline__ void joint_forward(float D, float d0, float delta, float ux, float uy, float u0x, float u0y,
+                                              const float (&R)[9], JointFwd& s) {
   float d = delta + D;
   s.mask = (d < 1.0f) ? 0.f : 1.f;
   d = (d < 1.0f) ? 1.0f : d;
-  s.d = d;
-  s.P.x = r.ux * d - r.u0x * d0;
-  s.P.y = r.uy * d - r.u0y * d0;
+  s.P.x = ux * d - u0x * d0;
+  s.P.y = uy * d - u0y * d0;
   s.P.z = d - d0;
-  s.Q = mat_vec(r.R, s.P);
+  s.Q = mat_vec(R, s.P);
   s.izq = fast_rcp(s.Q.z + D);
   s.qx = s.Q.x * s.izq;
   s.qy = s.Q.y * s.izq;
-}
-
-// pass-2 quantities and the per-row loss terms (L3d, rep_rot, bl_prior) via out[3] (uniform over the half-warp).
-__device__ __forceinline__ void row_consistency(const GeomArgs& A, const LaneMaps& m, float delta2, const RowIn& r,
-                                                RowVar& s, float (&out)[3]) {
-  const float D = A.maps.depth;
-  const float d0 = D < 1.0f ? 1.0f : D;
-  float d2 = delta2 + D;
-  s.mask2 = (d2 < 1.0f) ? 0.f : 1.f;
-  d2 = (d2 < 1.0f) ? 1.0f : d2;
-  s.d2 = d2;
-  // the root projects to (0, 0): its re-lifted position is (0, 0, d0)
-  s.P2.x = s.qx * d2;
-  s.P2.y = s.qy * d2;
-  s.P2.z = d2 - d0;
-  s.F.x = s.Q.x - s.P2.x; s.F.y = s.Q.y - s.P2.y; s.F.z = s.Q.z - s.P2.z;
-  s.L3d = sqrtf(half_sum(s.F.x * s.F.x + s.F.y * s.F.y + s.F.z * s.F.z));
-  s.S = matT_vec(r.R, s.P2);
-  s.izs = fast_rcp(s.S.z + D);
-  s.rx = s.S.x * s.izs;
-  s.ry = s.S.y * s.izs;
-  const float rep = half_sum(fabsf(s.rx - r.ux) + fabsf(s.ry - r.uy)) + (fabsf(r.u0x) + fabsf(r.u0y));
-  // bone lengths: this lane's bone joins its joint (child) to the parent joint
-  Vec3 Pp = shfl3(s.P, m.parent_src);
-  if (m.parent_is_root) { Pp.x = 0.f; Pp.y = 0.f; Pp.z = 0.f; }
-  s.e.x = Pp.x - s.P.x; s.e.y = Pp.y - s.P.y; s.e.z = Pp.z - s.P.z;
-  s.bl_len = sqrtf(s.e.x * s.e.x + s.e.y * s.e.y + s.e.z * s.e.z);
-  s.bl_imean = fast_rcp(half_sum(s.bl_len) * (1.f / 16.f));
-  s.bl_rho = s.bl_len * s.bl_imean;
-  const float bl = half_sum((m.crel - s.bl_rho) * (m.crel - s.bl_rho));
-  out[0] = s.L3d;
-  out[1] = rep;
-  out[2] = bl;
 }
 
 // =========================================================================================================
@@ -275,53 +253,60 @@ __device__ __forceinline__ void row_consistency(const GeomArgs& A, const LaneMap
 template <int V>
 __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const GeomArgs Ap) {
   __shared__ GeomArgs sA;
+  __shared__ GeomTabs sT;
   stage_args(&sA, Ap);
   const GeomArgs& A = sA;
-  LaneMaps m;
-  lane_maps(A, m);
-  const int half = m.lane >> 4;
-  const int npairs = (A.N + 1) / 2;
+  build_tabs<V>(A, sT, false);
+  const GeomTabs& T = sT;
+  Quad m;
+  quad_init(m);
+  const int warp = threadIdx.x >> 5, rl = m.lane >> 2;
+  const float D = A.maps.depth;
+  const float d0 = D < 1.0f ? 1.0f : D;                   // root depth: offset forced to 0 (:183), then clamped
+  const int n_iters = (A.N + kGeomRows - 1) / kGeomRows;
   const int stride = gridDim.x * kGeomWarps;
   // The loop bounds depend on blockIdx only (block-uniform trip count): the compiler can then prove that the warp is
-  // converged at every shuffle and emits plain SHFLs; a warp past the end works on a clamped row with writes masked.
-  const int warp = threadIdx.x >> 5;
-  auto row_of = [&](int pr) {                    // row this half-warp reads for pair `pr` (clamped to a valid row)
-    const int n = 2 * pr + half;
-    return n < A.N ? n : A.N - 1;
-  };
-  RawRow<V, 0> raw, raw_next;
-  load_raw(A, m, row_of(blockIdx.x * kGeomWarps + warp), raw);
-  for (int base = blockIdx.x * kGeomWarps; base < npairs; base += stride, raw = raw_next) {
-    const int pair = base + warp;
-    if (base + stride < npairs) load_raw(A, m, row_of(pair + stride), raw_next);
-    const bool valid = 2 * pair + half < A.N;    // uniform over the half-warp
+  // converged at every shuffle and emits plain SHFLs; rows past the end work on a clamped row with writes masked.
+  for (int base = blockIdx.x * kGeomWarps; base < n_iters; base += stride) {
+    const int n_raw = kGeomRows * (base + warp) + rl;
+    const bool valid = n_raw < A.N;                      // uniform over the quad
     RowIn r;
-    derive_row(A, m, raw, r);
+    load_row(A, m, valid ? n_raw : A.N - 1, r);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      RowVar s;
-      row_forward(A, raw.delta[v], r, s);
-      if (!valid) continue;
-      if (A.qfull[v]) {
-        float* qf = A.qfull[v] + r.n * 34;
-        qf[m.j] = s.qx;
-        qf[kJ + m.j] = s.qy;
-        if (m.sub == 0) { qf[0] = 0.f; qf[kJ] = 0.f; }          // root: projects to (0, 0)
+      float delta[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) delta[k] = __ldg(T.hp[v][m.j0 + k] + r.n * LINKS_HEAD_LD);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = m.j0 + k;
+        JointFwd s;
+        joint_forward(D, d0, delta[k], r.ux[k], r.uy[k], r.u0x, r.u0y, r.R, s);
+        if (!valid) continue;
+        if (A.qfull[v]) {
+          float* qf = A.qfull[v] + r.n * 34;
+          qf[j] = s.qx;
+          qf[kJ + j] = s.qy;
+        }
+        float* dst = T.qp[v][j];
+        if (dst) {
+          const int nj = T.njy[v][j];
+          dst += r.n * (2 * nj);
+          dst[0] = s.qx;
+          dst[nj] = s.qy;
+        }
       }
-      const int p = m.pnet[v];
-      if (p >= 0) {
-        const int nj = A.maps.n_joints[p];
-        float* dst = A.qpart[p] + r.n * (2 * nj);
-        dst[m.pidx[v]] = s.qx;
-        dst[nj + m.pidx[v]] = s.qy;
-      }
-      if (m.sub == 0) {
-        const int p0 = A.maps.part_net[v][0];
-        if (p0 >= 0) {
-          const int nj = A.maps.n_joints[p0];
-          float* dst = A.qpart[p0] + r.n * (2 * nj);
-          dst[A.maps.part_idx[v][0]] = 0.f;
-          dst[nj + A.maps.part_idx[v][0]] = 0.f;
+      if (valid && m.q == 0) {                             // root: projects to (0, 0)
+        if (A.qfull[v]) {
+          float* qf = A.qfull[v] + r.n * 34;
+          qf[0] = 0.f; qf[kJ] = 0.f;
+        }
+        float* dst = T.qp[v][0];
+        if (dst) {
+          const int nj = T.njy[v][0];
+          dst += r.n * (2 * nj);
+          dst[0] = 0.f;
+          dst[nj] = 0.f;
         }
       }
     }
@@ -331,174 +316,236 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
 // =========================================================================================================
 // losses + gradients.  kFull = false: loss sums and d/d(pass-2 heads) only (runs before the pass-2 backward);
 // kFull = true : complete backward to the pass-1 heads, d gamma (direct) and d a (runs after it).
-// V (number of pose variants, = maps.V) is a template parameter so that the variant loop unrolls: the per-variant lane
-// maps stay in registers and every shuffle sits in straight-line, provably convergent code.
+// V (number of pose variants, = maps.V) is a template parameter so that the variant loop unrolls; kT: also write the
+// transposed copies g*T (kept for the C ABI; the training step does not use them).
+// Per (row, variant): phase 1 = forward quantities of the lane's four joints + the row reductions (|F|, reprojection,
+// pair distance, bone lengths); phase 2 = bone-prior terms (need the mean bone length); phase 3 = backward per joint.
+// d/da and d/dgamma do not go through a 3x3 d/dR: with R = Rx(a) Ry(b) Rx(g), dR/da = [x]x R and dR/dg = R [x]x, so
+//   dL/da = sum_j  dQ . (x ^ Q)  -  (R dS) . (x ^ P2),      dL/dg = sum_j (R^T dQ) . (x ^ P)  -  dS . (x ^ S)
+// which reuses R dS and R^T dQ of the backward chain (x ^ v = (0, -v.z, v.y)).
 // =========================================================================================================
-template <bool kFull, int V>
+template <bool kFull, int V, bool kT = false>
 __global__ void __launch_bounds__(kGeomWarps * 32) geom_lossgrad_kernel(const GeomArgs Ap) {
   __shared__ float s_part[kGeomWarps][6];
   __shared__ GeomArgs sA;
+  __shared__ GeomTabs sT;
   stage_args(&sA, Ap);
   const GeomArgs& A = sA;
-  LaneMaps m;
-  lane_maps(A, m);
-  const int lane = m.lane;
-  const int warp = threadIdx.x >> 5;
-  const int half = lane >> 4;
+  build_tabs<V>(A, sT, kFull);
+  const GeomTabs& T = sT;
+  Quad m;
+  quad_init(m);
+  const int warp = threadIdx.x >> 5, rl = m.lane >> 2;
   const float invN = 1.f / static_cast<float>(A.N);
   const int npairs = A.N / 2;
   const float c3d = A.maps.w_3d * invN, c2d = A.maps.w_2d * invN, cbl = A.maps.w_bl * invN;
   const float cv = npairs > 0 ? A.maps.w_vel / static_cast<float>(npairs) : 0.f;
-  // which depth heads ever feed this lane's joint / the root joint (-> which gradient columns this lane writes)
-  bool feeds[2] = {false, false}, feeds_root[2] = {false, false};
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-#pragma unroll
-    for (int net = 0; net < 2; ++net) {
-      feeds[net] = feeds[net] || m.net[v] == net;
-      feeds_root[net] = feeds_root[net] || A.maps.src_net[v][0] == net;
-    }
-  }
-  const int col_root = A.maps.col[0];
-
-  float sums[4] = {0.f, 0.f, 0.f, 0.f};   // L3d, rep, pair, bl (raw sums of this half-warp's rows)
+  const float D = A.maps.depth;
+  const float d0 = D < 1.0f ? 1.0f : D;
+  float sums[4] = {0.f, 0.f, 0.f, 0.f};   // L3d, rep, pair, bl (raw sums; lane 0 of each quad accumulates its rows)
   float red_da = 0.f, red_eda = 0.f;
 
-  const int total_pairs = (A.N + 1) / 2;
+  const int n_iters = (A.N + kGeomRows - 1) / kGeomRows;
   const int stride = gridDim.x * kGeomWarps;
   // block-uniform trip count (see geom_forward_kernel): shuffles sit in provably convergent code
-  auto row_of = [&](int pr) {
-    const int n = 2 * pr + half;
-    return n < A.N ? n : A.N - 1;
-  };
-  RawRow<V, kFull ? 2 : 1> raw, raw_next;
-  load_raw(A, m, row_of(blockIdx.x * kGeomWarps + warp), raw);
-  for (int base = blockIdx.x * kGeomWarps; base < total_pairs; base += stride, raw = raw_next) {
-    const int pair = base + warp;
-    if (base + stride < total_pairs) load_raw(A, m, row_of(pair + stride), raw_next);
-    const bool vB = 2 * pair + 1 < A.N;                           // warp-uniform: the pair is complete
-    const bool valid = 2 * pair + half < A.N;                     // uniform over the half-warp
+  for (int base = blockIdx.x * kGeomWarps; base < n_iters; base += stride) {
+    const int n_raw = kGeomRows * (base + warp) + rl;
+    const bool valid = n_raw < A.N;                               // uniform over the quad
+    const bool vB = (n_raw | 1) < A.N;                            // uniform over the pair's 8 lanes: the pair is complete
     RowIn r;
-    derive_row(A, m, raw, r);
-    float dRm[9];                                                 // lane-partial d/dR
+    load_row(A, m, valid ? n_raw : A.N - 1, r);
+    float g1acc[4][2], g2acc[4][2];                               // [slot][net] d/d(head) of the slot's column
 #pragma unroll
-    for (int k = 0; k < 9; ++k) dRm[k] = 0.f;
-    float g1acc[2] = {0.f, 0.f};   // [net] d/d(pass-1 head) for this lane's column
-    float g2acc[2] = {0.f, 0.f};
+    for (int k = 0; k < 4; ++k) { g1acc[k][0] = g1acc[k][1] = g2acc[k][0] = g2acc[k][1] = 0.f; }
+    float da_acc = 0.f, dg_acc = 0.f;                             // lane-partial d/da, d/dgamma
 
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      RowVar t;
-      float o[3];
-      row_forward(A, raw.delta[v], r, t);
-      row_consistency(A, m, raw.delta2[v], r, t, o);
-      if (valid) { sums[0] += o[0]; sums[1] += o[1]; sums[3] += o[2]; }
-      // pairwise deformation (:250-254): E = (P - P') - (S - S'), ' = the other row of the pair
-      Vec3 E; E.x = E.y = E.z = 0.f;
-      float pnorm = 0.f;
+      // ---- everything this (row, variant) reads, issued together
+      float delta[4], delta2[4], xqx[4], xqy[4];
+      bool net1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = m.j0 + k;
+        net1[k] = A.maps.src_net[v][j] != 0;
+        delta[k] = __ldg(T.hp[v][j] + r.n * LINKS_HEAD_LD);
+        delta2[k] = __ldg(T.h2p[v][j] + r.n * LINKS_HEAD_LD);
+        xqx[k] = 0.f; xqy[k] = 0.f;
+        if (kFull) {
+          const float* df = T.dfx[v][j] + r.n * T.pitch_f[v][j];
+          const float* dl = T.dlx[v][j] + r.n * T.pitch_l[v][j];
+          const int nj = T.njy[v][j];
+          xqx[k] = __ldg(df) + __ldg(dl);
+          xqy[k] = __ldg(df + nj) + __ldg(dl + nj);
+        }
+      }
+      // ---- phase 1
+      JointFwd f[4];
+      float mask2[4], d2[4], izs[4], rx[4], ry[4], len[4];
+      Vec3 P2[4], F[4], S[4], E[4], e[4];
+      float f2 = 0.f, rep = 0.f, e2 = 0.f, lsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        joint_forward(D, d0, delta[k], r.ux[k], r.uy[k], r.u0x, r.u0y, r.R, f[k]);
+        // re-lift (:228-238); the root projects to (0, 0): its re-lifted position is (0, 0, d0)
+        float dd = delta2[k] + D;
+        mask2[k] = (dd < 1.0f) ? 0.f : 1.f;
+        dd = (dd < 1.0f) ? 1.0f : dd;
+        d2[k] = dd;
+        P2[k].x = f[k].qx * dd; P2[k].y = f[k].qy * dd; P2[k].z = dd - d0;
+        F[k].x = f[k].Q.x - P2[k].x; F[k].y = f[k].Q.y - P2[k].y; F[k].z = f[k].Q.z - P2[k].z;
+        f2 += F[k].x * F[k].x + F[k].y * F[k].y + F[k].z * F[k].z;
+        // rotate back and re-project (:242-247)
+        S[k] = matT_vec(r.R, P2[k]);
+        izs[k] = fast_rcp(S[k].z + D);
+        rx[k] = S[k].x * izs[k];
+        ry[k] = S[k].y * izs[k];
+        rep += fabsf(rx[k] - r.ux[k]) + fabsf(ry[k] - r.uy[k]);
+        // pairwise deformation (:250-254): E = (P - P') - (S - S'), ' = the other row of the pair
+        Vec3 dPS; dPS.x = f[k].P.x - S[k].x; dPS.y = f[k].P.y - S[k].y; dPS.z = f[k].P.z - S[k].z;
+        const float ox = __shfl_xor_sync(LINKS_FULL_MASK, dPS.x, 4);
+        const float oy = __shfl_xor_sync(LINKS_FULL_MASK, dPS.y, 4);
+        const float oz = __shfl_xor_sync(LINKS_FULL_MASK, dPS.z, 4);
+        E[k].x = vB ? dPS.x - ox : 0.f; E[k].y = vB ? dPS.y - oy : 0.f; E[k].z = vB ? dPS.z - oz : 0.f;
+        e2 += E[k].x * E[k].x + E[k].y * E[k].y + E[k].z * E[k].z;
+      }
+      // bone vectors (parent - child): see the parent table above
       {
-        Vec3 dPS; dPS.x = t.P.x - t.S.x; dPS.y = t.P.y - t.S.y; dPS.z = t.P.z - t.S.z;
-        const float ox = __shfl_xor_sync(LINKS_FULL_MASK, dPS.x, 16);
-        const float oy = __shfl_xor_sync(LINKS_FULL_MASK, dPS.y, 16);
-        const float oz = __shfl_xor_sync(LINKS_FULL_MASK, dPS.z, 16);
-        if (vB) { E.x = dPS.x - ox; E.y = dPS.y - oy; E.z = dPS.z - oz; }
-        pnorm = sqrtf(half_sum(E.x * E.x + E.y * E.y + E.z * E.z));
-        if (half == 0) sums[2] += pnorm;
+        const Vec3 prevP = shfl3(f[3].P, (m.lane + 31) & 31);     // slot 3 of the previous lane: joints 4, 8, 12
+        const Vec3 P8 = shfl3(f[3].P, m.gb | 1);                  // joint 8
+        Vec3 par[4];
+        par[0] = prevP; if (m.q == 0) { par[0].x = par[0].y = par[0].z = 0.f; }
+        par[1] = m.q == 3 ? P8 : f[0].P;
+        par[2] = m.q == 2 ? P8 : f[1].P; if (m.q == 1) { par[2].x = par[2].y = par[2].z = 0.f; }
+        par[3] = f[2].P; if (m.q == 0) { par[3].x = par[3].y = par[3].z = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          e[k].x = par[k].x - f[k].P.x; e[k].y = par[k].y - f[k].P.y; e[k].z = par[k].z - f[k].P.z;
+          len[k] = fast_sqrt(e[k].x * e[k].x + e[k].y * e[k].y + e[k].z * e[k].z);
+          lsum += len[k];
+        }
+      }
+      f2 = quad_sum(f2); rep = quad_sum(rep); e2 = quad_sum(e2); lsum = quad_sum(lsum);
+      const float L3d = fast_sqrt(f2);
+      const float pnorm = fast_sqrt(e2);
+      const float imean = fast_rcp(lsum * (1.f / 16.f));
+      // ---- phase 2: bone prior (:256-259)
+      float h[4], bl = 0.f, hl = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float t = A.maps.bone_rel[m.j0 - 1 + k] - len[k] * imean;
+        bl += t * t;
+        h[k] = -2.f * t * cbl;
+        hl += h[k] * len[k];
+      }
+      if (!kFull) {
+        bl = quad_sum(bl);
+        if (valid && m.q == 0) {
+          sums[0] += L3d;
+          sums[1] += rep + (fabsf(r.u0x) + fabsf(r.u0y));
+          sums[3] += bl;
+          if ((rl & 1) == 0) sums[2] += pnorm;
+        }
+      } else {
+        hl = quad_sum(hl);
       }
       const float ge = pnorm > 0.f ? cv / pnorm : 0.f;
-      // ---- d/dS: reprojection L1 (:247) + pair term
-      const float drx = c2d * ((t.rx > r.ux) ? 1.f : ((t.rx < r.ux) ? -1.f : 0.f));
-      const float dry = c2d * ((t.ry > r.uy) ? 1.f : ((t.ry < r.uy) ? -1.f : 0.f));
-      Vec3 dS;
-      dS.x = drx * t.izs - ge * E.x;
-      dS.y = dry * t.izs - ge * E.y;
-      dS.z = -(drx * t.rx + dry * t.ry) * t.izs - ge * E.z;
-      // ---- d/dP2 = R dS - c3d F / L3d   (root centring only feeds the root's own, constant, depth)
-      const float g3 = t.L3d > 0.f ? c3d / t.L3d : 0.f;
-      Vec3 dP2 = mat_vec(r.R, dS);
-      dP2.x -= g3 * t.F.x; dP2.y -= g3 * t.F.y; dP2.z -= g3 * t.F.z;
-      const float ddelta2 = t.mask2 * (dP2.x * t.qx + dP2.y * t.qy + dP2.z);
-      const int net = m.net[v];
-      g2acc[0] += net == 0 ? ddelta2 : 0.f;
-      g2acc[1] += net == 1 ? ddelta2 : 0.f;
-      if (kFull) {
-        // ---- d/dq: through P2 = (q d2) and the external consumers (flows, pass-2 lifters)
-        const float dqx = dP2.x * t.d2 + raw.xqx[v], dqy = dP2.y * t.d2 + raw.xqy[v];
-        // ---- d/dQ
-        Vec3 dQ;
-        dQ.x = g3 * t.F.x + dqx * t.izq;
-        dQ.y = g3 * t.F.y + dqy * t.izq;
-        dQ.z = g3 * t.F.z - (dqx * t.qx + dqy * t.qy) * t.izq;
-        // ---- d/dP = R^T dQ + pair + bones
-        Vec3 dP = matT_vec(r.R, dQ);
-        dP.x += ge * E.x; dP.y += ge * E.y; dP.z += ge * E.z;
-        {
-          const float h = -2.f * (m.crel - t.bl_rho) * cbl;
-          const float hl = half_sum(h * t.bl_len);
-          const float dl = (h - hl * (1.f / 16.f) * t.bl_imean) * t.bl_imean;
-          const float w = t.bl_len > 0.f ? dl * fast_rcp(t.bl_len) : 0.f;
-          Vec3 dv;                                   // d/d(P_parent) of this lane's bone; d/d(P_child) = -dv
-          dv.x = w * t.e.x; dv.y = w * t.e.y; dv.z = w * t.e.z;
-          dP.x -= dv.x; dP.y -= dv.y; dP.z -= dv.z;
-          const Vec3 nx = shfl3(dv, lane + 1);       // bone j (child j+1) lives in the next lane
-          if (m.has_next) { dP.x += nx.x; dP.y += nx.y; dP.z += nx.z; }
-          const Vec3 b10 = shfl3(dv, m.hbase | 10), b13 = shfl3(dv, m.hbase | 13);
-          if (m.j == 8) { dP.x += b10.x + b13.x; dP.y += b10.y + b13.y; dP.z += b10.z + b13.z; }
+      const float g3 = L3d > 0.f ? c3d / L3d : 0.f;
+      // ---- phase 3: backward per joint
+      Vec3 dP[4], dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // d/dS: reprojection L1 (:247) + pair term
+        const float drx = c2d * ((rx[k] > r.ux[k]) ? 1.f : ((rx[k] < r.ux[k]) ? -1.f : 0.f));
+        const float dry = c2d * ((ry[k] > r.uy[k]) ? 1.f : ((ry[k] < r.uy[k]) ? -1.f : 0.f));
+        Vec3 dS;
+        dS.x = drx * izs[k] - ge * E[k].x;
+        dS.y = dry * izs[k] - ge * E[k].y;
+        dS.z = -(drx * rx[k] + dry * ry[k]) * izs[k] - ge * E[k].z;
+        // d/dP2 = R dS - c3d F / L3d   (root centring only feeds the root's own, constant, depth)
+        const Vec3 RdS = mat_vec(r.R, dS);
+        Vec3 dP2;
+        dP2.x = RdS.x - g3 * F[k].x; dP2.y = RdS.y - g3 * F[k].y; dP2.z = RdS.z - g3 * F[k].z;
+        const float ddelta2 = mask2[k] * (dP2.x * f[k].qx + dP2.y * f[k].qy + dP2.z);
+        g2acc[k][0] += net1[k] ? 0.f : ddelta2;
+        g2acc[k][1] += net1[k] ? ddelta2 : 0.f;
+        if (kFull) {
+          // d/dq: through P2 = (q d2) and the external consumers (flows, pass-2 lifters)
+          const float dqx = dP2.x * d2[k] + xqx[k], dqy = dP2.y * d2[k] + xqy[k];
+          Vec3 dQ;
+          dQ.x = g3 * F[k].x + dqx * f[k].izq;
+          dQ.y = g3 * F[k].y + dqy * f[k].izq;
+          dQ.z = g3 * F[k].z - (dqx * f[k].qx + dqy * f[k].qy) * f[k].izq;
+          // d/dP = R^T dQ + pair + own bone (the children's bones are added below)
+          const Vec3 RtdQ = matT_vec(r.R, dQ);
+          const float dl = (h[k] - hl * (1.f / 16.f) * imean) * imean;
+          const float w = len[k] > 0.f ? dl * fast_rcp(len[k]) : 0.f;
+          dv[k].x = w * e[k].x; dv[k].y = w * e[k].y; dv[k].z = w * e[k].z;     // d/d(P_parent); d/d(P_child) = -dv
+          dP[k].x = RtdQ.x + ge * E[k].x - dv[k].x;
+          dP[k].y = RtdQ.y + ge * E[k].y - dv[k].y;
+          dP[k].z = RtdQ.z + ge * E[k].z - dv[k].z;
+          da_acc += (dQ.z * f[k].Q.y - dQ.y * f[k].Q.z) + (P2[k].z * RdS.y - P2[k].y * RdS.z);
+          dg_acc += (f[k].P.y * RtdQ.z - f[k].P.z * RtdQ.y) + (dS.y * S[k].z - dS.z * S[k].y);
         }
-        // ---- d/dR from Q = R P and S = R^T P2 (lane-partial; reduced once per row below)
-        const float dq3[3] = {dQ.x, dQ.y, dQ.z}, p3[3] = {t.P.x, t.P.y, t.P.z};
-        const float p23[3] = {t.P2.x, t.P2.y, t.P2.z}, ds3[3] = {dS.x, dS.y, dS.z};
+      }
+      if (kFull) {
+        // bones: the parent joint receives +dv of each child bone
+        const Vec3 nx = shfl3(dv[0], (m.lane + 1) & 31);           // bone of the next lane's slot 0 hangs on my slot 3
+        const Vec3 b11 = shfl3(dv[2], m.gb | 2), b14 = shfl3(dv[1], m.gb | 3);   // bones of joints 11 and 14 hang on joint 8
+        if (m.q != 3) { dP[0].x += dv[1].x; dP[0].y += dv[1].y; dP[0].z += dv[1].z; }
+        if (m.q != 1 && m.q != 2) { dP[1].x += dv[2].x; dP[1].y += dv[2].y; dP[1].z += dv[2].z; }
+        if (m.q != 0) { dP[2].x += dv[3].x; dP[2].y += dv[3].y; dP[2].z += dv[3].z; }
+        if (m.q != 3) { dP[3].x += nx.x; dP[3].y += nx.y; dP[3].z += nx.z; }
+        if (m.q == 1) { dP[3].x += b11.x + b14.x; dP[3].y += b11.y + b14.y; dP[3].z += b11.z + b14.z; }
 #pragma unroll
-        for (int ra = 0; ra < 3; ++ra)
-#pragma unroll
-          for (int cb = 0; cb < 3; ++cb) dRm[ra * 3 + cb] += dq3[ra] * p3[cb] + p23[ra] * ds3[cb];
-        // ---- lift
-        const float ddelta = t.mask * (dP.x * r.ux + dP.y * r.uy + dP.z);
-        g1acc[0] += net == 0 ? ddelta : 0.f;
-        g1acc[1] += net == 1 ? ddelta : 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const float ddelta = f[k].mask * (dP[k].x * r.ux[k] + dP[k].y * r.uy[k] + dP[k].z);     // lift
+          g1acc[k][0] += net1[k] ? 0.f : ddelta;
+          g1acc[k][1] += net1[k] ? ddelta : 0.f;
+        }
       }
     }
-    // ---- write head gradients (lane -> column col[j] of every net that feeds joint j in some variant; the root's
+    // ---- write head gradients (slot -> column col[j] of every net that feeds joint j in some variant; the root's
     //      columns receive zeros)
     if (valid) {
 #pragma unroll
       for (int net = 0; net < 2; ++net) {
-        __nv_bfloat16* g = kFull ? A.g1[net] : A.g2[net];
-        __nv_bfloat16* gT = kFull ? A.g1T[net] : A.g2T[net];
-        if (feeds[net]) {
-          const __nv_bfloat16 h = __float2bfloat16_rn(kFull ? g1acc[net] : g2acc[net]);
-          g[r.n * 64 + m.col] = h;
-          if (gT) gT[static_cast<size_t>(m.col) * A.ldT + A.colT0 + r.n] = h;
+        __nv_bfloat16* gT = kT ? (kFull ? A.g1T[net] : A.g2T[net]) : nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          __nv_bfloat16* g = T.gp[net][m.j0 + k];
+          if (g) {
+            const __nv_bfloat16 hv = __float2bfloat16_rn(kFull ? g1acc[k][net] : g2acc[k][net]);
+            g[r.n * 64] = hv;
+            if (kT && gT) gT[static_cast<size_t>(A.maps.col[m.j0 + k]) * A.ldT + A.colT0 + r.n] = hv;
+          }
         }
-        if (m.sub == 0 && feeds_root[net]) {
-          const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
-          g[r.n * 64 + col_root] = z;
-          if (gT) gT[static_cast<size_t>(col_root) * A.ldT + A.colT0 + r.n] = z;
+        if (m.q == 0) {
+          __nv_bfloat16* g = T.gp[net][0];
+          if (g) {
+            const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+            g[r.n * 64] = z;
+            if (kT && gT) gT[static_cast<size_t>(A.maps.col[0]) * A.ldT + A.colT0 + r.n] = z;
+          }
         }
       }
     }
     if (kFull) {
-      const float* Rr = r.R;
-      const float* d = dRm;
-      // dR/da: row1' = -row2, row2' = row1 ; dR/dgamma: col1' = col2, col2' = -col1
-      const float dav = half_sum(-(d[3] * Rr[6] + d[4] * Rr[7] + d[5] * Rr[8]) + (d[6] * Rr[3] + d[7] * Rr[4] + d[8] * Rr[5]));
-      const float dgv = half_sum((d[1] * Rr[2] + d[4] * Rr[5] + d[7] * Rr[8]) - (d[2] * Rr[1] + d[5] * Rr[4] + d[8] * Rr[7]));
-      if (valid) {
-        if (m.sub == 0) {
-          A.da[r.n] = dav;
-          A.dgamma[r.n] = dgv;
-        }
+      const float dav = quad_sum(da_acc), dgv = quad_sum(dg_acc);
+      if (valid && m.q == 0) {
+        A.da[r.n] = dav;
+        A.dgamma[r.n] = dgv;
         red_da += dav;
         red_eda += r.eps * dav;
       }
     }
   }
-  // ---- block reduction of the scalar sums (values are uniform over each half-warp: add the two halves)
+  // ---- block reduction of the scalar sums (lane 0 of every quad holds its rows' partial sums)
 #pragma unroll
-  for (int k = 0; k < 4; ++k) sums[k] += __shfl_xor_sync(LINKS_FULL_MASK, sums[k], 16);
-  red_da += __shfl_xor_sync(LINKS_FULL_MASK, red_da, 16);
-  red_eda += __shfl_xor_sync(LINKS_FULL_MASK, red_eda, 16);
-  if (lane == 0) {
+  for (int k = 0; k < 4; ++k) sums[k] = warp_sum(sums[k]);
+  red_da = warp_sum(red_da);
+  red_eda = warp_sum(red_eda);
+  if (m.lane == 0) {
     s_part[warp][0] = sums[0]; s_part[warp][1] = sums[1]; s_part[warp][2] = sums[2]; s_part[warp][3] = sums[3];
     s_part[warp][4] = red_da;  s_part[warp][5] = red_eda;
   }

@@ -148,7 +148,7 @@ SIM int sim_geom_loss(const LinksGeomMaps* maps, const float* u, const float* h0
   A.g2[0] = (bf16*)g20; A.g2[1] = (bf16*)g21; A.g2T[0] = (bf16*)g2T0; A.g2T[1] = (bf16*)g2T1; A.ldT = ldT; A.colT0 = colT0;
   const int pairs = (N + 1) / 2;
   (void)pairs;
-  hostsim::launch(dim3(1), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<false, 1>(A); else geom_lossgrad_kernel<false, 2>(A); });
+  hostsim::launch(dim3(1), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<false, 1, true>(A); else geom_lossgrad_kernel<false, 2, true>(A); });
   return 0;
 }
 SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float* h0, const float* h1, const float* a0,
@@ -163,7 +163,7 @@ SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float
   A.dgamma = dgamma; A.da = da; A.red = red;
   const int pairs = (N + 1) / 2;
   (void)pairs;
-  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<true, 1>(A); else geom_lossgrad_kernel<true, 2>(A); });
+  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<true, 1, true>(A); else geom_lossgrad_kernel<true, 2, true>(A); });
   return 0;
 }
 SIM int sim_geom_backward_angles(const float* a0, const float* a1, const float* eps, const float* stats, const float* dgamma,
