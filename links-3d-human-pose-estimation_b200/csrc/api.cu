@@ -229,6 +229,24 @@ static int geom_grid(int warps_needed) {
   return blocks < 148 * 16 ? blocks : 148 * 16;
 }
 
+// Launch a staged geometry kernel: plan the shared-memory staging, raise the kernel's dynamic shared-memory limit when
+// this launch needs more than any earlier one, launch.
+template <class Kernel>
+static int geom_launch(Kernel kernel, GeomArgs& A, int level, int* smem_limit, void* stream) {
+  int rc = geom_plan(A, level);
+  if (rc) return rc;
+  const size_t smem = geom_smem_bytes(A.st);
+  if (smem > 200 * 1024) return LINKS_E_RANGE;
+  if (static_cast<int>(smem) > *smem_limit) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    *smem_limit = static_cast<int>(smem);
+  }
+  const int iters = (A.N + A.st.rows - 1) / A.st.rows;
+  kernel<<<geom_grid(iters), kGeomWarps * 32, smem, links_stream(stream)>>>(A);
+  return links_launch_status();
+}
+
 static int check_maps(const LinksGeomMaps* m) {
   if (!m) return LINKS_E_ARG;
   if (m->V < 1 || m->V > 2) return LINKS_E_RANGE;
@@ -264,9 +282,14 @@ extern "C" __attribute__((visibility("default"))) int links_geom_forward(const L
   A.u = u; A.head[0] = head0; A.head[1] = head1; A.ang[0] = ang0; A.ang[1] = ang1;
   A.eps_x = eps_x; A.u_y = u_y; A.stats = stats; A.N = N;
   A.qpart[0] = qpart0; A.qpart[1] = qpart1; A.qfull[0] = q_full0; A.qfull[1] = q_full1;
-  if (maps->V == 1) geom_forward_kernel<1><<<geom_grid((N + kGeomRows - 1) / kGeomRows), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
-  else geom_forward_kernel<2><<<geom_grid((N + kGeomRows - 1) / kGeomRows), kGeomWarps * 32, 0, links_stream(stream)>>>(A);
-  return links_launch_status();
+  static int lim[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+  const bool full = q_full0 != nullptr || q_full1 != nullptr;
+  if (maps->V == 1) {
+    if (full) return geom_launch(geom_forward_kernel<1, true>, A, 0, &lim[0], stream);
+    return geom_launch(geom_forward_kernel<1, false>, A, 0, &lim[1], stream);
+  }
+  if (full) return geom_launch(geom_forward_kernel<2, true>, A, 0, &lim[2], stream);
+  return geom_launch(geom_forward_kernel<2, false>, A, 0, &lim[3], stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_geom_loss(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
@@ -290,17 +313,14 @@ extern "C" __attribute__((visibility("default"))) int links_geom_loss(const Link
   A.g2[0] = static_cast<__nv_bfloat16*>(g2_head0); A.g2[1] = static_cast<__nv_bfloat16*>(g2_head1);
   A.g2T[0] = static_cast<__nv_bfloat16*>(g2T_head0); A.g2T[1] = static_cast<__nv_bfloat16*>(g2T_head1);
   A.ldT = ldT; A.colT0 = colT0;
-  const int pairs = (N + kGeomRows - 1) / kGeomRows;   // warp iterations: kGeomRows rows each
   const bool tr = g2T_head0 != nullptr || g2T_head1 != nullptr;
-  const dim3 grid(geom_grid(pairs)), block(kGeomWarps * 32);
+  static int lim[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
   if (maps->V == 1) {
-    if (tr) geom_lossgrad_kernel<false, 1, true><<<grid, block, 0, links_stream(stream)>>>(A);
-    else geom_lossgrad_kernel<false, 1, false><<<grid, block, 0, links_stream(stream)>>>(A);
-  } else {
-    if (tr) geom_lossgrad_kernel<false, 2, true><<<grid, block, 0, links_stream(stream)>>>(A);
-    else geom_lossgrad_kernel<false, 2, false><<<grid, block, 0, links_stream(stream)>>>(A);
+    if (tr) return geom_launch(geom_lossgrad_kernel<false, 1, true>, A, 1, &lim[0], stream);
+    return geom_launch(geom_lossgrad_kernel<false, 1, false>, A, 1, &lim[1], stream);
   }
-  return links_launch_status();
+  if (tr) return geom_launch(geom_lossgrad_kernel<false, 2, true>, A, 1, &lim[2], stream);
+  return geom_launch(geom_lossgrad_kernel<false, 2, false>, A, 1, &lim[3], stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_geom_backward(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
@@ -328,17 +348,14 @@ extern "C" __attribute__((visibility("default"))) int links_geom_backward(const 
   A.g1T[0] = static_cast<__nv_bfloat16*>(g1T_head0); A.g1T[1] = static_cast<__nv_bfloat16*>(g1T_head1);
   A.ldT = ldT; A.colT0 = colT0;
   A.dgamma = dgamma_direct; A.da = da; A.red = red;
-  const int pairs = (N + kGeomRows - 1) / kGeomRows;   // warp iterations: kGeomRows rows each
   const bool tr = g1T_head0 != nullptr || g1T_head1 != nullptr;
-  const dim3 grid(geom_grid(pairs)), block(kGeomWarps * 32);
+  static int lim[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
   if (maps->V == 1) {
-    if (tr) geom_lossgrad_kernel<true, 1, true><<<grid, block, 0, links_stream(stream)>>>(A);
-    else geom_lossgrad_kernel<true, 1, false><<<grid, block, 0, links_stream(stream)>>>(A);
-  } else {
-    if (tr) geom_lossgrad_kernel<true, 2, true><<<grid, block, 0, links_stream(stream)>>>(A);
-    else geom_lossgrad_kernel<true, 2, false><<<grid, block, 0, links_stream(stream)>>>(A);
+    if (tr) return geom_launch(geom_lossgrad_kernel<true, 1, true>, A, 2, &lim[0], stream);
+    return geom_launch(geom_lossgrad_kernel<true, 1, false>, A, 2, &lim[1], stream);
   }
-  return links_launch_status();
+  if (tr) return geom_launch(geom_lossgrad_kernel<true, 2, true>, A, 2, &lim[2], stream);
+  return geom_launch(geom_lossgrad_kernel<true, 2, false>, A, 2, &lim[3], stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int links_geom_backward_angles(const float* ang0, const float* ang1, const float* eps_x, const float* stats,

@@ -38,6 +38,12 @@
 #ifndef LINKS_ADAM_PREFETCH
 #define LINKS_ADAM_PREFETCH 1
 #endif
+// L2 policy of the weight-gradient operand loads (G and X, both MN-major).  Every 256-column slice of G / X is streamed by
+// four tiles of the problem while the fused optimiser streams 26 B per parameter through the same L2: 0 = default policy,
+// 1 = evict_last on the TMA loads of weight-gradient tiles (the re-read operands outlive the once-touched p / m / v lines).
+#ifndef LINKS_WGRAD_EVICT_LAST
+#define LINKS_WGRAD_EVICT_LAST 0
+#endif
 
 namespace links {
 
@@ -649,6 +655,15 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// same with an L2 cache-policy operand (createpolicy encodings as used by CUTLASS: full-fraction evict_last)
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 // pair MMA: D[256 x N] (128 rows in each CTA's TMEM) += A[256 x 16] * B[N x 16]^T, operands split across the two CTAs
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -861,14 +876,20 @@ gemm_kernel(const __grid_constant__ typename KernelArgs<kChain>::type G) {
           } else {
 #pragma unroll
             for (int q = 0; q < BM / 64; ++q)
-              if (q < a_boxes) tma_load_2d_pair(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
+              if (q < a_boxes) {
+                if (LINKS_WGRAD_EVICT_LAST && b_mn) tma_load_2d_pair_hint(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK, kL2EvictLast);
+                else tma_load_2d_pair(sA + q * (BK * 128), &P.tmA, full, tc.tm * BM + q * 64, kb * BK);
+              }
           }
           if (!b_mn) {
             tma_load_2d_pair(sB, &P.tmB, full, kb * BK, tc.tn * BN + cta_rank * b_half);
           } else {
 #pragma unroll
             for (int q = 0; q < BN / 128; ++q)
-              if (q < b_boxes) tma_load_2d_pair(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK);
+              if (q < b_boxes) {
+                if (LINKS_WGRAD_EVICT_LAST && a_mn) tma_load_2d_pair_hint(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK, kL2EvictLast);
+                else tma_load_2d_pair(sB + q * (BK * 128), &P.tmB, full, tc.tn * BN + cta_rank * b_half + q * 64, kb * BK);
+              }
           }
         }
       }

@@ -134,7 +134,11 @@ class LifterStep:
         tiles = (N + 127) // 128
         r_win = self.cfg.get("reserve_window")
         if r_win is None:
-            r_win = min(2 * len(self.kinds) * tiles, n_sms // 2 - 2)
+            # one SM per part-flow CTA while that is at most one wave on under half of the machine (B <= 1024: the flows finish
+            # in one wave beside the window chains); for larger batches the flow CTAs come in many waves anyway and a small
+            # reservation measured best (profiles/r02_sweep_reserve_*.txt: B = 2048 / 4096 / 8192 steps 8 % faster with 16)
+            want = 2 * len(self.kinds) * tiles
+            r_win = want if want <= n_sms // 2 - 10 else 16
         r_tail = self.cfg.get("reserve_tail")
         if r_tail is None:
             r_tail = (min((B + 127) // 128, 16) if self.prefetch else 0) + (int(self.cfg.get("nccl_ctas") or 0) if self.world > 1 else 0)

@@ -8,6 +8,7 @@ from links_b200.mlp import MlpSet
 from links_b200 import init as INIT
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+PURE = len(sys.argv) > 2 and sys.argv[2] == "pure"      # weight gradients stored (no fused optimiser): bench.py's `roofline` launches
 N = 2 * B
 nj = [7, 10, 11, 11]
 m = MlpSet("lifter", [2 * n for n in nj], [{"downscale": n, "angles": 1} for n in nj], N, n_passes=2, train=True,
@@ -22,6 +23,7 @@ m.adam_prepare()
 cases = [("fwd0", lambda: m._chained(("c", 0), lambda: m._build_forward(0))),
          ("fwd1", lambda: m._chained(("c", 1), lambda: m._build_forward(1))),
          ("bwd1", lambda: m._chained(("c", 2), lambda: m._build_backward(1, True))),
+         ("bwd0+wgrad", lambda: m._chained(("c", 5), lambda: m._build_backward(0, False, None, True, False))) if PURE else
          ("bwd0+wgrad+adam", lambda: m._chained(("c", 6), lambda: m._build_backward(0, False, None, True, True)))]
 ops = [[op for op in chain() if hasattr(op, "plan")] for _, chain in cases]
 for rnd in range(2):

@@ -136,7 +136,8 @@ SIM int sim_geom_forward(const LinksGeomMaps* maps, const float* u, const float*
                          float* qp1, float* qf0, float* qf1) {
   GeomArgs A = base_args(maps, u, h0, h1, a0, a1, eps, uy, stats, N);
   A.qpart[0] = qp0; A.qpart[1] = qp1; A.qfull[0] = qf0; A.qfull[1] = qf1;
-  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_forward_kernel<1>(A); else geom_forward_kernel<2>(A); });   // grid-stride over row pairs
+  if (int rc = geom_plan(A, 0)) return rc;
+  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), geom_smem_bytes(A.st), [&] { if (A.maps.V == 1) geom_forward_kernel<1, true>(A); else geom_forward_kernel<2, true>(A); });   // grid-stride over row blocks
   return 0;
 }
 SIM int sim_geom_loss(const LinksGeomMaps* maps, const float* u, const float* h0, const float* h1, const float* a0,
@@ -148,7 +149,8 @@ SIM int sim_geom_loss(const LinksGeomMaps* maps, const float* u, const float* h0
   A.g2[0] = (bf16*)g20; A.g2[1] = (bf16*)g21; A.g2T[0] = (bf16*)g2T0; A.g2T[1] = (bf16*)g2T1; A.ldT = ldT; A.colT0 = colT0;
   const int pairs = (N + 1) / 2;
   (void)pairs;
-  hostsim::launch(dim3(1), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<false, 1, true>(A); else geom_lossgrad_kernel<false, 2, true>(A); });
+  if (int rc = geom_plan(A, 1)) return rc;
+  hostsim::launch(dim3(1), dim3(kGeomWarps * 32), geom_smem_bytes(A.st), [&] { if (A.maps.V == 1) geom_lossgrad_kernel<false, 1, true>(A); else geom_lossgrad_kernel<false, 2, true>(A); });
   return 0;
 }
 SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float* h0, const float* h1, const float* a0,
@@ -163,7 +165,8 @@ SIM int sim_geom_backward(const LinksGeomMaps* maps, const float* u, const float
   A.dgamma = dgamma; A.da = da; A.red = red;
   const int pairs = (N + 1) / 2;
   (void)pairs;
-  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), 0, [&] { if (A.maps.V == 1) geom_lossgrad_kernel<true, 1, true>(A); else geom_lossgrad_kernel<true, 2, true>(A); });
+  if (int rc = geom_plan(A, 2)) return rc;
+  hostsim::launch(dim3(2), dim3(kGeomWarps * 32), geom_smem_bytes(A.st), [&] { if (A.maps.V == 1) geom_lossgrad_kernel<true, 1, true>(A); else geom_lossgrad_kernel<true, 2, true>(A); });
   return 0;
 }
 SIM int sim_geom_backward_angles(const float* a0, const float* a1, const float* eps, const float* stats, const float* dgamma,
