@@ -279,9 +279,9 @@ __device__ __forceinline__ int tab_ld(const int* p, uint32_t tok) {
 #endif
 }
 // entry `field`[v][j0 + k] of the tables / root entry `field`[v][0] / map entry maps.`field`[v][j0 + k]
-#define GEOM_TAB(field, v, k) tab_ld(&T.field[v][m.j0 + (k)], M.tok)
+#define GEOM_TAB(field, v, k) tab_ld(&T.field[v][m.j0 + (k) * m.js], M.tok)
 #define GEOM_TAB0(field, v) tab_ld(&T.field[v][0], M.tok)
-#define GEOM_MAP(field, v, k) tab_ld(&A.maps.field[v][m.j0 + (k)], M.tok)
+#define GEOM_MAP(field, v, k) tab_ld(&A.maps.field[v][m.j0 + (k) * m.js], M.tok)
 
 // Shared-memory frame of a block: [GeomArgs][GeomTabs][input copy list][output copy list][per warp: in0 | in1 | out]
 struct GeomSmem {
@@ -421,13 +421,18 @@ static_assert(bone_parent(4) == 0 && bone_parent(8) == 7 && bone_parent(12) == 1
 
 // Lane-constant indexing state.
 struct Quad {
-  int lane, q, gb, j0;   // q = lane & 3; gb = first lane of this row's quad; j0 = 4 q + 1 = joint of slot 0
+  int lane, q, gb, j0, js;   // q = lane & 3; gb = first lane of this row's quad; slot k of the lane owns joint j0 + k * js
 };
+// kInterleaved = false: joints 4q+1 .. 4q+4 (the bone wiring of the loss / backward kernels assumes it);
+// kInterleaved = true : joints q+1, q+5, q+9, q+13 -- the four lanes of a row then read four CONSECUTIVE words of a staged
+// row for every slot, which together with the 4-word bank shift per row makes the gathers of a warp conflict-free.
+template <bool kInterleaved = false>
 __device__ __forceinline__ void quad_init(Quad& m) {
   m.lane = threadIdx.x & 31;
   m.q = m.lane & 3;
   m.gb = m.lane & ~3;
-  m.j0 = 4 * m.q + 1;
+  m.j0 = kInterleaved ? m.q + 1 : 4 * m.q + 1;
+  m.js = kInterleaved ? 4 : 1;
 }
 __device__ __forceinline__ float quad_sum(float v) {          // sum over the 4 lanes of a row (every lane receives it)
   v += __shfl_xor_sync(LINKS_FULL_MASK, v, 1);
@@ -464,8 +469,8 @@ __device__ __forceinline__ void load_row(const GeomStage& S, const Quad& m, cons
   const char* u = cur + S.u_off + rl * (2 * kJ * 4);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    r.ux[k] = lds_f(u, 4 * (m.j0 + k));
-    r.uy[k] = lds_f(u, 4 * (kJ + m.j0 + k));
+    r.ux[k] = lds_f(u, 4 * (m.j0 + k * m.js));
+    r.uy[k] = lds_f(u, 4 * (kJ + m.j0 + k * m.js));
   }
   r.u0x = lds_f(u, 0);
   r.u0y = lds_f(u, 4 * kJ);
@@ -510,7 +515,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
   const GeomTabs& T = *M.T;
   const GeomStage& S = A.st;
   Quad m;
-  quad_init(m);
+  quad_init<true>(m);
   const int warp = threadIdx.x >> 5, rl = m.lane >> 2;
   const int rs = rl * kGeomSp;
   const float D = A.maps.depth;
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
       for (int k = 0; k < 4; ++k) delta[k] = lds_f(cur, GEOM_TAB(hs, v, k) + rs);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int j = m.j0 + k;
+        const int j = m.j0 + k * m.js;
         JointFwd s;
         joint_forward(D, d0, delta[k], r.ux[k], r.uy[k], r.u0x, r.u0y, r.R, s);
         if (kQ && valid && A.qfull[v]) {
