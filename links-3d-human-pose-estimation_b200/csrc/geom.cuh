@@ -3,7 +3,7 @@
 // (V = 2 variants: 'left' / 'right' choice of combine_left_right_pred_1d, utils/helpers.py:40-53).
 //
 // Mapping: four lanes per row, eight consecutive rows (four row pairs) per warp.  Lane q of a row's quad owns joints
-// 4q+1 .. 4q+4 and the bones whose children they are ("slots" 0-3): the per-joint math of a slot is straight-line code over
+// q+1, q+5, q+9, q+13 and the bones whose children they are ("slots" 0-3): the per-joint math of a slot is straight-line code over
 // registers, the row-uniform work (rotation, reductions) is shared by 4 lanes instead of being replicated in 16, per-row
 // reductions are two xor-shuffles, the pairwise deformation loss (:250-254) couples rows 2k and 2k+1 = lanes l and l^4.
 // The root joint needs no slot: after root-centring (:188-192) its lifted, rotated, re-lifted and back-rotated positions
@@ -12,6 +12,7 @@
 // from (u, depth heads, angle heads, eps_x, u_y, stats).
 #pragma once
 #include "devdefs.cuh"
+#include "f2.cuh"
 
 namespace links {
 
@@ -118,31 +119,6 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 #else
   return sqrtf(x);
 #endif
-}
-
-// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 operations per lane and instruction)
-typedef float2 F2;
-__device__ __forceinline__ F2 f2_make(float a, float b) { return make_float2(a, b); }
-__device__ __forceinline__ F2 f2_splat(float a) { return make_float2(a, a); }
-#ifndef LINKS_HOSTSIM
-__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { return __fadd2_rn(a, b); }
-#else
-__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
-__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ F2 f2_add(F2 a, F2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-#endif
-// (qx, qy, qz) = R p  /  R^T p for two joints at once; R2[i] holds R[i] in both halves
-__device__ __forceinline__ void f2_matvec(const F2 (&R)[9], F2 px, F2 py, F2 pz, F2& qx, F2& qy, F2& qz) {
-  qx = f2_fma(R[2], pz, f2_fma(R[1], py, f2_mul(R[0], px)));
-  qy = f2_fma(R[5], pz, f2_fma(R[4], py, f2_mul(R[3], px)));
-  qz = f2_fma(R[8], pz, f2_fma(R[7], py, f2_mul(R[6], px)));
-}
-__device__ __forceinline__ void f2_matTvec(const F2 (&R)[9], F2 px, F2 py, F2 pz, F2& qx, F2& qy, F2& qz) {
-  qx = f2_fma(R[6], pz, f2_fma(R[3], py, f2_mul(R[0], px)));
-  qy = f2_fma(R[7], pz, f2_fma(R[4], py, f2_mul(R[1], px)));
-  qz = f2_fma(R[8], pz, f2_fma(R[5], py, f2_mul(R[2], px)));
 }
 
 struct Vec3 { float x, y, z; };
@@ -409,30 +385,31 @@ __device__ __forceinline__ float lds_f(const char* base, int off) { return *rein
 // bone table (utils/helpers.py:140-141): bone b joins parent kBoneParent[b] and child b+1 (4 bits per entry)
 constexpr unsigned long long kBoneParent = 0xfe8cb89870540210ull;
 __host__ __device__ constexpr int bone_parent(int child) { return static_cast<int>((kBoneParent >> (4 * (child - 1))) & 15ull); }
-// The quad mapping below hard-wires where a slot finds the parent joint of its bone; tie it to the table.
-//   slot 0 (joints 1, 5, 9, 13): root for quad lane 0, else slot 3 of the previous lane (joints 4, 8, 12)
-//   slot 1 (2, 6, 10, 14): own slot 0, except joint 14 <- joint 8 (lane 1, slot 3)
-//   slot 2 (3, 7, 11, 15): own slot 1, except joint 7 <- root and joint 11 <- joint 8
-//   slot 3 (4, 8, 12, 16): own slot 2, except joint 4 <- root
-static_assert(bone_parent(1) == 0 && bone_parent(5) == 4 && bone_parent(9) == 8 && bone_parent(13) == 12, "slot 0 parents");
-static_assert(bone_parent(2) == 1 && bone_parent(6) == 5 && bone_parent(10) == 9 && bone_parent(14) == 8, "slot 1 parents");
-static_assert(bone_parent(3) == 2 && bone_parent(7) == 0 && bone_parent(11) == 8 && bone_parent(15) == 14, "slot 2 parents");
-static_assert(bone_parent(4) == 0 && bone_parent(8) == 7 && bone_parent(12) == 11 && bone_parent(16) == 15, "slot 3 parents");
+// The quad mapping below hard-wires where a slot finds the parent joint of its bone; tie it to the table.  Lane q of a
+// row's quad owns joints q+1, q+5, q+9, q+13 (slots 0-3).  For most bones the parent is the SAME slot of the previous lane
+// (for lane 0: the previous slot of lane 3), so one rotating exchange per slot serves them:
+//   slot 0 (joints 1, 2, 3, 4)    : root, joint 1, joint 2, root
+//   slot 1 (joints 5, 6, 7, 8)    : joint 4, joint 5, root, joint 7
+//   slot 2 (joints 9, 10, 11, 12) : joint 8, joint 9, joint 8 (lane 3, slot 1: broadcast), joint 11
+//   slot 3 (joints 13, 14, 15, 16): joint 12, joint 8 (broadcast), joint 14, joint 15
+static_assert(bone_parent(1) == 0 && bone_parent(2) == 1 && bone_parent(3) == 2 && bone_parent(4) == 0, "slot 0 parents");
+static_assert(bone_parent(5) == 4 && bone_parent(6) == 5 && bone_parent(7) == 0 && bone_parent(8) == 7, "slot 1 parents");
+static_assert(bone_parent(9) == 8 && bone_parent(10) == 9 && bone_parent(11) == 8 && bone_parent(12) == 11, "slot 2 parents");
+static_assert(bone_parent(13) == 12 && bone_parent(14) == 8 && bone_parent(15) == 14 && bone_parent(16) == 15, "slot 3 parents");
 
 // Lane-constant indexing state.
 struct Quad {
   int lane, q, gb, j0, js;   // q = lane & 3; gb = first lane of this row's quad; slot k of the lane owns joint j0 + k * js
 };
-// kInterleaved = false: joints 4q+1 .. 4q+4 (the bone wiring of the loss / backward kernels assumes it);
-// kInterleaved = true : joints q+1, q+5, q+9, q+13 -- the four lanes of a row then read four CONSECUTIVE words of a staged
-// row for every slot, which together with the 4-word bank shift per row makes the gathers of a warp conflict-free.
-template <bool kInterleaved = false>
+// Joints q+1, q+5, q+9, q+13: the four lanes of a row read four CONSECUTIVE words of a staged row for every slot, which
+// together with the 4-word bank shift per staged row makes the gathers of a warp conflict-free (a lane owning four
+// consecutive joints costs 4-way bank conflicts on every gather: forward kernel 0.60 -> 0.73 of HBM peak).
 __device__ __forceinline__ void quad_init(Quad& m) {
   m.lane = threadIdx.x & 31;
   m.q = m.lane & 3;
   m.gb = m.lane & ~3;
-  m.j0 = kInterleaved ? m.q + 1 : 4 * m.q + 1;
-  m.js = kInterleaved ? 4 : 1;
+  m.j0 = m.q + 1;
+  m.js = 4;
 }
 __device__ __forceinline__ float quad_sum(float v) {          // sum over the 4 lanes of a row (every lane receives it)
   v += __shfl_xor_sync(LINKS_FULL_MASK, v, 1);
@@ -515,7 +492,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32) geom_forward_kernel(const Geo
   const GeomTabs& T = *M.T;
   const GeomStage& S = A.st;
   Quad m;
-  quad_init<true>(m);
+  quad_init(m);
   const int warp = threadIdx.x >> 5, rl = m.lane >> 2;
   const int rs = rl * kGeomSp;
   const float D = A.maps.depth;
@@ -647,7 +624,6 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
       bool net1[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int j = m.j0 + k;
         net1[k] = GEOM_MAP(src_net, v, k) != 0;
         delta[k] = lds_f(cur, GEOM_TAB(hs, v, k) + rs);
         delta2[k] = lds_f(cur, GEOM_TAB(h2s, v, k) + rl * GEOM_TAB(h2p, v, k));
@@ -721,16 +697,20 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
       }
       // bone vectors (parent - child): see the parent table above
       {
-        Vec3 P3; P3.x = Px[1].y; P3.y = Py[1].y; P3.z = Pz[1].y;   // slot 3
-        const Vec3 prevP = shfl3(P3, (m.lane + 31) & 31);          // slot 3 of the previous lane: joints 4, 8, 12
-        const Vec3 P8 = shfl3(P3, m.gb | 1);                       // joint 8
+        Vec3 Ps[4];
+        Ps[0].x = Px[0].x; Ps[0].y = Py[0].x; Ps[0].z = Pz[0].x;
+        Ps[1].x = Px[0].y; Ps[1].y = Py[0].y; Ps[1].z = Pz[0].y;
+        Ps[2].x = Px[1].x; Ps[2].y = Py[1].x; Ps[2].z = Pz[1].x;
+        Ps[3].x = Px[1].y; Ps[3].y = Py[1].y; Ps[3].z = Pz[1].y;
+        const int src = m.gb | ((m.q + 3) & 3);                  // previous lane of the quad (lane 0 <- lane 3)
         Vec3 par[4];
-        par[0] = prevP; if (m.q == 0) { par[0].x = par[0].y = par[0].z = 0.f; }
-        if (m.q == 3) par[1] = P8; else { par[1].x = Px[0].x; par[1].y = Py[0].x; par[1].z = Pz[0].x; }
-        if (m.q == 2) par[2] = P8; else { par[2].x = Px[0].y; par[2].y = Py[0].y; par[2].z = Pz[0].y; }
-        if (m.q == 1) { par[2].x = par[2].y = par[2].z = 0.f; }
-        par[3].x = Px[1].x; par[3].y = Py[1].x; par[3].z = Pz[1].x;
-        if (m.q == 0) { par[3].x = par[3].y = par[3].z = 0.f; }
+        par[0] = shfl3(Ps[0], src);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) par[k] = shfl3(m.q == 3 ? Ps[k - 1] : Ps[k], src);   // lane 3 hands lane 0 its previous slot
+        const Vec3 P8 = shfl3(Ps[1], m.gb | 3);                  // joint 8
+        if (m.q == 0 || m.q == 3) { par[0].x = par[0].y = par[0].z = 0.f; }              // joints 1, 4 hang on the root
+        if (m.q == 2) { par[1].x = par[1].y = par[1].z = 0.f; par[2] = P8; }             // joint 7 <- root, joint 11 <- joint 8
+        if (m.q == 1) par[3] = P8;                                                        // joint 14 <- joint 8
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           ex[p] = f2_fma(Px[p], m1, f2_make(par[2 * p].x, par[2 * p + 1].x));
@@ -753,8 +733,8 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
         const F2 nim = f2_splat(-imean), m2c = f2_splat(-2.f * cbl);
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-          const F2 crel = f2_make(__uint_as_float(static_cast<unsigned>(tab_ld(reinterpret_cast<const int*>(&A.maps.bone_rel[m.j0 - 1 + 2 * p]), M.tok))),
-                                  __uint_as_float(static_cast<unsigned>(tab_ld(reinterpret_cast<const int*>(&A.maps.bone_rel[m.j0 + 2 * p]), M.tok))));
+          const F2 crel = f2_make(__uint_as_float(static_cast<unsigned>(tab_ld(reinterpret_cast<const int*>(&A.maps.bone_rel[m.j0 - 1 + (2 * p) * m.js]), M.tok))),
+                                  __uint_as_float(static_cast<unsigned>(tab_ld(reinterpret_cast<const int*>(&A.maps.bone_rel[m.j0 - 1 + (2 * p + 1) * m.js]), M.tok))));
           const F2 t = f2_fma(len[p], nim, crel);
           bla = f2_fma(t, t, bla);
           h[p] = f2_mul(t, m2c);
@@ -819,19 +799,26 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
         }
       }
       if (kFull) {
-        // bones: the parent joint receives +dv of each child bone (slot k = element k & 1 of pair k >> 1)
-        Vec3 dv0, dv1, dv2, dv3;
-        dv0.x = dvx[0].x; dv0.y = dvy[0].x; dv0.z = dvz[0].x;
-        dv1.x = dvx[0].y; dv1.y = dvy[0].y; dv1.z = dvz[0].y;
-        dv2.x = dvx[1].x; dv2.y = dvy[1].x; dv2.z = dvz[1].x;
-        dv3.x = dvx[1].y; dv3.y = dvy[1].y; dv3.z = dvz[1].y;
-        const Vec3 nx = shfl3(dv0, (m.lane + 1) & 31);             // bone of the next lane's slot 0 hangs on my slot 3
-        const Vec3 b11 = shfl3(dv2, m.gb | 2), b14 = shfl3(dv1, m.gb | 3);   // bones of joints 11 and 14 hang on joint 8
-        if (m.q != 3) { dPx[0].x += dv1.x; dPy[0].x += dv1.y; dPz[0].x += dv1.z; }
-        if (m.q != 1 && m.q != 2) { dPx[0].y += dv2.x; dPy[0].y += dv2.y; dPz[0].y += dv2.z; }
-        if (m.q != 0) { dPx[1].x += dv3.x; dPy[1].x += dv3.y; dPz[1].x += dv3.z; }
-        if (m.q != 3) { dPx[1].y += nx.x; dPy[1].y += nx.y; dPz[1].y += nx.z; }
-        if (m.q == 1) { dPx[1].y += b11.x + b14.x; dPy[1].y += b11.y + b14.y; dPz[1].y += b11.z + b14.z; }
+        // bones: the parent joint receives +dv of each child bone (slot k = element k & 1 of pair k >> 1).  Mirror of the
+        // forward exchange: the child of (lane q, slot k) is slot k of the NEXT lane (for lane 3: slot k + 1 of lane 0).
+        Vec3 dvs[4];
+        dvs[0].x = dvx[0].x; dvs[0].y = dvy[0].x; dvs[0].z = dvz[0].x;
+        dvs[1].x = dvx[0].y; dvs[1].y = dvy[0].y; dvs[1].z = dvz[0].y;
+        dvs[2].x = dvx[1].x; dvs[2].y = dvy[1].x; dvs[2].z = dvz[1].x;
+        dvs[3].x = dvx[1].y; dvs[3].y = dvy[1].y; dvs[3].z = dvz[1].y;
+        const int nxt = m.gb | ((m.q + 1) & 3);
+        Vec3 W[4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) W[k] = shfl3(m.q == 0 ? dvs[k + 1] : dvs[k], nxt);   // lane 0 hands lane 3 its next slot
+        W[3] = shfl3(dvs[3], nxt);
+        const Vec3 b11 = shfl3(dvs[2], m.gb | 2), b14 = shfl3(dvs[3], m.gb | 1);          // bones of joints 11, 14 hang on joint 8
+        // not a child: joint 4 (root) for joint 3; joints 7 (root), 11 (joint 8) for joints 6, 10; joint 14 (joint 8) for joint 13;
+        // joint 16 has no child
+        if (m.q != 2) { dPx[0].x += W[0].x; dPy[0].x += W[0].y; dPz[0].x += W[0].z; }
+        if (m.q != 1) { dPx[0].y += W[1].x; dPy[0].y += W[1].y; dPz[0].y += W[1].z; }
+        if (m.q != 1) { dPx[1].x += W[2].x; dPy[1].x += W[2].y; dPz[1].x += W[2].z; }
+        if (m.q == 1 || m.q == 2) { dPx[1].y += W[3].x; dPy[1].y += W[3].y; dPz[1].y += W[3].z; }
+        if (m.q == 3) { dPx[0].y += b11.x + b14.x; dPy[0].y += b11.y + b14.y; dPz[0].y += b11.z + b14.z; }
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
           const F2 dd1 = f2_mul(mask[p], f2_fma(dPy[p], uy2[p], f2_fma(dPx[p], ux2[p], dPz[p])));     // lift
@@ -853,7 +840,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
         if (kT) {
           __nv_bfloat16* gT = kFull ? A.g1T[net] : A.g2T[net];
           if (gT && valid && go != S.trash_off)
-            gT[static_cast<size_t>(A.maps.col[m.j0 + k]) * A.ldT + A.colT0 + r.n] = hv;
+            gT[static_cast<size_t>(A.maps.col[m.j0 + k * m.js]) * A.ldT + A.colT0 + r.n] = hv;
         }
       }
       if (kT && m.q == 0 && T.gs[net][0] != S.trash_off) {

@@ -9,6 +9,7 @@
 #pragma once
 #include "devdefs.cuh"
 #include "stage.cuh"
+#include "f2.cuh"
 
 namespace links {
 
@@ -63,10 +64,80 @@ __device__ __forceinline__ void load_pose(const float* row, int J, int rot, Pose
 }
 
 // ---- MPJPE (metrics_batch.py:8-24): mean joint distance after root-centring (+ optional norm matching) ----------
+// Joints (2p, 2p + 1) of a pose as one packed value; compile-time joint counts only (JT = 17 / 16).
+template <int JT>
+__device__ __forceinline__ F2 pose_pair(const PoseRegs<JT>& P, int a, int p) { return f2_make(P.c[a][2 * p], P.c[a][2 * p + 1]); }
+
 template <int JT>
 __device__ __forceinline__ float mpjpe_regs(const PoseRegs<JT>& R, const PoseRegs<JT>& P, const float (&r0)[3],
                                             const float (&p0)[3], int J, int rot, int use_scaling, float* dist_out,
                                             float* max_out) {
+  if constexpr (JT >= 2) {
+    // joint pairs in packed f32x2 arithmetic (half the issue slots); an odd last joint runs in scalar code
+    constexpr int NP = JT / 2;
+    const F2 m1 = f2_splat(-1.f);
+    F2 np0[3], r02[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { np0[a] = f2_splat(-p0[a]); r02[a] = f2_splat(r0[a]); }
+    float scale = 1.f;
+    if (use_scaling) {
+      F2 sp2 = f2_splat(0.f), sr2 = f2_splat(0.f);
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const F2 x = f2_add(pose_pair<JT>(P, a, p), np0[a]);
+          const F2 ny = f2_fma(pose_pair<JT>(R, a, p), m1, r02[a]);
+          sp2 = f2_fma(x, x, sp2);
+          sr2 = f2_fma(ny, ny, sr2);
+        }
+      }
+      float sp = sp2.x + sp2.y, sr = sr2.x + sr2.y;
+      if (JT & 1) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float x = P.c[a][JT - 1] - p0[a], y = R.c[a][JT - 1] - r0[a];
+          sp += x * x;
+          sr += y * y;
+        }
+      }
+      scale = sqrtf(sr) / sqrtf(sp);
+    }
+    const F2 sc2 = f2_splat(scale);
+    float acc = 0.f, mx = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      F2 d2 = f2_splat(0.f);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const F2 x = f2_add(pose_pair<JT>(P, a, p), np0[a]);
+        const F2 ny = f2_fma(pose_pair<JT>(R, a, p), m1, r02[a]);      // -(R - r0)
+        const F2 e = f2_fma(x, sc2, ny);
+        d2 = f2_fma(e, e, d2);
+      }
+      const float da = sqrtf(d2.x), db = sqrtf(d2.y);
+      if (dist_out) {
+        dist_out[rot ? slot_joint<JT>(2 * p, rot, J) : 2 * p] = da;
+        dist_out[rot ? slot_joint<JT>(2 * p + 1, rot, J) : 2 * p + 1] = db;
+      }
+      acc += da + db;
+      mx = fmaxf(mx, fmaxf(da, db));
+    }
+    if (JT & 1) {
+      float d2 = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float e = (P.c[a][JT - 1] - p0[a]) * scale - (R.c[a][JT - 1] - r0[a]);
+        d2 += e * e;
+      }
+      const float d = sqrtf(d2);
+      if (dist_out) dist_out[rot ? slot_joint<JT>(JT - 1, rot, J) : JT - 1] = d;
+      acc += d;
+      mx = fmaxf(mx, d);
+    }
+    if (max_out) *max_out = mx;
+    return acc / static_cast<float>(J);
+  } else {
   float scale = 1.f;
   if (use_scaling) {
     float sp = 0.f, sr = 0.f;
@@ -99,6 +170,7 @@ __device__ __forceinline__ float mpjpe_regs(const PoseRegs<JT>& R, const PoseReg
   }
   if (max_out) *max_out = mx;
   return acc / static_cast<float>(J);
+  }
 }
 
 // ---- 3x3 one-sided Jacobi SVD -> polar factor Q = U V^T and sum of singular values ----------------------
@@ -233,30 +305,87 @@ struct PaFit {
 template <int JT>
 __device__ __forceinline__ void pa_fit(const PoseRegs<JT>& R, const PoseRegs<JT>& P, int J, PaFit& f) {
   const float invJ = 1.f / static_cast<float>(J);
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { f.mr[a] = 0.f; f.mp[a] = 0.f; }
-#pragma unroll
-  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
-    if (JT == 0 && k >= J) break;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { f.mr[a] += R.c[a][k]; f.mp[a] += P.c[a][k]; }
-  }
-#pragma unroll
-  for (int a = 0; a < 3; ++a) { f.mr[a] *= invJ; f.mp[a] *= invJ; }
   float ssr = 0.f, ssp = 0.f;
   float A[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+  if constexpr (JT >= 2) {
+    // joint pairs in packed f32x2 arithmetic; an odd last joint runs in scalar code
+    constexpr int NP = JT / 2;
+    F2 smr[3], smp[3];
 #pragma unroll
-  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
-    if (JT == 0 && k >= J) break;
-    float x[3], y[3];
+    for (int a = 0; a < 3; ++a) { smr[a] = f2_splat(0.f); smp[a] = f2_splat(0.f); }
 #pragma unroll
-    for (int a = 0; a < 3; ++a) { x[a] = R.c[a][k] - f.mr[a]; y[a] = P.c[a][k] - f.mp[a]; }
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { smr[a] = f2_add(smr[a], pose_pair<JT>(R, a, p)); smp[a] = f2_add(smp[a], pose_pair<JT>(P, a, p)); }
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      ssr += x[a] * x[a];
-      ssp += y[a] * y[a];
+      f.mr[a] = smr[a].x + smr[a].y;
+      f.mp[a] = smp[a].x + smp[a].y;
+      if (JT & 1) { f.mr[a] += R.c[a][JT - 1]; f.mp[a] += P.c[a][JT - 1]; }
+      f.mr[a] *= invJ; f.mp[a] *= invJ;
+    }
+    F2 nmr[3], nmp[3], A2[3][3];
+    F2 ssr2 = f2_splat(0.f), ssp2 = f2_splat(0.f);
 #pragma unroll
-      for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
+    for (int a = 0; a < 3; ++a) {
+      nmr[a] = f2_splat(-f.mr[a]); nmp[a] = f2_splat(-f.mp[a]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) A2[a][b] = f2_splat(0.f);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      F2 x[3], y[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { x[a] = f2_add(pose_pair<JT>(R, a, p), nmr[a]); y[a] = f2_add(pose_pair<JT>(P, a, p), nmp[a]); }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ssr2 = f2_fma(x[a], x[a], ssr2);
+        ssp2 = f2_fma(y[a], y[a], ssp2);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) A2[a][b] = f2_fma(x[a], y[b], A2[a][b]);
+      }
+    }
+    ssr = ssr2.x + ssr2.y; ssp = ssp2.x + ssp2.y;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) A[a][b] = A2[a][b].x + A2[a][b].y;
+    if (JT & 1) {
+      float x[3], y[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { x[a] = R.c[a][JT - 1] - f.mr[a]; y[a] = P.c[a][JT - 1] - f.mp[a]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ssr += x[a] * x[a];
+        ssp += y[a] * y[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { f.mr[a] = 0.f; f.mp[a] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+      if (JT == 0 && k >= J) break;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { f.mr[a] += R.c[a][k]; f.mp[a] += P.c[a][k]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { f.mr[a] *= invJ; f.mp[a] *= invJ; }
+#pragma unroll
+    for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+      if (JT == 0 && k >= J) break;
+      float x[3], y[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { x[a] = R.c[a][k] - f.mr[a]; y[a] = P.c[a][k] - f.mp[a]; }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ssr += x[a] * x[a];
+        ssp += y[a] * y[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) A[a][b] += x[a] * y[b];
+      }
     }
   }
   const float nr1 = sqrtf(ssr), np1 = sqrtf(ssp);                           // unit Frobenius norm (mode 1)
@@ -281,8 +410,50 @@ template <int JT, int WANT>
 __device__ __forceinline__ void pa_errors(const PoseRegs<JT>& R, const PoseRegs<JT>& P, int J, int rot, const PaFit& f,
                                           float& e_best, float& e_batch, float* aligned) {
   float acc1 = 0.f, acc0 = 0.f;
+  constexpr int kFirstScalar = (JT >= 2) ? (JT / 2) * 2 : 0;       // joints below it run pairwise in packed f32x2 arithmetic
+  if constexpr (JT >= 2) {
+    constexpr int NP = JT / 2;
+    F2 Q2[3][3], nmr[3], nmp[3];
 #pragma unroll
-  for (int k = 0; k < PoseRegs<JT>::kCap; ++k) {
+    for (int a = 0; a < 3; ++a) {
+      nmr[a] = f2_splat(-f.mr[a]); nmp[a] = f2_splat(-f.mp[a]);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) Q2[a][b] = f2_splat(f.Q[a][b]);
+    }
+    const F2 ng1 = f2_splat(-f.g1), ng0 = f2_splat(-f.g0), ng0d = f2_splat(-f.g0 * f.det);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      F2 y[3], x[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { y[a] = f2_add(pose_pair<JT>(P, a, p), nmp[a]); x[a] = f2_add(pose_pair<JT>(R, a, p), nmr[a]); }
+      F2 d1 = f2_splat(0.f), d0 = f2_splat(0.f);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const F2 q = f2_fma(Q2[a][2], y[2], f2_fma(Q2[a][1], y[1], f2_mul(Q2[a][0], y[0])));
+        if (WANT & 2) {
+          const F2 e1 = f2_fma(q, ng1, x[a]);                      // x - g1 q
+          if (WANT == 2 && aligned) {
+            aligned[a * J + (rot ? slot_joint<JT>(2 * p, rot, J) : 2 * p)] = f.g1 * q.x + f.mr[a];
+            aligned[a * J + (rot ? slot_joint<JT>(2 * p + 1, rot, J) : 2 * p + 1)] = f.g1 * q.y + f.mr[a];
+          }
+          d1 = f2_fma(e1, e1, d1);
+        }
+        if (WANT & 1) {
+          const F2 e0 = f2_fma(q, a == 2 ? ng0d : ng0, x[a]);      // last ROW of R scaled by det (metrics_batch.py:145-147)
+          if (WANT == 1 && aligned) {
+            const float gz = a == 2 ? f.g0 * f.det : f.g0;
+            aligned[a * J + (rot ? slot_joint<JT>(2 * p, rot, J) : 2 * p)] = gz * q.x + f.mr[a];
+            aligned[a * J + (rot ? slot_joint<JT>(2 * p + 1, rot, J) : 2 * p + 1)] = gz * q.y + f.mr[a];
+          }
+          d0 = f2_fma(e0, e0, d0);
+        }
+      }
+      if (WANT & 2) acc1 += approx_sqrt(d1.x) + approx_sqrt(d1.y);
+      if (WANT & 1) acc0 += approx_sqrt(d0.x) + approx_sqrt(d0.y);
+    }
+  }
+#pragma unroll
+  for (int k = kFirstScalar; k < PoseRegs<JT>::kCap; ++k) {
     if (JT == 0 && k >= J) break;
     float y[3], x[3];
 #pragma unroll

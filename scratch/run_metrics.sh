@@ -1,0 +1,5 @@
+set -x
+python -m pytest tests/test_kernels_flow_metrics.py tests/test_gpu_dropin.py tests/test_gpu_occ_eval.py tests/test_gpu_parity_baseline_sizes.py -x -q -m gpu 2>&1 | tail -30 > gpurun_out/r02_t_metrics.log
+python bench_kernels.py > gpurun_out/r02_kernels_isolated_v12.json 2> gpurun_out/r02_bk12.err
+M="gpu__time_duration.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"
+ncu --metrics $M --clock-control none -k regex:"eval_lift" --csv --log-file gpurun_out/r02_ncu_eval_v12.csv python scratch/geom_prof.py lt > gpurun_out/r02_ncu_eval_v12.log 2>&1
