@@ -557,10 +557,14 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": dict({"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                               "frac": achieved / peaks["bf16_burst"], "traffic": traffic,
-                              "traffic_note": "traffic = mean dram read+write bytes per GEMM launch from this round's ncu "
-                                              "--set full capture (profiles/r02_gemm_traffic.json; null until captured); "
-                                              "algorithmic operand bytes: %.1f MB per (2048 x 1024 x 1024) layer problem "
-                                              "(A, W, out in bf16)" % ((2048 * 1024 * 2 * 2 + 1024 * 1024 * 2) / 1e6),
+                              "traffic_note": "traffic = mean dram read+write bytes per chain launch from this round's ncu "
+                                              "--set full capture of the same four launches at B=1024 "
+                                              "(profiles/r02_gemm_traffic.json: 551 / 192 / 460 / 2219 MB); algorithmic operand "
+                                              "bytes: %.1f MB per (2048 x 1024 x 1024) layer problem (A, W, out in bf16), i.e. "
+                                              "~0.65 / 0.39 / 0.39 GB for the forward / pass-2 dgrad chains (measured traffic is "
+                                              "BELOW it: layer outputs are consumed from L2) and ~1.45 GB for pass-1 dgrad + "
+                                              "weight gradients (measured 1.5x: G / X slices re-read by the 4 tiles that share "
+                                              "them)" % ((2048 * 1024 * 2 * 2 + 1024 * 1024 * 2) / 1e6),
                               "flops_per_launch": gemm_flops / n_gemm_launches,
                               "us_per_launch": ms_gemm * 1e3 / n_gemm_launches,
                               "launches_per_step": n_gemm_launches,

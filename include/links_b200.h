@@ -263,7 +263,10 @@ int links_geom_forward(const LinksGeomMaps* maps, const float* u, const float* h
 
 /* Re-lift consistency / reprojection / pairwise / bone losses and their gradient w.r.t. the pass-2
  * depth heads (:228-259).  loss_sums[4] += (sum L3d, sum rep_rot, sum pair, sum bl) (un-normalised);
- * g2_head[p] bf16 [N,64] = dLoss/d(pass-2 head p) (+ transposed copies at column colT0). */
+ * g2_head[p] bf16 [N,64] = dLoss/d(pass-2 head p) (+ transposed copies at column colT0).
+ * The rows leave the kernel as whole 16-byte chunks: inside the chunks that hold a fed column, columns that no
+ * joint feeds (the root's included) are written as zero; chunks beyond the last used column are not touched.
+ * u, the dense part tensors and the gradient rows must be 16-byte aligned (LINKS_E_ALIGN); N <= 2^25 - 8. */
 int links_geom_loss(const LinksGeomMaps* maps, const float* u, const float* head0, const float* head1,
                     const float* ang0, const float* ang1, const float* eps_x, const float* u_y,
                     const float* stats, const float* head2_0, const float* head2_1, int N,
