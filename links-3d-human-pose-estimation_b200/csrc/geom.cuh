@@ -157,17 +157,17 @@ struct GeomCopy {        // one 16-byte copy of the per-iteration list
   int soff;              // offset in the staging buffer
 };
 // Per-block lookup tables (shared memory, built once per block): staging-buffer byte offsets (row 0) of what a lane reads
-// or writes for joint j in variant v plus the row pitch of that slice; the lane adds rl * pitch.  Entries without a source point at zero bytes (pitch 0); entries without a destination are -1.
+// or writes for joint j in variant v; the lane adds its row offset (rl * kGeomSp for strided slices, rl * pitch for contiguous
+// ones).  Entries without a source point at zero bytes (pitch 0); entries without a destination are -1.
 struct GeomTabs {
-  int hs[2][kJ], hp[2][kJ];      // pass-1 depth-head output (strided): offset, row pitch
-  int h2s[2][kJ], h2p[2][kJ];    // pass-2 depth-head output (strided)
+  int hs[2][kJ];        // pass-1 depth-head output (strided)
+  int h2s[2][kJ];       // pass-2 depth-head output (strided)
   int dls[2][kJ];       // d/d(projected x) from the pass-2 lifter input gradient (strided); y sits njy4 bytes further
   int dfs[2][kJ];       // ... from the part flow (contiguous, pitch dfp); y sits njy4 bytes further
   int dfp[2][kJ];       // row pitch (bytes) of the joint's part: flow gradient rows and projected-part output rows
-  int dsp[2][kJ];       // row pitch of dls
   int njy4[2][kJ];
   int qps[2][kJ];       // projected x in the output buffer (contiguous, pitch dfp); scratch if the joint has no part
-  int gs[2][kJ], gp[2][kJ];      // [net][j]: head-gradient element in the output buffer (strided); scratch if net never feeds j
+  int gs[2][kJ];        // [net][j]: head-gradient element in the output buffer (strided); scratch if net never feeds j
 };
 #ifndef LINKS_HOSTSIM
 __device__ __forceinline__ void geom_cp16(void* sdst, const void* gsrc) {
@@ -217,14 +217,11 @@ __device__ __forceinline__ void build_tabs(const GeomArgs& A, GeomTabs& T, bool 
       for (int w = 0; w < V; ++w) fed = fed || A.maps.src_net[w][j] == v;
       __nv_bfloat16* g = full ? A.g1[v] : A.g2[v];
       T.gs[v][j] = (fed && g) ? S.g_off[v] + 2 * A.maps.col[j] : S.trash_off;
-      T.gp[v][j] = (fed && g) ? S.g_sp[v] : S.trash_sp;
     }
     if (v >= V) continue;
     const int net = A.maps.src_net[v][j], col = A.maps.col[j];
     T.hs[v][j] = S.head_off[net] + 4 * col;
-    T.hp[v][j] = S.head_sp[net];
     T.h2s[v][j] = A.head2[net] ? S.head2_off[net] + 4 * col : S.zero_off;
-    T.h2p[v][j] = A.head2[net] ? S.head2_sp[net] : 0;
     const int pn = A.maps.part_net[v][j];
     const bool has = pn >= 0;
     const int pi = has ? pn : 0;
@@ -233,7 +230,6 @@ __device__ __forceinline__ void build_tabs(const GeomArgs& A, GeomTabs& T, bool 
     T.dfs[v][j] = ext ? S.dflow_off[pi] + 4 * idx : S.zero_off;
     T.dls[v][j] = ext ? S.dlift_off[pi] + 4 * idx : S.zero_off;
     T.dfp[v][j] = (ext || (has && A.qpart[pi])) ? 8 * nj : 0;
-    T.dsp[v][j] = ext ? S.dlift_sp[pi] : 0;
     T.njy4[v][j] = ext || (has && A.qpart[pi]) ? 4 * nj : 0;
     T.qps[v][j] = (has && A.qpart[pi]) ? S.qpart_off[pi] + 4 * idx : S.trash_off;
   }
@@ -626,11 +622,11 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
       for (int k = 0; k < 4; ++k) {
         net1[k] = GEOM_MAP(src_net, v, k) != 0;
         delta[k] = lds_f(cur, GEOM_TAB(hs, v, k) + rs);
-        delta2[k] = lds_f(cur, GEOM_TAB(h2s, v, k) + rl * GEOM_TAB(h2p, v, k));
+        delta2[k] = lds_f(cur, GEOM_TAB(h2s, v, k) + rs);
         xqx[k] = 0.f; xqy[k] = 0.f;
         if (kFull) {
           const char* df = cur + GEOM_TAB(dfs, v, k) + rl * GEOM_TAB(dfp, v, k);
-          const char* dl = cur + GEOM_TAB(dls, v, k) + rl * GEOM_TAB(dsp, v, k);
+          const char* dl = cur + GEOM_TAB(dls, v, k) + rs;
           const int ny = GEOM_TAB(njy4, v, k);
           xqx[k] = lds_f(df, 0) + lds_f(dl, 0);
           xqy[k] = lds_f(df, ny) + lds_f(dl, ny);
@@ -836,7 +832,7 @@ __global__ void __launch_bounds__(kGeomWarps * 32, kFull ? 3 : 4) geom_lossgrad_
       for (int k = 0; k < 4; ++k) {
         const int go = GEOM_TAB(gs, net, k);              // scratch if `net` never feeds this joint
         const __nv_bfloat16 hv = __float2bfloat16_rn(kFull ? g1acc[k][net] : g2acc[k][net]);
-        *reinterpret_cast<__nv_bfloat16*>(outb + go + rl * GEOM_TAB(gp, net, k)) = hv;
+        *reinterpret_cast<__nv_bfloat16*>(outb + go + rs) = hv;
         if (kT) {
           __nv_bfloat16* gT = kFull ? A.g1T[net] : A.g2T[net];
           if (gT && valid && go != S.trash_off)
@@ -955,8 +951,9 @@ inline int geom_plan(GeomArgs& A, int level) {
     chunks += rows * R.cpr;
     i = k;
   }
-  S.zero_off = in_off;                           // never a copy destination: stays zero
-  in_off += 16;
+  // bytes [128, 144) of every row slot of a strided slice are never a copy destination: they stay zero and serve, with the
+  // strided row offset or with pitch 0, as the source of entries that have none
+  S.zero_off = S.in[0].soff + 128;
   int rc = 0;
   auto contig_in = [&](const void* p, int pitch, int* slot) {
     if (p == nullptr) return;
@@ -1003,9 +1000,14 @@ inline int geom_plan(GeomArgs& A, int level) {
     }
   }
   // destinations that do not exist (a net that never feeds a joint, a joint outside every part) land in a scratch slice
-  S.trash_off = out_off;
-  S.trash_sp = level == 0 ? 0 : 16;              // forward: contiguous-form entries only (pitch 0)
-  out_off += level == 0 ? 16 : rows * 16;
+  // (strided form: the unused tail of the first gradient slice's row slots; contiguous form, pitch 0: one 16-byte slot)
+  if (level >= 1 && n_out > 0) {
+    S.trash_off = S.out[0].soff + 128;
+  } else {
+    S.trash_off = out_off;
+    out_off += level == 0 ? 16 : rows * kGeomSp;
+  }
+  S.trash_sp = level == 0 ? 0 : kGeomSp;
   S.n_out = n_out; S.out_bytes = out_off; S.out_chunks = ochunks;
   if (ochunks > 32 * kGeomMaxOutIters) return LINKS_E_RANGE;
   return rc;

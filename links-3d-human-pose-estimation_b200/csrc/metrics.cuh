@@ -642,15 +642,15 @@ __global__ void __launch_bounds__(256) threshold_counts_kernel(const float* __re
 
 // Eval fusion (eval_h36m.py:58-97): pred = [x*d, y*d, d] with d = depth_off + depth (no clamp, not centred);
 // sums3 += (sum N-MPJPE(root 0, scaled), sum PA-MPJPE 'best', sum PA-MPJPE batch).  J = 17.
-// The depth rows (17 of ld_depth floats used) are bulk-copied whole and compacted to stride 17 in shared memory.
+// The depth rows (17 of ld_depth floats used) are bulk-copied whole and compacted IN PLACE to stride 17 in shared memory
+// (30 KB per block: 7 blocks per SM).
 constexpr int kEvalMaxLd = 32;
-__global__ void __launch_bounds__(kPosesPerBlock, 6) eval_lift_score_kernel(
+__global__ void __launch_bounds__(kPosesPerBlock, 7) eval_lift_score_kernel(
     const float* __restrict__ poses_2d, const float* __restrict__ depth_off, int ld_depth,
     const float* __restrict__ gt, int M, float depth, double* sums3) {
   __shared__ __align__(128) float s_ref[kPosesPerBlock * kRowStride];
   __shared__ __align__(128) float s_2d[kPosesPerBlock * 34];
-  __shared__ __align__(128) float s_draw[kPosesPerBlock * kEvalMaxLd];
-  __shared__ __align__(16) float s_d[kPosesPerBlock * 17];
+  __shared__ __align__(128) float s_draw[kPosesPerBlock * kEvalMaxLd];   // raw depth rows, compacted in place to stride 17
   __shared__ __align__(8) uint64_t s_bar[1];
   __shared__ double s_red[2];
   constexpr int J = 17;
@@ -680,7 +680,7 @@ __global__ void __launch_bounds__(kPosesPerBlock, 6) eval_lift_score_kernel(
           stage_issue(rq, s_bar, false);
           for (int i = threadIdx.x; i < npos * J; i += blockDim.x) {
             const int r = i / J, j = i - r * J;
-            s_d[i] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j];
+            s_draw[i] = depth_off[static_cast<size_t>(pose0 + r) * ld_depth + j];
           }
         }
         return bulk;
@@ -690,15 +690,22 @@ __global__ void __launch_bounds__(kPosesPerBlock, 6) eval_lift_score_kernel(
         const int pose0 = chunk * kPosesPerBlock;
         const int npos = min(kPosesPerBlock, M - pose0);
         if (npos == kPosesPerBlock && depth_bulk) {     // block-uniform
-          for (int i = threadIdx.x; i < kPosesPerBlock * J; i += blockDim.x) {
+          // in place (the compact image overlaps the rows it is read from): through registers, between two barriers
+          float tmp[J];
+#pragma unroll
+          for (int mm = 0; mm < J; ++mm) {
+            const int i = threadIdx.x + kPosesPerBlock * mm;
             const int r = i / J, j = i - r * J;
-            s_d[i] = s_draw[r * ld_depth + j];
+            tmp[mm] = s_draw[r * ld_depth + j];
           }
+          __syncthreads();
+#pragma unroll
+          for (int mm = 0; mm < J; ++mm) s_draw[threadIdx.x + kPosesPerBlock * mm] = tmp[mm];
           __syncthreads();
         }
         if (t < npos) {
           const float* q = s_2d + t * 34;
-          const float* dd = s_d + t * J;
+          const float* dd = s_draw + t * J;
           auto lift = [&](PoseRegs<17>& P) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
