@@ -58,6 +58,15 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+class View:
+    """Element `offset` of `base` as a pointer argument: column-offset views into one packed buffer (the way the lifter
+    engine hands the geometry kernels the four head outputs of a pass, all living in one [N, 32] row)."""
+
+    def __init__(self, base, offset):
+        assert base.flags["C_CONTIGUOUS"]
+        self.base, self.offset = base, int(offset)
+
+
 def bf16_to_f32(a_u16):
     return (a_u16.astype(np.uint32) << 16).view(np.float32)
 
@@ -101,7 +110,12 @@ class SimBackend:
         self.L = sim()
 
     def call(self, fn, *args):
-        conv = [ptr(a) if isinstance(a, np.ndarray) else a for a in args]
+        conv = []
+        for a in args:
+            if isinstance(a, View):
+                conv.append(C.c_void_p(a.base.ctypes.data + a.offset * a.base.itemsize))
+            else:
+                conv.append(ptr(a) if isinstance(a, np.ndarray) else a)
         return getattr(self.L, "sim_" + fn)(*conv)
 
     def packed_floats(self, C_, nb):
@@ -118,12 +132,15 @@ class CudaBackend:
 
     def call(self, fn, *args):
         import torch
-        dev, conv = [], []
+        dev, conv, up = [], [], {}
         for a in args:
-            if isinstance(a, np.ndarray):
-                t = torch.from_numpy(a).cuda()
-                dev.append((a, t))
-                conv.append(t.data_ptr())
+            base = a.base if isinstance(a, View) else a
+            if isinstance(base, np.ndarray):
+                if id(base) not in up:                      # views into one buffer share one device copy
+                    up[id(base)] = torch.from_numpy(base).cuda()
+                    dev.append((base, up[id(base)]))
+                t = up[id(base)]
+                conv.append(t.data_ptr() + (a.offset * base.itemsize if isinstance(a, View) else 0))
             else:
                 conv.append(a)
         stream = torch.cuda.current_stream().cuda_stream

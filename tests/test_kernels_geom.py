@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from hostsim_util import bf16_to_f32, backend_params
+from hostsim_util import View, bf16_to_f32, backend_params
 from links_b200 import maps as MP
 from oracle import geometry as OG
 from oracle import steps as OS
@@ -158,3 +158,63 @@ def test_geometry_kernels_match_oracle(kind, N, clamp, root_zero, backend):
         got = bf16_to_f32(ga[p])[:, 0]
         scale = np.abs(ref["dA"][p]).max()
         np.testing.assert_allclose(got, ref["dA"][p][:, 0], rtol=8e-3, atol=5e-5 * scale)
+
+
+@pytest.mark.parametrize("kind,N", [("lt", 37), ("lr", 64)])
+@backend_params
+def test_packed_head_rows_equal_separate_arrays(kind, N, backend):
+    """The staging plan groups strided tensors whose used columns share one 128-byte window (the packed head rows of
+    MlpSet(head_groups=...)): forward / loss / backward on column-offset views into ONE [N, 32] buffer per pass must equal,
+    bit for bit, the same calls on four separate arrays (one staged region instead of four; same arithmetic)."""
+    L = backend
+    cfg = dict(OS.DEFAULT_CFG)
+    inp = make_inputs(kind, N, seed=91 + N)
+    m = MP.geom_maps(kind, cfg)
+    nj = inp["nj"]
+    stats = np.zeros(2, np.float32)
+    assert L.call("elev_stats", inp["angs"][0], inp["angs"][1], N, stats) == 0
+    c_ang = (nj[0] + nj[1], nj[0] + nj[1] + 1)
+    pack1, pack2 = np.zeros((N, HEAD_LD), np.float32), np.zeros((N, HEAD_LD), np.float32)
+    for p, c0 in enumerate((0, nj[0])):
+        pack1[:, c0:c0 + nj[p]] = inp["heads"][p][:, :nj[p]]
+        pack2[:, c0:c0 + nj[p]] = inp["heads2"][p][:, :nj[p]]
+        pack1[:, c_ang[p]] = inp["angs"][p][:, 0]
+
+    def run(packed):
+        if packed:
+            heads = [View(pack1, 0), View(pack1, nj[0])]
+            angs = [View(pack1, c_ang[0]), View(pack1, c_ang[1])]
+            heads2 = [View(pack2, 0), View(pack2, nj[0])]
+        else:
+            heads, angs, heads2 = inp["heads"], inp["angs"], inp["heads2"]
+        common = [inp["u"], heads[0], heads[1], angs[0], angs[1], inp["eps"], inp["uy"], stats]
+        qp = [np.zeros((N, 2 * nj[p]), np.float32) for p in range(2)]
+        assert L.call("geom_forward", C.byref(m), *common, N, qp[0], qp[1], None, None) == 0
+        sums = np.zeros(4, np.float32)
+        g2 = [np.zeros((N, 64), np.uint16) for _ in range(2)]
+        assert L.call("geom_loss", C.byref(m), *common, heads2[0], heads2[1], N, sums, g2[0], g2[1], None, None, 0, 0) == 0
+        g1 = [np.zeros((N, 64), np.uint16) for _ in range(2)]
+        dgam, da, red = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros(2, np.float32)
+        assert L.call("geom_backward", C.byref(m), *common, heads2[0], heads2[1], inp["ext"][0], inp["ext"][1],
+                      inp["ext_l"][0], inp["ext_l"][1], N, g1[0], g1[1], None, None, 0, 0, dgam, da, red) == 0
+        return qp + g2 + g1 + [dgam, da]
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+
+
+@backend_params
+def test_unaligned_dense_tensor_is_refused(backend):
+    """Dense tensors are staged in 16-byte chunks: a pose buffer that is not 16-byte aligned is an error, not a fault."""
+    L = backend
+    N = 16
+    cfg = dict(OS.DEFAULT_CFG)
+    inp = make_inputs("lt", N, seed=3)
+    m = MP.geom_maps("lt", cfg)
+    stats = np.array([0.1, 0.2], np.float32)
+    big = np.zeros(N * 34 + 4, np.float32)
+    qp = [np.zeros((N, 14), np.float32), np.zeros((N, 20), np.float32)]
+    rc = L.call("geom_forward", C.byref(m), View(big, 1), inp["heads"][0], inp["heads"][1], inp["angs"][0], inp["angs"][1],
+                inp["eps"], inp["uy"], stats, N, qp[0], qp[1], None, None)
+    assert rc == -2          # LINKS_E_ALIGN
