@@ -32,8 +32,7 @@ struct GeomRegion {
   int pitch;            // bytes between rows in global memory
   int cpr;              // strided: 16-byte chunks staged per row; contiguous (the 8-row block is one range): 0
   int soff;             // byte offset of the slice in the warp's staging buffer
-  int spitch;           // strided: bytes between rows in the staging buffer = an ODD number of 16-byte chunks >= cpr, so that
-                        // the 8 rows of a warp start in 8 different bank groups
+  int spitch;           // strided: bytes between rows in the staging buffer (kGeomSp)
 };
 struct GeomStage {
   int rows;                                   // rows a warp stages per iteration: 8 (four lanes per row) or 32 (one lane per row)
@@ -43,13 +42,12 @@ struct GeomStage {
   int in_chunks, out_chunks;                  // 16-byte copies per warp iteration
   // byte offsets (row 0) of the logical tensors inside the input / output staging buffers
   int u_off, eps_off, uy_off;                 // contiguous: row pitch 136 / 4 / 4
-  int head_off[2], ang_off[2], head2_off[2], dlift_off[2];     // strided; row pitches:
-  int head_sp[2], ang_sp[2], head2_sp[2], dlift_sp[2];
+  int head_off[2], ang_off[2], head2_off[2], dlift_off[2];     // strided (row pitch kGeomSp)
   int dflow_off[2];                           // contiguous: row pitch 8 n_joints
   int qpart_off[2];                           // output, contiguous: row pitch 8 n_joints
-  int g_off[2], g_sp[2];                      // output, strided
+  int g_off[2];                               // output, strided
   int zero_off;                               // input buffers: 16 bytes that are never written (= 0); used with pitch 0
-  int trash_off, trash_sp;                    // output buffer: a strided slice nobody copies out
+  int trash_off;                              // output buffer: bytes nobody copies out (strided form, or pitch 0)
 };
 
 struct GeomArgs {
@@ -93,13 +91,6 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(LINKS_FULL_MASK, v, o);
   return v;
 }
-// sum over the 16 lanes of a half-warp (every lane of the half receives it)
-__device__ __forceinline__ float half_sum(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(LINKS_FULL_MASK, v, o);
-  return v;
-}
-
 // 1/x and sqrt(x) by the hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp, one instruction each, no denormal or
 // range fix-up code): the projections divide by depths ~ 10, the roots are of sums of squares -- far from the range limits
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -447,7 +438,7 @@ __device__ __forceinline__ void load_row(const GeomStage& S, const Quad& m, cons
   }
   r.u0x = lds_f(u, 0);
   r.u0y = lds_f(u, 4 * kJ);
-  const float ang0 = lds_f(cur, S.ang_off[0] + rl * S.ang_sp[0]), ang1 = lds_f(cur, S.ang_off[1] + rl * S.ang_sp[1]);
+  const float ang0 = lds_f(cur, S.ang_off[0] + rl * kGeomSp), ang1 = lds_f(cur, S.ang_off[1] + rl * kGeomSp);
   r.eps = lds_f(cur, S.eps_off + 4 * rl);
   const float uyaw = lds_f(cur, S.uy_off + 4 * rl);
   const float gamma = 0.5f * (ang0 + ang1);
@@ -920,14 +911,6 @@ inline int geom_plan(GeomArgs& A, int level) {
     items[k] = t;
   }
   int in_off = 0, n_in = 0, chunks = 0;
-  int* sp_slot[10];
-  for (int i = 0; i < n_items; ++i) {            // the pitch word of each logical tensor sits right after its offset arrays
-    int* o = items[i].slot;
-    sp_slot[i] = (o >= S.head_off && o < S.head_off + 2) ? S.head_sp + (o - S.head_off)
-               : (o >= S.ang_off && o < S.ang_off + 2) ? S.ang_sp + (o - S.ang_off)
-               : (o >= S.head2_off && o < S.head2_off + 2) ? S.head2_sp + (o - S.head2_off)
-               : S.dlift_sp + (o - S.dlift_off);
-  }
   for (int i = 0; i < n_items;) {
     const char* lo = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(items[i].p) & ~static_cast<uintptr_t>(15));
     const char* hi = items[i].p + items[i].used;
@@ -943,10 +926,7 @@ inline int geom_plan(GeomArgs& A, int level) {
     R.cpr = static_cast<int>((hi - lo + 15) / 16);
     R.soff = in_off;
     R.spitch = kGeomSp;
-    for (int q = i; q < k; ++q) {
-      *items[q].slot = in_off + static_cast<int>(items[q].p - lo);
-      *sp_slot[q] = R.spitch;
-    }
+    for (int q = i; q < k; ++q) *items[q].slot = in_off + static_cast<int>(items[q].p - lo);
     in_off += rows * R.spitch;
     chunks += rows * R.cpr;
     i = k;
@@ -994,7 +974,6 @@ inline int geom_plan(GeomArgs& A, int level) {
       R.g = reinterpret_cast<char*>(g); R.pitch = 128; R.cpr = (2 * (maxcol[h] + 1) + 15) / 16; R.soff = out_off;
       R.spitch = kGeomSp;
       S.g_off[h] = out_off;
-      S.g_sp[h] = R.spitch;
       out_off += rows * R.spitch;
       ochunks += rows * R.cpr;
     }
@@ -1007,7 +986,6 @@ inline int geom_plan(GeomArgs& A, int level) {
     S.trash_off = out_off;
     out_off += level == 0 ? 16 : rows * kGeomSp;
   }
-  S.trash_sp = level == 0 ? 0 : kGeomSp;
   S.n_out = n_out; S.out_bytes = out_off; S.out_chunks = ochunks;
   if (ochunks > 32 * kGeomMaxOutIters) return LINKS_E_RANGE;
   return rc;
