@@ -517,7 +517,7 @@ def run_gpu(args):
     if rank == 0:
         parity, cpu_base = None, None
         if not args.skip_cpu:
-            cpu_sec, cores, ref_first = cpu_steps(B, 3, 1, first_losses=True)
+            cpu_sec, cores, ref_first = cpu_steps(B, 15, 1, first_losses=True)      # ~10 s of CPU work
             worst, per = 0.0, {}
             for kind in ("lt", "lr"):
                 for k, v in first_losses[kind].items():
