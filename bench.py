@@ -527,7 +527,7 @@ def run_gpu(args):
             parity = {"what": "first-step losses (fresh weights) of the LT and LR steps at B=%d vs the CPU oracle (fp32)" % B,
                       "tolerance_rel": 1e-3, "max_rel_err": worst, "ok": bool(worst <= 1e-3), "losses": per}
             cpu_base = {"value": B / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), 3 timed "
+                        "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), 15 timed "
                                   "steps after 1 warm-up" % B}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
