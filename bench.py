@@ -233,16 +233,16 @@ def extra_configs(args, timed, world, rank, pg, peaks):
     ft = FlowTrainStep(34, INIT.init_flow_params(34, 40), B1, lr=2e-4)
     x2d, _ = synth_poses(B1, seed=77 + rank)
     ft.x.copy_(torch.from_numpy(x2d)); ft.noise.normal_()
-    for _ in range(3):
-        ft.step()
+    for _ in range(4):
+        ft.run()                              # eager, capture + replay, replays (what the drop-in script does)
     n1 = 20
-    ms = timed(ft.step, n1) / n1
+    ms = timed(ft.run, n1) / n1
     # per data pose: sampling (fwd + rev = 2 subnet passes) on 1 row, NLL fwd + reversible bwd (3 passes) on 2 rows,
     # parameter-gradient GEMMs (hidden recompute K=64 padded, dgrad, 2 wgrads) on 2 rows
     macs_pass = 427040
     flops1 = 2.0 * (2 * macs_pass + 2 * 3 * macs_pass + 2 * 8 * (64 * 1024 + 3 * 34 * 1024))
     out.append({"config": "configs[0]: full-pose GLOW flow training step (sample, NLL fwd/bwd on [x ; s], Adam), B=256 per GPU, "
-                          "independent replicas",
+                          "independent replicas, CUDA-graph replay",
                 "value": world * B1 / (ms * 1e-3), "unit": "poses/s", "ms_per_step": ms, "n_gpus": world,
                 "roofline": {"bound": "tensor", "achieved": flops1 * B1 / (ms * 1e-3) / 1e12, "peak": burst, "unit": "TFLOP/s",
                              "frac": flops1 * B1 / (ms * 1e-3) / 1e12 / burst,

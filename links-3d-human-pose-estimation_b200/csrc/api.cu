@@ -420,8 +420,9 @@ extern "C" __attribute__((visibility("default"))) int links_flow_pack(int C, int
     A.gs[k] = gscale[k]; A.go[k] = goffset[k]; A.wp[k] = wperm[k]; A.wpi[k] = wperm_inv[k];
   }
   A.packed = packed; A.C = C; A.n_blocks = n_blocks;
-  flow_pack_kernel<<<n_blocks, 256, 0, links_stream(stream)>>>(A);
-  flow_tc_pack_kernel<<<n_blocks, 256, 0, links_stream(stream)>>>(
+  const dim3 pack_grid(n_blocks, kFlowPackSplit);
+  flow_pack_kernel<<<pack_grid, 256, 0, links_stream(stream)>>>(A);
+  flow_tc_pack_kernel<<<pack_grid, 256, 0, links_stream(stream)>>>(
       A, reinterpret_cast<unsigned char*>(packed + static_cast<size_t>(flow_block_floats(C)) * n_blocks));
   return links_launch_status();
 }

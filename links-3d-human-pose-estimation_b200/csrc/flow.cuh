@@ -44,12 +44,15 @@ struct FlowPackArgs {
   int C, n_blocks;
 };
 
-// grid = (n_blocks), block = 256
+// grid = (n_blocks, kFlowPackSplit), block = 256: the flow training step re-packs after every Adam update, so the record
+// loop of a coupling block is spread over kFlowPackSplit CTAs (one CTA per block took ~80 us); slice 0 also writes the tail
+constexpr int kFlowPackSplit = 16;
 __global__ void flow_pack_kernel(const FlowPackArgs A) {
   const int k = blockIdx.x;
   const int C = A.C, c1 = flow_c1(C), c2 = flow_c2(C), Sh = flow_sh(C);
   float* P = A.packed + static_cast<size_t>(k) * flow_block_floats(C);
-  for (int e = threadIdx.x; e < kFlowHidden * Sh; e += blockDim.x) {
+  const int e_step = blockDim.x * gridDim.y;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < kFlowHidden * Sh; e += e_step) {
     const int h = e / Sh, i = e - h * Sh;
     float v = 0.f;
     if (i == 0) v = A.b0[k][h];
@@ -57,6 +60,7 @@ __global__ void flow_pack_kernel(const FlowPackArgs A) {
     else if (i <= c1 + 2 * c2) v = A.w2[k][static_cast<size_t>(i - 1 - c1) * kFlowHidden + h];
     P[e] = v;
   }
+  if (blockIdx.y != 0) return;
   float* T = P + kFlowHidden * Sh;
   for (int i = threadIdx.x; i < 2 * c2; i += blockDim.x) T[i] = A.b2[k][i];
   float* G = T + 2 * c2;

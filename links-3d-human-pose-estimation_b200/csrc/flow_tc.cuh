@@ -63,8 +63,12 @@ __device__ __forceinline__ void tc_split(float v, __nv_bfloat16& hi, __nv_bfloat
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// grid = (n_blocks, kFlowPackSplit): the element loops of one coupling block are spread over the CTAs of its grid row
+// (a single CTA per block needed ~0.5 ms -- a third of the B = 256 flow training step, which re-packs every step);
+// slice 0 also writes the fp32 tail.
 __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_packed) {
   const int k = blockIdx.x;
+  const int e_first = blockIdx.y * blockDim.x + threadIdx.x, e_step = blockDim.x * gridDim.y;
   const int C = A.C, c1 = flow_c1(C), c2 = flow_c2(C);
   const int n2p = tc_n2p(C), n4p = tc_n4p(C), s3 = tc_k3slabs(C);
   const int fw = tc_fw_bytes(C), bw = tc_bw_bytes(C);
@@ -75,7 +79,7 @@ __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_pack
   const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
   // ---- forward sets
   const int fw_elems = fw / 2;
-  for (int e = threadIdx.x; e < kTcChunks * fw_elems; e += blockDim.x) {
+  for (int e = e_first; e < kTcChunks * fw_elems; e += e_step) {
     const int c = e / fw_elems;
     int i = e - c * fw_elems;
     unsigned char* base = P + static_cast<size_t>(c) * fw;
@@ -110,7 +114,7 @@ __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_pack
   // ---- backward sets
   unsigned char* PB = P + static_cast<size_t>(kTcChunks) * fw;
   const int bw_elems = bw / 2;
-  for (int e = threadIdx.x; e < kTcChunks * bw_elems; e += blockDim.x) {
+  for (int e = e_first; e < kTcChunks * bw_elems; e += e_step) {
     const int c = e / bw_elems;
     int i = e - c * bw_elems;
     unsigned char* base = PB + static_cast<size_t>(c) * bw;
@@ -155,6 +159,7 @@ __global__ void flow_tc_pack_kernel(const FlowPackArgs A, unsigned char* tc_pack
     *reinterpret_cast<__nv_bfloat16*>(base + off) = val;
   }
   // ---- fp32 tail
+  if (blockIdx.y != 0) return;
   float* T = reinterpret_cast<float*>(P + static_cast<size_t>(kTcChunks) * (fw + bw));
   float* b2 = T;
   float* g = b2 + 2 * c2;

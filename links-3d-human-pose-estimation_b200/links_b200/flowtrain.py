@@ -27,7 +27,41 @@ def _rup(x, m):
     return (x + m - 1) // m * m
 
 
-class FlowTrainStep:
+class _GraphReplay:
+    """step() behind a CUDA graph (the flow steps are 20-odd short launches: launch-bound when issued eagerly).
+    run(): first call eager (lazy plans / workspaces), second call captures, later calls replay.  The inputs (x, noise)
+    are static buffers refilled by the caller on the same stream; the learning rate is a device word (set_lr)."""
+    graph = None
+    _ran = 0
+
+    def capture(self, warmup=1):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = g
+        return g
+
+    def run(self, use_graph=True):
+        if self.graph is not None:
+            self.graph.replay()
+        elif use_graph and self._ran >= 1 and self._graph_ok():
+            self.capture(warmup=0).replay()
+        else:
+            self.step()
+        self._ran += 1
+
+    def _graph_ok(self):
+        return True
+
+
+class FlowTrainStep(_GraphReplay):
     def __init__(self, C_dim, params, batch, n_blocks=8, lr=2e-4, weight_decay=0.0, device="cuda", process_group=None,
                  external_rows=False):
         """params: FrEIA-layout state dict; batch: rows of x per step (the kernel sees 2*batch rows).
@@ -56,6 +90,18 @@ class FlowTrainStep:
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self.P, self.Gd = [], []          # per block: name -> view
         off = 0
+        # every block owns the same span of the flat buffers: [nb, ...] strided views address one tensor of all blocks
+        numel = {n: int(torch.tensor(shapes[n]).prod()) for n in _NAMES}
+        span = sum(_rup(numel[n], 64) for n in _NAMES)
+        first, o = {}, 0
+        for n in _NAMES:
+            first[n] = o
+            o += _rup(numel[n], 64)
+
+        def all_blocks(flat, n):
+            return torch.as_strided(flat, (nb,) + tuple(shapes[n]), (span,) + tuple(torch.empty(shapes[n]).stride()), first[n])
+        self._w1_all, self._w2_all = all_blocks(self.master, "subnet.0.weight"), all_blocks(self.master, "subnet.2.weight")
+        self._dgs_all, self._dgo_all = all_blocks(self.grad, "global_scale"), all_blocks(self.grad, "global_offset")
         for k in range(nb):
             pv, gv = {}, {}
             for n in _NAMES:
@@ -80,8 +126,13 @@ class FlowTrainStep:
         self.x = torch.zeros(batch, C_dim, **f32)
         self.noise = torch.zeros(batch, C_dim, **f32)
         self.u = torch.zeros(M, C_dim, **f32)
-        self.nll_sum = torch.zeros(1, **f32)
         self.loss = torch.zeros(1, **f32)
+        # staging of the global-affine gradients (atomically accumulated by the kernel, [n_blocks, C] contiguous each) and
+        # the NLL sum: ONE buffer, cleared by one launch per step
+        self._acc = torch.zeros(2 * nb * C_dim + 1, **f32)
+        self._dgs = self._acc[:nb * C_dim].view(nb, 1, C_dim)
+        self._dgo = self._acc[nb * C_dim:2 * nb * C_dim].view(nb, 1, C_dim)
+        self.nll_sum = self._acc[2 * nb * C_dim:]
         self._refresh_shadows()
         self._plans = None
 
@@ -95,10 +146,9 @@ class FlowTrainStep:
         return sd
 
     def _refresh_shadows(self):
-        with torch.no_grad():
-            for k in range(self.nb):
-                self.W1b[k, :, :self.c1] = self.P[k]["subnet.0.weight"]
-                self.W2b[k, :2 * self.c2] = self.P[k]["subnet.2.weight"]
+        with torch.no_grad():                                   # all blocks at once: two cast launches
+            self.W1b[:, :, :self.c1].copy_(self._w1_all)
+            self.W2b[:, :2 * self.c2].copy_(self._w2_all)
         self.flow.repack(self.state_dict())
 
     def _prob(self, A, B, M, N, K, lda, ldb, **kw):
@@ -143,18 +193,9 @@ class FlowTrainStep:
             self._build_plans()
         if not self.external_rows:
             self.flow.sample(self.x, self.noise, self.u)           # [x ; s], s detached with the root joint zeroed
-        self.nll_sum.zero_()
-        # global-affine gradients are accumulated atomically: clear their slots of the flat gradient buffer
-        for k in range(self.nb):
-            self.Gd[k]["global_scale"].zero_()
-            self.Gd[k]["global_offset"].zero_()
-        # d_gscale / d_goffset live at a fixed stride inside the flat buffer: pass block 0's pointers + use per-block
-        # contiguous staging so the kernel's [n_blocks, C] indexing holds
-        if not hasattr(self, "_dgs"):
-            self._dgs = torch.zeros(self.nb, self.C, dtype=torch.float32, device=self.device)
-            self._dgo = torch.zeros(self.nb, self.C, dtype=torch.float32, device=self.device)
-        self._dgs.zero_()
-        self._dgo.zero_()
+        # the NLL sum and the global-affine gradients are accumulated atomically into contiguous [n_blocks, C] staging
+        # (their slots of the flat gradient buffer sit one block span apart): one clear before, two strided copies after
+        self._acc.zero_()
         check(L.links_flow_nll_train(self.flow.packed.data_ptr(), self.C, self.nb, self.u.data_ptr(), self.M, 1.0 / self.B,
                                      self.nll_sum.data_ptr(), None, self.X1.data_ptr(), self.DS.data_ptr(),
                                      self._dgs.data_ptr(), self._dgo.data_ptr(), self.flow.stash_for(self.M).data_ptr(), st),
@@ -163,10 +204,9 @@ class FlowTrainStep:
         for arr, n in gemms:
             check(L.links_gemm_grouped(arr, n, st), "links_gemm_grouped")
         check(L.links_colsum_bf16_batched(carr, cn, st), "links_colsum_bf16_batched")
-        for k in range(self.nb):
-            self.Gd[k]["global_scale"].copy_(self._dgs[k:k + 1])
-            self.Gd[k]["global_offset"].copy_(self._dgo[k:k + 1])
-        self.loss.copy_(self.nll_sum / self.B)                      # dist_2d + dist_2d_sample
+        self._dgs_all.copy_(self._dgs)
+        self._dgo_all.copy_(self._dgo)
+        torch.mul(self.nll_sum, 1.0 / self.B, out=self.loss)        # dist_2d + dist_2d_sample
 
     def optimizer_step(self):
         if self.world > 1:
@@ -181,6 +221,9 @@ class FlowTrainStep:
         self.forward_backward()
         self.optimizer_step()
 
+    def _graph_ok(self):
+        return self.world == 1          # data-parallel: the gradient all-reduce stays an eager NCCL call
+
     def set_lr(self, lr):
         self.lr = lr
         self.lr_dev.fill_(float(lr))          # read on the device by the Adam kernel (graph replays follow the scheduler)
@@ -189,7 +232,7 @@ class FlowTrainStep:
         return {"loss": self.loss.item()}
 
 
-class PartFlowTrainer:
+class PartFlowTrainer(_GraphReplay):
     """Joint training step of the four part flows (reference train_leg_torso_left_right_norm_flow.py:100-198).
 
         parts of the data              -> NLL under the leg / torso / left / right flows           (:108-127)
@@ -228,6 +271,9 @@ class PartFlowTrainer:
                 st.step()
         for n in self.NAMES:
             main.wait_stream(self.streams[n])
+
+    def _graph_ok(self):
+        return all(st.world == 1 for st in self.steps.values())
 
     def set_lr(self, lr):
         for st in self.steps.values():

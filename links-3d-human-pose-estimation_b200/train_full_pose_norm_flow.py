@@ -32,7 +32,7 @@ if __name__ == "__main__":
         for xb in loader:
             step.x.copy_(xb, non_blocking=True)
             step.noise.normal_(generator=gen_dev)
-            step.step()
+            step.run(use_graph=not args.no_graph)      # CUDA-graph replay from the third step on
             n_steps += 1
             if rank == 0 and n_steps % args.log_every == 0:
                 print("epoch %d step %d  loss=%.5f  (%.0f poses/s)" % (epoch, n_steps, step.loss_dict()["loss"],

@@ -38,7 +38,7 @@ if __name__ == "__main__":
         for xb in loader:
             trainer.x.copy_(xb, non_blocking=True)
             trainer.noise.normal_(generator=gen_dev)
-            trainer.step()
+            trainer.run(use_graph=not args.no_graph)   # CUDA-graph replay from the third step on
             n_steps += 1
             if rank == 0 and n_steps % args.log_every == 0:
                 d = trainer.loss_dict()

@@ -198,7 +198,7 @@ SIM int sim_flow_pack(int C, int nb, const float* const* w0, const float* const*
     A.w0[k] = w0[k]; A.b0[k] = b0[k]; A.w2[k] = w2[k]; A.b2[k] = b2[k]; A.gs[k] = gs[k]; A.go[k] = go[k]; A.wp[k] = wp[k]; A.wpi[k] = wpi[k];
   }
   A.packed = packed; A.C = C; A.n_blocks = nb;
-  hostsim::launch(dim3(nb), dim3(256), 0, [&] { flow_pack_kernel(A); });
+  hostsim::launch(dim3(nb, kFlowPackSplit), dim3(256), 0, [&] { flow_pack_kernel(A); });
   return 0;
 }
 template <int C, int MODE>

@@ -83,3 +83,50 @@ def test_part_flow_trainer_vs_oracle():
         e = rel_fro(tr.steps[n].Gd[2]["subnet.2.weight"].cpu(), pn[n]["module_list.2.subnet.2.weight"].grad)
         assert e < 4e-2, (n, e)
     assert abs(got["loss"] - ref["loss"].item()) <= 1e-3 * abs(ref["loss"].item())
+
+
+@pytest.mark.parametrize("which", ["full", "parts"])
+def test_graph_replay_equals_eager_steps(which):
+    """run() (eager first step, then one captured CUDA graph replayed; what the drop-in scripts call) follows the same
+    trajectory as step() launched eagerly: same losses every step, same parameters after five steps.  Also pins the
+    all-blocks strided views (shadow casts, global-affine gradient slots) against the per-block parameter views."""
+    from links_b200.flowtrain import FlowTrainStep, PartFlowTrainer
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF
+    B = 64
+    x2d, _ = synth_poses(B, seed=31)
+    g = torch.Generator().manual_seed(11)
+    xs = torch.from_numpy(x2d).cuda()
+    noises = [torch.randn(B, 34, generator=g).cuda() for _ in range(5)]
+
+    def make():
+        if which == "full":
+            return FlowTrainStep(34, OF.init_flow_params(34, 77, perturb=0.3), B, weight_decay=1e-5)
+        width = {"legs": 14, "torso": 20, "left": 22, "right": 22}
+        parts = {n: OF.init_flow_params(width[n], 60 + i, perturb=0.3) for i, n in enumerate(PartFlowTrainer.NAMES)}
+        return PartFlowTrainer(OF.init_flow_params(34, 40, perturb=0.3), parts, B)
+
+    def masters(t):
+        return [t.master] if which == "full" else [t.steps[n].master for n in PartFlowTrainer.NAMES]
+
+    a, b = make(), make()
+    for it in range(5):
+        for t in (a, b):
+            t.x.copy_(xs); t.noise.copy_(noises[it])
+        a.step()
+        b.run()
+        la, lb = a.loss_dict()["loss"], b.loss_dict()["loss"]
+        assert np.isfinite(la) and abs(la - lb) <= 2e-5 * abs(la), (it, la, lb)       # atomics: summation order only
+    assert b.graph is not None
+    for ma, mb in zip(masters(a), masters(b)):
+        d = (ma - mb).abs()
+        # atomically accumulated global-affine gradients differ in their last bits between runs; Adam turns that into at
+        # most a fraction of one update (lr = 2e-4) on entries whose gradient is ~0
+        assert d.max().item() <= 1e-4 and d.mean().item() <= 1e-6, (d.max().item(), d.mean().item())
+    if which == "full":
+        # the strided all-blocks views are the per-block views
+        for k in (0, 5):
+            assert a._w1_all[k].data_ptr() == a.P[k]["subnet.0.weight"].data_ptr()
+            assert a._dgo_all[k].data_ptr() == a.Gd[k]["global_offset"].data_ptr()
+            assert torch.equal(a.W1b[k, :, :a.c1].float(), a.P[k]["subnet.0.weight"].bfloat16().float())
+            assert torch.equal(a.W2b[k, :2 * a.c2].float(), a.P[k]["subnet.2.weight"].bfloat16().float())
