@@ -8,7 +8,11 @@ from .shard import shard_bounds
 
 
 class ArrayLoader:
-    """Epochs of shuffled, equally sized batches of this rank's contiguous shard of (poses_2d [n,34], poses_3d [n,51])."""
+    """Epochs of shuffled, equally sized batches of this rank's contiguous shard of (poses_2d [n,34], poses_3d [n,51]).
+
+    Difference from the reference's DataLoader (train_leg_torso_lifter.py:385, drop_last=False): the final PARTIAL batch
+    of an epoch is dropped -- the step objects own static buffers of one batch size and replay a captured CUDA graph.
+    The permutation is redrawn every epoch, so the dropped poses differ from epoch to epoch."""
 
     def __init__(self, x2d, gt, batch_global, rank=0, world=1, seed=0, shuffle=True, pin=True):
         n = x2d.shape[0]
