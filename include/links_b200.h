@@ -334,6 +334,14 @@ int links_flow_nll_train(const float* packed, int C, int n_blocks, const float* 
  * dx = (dz/dx)^T gz + (d log_jac_det/dx)^T gld  (gld may be NULL = 0).  Backs autograd of the FrEIA shim. */
 int links_flow_vjp(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,
                    const float* gld, float* dx, void* stream);
+/* The same vector-Jacobian product with the parameter-gradient exports of links_flow_nll_train (ex_x1, ex_dsub, d_gscale,
+ * d_goffset; same layouts, d_gscale / d_goffset accumulated) for arbitrary seeds (gz, gld): what autograd needs when a flow
+ * is trained THROUGH the reference's call `z, jac = inn(x)` (train_full_pose_norm_flow.py:75-98,
+ * train_leg_torso_left_right_norm_flow.py:108-166) instead of through the fused NLL step.  dx may be NULL.
+ * Tensor-core kernel; C in {14, 20, 22, 32, 34}. */
+int links_flow_vjp_train(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,
+                         const float* gld, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale, float* d_goffset,
+                         float* stash, void* stream);
 /* Sampling block (train_leg_torso_lifter.py:133-142): out = [x ; s], s = inn^-1(z + 0.2*noise*z) with
  * the root joint zeroed; C must be 34.  out is [2M,34]. */
 int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,

@@ -553,6 +553,21 @@ extern "C" __attribute__((visibility("default"))) int links_flow_vjp(const float
   return launch_flow<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
 }
 
+extern "C" __attribute__((visibility("default"))) int links_flow_vjp_train(const float* packed, int C, int n_blocks, const float* x, int M, const float* gz,
+                                    const float* gld, float* dx, void* ex_x1, void* ex_dsub, float* d_gscale,
+                                    float* d_goffset, float* stash, void* stream) {
+  LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(gz); LINKS_CHECK_PTR(ex_x1); LINKS_CHECK_PTR(ex_dsub);
+  LINKS_CHECK_PTR(d_gscale); LINKS_CHECK_PTR(d_goffset); LINKS_CHECK_ALIGN16(packed);
+  if (M < 1 || n_blocks < 1 || n_blocks > kFlowMaxBlocks) return LINKS_E_RANGE;
+  if (stash != nullptr) LINKS_CHECK_ALIGN16(stash);
+  FlowArgs A;
+  memset(&A, 0, sizeof(A));
+  A.packed = packed; A.x = x; A.out = dx; A.gz = gz; A.gld = gld; A.M = M; A.n_blocks = n_blocks;
+  A.ex_x1 = ex_x1; A.ex_dsub = ex_dsub; A.d_gscale = d_gscale; A.d_goffset = d_goffset;
+  A.stash = stash;
+  return launch_flow_tc_only<FLOW_NLL_FWDBWD>(C, A, links_stream(stream));
+}
+
 extern "C" __attribute__((visibility("default"))) int links_flow_sample(const float* packed, int n_blocks, const float* x, const float* noise, int M,
                                  float* out, void* stream) {
   LINKS_CHECK_PTR(packed); LINKS_CHECK_PTR(x); LINKS_CHECK_PTR(noise); LINKS_CHECK_PTR(out); LINKS_CHECK_ALIGN16(packed);

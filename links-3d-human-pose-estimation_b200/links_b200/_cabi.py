@@ -103,6 +103,7 @@ SIGNATURES = {
     "links_flow_sample": (ci, [vp, ci, vp, vp, ci, vp]),
     "links_flow_vjp": (ci, [vp, ci, ci, vp, ci, vp, vp, vp]),
     "links_flow_nll_train": (ci, [vp, ci, ci, vp, ci, cf, vp, vp, vp, vp, vp, vp, vp]),
+    "links_flow_vjp_train": (ci, [vp, ci, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp]),
     "links_mpjpe": (ci, [vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]),
     "links_threshold_counts": (ci, [vp, sz, vp, ci, ci, vp]),
     "links_pmpjpe": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),

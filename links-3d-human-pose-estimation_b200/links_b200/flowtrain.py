@@ -63,13 +63,14 @@ class _GraphReplay:
 
 class FlowTrainStep(_GraphReplay):
     def __init__(self, C_dim, params, batch, n_blocks=8, lr=2e-4, weight_decay=0.0, device="cuda", process_group=None,
-                 external_rows=False):
+                 external_rows=False, rows=None):
         """params: FrEIA-layout state dict; batch: rows of x per step (the kernel sees 2*batch rows).
         external_rows: the caller fills self.u ([2*batch, C] = [data rows ; sampled rows]) itself instead of the flow
-        drawing samples from its own inverse (the part-flow trainer samples from a frozen full-pose flow)."""
+        drawing samples from its own inverse (the part-flow trainer samples from a frozen full-pose flow).
+        rows: row count of the workspaces when the object only serves vjp() (the FrEIA shim's autograd)."""
         self.external_rows = external_rows
         self.C, self.nb, self.B = C_dim, n_blocks, batch
-        self.M = 2 * batch
+        self.M = 2 * batch if rows is None else int(rows)
         self.c1, self.c2 = C_dim - C_dim // 2, C_dim // 2
         self.lr, self.wd = lr, weight_decay
         self.lib = _cabi.lib()
@@ -200,13 +201,37 @@ class FlowTrainStep(_GraphReplay):
                                      self.nll_sum.data_ptr(), None, self.X1.data_ptr(), self.DS.data_ptr(),
                                      self._dgs.data_ptr(), self._dgo.data_ptr(), self.flow.stash_for(self.M).data_ptr(), st),
               "links_flow_nll_train")
+        self._param_grads()
+        torch.mul(self.nll_sum, 1.0 / self.B, out=self.loss)        # dist_2d + dist_2d_sample
+
+    def _param_grads(self):
+        """Exports of the fused kernel (X1, DS, global-affine sums) -> every parameter gradient in self.grad / self.Gd."""
+        L = self.lib
+        st = torch.cuda.current_stream().cuda_stream
         gemms, (carr, cn) = self._plans
         for arr, n in gemms:
             check(L.links_gemm_grouped(arr, n, st), "links_gemm_grouped")
         check(L.links_colsum_bf16_batched(carr, cn, st), "links_colsum_bf16_batched")
         self._dgs_all.copy_(self._dgs)
         self._dgo_all.copy_(self._dgo)
-        torch.mul(self.nll_sum, 1.0 / self.B, out=self.loss)        # dist_2d + dist_2d_sample
+
+    def vjp(self, x, gz, gld=None, dx=None):
+        """(z, log_jac_det) = inn(x) differentiated for arbitrary seeds: dx = J^T (gz, gld) (optional) and the gradient of
+        every trainable parameter (-> self.Gd[k][name]), one fused kernel launch + the parameter-gradient GEMMs.
+        x, gz: contiguous fp32 [rows, C]; gld: fp32 [rows] or None.  Backs autograd of the FrEIA shim when a flow is
+        trained through `inn(x)` (train_full_pose_norm_flow.py:75-98)."""
+        assert x.shape == (self.M, self.C) and gz.shape == x.shape and x.is_contiguous() and gz.is_contiguous()
+        if self._plans is None:
+            self._build_plans()
+        self._acc.zero_()
+        check(self.lib.links_flow_vjp_train(self.flow.packed.data_ptr(), self.C, self.nb, x.data_ptr(), self.M, gz.data_ptr(),
+                                            gld.data_ptr() if gld is not None else None,
+                                            dx.data_ptr() if dx is not None else None, self.X1.data_ptr(),
+                                            self.DS.data_ptr(), self._dgs.data_ptr(), self._dgo.data_ptr(),
+                                            self.flow.stash_for(self.M).data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream), "links_flow_vjp_train")
+        self._param_grads()
+        return dx
 
     def optimizer_step(self):
         if self.world > 1:

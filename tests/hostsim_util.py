@@ -41,7 +41,7 @@ def sim():
         open(stamp, "w").write(dig)
     L = C.CDLL(SO)
     for name, (res, args) in _cabi.SIGNATURES.items():
-        if name in ("links_flow_nll_train", "links_adam_zero", "links_peer_barrier"):      # tensor-core-only / multi-GPU entry points: no CPU build
+        if name in ("links_flow_nll_train", "links_flow_vjp_train", "links_adam_zero", "links_peer_barrier"):      # tensor-core-only / multi-GPU entry points: no CPU build
             continue
         fn = getattr(L, name.replace("links_", "sim_"))
         fn.restype, fn.argtypes = res, list(args)

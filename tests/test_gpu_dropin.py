@@ -80,17 +80,54 @@ def test_freia_shim_matches_oracle_and_fixture(golden):
     np.testing.assert_allclose(xr.cpu().numpy(), G["x"], rtol=1e-3, atol=2e-5)
     for q in inn.parameters():
         q.requires_grad = True
-    # un-frozen flow (the state at every reference call site): input gradients still flow, parameters get none
+    # un-frozen flow (the state at every reference call site): autograd now also delivers the parameter gradients,
+    # as FrEIA does (train_full_pose_norm_flow.py:75-98 trains the flow through this very call)
     x2 = torch.from_numpy(G["x"]).cuda().requires_grad_(True)
-    Ff.SequenceINN._warned = False
-    with pytest.warns(UserWarning):
-        z2, ld2 = inn(x2)
+    z2, ld2 = inn(x2)
     (0.5 * torch.sum(z2 ** 2, 1) - ld2).mean().backward()
     np.testing.assert_allclose(x2.grad.cpu().numpy(), xo.grad.numpy(), rtol=2e-3, atol=1e-5)
-    assert all(q.grad is None for q in inn.parameters())
-    inn.strict_param_grads = True
-    with pytest.raises(NotImplementedError):
-        inn(x.detach())
+    from oracle import steps as OS
+    pn = OS.params_require_grad(params)
+    zo2, ldo2 = OF.inn_forward(torch.from_numpy(G["x"]), pn)
+    OF.nll(zo2, ldo2).mean().backward()
+    named = dict(inn.named_parameters())
+    for k in (0, 3, 7):
+        for n, tol in (("subnet.0.weight", 4e-2), ("subnet.0.bias", 4e-2), ("subnet.2.weight", 4e-2), ("subnet.2.bias", 2e-2),
+                       ("global_scale", 2e-3), ("global_offset", 2e-3)):
+            key = "module_list.%d.%s" % (k, n)
+            got, ref = named[key].grad.cpu(), pn[key].grad
+            assert got.shape == ref.shape
+            e = ((got - ref).norm() / ref.norm()).item()
+            assert e < tol, (key, e)
+    assert named["module_list.0.w_perm"].grad is None
+    # a second call before one backward (data rows + sampled rows in the reference step) accumulates into .grad
+    g_before = named["module_list.3.subnet.2.weight"].grad.clone()
+    za, lda = inn(x2.detach())
+    zb, ldb = inn(x2.detach())
+    ((0.5 * torch.sum(za ** 2, 1) - lda).mean() + (0.5 * torch.sum(zb ** 2, 1) - ldb).mean()).backward()
+    g_after = named["module_list.3.subnet.2.weight"].grad
+    assert ((g_after - 3 * g_before).norm() / g_before.norm()).item() < 1e-3
+    # a torch optimiser step changes the parameters: the next call sees the new values (forward AND gradient engine)
+    opt = torch.optim.SGD(inn.parameters(), lr=1e-2)
+    opt.step()
+    opt.zero_grad()
+    z3, ld3 = inn(x2.detach())
+    (0.5 * torch.sum(z3 ** 2, 1) - ld3).mean().backward()
+    p3 = {k: v.detach().cpu().clone() for k, v in inn.state_dict().items()}
+    pn3 = OS.params_require_grad(p3)
+    zo3, ldo3 = OF.inn_forward(torch.from_numpy(G["x"]), pn3)
+    OF.nll(zo3, ldo3).mean().backward()
+    np.testing.assert_allclose(z3.detach().cpu().numpy(), zo3.detach().numpy(), rtol=2e-3, atol=2e-4)
+    key = "module_list.5.subnet.2.weight"
+    e = ((named[key].grad.cpu() - pn3[key].grad).norm() / pn3[key].grad.norm()).item()
+    assert e < 4e-2, e
+    # opt-out used by code that never reads the flow's gradients (the lifter trainers)
+    inn.input_grad_only = True
+    opt.zero_grad(set_to_none=True)
+    x4 = torch.from_numpy(G["x"]).cuda().requires_grad_(True)
+    z4, ld4 = inn(x4)
+    (0.5 * torch.sum(z4 ** 2, 1) - ld4).mean().backward()
+    assert x4.grad is not None and all(q.grad is None for q in inn.parameters())
 
 
 def test_metrics_batch_dropin_vs_reference_golden(golden):
@@ -166,3 +203,63 @@ def test_module_called_twice_before_backward():
             mod = getattr(mod, part)
         assert rel_fro(mod.weight.grad.cpu(), pq[name + ".weight"].grad) < 8e-2, name
     assert q.res_common.l1.weight.grad is None
+
+
+def test_reference_flow_training_loop_runs_on_the_shim():
+    """The reference's own flow trainer body (train_full_pose_norm_flow.py:67-98: `z, jac = inn(x)`, no-grad sampling
+    through `inn(z, rev=True)`, `inn(samples)`, `loss.backward()`, `torch.optim.Adam`) executed against the FrEIA shim:
+    losses and the parameter trajectory follow the oracle's autograd + Adam on the FrEIA restatement."""
+    import FrEIA.framework as Ff
+    import FrEIA.modules as Fm
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, steps as OS
+    from utils.helpers import subnet_fc
+    B = 100                                     # not a multiple of the 64-row GEMM boxes / the 128-row flow tiles
+    params = OF.init_flow_params(34, 91, perturb=0.3)
+    inn_2d = Ff.SequenceINN(34)
+    for _ in range(8):
+        inn_2d.append(Fm.AllInOneBlock, subnet_constructor=subnet_fc, permute_soft=True)
+    inn_2d.load_state_dict(params)
+    inn_2d.cuda()
+    optimizer = torch.optim.Adam(inn_2d.parameters(), lr=2e-4, weight_decay=1e-5)
+    pn = OS.params_require_grad(params)
+    for k in list(pn):
+        if "w_perm" in k:
+            pn[k].requires_grad_(False)
+    opt_ref = torch.optim.Adam([v for v in pn.values() if v.requires_grad], lr=2e-4, weight_decay=1e-5)
+    x2d, _ = synth_poses(B, seed=41)
+    g = torch.Generator().manual_seed(13)
+    for it in range(3):
+        x = torch.from_numpy(x2d)
+        noise = torch.randn(B, 34, generator=g)
+        inp_poses = x.cuda()
+        # ---- reference step body
+        z, log_jac_det = inn_2d(inp_poses)
+        dist_2d = (0.5 * torch.sum(z ** 2, 1) - log_jac_det).mean()
+        with torch.no_grad():
+            z_noisy = z + 0.2 * noise.cuda() * z                      # add_noise (utils/helpers.py:298-308) with fixed draws
+            samples, _ = inn_2d(z_noisy, rev=True)
+            samples = samples.reshape(-1, 2, 17)
+            samples[:, :, [0]] = 0.0
+            samples = samples.reshape(-1, 34)
+        z_s, jac_s = inn_2d(samples)
+        dist_2d_sample = (0.5 * torch.sum(z_s ** 2, 1) - jac_s).mean()
+        loss = dist_2d + dist_2d_sample
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        # ---- oracle
+        opt_ref.zero_grad()
+        ref = OS.flow_step(x, pn, noise)
+        ref["loss"].backward()
+        opt_ref.step()
+        assert abs(loss.item() - ref["loss"].item()) <= (1e-3 if it == 0 else 5e-3) * abs(ref["loss"].item()), \
+            (it, loss.item(), ref["loss"].item())
+    named = dict(inn_2d.named_parameters())
+    for n in ("subnet.0.weight", "subnet.2.weight", "global_scale", "global_offset"):
+        key = "module_list.4." + n
+        d_gpu = named[key].detach().cpu() - params[key]
+        d_ref = pn[key].detach() - params[key]
+        cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
+        assert cos.item() > 0.9, (n, cos.item())
+    assert torch.equal(named["module_list.4.w_perm"].detach().cpu(), params["module_list.4.w_perm"])
