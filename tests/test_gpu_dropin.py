@@ -263,3 +263,136 @@ def test_reference_flow_training_loop_runs_on_the_shim():
         cos = (d_gpu * d_ref).sum() / (d_gpu.norm() * d_ref.norm())
         assert cos.item() > 0.9, (n, cos.item())
     assert torch.equal(named["module_list.4.w_perm"].detach().cpu(), params["module_list.4.w_perm"])
+
+
+def test_reference_lifter_step_runs_on_the_dropin_modules():
+    """The leg/torso training step written the way the reference writes it (train_leg_torso_lifter.py:123-276) -- nn.Module
+    lifters called twice, FrEIA flows with requires_grad=True parameters no optimiser owns, utils.helpers /
+    rotation_conversions glue, in-place masked assignments, loss.backward(), two torch.optim.Adam -- executed on the
+    drop-in modules (CUDA) and compared with the oracle step (CPU fp32): every loss term, the gradient that reaches the
+    input of the flows' consumers (through the weights' first Adam update direction)."""
+    import math
+    import FrEIA.framework as Ff
+    import FrEIA.modules as Fm
+    from links_b200.synth import synth_poses
+    from oracle import flow as OF, nets as ON, steps as OS
+    from utils.helpers import get_bone_lengths_all, perspective_projection, subnet_fc
+    from utils.models_def import Leg_Lifter, Torso_Lifter
+    from utils.rotation_conversions import euler_angles_to_matrix
+    dev = "cuda"
+    B, depth_t = 48, 10.0
+    p_leg, p_torso = ON.init_lifter_params(7, 11), ON.init_lifter_params(10, 12)
+    f_leg, f_torso = OF.init_flow_params(14, 41, perturb=0.3), OF.init_flow_params(20, 42, perturb=0.3)
+    f_full = OF.init_flow_params(34, 40, perturb=0.3)
+    legs_lifter = Leg_Lifter(use_batchnorm=False, num_joints=7, use_dropout=False, d_rate=0.25).cuda()
+    torso_lifter = Torso_Lifter(use_batchnorm=False, num_joints=10, use_dropout=False, d_rate=0.25).cuda()
+    legs_lifter.load_state_dict(p_leg, strict=False)
+    torso_lifter.load_state_dict(p_torso, strict=False)
+
+    def make_inn(C, params):
+        inn = Ff.SequenceINN(C)
+        for _ in range(8):
+            inn.append(Fm.AllInOneBlock, subnet_constructor=subnet_fc, permute_soft=True)
+        inn.load_state_dict(params)
+        return inn.cuda()
+    leg_inn_2d, torso_inn_2d, inn_2d = make_inn(14, f_leg), make_inn(20, f_torso), make_inn(34, f_full)
+    leg_opt = torch.optim.Adam(legs_lifter.parameters(), lr=2e-4, weight_decay=1e-5)
+    torso_opt = torch.optim.Adam(torso_lifter.parameters(), lr=2e-4, weight_decay=1e-5)
+    x2d, _ = synth_poses(B, seed=3)
+    g = torch.Generator().manual_seed(8)
+    x, noise = torch.from_numpy(x2d), torch.randn(B, 34, generator=g)
+    eps_x, u_y = torch.randn(2 * B, generator=g), torch.rand(2 * B, generator=g)
+    cfg = OS.DEFAULT_CFG
+    bone_rel = torch.tensor(OS.G.BONE_REL_MPI, dtype=torch.float32)
+
+    # ---------------- the step, reference style, on the drop-in modules
+    leg_opt.zero_grad()
+    torso_opt.zero_grad()
+    inp_poses = x.to(dev)
+    with torch.no_grad():                                               # :133-142
+        z, _ = inn_2d(inp_poses)
+        z = z + 0.2 * noise.to(dev) * z
+        sampled_poses, _ = inn_2d(z, rev=True)
+        sampled_poses = sampled_poses.reshape(-1, 2, 17)
+        sampled_poses[:, :, [0]] = 0.0
+        sampled_poses = sampled_poses.reshape(-1, 34)
+    inp_poses = torch.cat((inp_poses, sampled_poses.data), dim=0)
+    n = inp_poses.shape[0]
+    inp_legs = inp_poses.reshape(-1, 2, 17)[:, :, :7].reshape(-1, 14)
+    inp_torso = inp_poses.reshape(-1, 2, 17)[:, :, 7:].reshape(-1, 20)
+    legs_pred, legs_angle = legs_lifter(inp_legs)
+    torso_pred, torso_angle = torso_lifter(inp_torso)
+    props = (legs_angle + torso_angle) / 2
+    pred = torch.cat((legs_pred, torso_pred), dim=1)
+    pred[:, 0] = 0.0
+    zeros = torch.zeros((n, 1), device=dev)
+    R_comp = euler_angles_to_matrix(torch.cat((torch.ones((n, 1), device=dev) * props, zeros, zeros), dim=1), 'XYZ')
+    elevation = torch.cat((props.mean().reshape(1), props.std().reshape(1)))
+    x_ang = (-elevation[0]) + elevation[1] * eps_x.to(dev).reshape(n, 1)
+    y_ang = (u_y.to(dev).reshape(n, 1) - 0.5) * 1.99 * math.pi
+    Rx = euler_angles_to_matrix(torch.cat((x_ang, zeros, zeros), dim=1), 'XYZ')
+    Ry = euler_angles_to_matrix(torch.cat((zeros, y_ang, zeros), dim=1), 'XYZ')
+    R = Rx @ (Ry @ R_comp)
+    depth = pred + depth_t
+    depth[depth < 1.0] = 1.0
+    pred_3d = torch.cat(((inp_poses.reshape(-1, 2, 17) * depth.reshape(-1, 1, 17).repeat(1, 2, 1)).reshape(-1, 34), depth),
+                        dim=1).reshape(-1, 3, 17)
+    pred_3d = pred_3d - pred_3d[:, :, [0]]
+    rot_poses = (R.matmul(pred_3d)).reshape(-1, 51)
+    rot_2d = perspective_projection(torch.cat((rot_poses[:, 0:34], rot_poses[:, 34:51] + depth_t), dim=1))
+    torso_norm = rot_2d.reshape(-1, 2, 17)[:, :, 7:].reshape(-1, 20)
+    leg_norm = rot_2d.reshape(-1, 2, 17)[:, :, :7].reshape(-1, 14)
+    z, jac = leg_inn_2d(leg_norm)
+    leg_likeli = (0.5 * torch.sum(z ** 2, 1) - jac).mean()
+    z, jac = torso_inn_2d(torso_norm)
+    torso_likeli = (0.5 * torch.sum(z ** 2, 1) - jac).mean()
+    likeli = torso_likeli + leg_likeli
+    legs_pred_rot, _ = legs_lifter(leg_norm)
+    torso_pred_rot, _ = torso_lifter(torso_norm)
+    pred_rot = torch.cat((legs_pred_rot, torso_pred_rot), dim=1)
+    pred_rot[:, 0] = 0.0
+    pred_rot_depth = pred_rot + depth_t
+    pred_rot_depth[pred_rot_depth < 1.0] = 1.0
+    pred_3d_rot = torch.cat(((rot_2d.reshape(-1, 2, 17) * pred_rot_depth.reshape(-1, 1, 17).repeat(1, 2, 1)).reshape(-1, 34),
+                             pred_rot_depth), dim=1).reshape(-1, 3, 17)
+    pred_3d_rot = pred_3d_rot - pred_3d_rot[:, :, [0]]
+    L3d = (rot_poses - pred_3d_rot.reshape(-1, 51)).norm(dim=1).mean()
+    re_rot_3d = (R.permute(0, 2, 1) @ pred_3d_rot).reshape(-1, 51)
+    re_rot_2d = perspective_projection(torch.cat((re_rot_3d[:, 0:34], re_rot_3d[:, 34:51] + depth_t), dim=1))
+    rep_rot = (re_rot_2d - inp_poses).abs().sum(dim=1).mean()
+    num_pairs = n // 2
+    pose_pairs = pred_3d[0:2 * num_pairs].reshape(2 * num_pairs, 51).reshape(-1, 2, 51)
+    pairs_re = re_rot_3d[0:2 * num_pairs].reshape(-1, 2, 51)
+    vel = ((pose_pairs[:, 0] - pose_pairs[:, 1]) - (pairs_re[:, 0] - pairs_re[:, 1])).norm(dim=1).mean()
+    bl = get_bone_lengths_all(pred_3d.reshape(-1, 51))
+    rel_bl = bl / bl.mean(dim=1, keepdim=True)
+    bl_prior = (bone_rel.to(dev) - rel_bl).square().sum(dim=1).mean()
+    loss = cfg["weight_likeli"] * likeli + cfg["weight_2d"] * rep_rot + cfg["weight_3d"] * L3d + \
+        cfg["weight_velocity"] * vel + cfg["weight_bl"] * bl_prior
+    loss.backward()
+    torso_opt.step()
+    leg_opt.step()
+    got = {"L3d": L3d, "rep_rot": rep_rot, "re_rot_3d": vel, "bl_prior": bl_prior, "leg_likeli": leg_likeli,
+           "torso_likeli": torso_likeli, "likeli": likeli, "loss": loss}
+
+    # ---------------- the oracle step (CPU fp32) on the same inputs
+    pl, pt = OS.params_require_grad(p_leg), OS.params_require_grad(p_torso)
+    opts = OS.make_adam([pl, pt])
+    u = OS.sample_poses(x, f_full, noise)
+    ref = OS.lt_step(u, pl, pt, f_leg, f_torso, eps_x, u_y, cfg, bone_rel)
+    ref["loss"].backward()
+    for o in opts:
+        o.step()
+    for k, v in got.items():
+        r = ref[k].item()
+        assert abs(v.item() - r) <= 2e-3 * abs(r) + 1e-6, (k, v.item(), r)
+    # first Adam update = -lr * sign(gradient) (up to eps): the two implementations moved the weights the same way
+    for mod, pd, p0 in ((legs_lifter, pl, p_leg), (torso_lifter, pt, p_torso)):
+        named = dict(mod.named_parameters())
+        for key in ("upscale.weight", "res_pose2.l1.weight", "res_angle1.l2.weight", "downscale.weight", "angles.bias"):
+            d_gpu = (named[key].detach().cpu() - p0[key]).flatten()
+            d_ref = (pd[key].detach() - p0[key]).flatten()
+            agree = (torch.sign(d_gpu) == torch.sign(d_ref)).float().mean().item()
+            assert agree > 0.9, (key, agree)
+    # the flows' parameters got gradients too (requires_grad=True, like in the reference), nobody steps them
+    assert next(leg_inn_2d.module_list[0].subnet.parameters()).grad is not None
