@@ -32,6 +32,11 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 os.environ.setdefault("WANDB_MODE", "disabled")
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  Rank 0 alone runs the CPU legs (the oracle step behind `parity`, the whole
+# `--impl reference` arm) and those want every host core: lift the cap for rank 0 before torch initialises its thread pools.
+if (os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1"
+        and int(os.environ.get("WORLD_SIZE", "1")) > 1):
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 METRIC = "lifter_train_step_poses_per_sec"
 UNIT = "poses/s"
@@ -522,7 +527,11 @@ def run_gpu(args):
     if rank == 0:
         parity, cpu_base = None, None
         if not args.skip_cpu:
-            cpu_sec, cores, ref_first = cpu_steps(B, 15, 1, first_losses=True)      # ~10 s of CPU work
+            # the timed CPU leg belongs to rank 0 at N = 1 only (~10 s of CPU work); data-parallel runs keep the single
+            # oracle step the `parity` object needs (measured at N = 2 / 8: the same leg beside the other ranks' spinning
+            # host threads is 20-30 x slower and would add minutes to every scaling run)
+            n_cpu = 15 if world == 1 else 0
+            cpu_sec, cores, ref_first = cpu_steps(B, n_cpu, 1, first_losses=True)
             worst, per = 0.0, {}
             for kind in ("lt", "lr"):
                 for k, v in first_losses[kind].items():
@@ -531,9 +540,10 @@ def run_gpu(args):
                     worst = max(worst, e)
             parity = {"what": "first-step losses (fresh weights) of the LT and LR steps at B=%d vs the CPU oracle (fp32)" % B,
                       "tolerance_rel": 1e-3, "max_rel_err": worst, "ok": bool(worst <= 1e-3), "losses": per}
-            cpu_base = {"value": B / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), 15 timed "
-                                  "steps after 1 warm-up" % B}
+            if n_cpu:
+                cpu_base = {"value": B / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), %d "
+                                      "timed steps after 1 warm-up" % (B, n_cpu)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
