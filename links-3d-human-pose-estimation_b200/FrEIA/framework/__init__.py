@@ -79,6 +79,7 @@ class SequenceINN(nn.Module):
         self.module_list.append(module)
         self.shapes.append(self.shapes[-1])
         self._pk = None
+        self._geng = {}
 
     def __len__(self):
         return len(self.module_list)
