@@ -170,6 +170,41 @@ def cpu_steps(batch, steps, warmup, first_losses=False):
     return sum(times) / max(len(times), 1), cores, (first if first_losses else None)
 
 
+def cpu_flow_steps(batch, steps, warmup):
+    """BASELINE config #1 on the host cores: the full-pose flow training step of the CPU oracle (train_full_pose_norm_flow.py:
+    67-98: NLL of the data + NLL of the flow's own noisy samples, Adam) -> the `cpu_baseline` object of configs[0]."""
+    import torch
+    from links_b200 import init as INIT
+    from links_b200.synth import synth_poses
+    from oracle import steps as OS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = INIT.init_flow_params(34, 40)
+    pn = OS.params_require_grad(params)
+    for k in pn:
+        if "w_perm" in k:
+            pn[k].requires_grad_(False)
+    opt = torch.optim.Adam([v for v in pn.values() if v.requires_grad], lr=2e-4, weight_decay=1e-5)
+    x2d, _ = synth_poses(batch, seed=77)
+    x = torch.from_numpy(x2d)
+    gen = torch.Generator().manual_seed(5)
+    times = []
+    for it in range(warmup + steps):
+        noise = torch.randn(batch, 34, generator=gen)
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = OS.flow_step(x, pn, noise)
+        out["loss"].backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {"value": batch / sec, "unit": UNIT, "ms_per_step": sec * 1e3, "cores": cores, "kind": "port",
+            "sample": "oracle port (PyTorch CPU fp32) of the flow training step, B=%d, %d timed steps after %d warm-ups"
+                      % (batch, steps, warmup)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -540,6 +575,11 @@ def run_gpu(args):
                     worst = max(worst, e)
             parity = {"what": "first-step losses (fresh weights) of the LT and LR steps at B=%d vs the CPU oracle (fp32)" % B,
                       "tolerance_rel": 1e-3, "max_rel_err": worst, "ok": bool(worst <= 1e-3), "losses": per}
+            if n_cpu and extras:
+                try:        # config #1 is quoted on the reference's CPU path: time the oracle's flow step beside the GPU number
+                    extras[0]["cpu_baseline"] = cpu_flow_steps(256, 20, 2)
+                except Exception as exc:      # a reported baseline must never take the bench line down
+                    extras[0]["cpu_baseline"] = {"error": repr(exc)[:200]}
             if n_cpu:
                 cpu_base = {"value": B / cpu_sec, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": "oracle port (PyTorch CPU fp32), LT+LR step on %d-pose batches (the bench batch), %d "
